@@ -1,0 +1,119 @@
+/* tru_b200.h - C ABI of libtru_b200.so: the B200 (sm_100a) TRU-Net hot path.
+ *
+ * Every entry point replaces a piece of the reference's Python hot path
+ * (Okrio/tinyrecurrentunet; file:line cited per function).  The reference has
+ * no FFI of its own (it is pure Python on PyTorch); the binding a maintainer
+ * would add is a ctypes stub inside torch.autograd.Function - see
+ * INTEGRATION.md and tinyrecurrentunet_b200/_lib.py.
+ *
+ * Conventions
+ *  - All tensors are contiguous fp32 device memory owned by the caller; the
+ *    library never allocates, frees or retains device memory (except static
+ *    twiddle tables).  Workspaces are sized by the *_workspace_bytes calls.
+ *  - All work is enqueued on `stream` (a cudaStream_t passed as void*); no
+ *    host synchronisation except the one-time tru_init().
+ *  - Return value: 0 on success, TRU_ERR_* (<0) otherwise; CUDA errors are
+ *    returned as -1000 - cudaError_t.  tru_last_error() gives a thread-local
+ *    message.  Nothing throws or exits.  There is NO CPU fallback: devices
+ *    other than sm_100 return TRU_ERR_ARCH.
+ *  - Activation layout inside the network is channels-last [B*T][L][C]; the
+ *    network boundary keeps the reference layouts (B,T,4,F) in and (B,T,8,F)
+ *    out.
+ */
+#ifndef TRU_B200_H
+#define TRU_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRU_ABI_VERSION 1
+#define TRU_OK 0
+#define TRU_ERR_ARG (-1)        /* bad shape / null pointer / unsupported size */
+#define TRU_ERR_WORKSPACE (-2)  /* workspace too small */
+#define TRU_ERR_ARCH (-3)       /* device is not sm_100 */
+#define TRU_ERR_ALIGN (-4)      /* pointer not 16-byte aligned */
+
+#define TRU_NFFT 512
+#define TRU_HOP 128
+#define TRU_NBINS 257
+
+int tru_abi_version(void);
+const char* tru_last_error(void);
+/* One-time per-device table initialisation (synchronous).  Called lazily by
+ * every entry point; call it explicitly before CUDA-graph capture. */
+int tru_init(void);
+
+/* ------------------------------------------------------------------ *
+ * Front end: dataset.py:246-272 (ProcessAudio.forward), :56-76 (pcenfunc)
+ * audio (B,N) -> feats (B,T',4,257), T' = 1 + N/128.
+ * ------------------------------------------------------------------ */
+typedef struct {
+  int batch;       /* B */
+  int n_samples;   /* N  (> 256) */
+  double pcen_eps, pcen_s, pcen_alpha, pcen_delta, pcen_r; /* dataset.py:57 defaults 1e-6 .025 .98 2 .5 */
+} TruFrontendDesc;
+
+size_t tru_frontend_workspace_bytes(const TruFrontendDesc* d);
+/* pcen_state_in / pcen_state_out: optional (B,257) smoother state M (D11). */
+int tru_frontend_fwd(const TruFrontendDesc* d, const float* audio,
+                     const float* pcen_state_in, float* feats,
+                     float* pcen_state_out, void* workspace,
+                     size_t workspace_bytes, void* stream);
+/* Streaming step: frames (S,512) already framed by the caller (centre = the
+ * reference's reflect-padded framing), state (S,257) in/out, feats (S,4,257). */
+int tru_frontend_step(const TruFrontendDesc* d, const float* frames,
+                      float* pcen_state, float* feats, void* stream);
+
+/* ------------------------------------------------------------------ *
+ * Back end: dataset.py:182-203 (mod_phase), phm.py:31-45 (PhaseAwareMask),
+ * dataset.py:293-296 (torch.istft, rectangular window, centre).
+ * net_out (B,T',C,257) -> audio (B, 128 (T'-1)).
+ * ------------------------------------------------------------------ */
+typedef struct {
+  int batch;      /* B */
+  int n_frames;   /* T' */
+  int n_channels; /* C: 8 for the network output, 3 for ProcessAudio.backward */
+  int ch_mag, ch_sin, ch_cos;   /* set 0 ("mixture"): 0,2,3 */
+  int ch_sin1, ch_cos1;         /* set 1 ("noise"):   6,7 ; ignored if !use_mask */
+  int use_mask;                 /* 1: beta-sigmoid mask; 0: plain mod_phase+iSTFT */
+  double beta;
+} TruBackendDesc;
+
+int tru_backend_fwd(const TruBackendDesc* d, const float* net_out, float* audio,
+                    void* stream);
+/* grad_audio (B, 128 (T'-1)) -> grad_net_out (B,T',C,257) (fully written). */
+int tru_backend_bwd(const TruBackendDesc* d, const float* net_out,
+                    const float* grad_audio, float* grad_net_out, void* stream);
+
+/* ------------------------------------------------------------------ *
+ * Loss: stft_loss.py:9-166 (MultiResolutionSTFTLoss, band="full") fused with
+ * util.py:239-240 (L1).  x = prediction, y = target, both (B,N).
+ * sums layout (double[16]): for r<3: [4r+0] sum (|Y|-|X|)^2, [4r+1] sum |Y|^2,
+ * [4r+2] sum |ln|Y| - ln|X||, [4r+3] unused;  [12] sum |x-y|.
+ * out (float[3]) = {l1, sc_loss, mag_loss}.
+ * ------------------------------------------------------------------ */
+typedef struct {
+  int batch;
+  int n_samples;
+  int n_res;              /* <= 3 */
+  int fft_size[3];        /* each in {512,1024,2048} */
+  int hop_size[3];
+  int win_length[3];      /* <= fft_size */
+  double sc_lambda, mag_lambda;
+} TruLossDesc;
+
+int tru_loss_fwd(const TruLossDesc* d, const float* x, const float* y,
+                 const float* const* windows, double* sums, float* out,
+                 void* stream);
+/* grad_out (float[3], device): upstream grads of {l1, sc_loss, mag_loss}. */
+int tru_loss_bwd(const TruLossDesc* d, const float* x, const float* y,
+                 const float* const* windows, const double* sums,
+                 const float* grad_out, float* grad_x, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRU_B200_H */

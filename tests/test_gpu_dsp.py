@@ -1,0 +1,166 @@
+"""GPU parity: fused front end / back end / loss kernels (through the C ABI) vs
+the CPU oracle and the committed golden vectors.  Tolerances are the north
+star's: <=1e-4 on features, mask/audio and loss; <=1e-3 on gradients."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import tru_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+FEAT_TOL = 1e-4
+GRAD_TOL = 1e-3
+
+
+def check_feats(got, ref, audio):
+    """Feature parity (<=1e-4).  ch0/ch1 (log-mag, PCEN) are compared directly.  The
+    phase features sin/cos(angle X) are ill-conditioned where |X| -> 0: the fp32
+    oracle itself is ~2e-3 away from an fp64 evaluation there (parity
+    notes), so they are compared (a) weighted by |X|/max|X| everywhere and (b)
+    directly wherever |X| >= 1e-2 max|X|."""
+    got = got.detach().cpu()
+    ref = ref.detach().cpu()
+    mag = O.stft_rect(audio.cpu()).abs().transpose(1, 2).reshape(ref[..., 0, :].shape)
+    for ch in (0, 1):      # relative to the channel's full scale (|log-mag| <= 1, PCEN ~ 5)
+        err = (got[..., ch, :] - ref[..., ch, :]).abs().max().item() / ref[..., ch, :].abs().max().item()
+        assert err <= FEAT_TOL, (ch, err)
+    big = mag >= 1e-2 * mag.max()
+    for ch in (2, 3):
+        d = (got[..., ch, :] - ref[..., ch, :]).abs()
+        assert (d * mag).max().item() / mag.max().item() <= FEAT_TOL * 0.1, ch
+        assert d[big].max().item() <= FEAT_TOL, (ch, d[big].max().item())
+
+
+def rel(a, b):
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def T():
+    import tinyrecurrentunet_b200 as t
+    from tinyrecurrentunet_b200 import ops, dataset, stft_loss
+    assert torch.cuda.is_available()
+    return dict(ops=ops, dataset=dataset, stft_loss=stft_loss)
+
+
+@pytest.mark.parametrize("B,N", [(3, 64000), (2, 128 * 37 + 61), (1, 300), (5, 2048)])
+def test_frontend_matches_oracle(T, B, N):
+    _, noisy = O.synthetic_batch(B, n=N)
+    ref = O.frontend(noisy)
+    got = T["ops"].frontend(noisy.cuda()).cpu()
+    assert got.shape == ref.shape == (B, 1 + N // 128, 4, 257)
+    check_feats(got, ref, noisy)
+
+
+def test_frontend_matches_reference_golden(T, golden_dir):
+    g = np.load(os.path.join(golden_dir, "dataset_ref.npz"))
+    audio = torch.from_numpy(g["audio"]).view(1, 1, -1)
+    got = T["dataset"].ProcessAudio()(audio.cuda()).cpu()          # (T',4,F), reference call shape
+    ref3 = torch.from_numpy(g["feats3"])
+    ref4 = torch.stack((ref3[:, 0], torch.from_numpy(g["pcen"])[0], ref3[:, 1], ref3[:, 2]), dim=1)
+    check_feats(got, ref4, audio.view(1, -1))
+
+
+def test_frontend_state_and_streaming_step(T):
+    ops = T["ops"]
+    _, noisy = O.synthetic_batch(4, n=128 * 50)
+    x = noisy.cuda()
+    feats, state = ops.frontend(x, return_state=True)
+    ref, ref_state = O.frontend(noisy, return_state=True)
+    check_feats(feats, ref, noisy)
+    assert rel(state, ref_state) <= FEAT_TOL
+    # streaming: frame t of the reflect-padded signal, one step at a time (D11)
+    xp = torch.nn.functional.pad(x.unsqueeze(1), (256, 256), mode="reflect").squeeze(1)
+    st = torch.zeros(4, 257, device="cuda")
+    outs = []
+    for t in range(feats.shape[1]):
+        fr = xp[:, 128 * t:128 * t + 512].contiguous()
+        f = ops.frontend_step(fr, st)
+        outs.append(f)
+    check_feats(torch.stack(outs, 1), ref, noisy)
+    assert rel(st, state) <= FEAT_TOL
+
+
+@pytest.mark.parametrize("B,T_", [(2, 40), (1, 2), (3, 95)])
+def test_mask_istft_forward_backward(T, B, T_):
+    torch.manual_seed(B * 100 + T_)
+    out = torch.randn(B, T_, 8, 257)
+    out[:, :, 0] = out[:, :, 0] * 0.6          # some values beyond the clamp at +-1
+    out[:, :, 4] = out[:, :, 4] * 0.6
+    ref_in = out.clone().requires_grad_(True)
+    ref = O.backend(ref_in)
+    w = torch.randn_like(ref)
+    (ref * w).sum().backward()
+    x = out.cuda().requires_grad_(True)
+    got = T["ops"].mask_istft(x)
+    assert got.shape == ref.shape
+    assert rel(got, ref) <= FEAT_TOL
+    (got * w.cuda()).sum().backward()
+    assert rel(x.grad, ref_in.grad) <= GRAD_TOL
+    assert torch.count_nonzero(x.grad[:, :, [1, 4, 5]]) == 0
+
+
+def test_istft_matches_reference_golden_and_roundtrip(T, golden_dir):
+    g = np.load(os.path.join(golden_dir, "dataset_ref.npz"))
+    dp = T["dataset"].ProcessAudio()
+    feats3 = torch.from_numpy(g["feats3"]).cuda()
+    back = dp.backward(feats3).cpu()
+    assert rel(back, torch.from_numpy(g["backward"])) <= FEAT_TOL
+    # encode -> decode round trip at full size
+    _, noisy = O.synthetic_batch(2, n=64000)
+    x = 0.25 * noisy.cuda()          # keep |X| inside the log-mag clamp range (<= 10^(25/20))
+    rec = dp.backward(dp(x))
+    assert rel(rec, x) <= FEAT_TOL
+
+
+@pytest.mark.parametrize("B,N", [(2, 6000), (3, 16000), (1, 64000)])
+def test_mrstft_l1_forward_backward(T, B, N):
+    torch.manual_seed(N)
+    clean, noisy = O.synthetic_batch(B, n=N)
+    x_ref = noisy.clone().requires_grad_(True)
+    sc, mg = O.mrstft_loss(x_ref, clean)
+    l1 = torch.nn.functional.l1_loss(x_ref, clean)
+    (0.7 * l1 + 1.3 * sc + 0.9 * mg).backward()
+    mr = T["stft_loss"].MultiResolutionSTFTLoss(
+        fft_sizes=[512, 1024, 2048], hop_sizes=[50, 120, 240], win_lengths=[240, 600, 1200],
+        sc_lambda=0.5, mag_lambda=0.5).cuda()
+    x = noisy.cuda().requires_grad_(True)
+    l1g, scg, mgg = mr.forward_with_l1(x, clean.cuda())
+    assert rel(l1g, l1) <= FEAT_TOL and rel(scg, sc) <= FEAT_TOL and rel(mgg, mg) <= FEAT_TOL
+    (0.7 * l1g + 1.3 * scg + 0.9 * mgg).backward()
+    assert rel(x.grad, x_ref.grad) <= GRAD_TOL
+
+
+def test_mrstft_matches_reference_golden(T, golden_dir):
+    g = np.load(os.path.join(golden_dir, "stft_loss_ref.npz"))
+    mr = T["stft_loss"].MultiResolutionSTFTLoss(
+        fft_sizes=[512, 1024, 2048], hop_sizes=[50, 120, 240], win_lengths=[240, 600, 1200],
+        sc_lambda=0.5, mag_lambda=0.5).cuda()
+    x = torch.from_numpy(g["x"]).cuda().requires_grad_(True)
+    sc, mg = mr(x, torch.from_numpy(g["y"]).cuda())
+    (sc + mg).backward()
+    assert rel(sc, torch.from_numpy(g["sc"])) <= FEAT_TOL
+    assert rel(mg, torch.from_numpy(g["mag"])) <= FEAT_TOL
+    assert rel(x.grad, torch.from_numpy(g["grad_x"])) <= GRAD_TOL
+
+
+def test_single_resolution_stftloss_class(T):
+    clean, noisy = O.synthetic_batch(2, n=8000)
+    f = T["stft_loss"].STFTLoss(1024, 120, 600).cuda()
+    sc, mg = f(noisy.cuda(), clean.cuda())
+    xm = O.stft_mag(noisy, 1024, 120, 600)
+    ym = O.stft_mag(clean, 1024, 120, 600)
+    assert rel(sc, torch.norm(ym - xm) / torch.norm(ym)) <= FEAT_TOL
+    assert rel(mg, torch.nn.functional.l1_loss(torch.log(ym), torch.log(xm))) <= FEAT_TOL
+
+
+def test_errors_are_loud(T):
+    with pytest.raises(Exception):
+        T["ops"].frontend(torch.zeros(1, 64000))                 # CPU tensor: no CPU path
+    with pytest.raises(Exception):
+        T["ops"].frontend(torch.zeros(1, 200, device="cuda"))    # N <= 256: reflect pad impossible

@@ -1,0 +1,93 @@
+"""ctypes binding of libtru_b200.so (include/tru_b200.h).
+
+There is deliberately no fallback: if the shared library is missing the import
+fails loudly, and every call that returns a non-zero status raises."""
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libtru_b200.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        "tinyrecurrentunet_b200: %s not found. Build it with "
+        "`python -m tinyrecurrentunet_b200.build` (needs nvcc, targets sm_100a). "
+        "There is no CPU/PyTorch fallback for this path." % LIB_PATH)
+
+lib = C.CDLL(LIB_PATH)
+
+c_float_p = C.c_void_p     # raw device pointers are passed as integers
+c_stream = C.c_void_p
+
+
+class TruFrontendDesc(C.Structure):
+    _fields_ = [("batch", C.c_int), ("n_samples", C.c_int),
+                ("pcen_eps", C.c_double), ("pcen_s", C.c_double), ("pcen_alpha", C.c_double),
+                ("pcen_delta", C.c_double), ("pcen_r", C.c_double)]
+
+
+class TruBackendDesc(C.Structure):
+    _fields_ = [("batch", C.c_int), ("n_frames", C.c_int), ("n_channels", C.c_int),
+                ("ch_mag", C.c_int), ("ch_sin", C.c_int), ("ch_cos", C.c_int),
+                ("ch_sin1", C.c_int), ("ch_cos1", C.c_int), ("use_mask", C.c_int),
+                ("beta", C.c_double)]
+
+
+class TruLossDesc(C.Structure):
+    _fields_ = [("batch", C.c_int), ("n_samples", C.c_int), ("n_res", C.c_int),
+                ("fft_size", C.c_int * 3), ("hop_size", C.c_int * 3), ("win_length", C.c_int * 3),
+                ("sc_lambda", C.c_double), ("mag_lambda", C.c_double)]
+
+
+def _sig(name, restype, argtypes):
+    fn = getattr(lib, name)
+    fn.restype = restype
+    fn.argtypes = argtypes
+    return fn
+
+
+_sig("tru_abi_version", C.c_int, [])
+_sig("tru_last_error", C.c_char_p, [])
+_sig("tru_init", C.c_int, [])
+_sig("tru_frontend_workspace_bytes", C.c_size_t, [C.POINTER(TruFrontendDesc)])
+_sig("tru_frontend_fwd", C.c_int, [C.POINTER(TruFrontendDesc), c_float_p, c_float_p, c_float_p, c_float_p,
+                                  C.c_void_p, C.c_size_t, c_stream])
+_sig("tru_frontend_step", C.c_int, [C.POINTER(TruFrontendDesc), c_float_p, c_float_p, c_float_p, c_stream])
+_sig("tru_backend_fwd", C.c_int, [C.POINTER(TruBackendDesc), c_float_p, c_float_p, c_stream])
+_sig("tru_backend_bwd", C.c_int, [C.POINTER(TruBackendDesc), c_float_p, c_float_p, c_float_p, c_stream])
+_sig("tru_loss_fwd", C.c_int, [C.POINTER(TruLossDesc), c_float_p, c_float_p, C.POINTER(C.c_void_p),
+                              C.c_void_p, c_float_p, c_stream])
+_sig("tru_loss_bwd", C.c_int, [C.POINTER(TruLossDesc), c_float_p, c_float_p, C.POINTER(C.c_void_p),
+                              C.c_void_p, c_float_p, c_float_p, c_stream])
+
+EXPORTS = ["tru_abi_version", "tru_last_error", "tru_init", "tru_frontend_workspace_bytes",
+           "tru_frontend_fwd", "tru_frontend_step", "tru_backend_fwd", "tru_backend_bwd",
+           "tru_loss_fwd", "tru_loss_bwd"]
+
+
+class TruError(RuntimeError):
+    pass
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib.tru_last_error()
+        raise TruError("%s failed (%d): %s" % (what or "libtru_b200", rc, msg.decode() if msg else "?"))
+
+
+def ptr(t):
+    """Raw device pointer of a contiguous fp32/fp64 CUDA tensor (or None)."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise TruError("tinyrecurrentunet_b200 ops need CUDA tensors (sm_100a); there is no CPU path")

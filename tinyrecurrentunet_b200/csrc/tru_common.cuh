@@ -1,0 +1,69 @@
+// Common host/device helpers for libtru_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/tru_b200.h"
+
+namespace tru {
+
+// ---- error reporting (thread-local, never throws) ---------------------------
+char* last_error_buf();
+int set_error(int code, const char* fmt, ...);
+int ensure_init();                       // tables + arch check, lazily
+const float2* twiddle_table();           // device pointer: exp(-2*pi*i*k/2048), k<2048
+int sm_count();
+
+#define TRU_CUDA(call)                                                         \
+  do {                                                                         \
+    cudaError_t e__ = (call);                                                  \
+    if (e__ != cudaSuccess)                                                    \
+      return tru::set_error(-1000 - (int)e__, "%s:%d %s: %s", __FILE__,        \
+                            __LINE__, #call, cudaGetErrorString(e__));         \
+  } while (0)
+
+#define TRU_LAUNCH_CHECK()                                                     \
+  do {                                                                         \
+    cudaError_t e__ = cudaGetLastError();                                      \
+    if (e__ != cudaSuccess)                                                    \
+      return tru::set_error(-1000 - (int)e__, "%s:%d launch: %s", __FILE__,    \
+                            __LINE__, cudaGetErrorString(e__));                \
+  } while (0)
+
+#define TRU_REQUIRE(cond, code, ...)                                           \
+  do {                                                                         \
+    if (!(cond)) return tru::set_error(code, __VA_ARGS__);                     \
+  } while (0)
+
+static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+#if defined(__CUDACC__)
+// ---- device helpers ---------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// reflect index (torch pad_mode="reflect"): valid for -n < k < 2n-1
+__device__ __forceinline__ int reflect_idx(int k, int n) {
+  k = k < 0 ? -k : k;
+  return k >= n ? 2 * (n - 1) - k : k;
+}
+#endif
+
+}  // namespace tru
