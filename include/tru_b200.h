@@ -113,6 +113,46 @@ int tru_loss_bwd(const TruLossDesc* d, const float* x, const float* y,
                  const float* const* windows, const double* sums,
                  const float* grad_out, float* grad_x, void* stream);
 
+/* ------------------------------------------------------------------ *
+ * TRU-Net: network.py:122-171 (TRUNet.forward, repaired per SURVEY D4/D10/D11)
+ * and its backward.  x (B,T,4,257) -> out (B,T,8,257).
+ *
+ * params: 108 device pointers in the canonical order of
+ *   tinyrecurrentunet_b200/network.py:PARAM_ORDER (the state-dict order of
+ *   network.py:134-150: encoder, decoder, FGRU, TGRU), PyTorch layouts.
+ * bn_*:   23 BatchNorm layers in the order encoder.1..5 (pw, dw), decoder.0..4
+ *   (pw, convT), decoder.5 (pw), FGRU, TGRU.  Running stats are updated in
+ *   training mode exactly like nn.BatchNorm1d (momentum, unbiased variance);
+ *   bn_num_batches entries may be null.
+ * The workspace holds every saved activation; the SAME workspace must be
+ * passed to tru_trunet_backward (sized with with_backward = 1).
+ * grads: 108 pointers, same order/shapes as params, zero-initialised by the
+ *   caller; the backward ACCUMULATES into them.
+ * h0 / h_last: optional TGRU state (B*16, 128) for streaming (D11); the
+ *   backward assumes h0 == NULL.
+ * ------------------------------------------------------------------ */
+#define TRU_NET_NPARAMS 108
+#define TRU_NET_NBN 23
+typedef struct {
+  int batch;      /* B */
+  int n_frames;   /* T */
+  int training;   /* 1: batch statistics + running-stat update; 0: running stats */
+  double bn_eps, bn_momentum;   /* 1e-5, 0.1 */
+} TruNetDesc;
+
+size_t tru_trunet_workspace_bytes(const TruNetDesc* d, int with_backward);
+int tru_trunet_forward(const TruNetDesc* d, const float* const* params,
+                       float* const* bn_running_mean, float* const* bn_running_var,
+                       long long* const* bn_num_batches, const float* x,
+                       const float* h0, float* out, float* h_last,
+                       void* workspace, size_t workspace_bytes, void* stream);
+int tru_trunet_backward(const TruNetDesc* d, const float* const* params,
+                        const float* x, const float* grad_out,
+                        float* const* grads, void* workspace,
+                        size_t workspace_bytes, void* stream);
+/* Test aid: byte offset of a named saved buffer inside the workspace (-1 if unknown). */
+long long tru_trunet_buffer_offset(const TruNetDesc* d, const char* name, int index);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,284 @@
+"""GPU parity: TRU-Net forward / backward / streaming through the C ABI vs the CPU
+oracle (same weights, same inputs).  <=1e-4 relative on outputs, <=1e-3 on gradients."""
+import ctypes as C
+
+import pytest
+import torch
+
+from oracle import tru_oracle as O
+
+pytestmark = pytest.mark.gpu
+OUT_TOL = 1e-4
+GRAD_TOL = 1e-3
+
+
+def rel(a, b):
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def make_pair(seed=0):
+    from tinyrecurrentunet_b200 import network
+    torch.manual_seed(seed)
+    ref = O.randomize_bn(O.TRUNet(), seed)
+    net = network.TRUNet(3, 64, 3, 128, [5, 3], [2, 1], 192)
+    net.load_state_dict(ref.state_dict())
+    return ref, net.cuda()
+
+
+def feats_like(B, T, seed):
+    """Features with the statistics of the real front end (log-mag, PCEN, sin, cos)."""
+    _, noisy = O.synthetic_batch(B, n=128 * (T - 1), first=seed)
+    return O.frontend(noisy)
+
+
+def oracle_intermediates(ref, x, keep_graph=False):
+    """Pre-BN conv outputs / GRU outputs of the oracle, as channels-last (BT, L, C)."""
+    got = {}
+    hooks = []
+
+    def cap(name, tr=True):
+        def fn(_m, _i, o):
+            o = o[0] if isinstance(o, tuple) else o
+            if keep_graph:
+                o.retain_grad()
+                got[name] = (o, tr)
+            else:
+                got[name] = (o.transpose(1, 2) if tr else o).detach().contiguous()
+        return fn
+    hooks.append(ref.encoder[0].register_forward_hook(cap("A0")))
+    for i in range(1, 6):
+        seq = ref.encoder[i].DepthwiseSeparableConv1d
+        hooks.append(seq[0].register_forward_hook(cap("Zp%d" % i)))
+        hooks.append(seq[3].register_forward_hook(cap("Zd%d" % i)))
+    hooks.append(ref.FGRU.GRU.register_forward_hook(cap("HF", tr=False)))
+    hooks.append(ref.FGRU.conv[0].register_forward_hook(cap("ZFp")))
+    hooks.append(ref.TGRU.GRU.register_forward_hook(cap("HT_seq", tr=False)))
+    hooks.append(ref.TGRU.conv[0].register_forward_hook(cap("ZTp_seq")))
+    for d in range(6):
+        seq = list(ref.decoder[d].children())[0]
+        hooks.append(seq[0].register_forward_hook(cap("ZDp%d" % d)))
+        if d < 5:
+            hooks.append(seq[3].register_forward_hook(cap("ZDt%d" % d)))
+    y = ref(x)
+    for h in hooks:
+        h.remove()
+    if keep_graph:
+        return y, got
+    B, T = x.shape[0], x.shape[1]
+    for k in ("HT_seq", "ZTp_seq"):          # (B*16, T, C) -> (B*T, 16, C)
+        v = got.pop(k)
+        got[k[:-4]] = v.view(B, 16, T, -1).permute(0, 2, 1, 3).reshape(B * T, 16, -1).contiguous()
+    return y, got
+
+
+def gpu_buffer(net, name, index, shape):
+    from tinyrecurrentunet_b200 import _lib as L
+    off = L.lib.tru_trunet_buffer_offset(C.byref(net._last_desc), name.encode(), index)
+    assert off >= 0, name
+    n = 1
+    for s in shape:
+        n *= s
+    return net._last_ws[off:off + 4 * n].view(torch.float32).view(shape).cpu()
+
+
+def compare_intermediates(net, got, B, T):
+    rows = []
+    names = [("A0", "A0", 0)] + [("Zp%d" % i, "Zp", i) for i in range(1, 6)] + [("Zd%d" % i, "Zd", i) for i in range(1, 6)]
+    names += [("HF", "HF", 0), ("ZFp", "ZFp", 0), ("HT", "HT", 0), ("ZTp", "ZTp", 0)]
+    names += [("ZDp%d" % d, "ZDp", d) for d in range(6)] + [("ZDt%d" % d, "ZDt", d) for d in range(5)]
+    order = ["A0"] + [n for i in range(1, 6) for n in ("Zp%d" % i, "Zd%d" % i)] + ["HF", "ZFp", "HT", "ZTp"]
+    for d in range(6):
+        order += ["ZDp%d" % d] + (["ZDt%d" % d] if d < 5 else [])
+    lut = {a: (b, c) for a, b, c in names}
+    for key in order:
+        ref = got[key]
+        mine = gpu_buffer(net, lut[key][0], lut[key][1], tuple(ref.shape))
+        rows.append((key, rel(mine, ref)))
+    return rows
+
+
+@pytest.mark.parametrize("training", [False, True])
+def test_forward_matches_oracle(training):
+    ref, net = make_pair(1)
+    B, T = 2, 7
+    x = feats_like(B, T, 3)
+    ref.train(training)
+    net.train(training)
+    net._debug_keep_ws = True
+    with torch.no_grad():
+        y_ref, inter = oracle_intermediates(ref, x)
+        y = net(x.cuda())
+    rows = compare_intermediates(net, inter, B, T)
+    print("\n".join("%-6s %.3e" % r for r in rows))
+    bad = [r for r in rows if not r[1] <= OUT_TOL]
+    assert not bad, bad
+    assert y.shape == (B, T, 8, 257)
+    assert rel(y, y_ref) <= OUT_TOL
+    if training:                                  # running statistics updated like nn.BatchNorm1d
+        sd_ref, sd = ref.state_dict(), net.state_dict()
+        for k in sd_ref:
+            if "running" in k:
+                assert rel(sd[k], sd_ref[k]) <= OUT_TOL, k
+            if "num_batches" in k:
+                assert int(sd[k]) == int(sd_ref[k]) == 1, k
+
+
+BN_OF = dict([("Zp%d" % i, 2 * (i - 1)) for i in range(1, 6)] + [("Zd%d" % i, 2 * (i - 1) + 1) for i in range(1, 6)]
+             + [("ZDp%d" % d, 10 + 2 * d) for d in range(6)] + [("ZDt%d" % d, 11 + 2 * d) for d in range(5)]
+             + [("ZFp", 21), ("ZTp", 22)])
+
+
+def compare_intermediate_grads(net, got, B, T):
+    """dZ (grad w.r.t. each pre-BN conv output) of the oracle vs q0*dY + q1*Z + q2 of the CUDA path."""
+    rows = []
+    small = gpu_buffer(net, "small", 0, (23, 7, 128))
+    keys = ["ZDp5"] + [k for d in range(4, -1, -1) for k in ("ZDt%d" % d, "ZDp%d" % d)] + ["ZTp", "ZFp"]
+    keys += [k for i in range(5, 0, -1) for k in ("Zd%d" % i, "Zp%d" % i)]
+    for key in keys:
+        t, tr = got[key if key != "ZTp" else "ZTp_seq"]
+        g = t.grad.transpose(1, 2) if tr else t.grad
+        if key == "ZTp":
+            g = g.reshape(B, 16, T, -1).permute(0, 2, 1, 3).reshape(B * T, 16, -1)
+        shape = tuple(g.shape)
+        name, idx = (key[:-1], int(key[-1])) if key[-1].isdigit() else (key, 0)
+        dy = gpu_buffer(net, "d" + name, idx, shape)
+        z = gpu_buffer(net, name, idx, shape)
+        Cn = shape[-1]
+        q0, q1, q2 = (small[BN_OF[key], j, :Cn] for j in (4, 5, 6))
+        rows.append((key, rel(q0 * dy + q1 * z + q2, g)))
+    return rows
+
+
+BN_KEYS = ([k for i in range(1, 6) for k in (("Zp", i), ("Zd", i))] + [k for d in range(5) for k in (("ZDp", d), ("ZDt", d))]
+           + [("ZDp", 5), ("ZFp", 0), ("ZTp", 0)])
+
+
+def relu_mask_mismatches(ref, net, fwd_ref, B, T):
+    """Number of ReLU inputs whose sign differs between the oracle and the CUDA forward.
+
+    Gradients are discontinuous in the ReLU mask.  Pre-activations agree to ~1e-6
+    absolute, so among the ~10^6 ReLU inputs of these test shapes an element within
+    rounding distance of zero gets a different mask every other seed; on such tiny
+    shapes ONE flipped element moves BN-coupled gradients by percents in BOTH
+    implementations' favour.  Gradient parity is therefore asserted on seeds where the
+    two forwards took identical ReLU branches (checked exactly, here)."""
+    from tinyrecurrentunet_b200 import network
+    masks = {}
+    hooks = []
+    mods = dict(ref.named_modules())
+    for idx, name in enumerate(network.BN_ORDER):
+        hooks.append(mods[name].register_forward_hook(
+            lambda _m, _i, o, idx=idx: masks.__setitem__(idx, (o.detach() > 0).transpose(1, 2).contiguous())))
+    hooks.append(ref.encoder[0].StandardConv1d[0].register_forward_hook(
+        lambda _m, _i, o: masks.__setitem__("A0", (o.detach() > 0).transpose(1, 2).contiguous())))
+    out = fwd_ref()
+    for h in hooks:
+        h.remove()
+    small = gpu_buffer(net, "small", 0, (23, 7, 128))
+    bad = int((masks["A0"] != (gpu_buffer(net, "A0", 0, tuple(masks["A0"].shape)) > 0)).sum())
+    for idx, (name, k) in enumerate(BN_KEYS):
+        m = masks[idx]
+        if name == "ZTp":
+            m = m.reshape(B, 16, T, -1).permute(0, 2, 1, 3).reshape(B * T, 16, -1)
+        z = gpu_buffer(net, name, k, tuple(m.shape))
+        Cn = m.shape[-1]
+        bad += int((m != (z * small[idx, 0, :Cn] + small[idx, 1, :Cn] > 0)).sum())
+    return bad, out
+
+
+def test_backward_matches_oracle():
+    B, T = 2, 6
+    for seed in range(2, 22):
+        ref, net = make_pair(seed)
+        x = feats_like(B, T, seed + 3)
+        ref.train()
+        net.train()
+        net._debug_keep_ws = True
+        w = torch.randn(B, T, 8, 257)
+        y = net(x.cuda())
+        holder = {}
+
+        def fwd_ref():
+            holder["r"] = oracle_intermediates(ref, x, keep_graph=True)
+        flips, _ = relu_mask_mismatches(ref, net, fwd_ref, B, T)
+        print("seed", seed, "ReLU mask mismatches:", flips)
+        if flips == 0:
+            break
+    else:
+        raise AssertionError("no seed with identical ReLU masks")
+    y_ref, inter = holder["r"]
+    (y_ref * w).sum().backward()
+    (y * w.cuda()).sum().backward()
+    print("\n".join("d%-6s %.3e" % r for r in compare_intermediate_grads(net, inter, B, T)))
+    gref = dict(ref.named_parameters())
+    rows = []
+    gmax = max(p.grad.abs().max().item() for p in gref.values())
+    for k, p in net.named_parameters():
+        assert p.grad is not None, k
+        g, r = p.grad.cpu(), gref[k].grad
+        # conv biases in front of a training-mode BN have an exactly-zero true gradient;
+        # both sides only hold rounding noise there, so scale by the global gradient size.
+        scale = max(r.abs().max().item(), 1e-3 * gmax)
+        rows.append((k, (g - r).abs().max().item() / scale))
+    print("\n".join("%-55s %.3e" % r for r in rows))
+    bad = [r for r in rows if not r[1] <= GRAD_TOL]
+    assert not bad, bad
+
+
+def test_eval_batched_equals_single_and_streaming():
+    ref, net = make_pair(3)
+    net.eval()
+    ref.eval()
+    B, T = 3, 9
+    x = feats_like(B, T, 7)
+    xg = x.cuda()
+    with torch.no_grad():
+        y = net(xg)
+        y1 = net(xg[1])                           # 3-D call == batch element (D10)
+        assert y1.shape == (T, 8, 257)
+        assert rel(y1, y[1]) <= 1e-5
+        h = torch.zeros(B * 16, 128, device="cuda")
+        outs = []
+        for t in range(T):                        # streaming == offline (D11)
+            o, h = net.step(xg[:, t], h)
+            outs.append(o)
+        assert rel(torch.stack(outs, 1), y) <= OUT_TOL
+        y_ref, h_ref = ref(x, return_state=True)
+        assert rel(y, y_ref) <= OUT_TOL
+        y2, hl = net(xg, return_state=True)
+        assert rel(hl, h_ref[0]) <= OUT_TOL and rel(h, h_ref[0]) <= OUT_TOL
+
+
+def test_loss_fn_end_to_end_matches_oracle():
+    """audio -> features -> net -> mask+iSTFT -> loss, both sides end to end.
+
+    Loss values must agree to 1e-4.  Per-parameter gradient parity (1e-3) is proven
+    stage by stage (network backward on identical ReLU masks above; back end and loss
+    backward in test_gpu_dsp.py).  End to end the two front ends legitimately differ by
+    ~2e-3 in the phase features of near-silent bins (see check_feats in test_gpu_dsp.py),
+    which flips a few ReLU masks, so here the whole gradient vector is compared in the
+    L2 sense."""
+    from tinyrecurrentunet_b200 import stft_loss, util
+    B, N = 2, 128 * 20
+    ref, net = make_pair(4)
+    clean, noisy = O.synthetic_batch(B, n=N, first=4)
+    ref.train()
+    net.train()
+    loss_ref, d_ref, den_ref = O.loss_fn(ref, clean, noisy)
+    loss_ref.backward()
+    mr = stft_loss.MultiResolutionSTFTLoss(fft_sizes=[512, 1024, 2048], hop_sizes=[50, 120, 240],
+                                           win_lengths=[240, 600, 1200], sc_lambda=0.5, mag_lambda=0.5).cuda()
+    loss, d = util.loss_fn(net, (clean.cuda(), noisy.cuda()), ell_p=1, ell_p_lambda=1, stft_lambda=1, mrstftloss=mr)
+    loss.backward()
+    assert rel(loss, loss_ref) <= OUT_TOL
+    for k in ("l1", "stft_sc", "stft_mag"):
+        assert rel(d[k], d_ref[k]) <= OUT_TOL, k
+    gref = dict(ref.named_parameters())
+    num = den = 0.0
+    for k, p in net.named_parameters():
+        assert torch.isfinite(p.grad).all(), k
+        num += (p.grad.cpu().double() - gref[k].grad.double()).pow(2).sum().item()
+        den += gref[k].grad.double().pow(2).sum().item()
+    assert (num / den) ** 0.5 <= 2e-2, (num / den) ** 0.5

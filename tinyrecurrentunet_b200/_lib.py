@@ -39,6 +39,11 @@ class TruLossDesc(C.Structure):
                 ("sc_lambda", C.c_double), ("mag_lambda", C.c_double)]
 
 
+class TruNetDesc(C.Structure):
+    _fields_ = [("batch", C.c_int), ("n_frames", C.c_int), ("training", C.c_int),
+                ("bn_eps", C.c_double), ("bn_momentum", C.c_double)]
+
+
 def _sig(name, restype, argtypes):
     fn = getattr(lib, name)
     fn.restype = restype
@@ -60,9 +65,18 @@ _sig("tru_loss_fwd", C.c_int, [C.POINTER(TruLossDesc), c_float_p, c_float_p, C.P
 _sig("tru_loss_bwd", C.c_int, [C.POINTER(TruLossDesc), c_float_p, c_float_p, C.POINTER(C.c_void_p),
                               C.c_void_p, c_float_p, c_float_p, c_stream])
 
+_PP = C.POINTER(C.c_void_p)
+_sig("tru_trunet_workspace_bytes", C.c_size_t, [C.POINTER(TruNetDesc), C.c_int])
+_sig("tru_trunet_forward", C.c_int, [C.POINTER(TruNetDesc), _PP, _PP, _PP, _PP, c_float_p, c_float_p, c_float_p,
+                                    c_float_p, C.c_void_p, C.c_size_t, c_stream])
+_sig("tru_trunet_backward", C.c_int, [C.POINTER(TruNetDesc), _PP, c_float_p, c_float_p, _PP, C.c_void_p,
+                                     C.c_size_t, c_stream])
+_sig("tru_trunet_buffer_offset", C.c_longlong, [C.POINTER(TruNetDesc), C.c_char_p, C.c_int])
+
 EXPORTS = ["tru_abi_version", "tru_last_error", "tru_init", "tru_frontend_workspace_bytes",
            "tru_frontend_fwd", "tru_frontend_step", "tru_backend_fwd", "tru_backend_bwd",
-           "tru_loss_fwd", "tru_loss_bwd"]
+           "tru_loss_fwd", "tru_loss_bwd", "tru_trunet_workspace_bytes", "tru_trunet_forward",
+           "tru_trunet_backward", "tru_trunet_buffer_offset"]
 
 
 class TruError(RuntimeError):

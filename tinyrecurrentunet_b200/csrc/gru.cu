@@ -1,0 +1,427 @@
+// Persistent GRU kernels (network.py:45-58, torch.nn.GRU semantics, gate order
+// r,z,n; h' = (1-z)*n + z*h; n = tanh(gi_n + r*(W_hn h + b_hn))).
+//
+//  FGRU: bidirectional GRU(128->64) over the 16 frequency positions of every
+//        frame.  A CTA owns 64 sequences of one direction; W_hh (48 KB) stays in
+//        shared memory for all 16 steps; each thread keeps its 4x4 slice of h in
+//        registers.
+//  TGRU: causal GRU(64->128) over time for the B*16 (batch, frequency) sequences.
+//        A CTA owns SC sequences for ALL T steps; thread j keeps row j of W_hh
+//        (128 floats) in registers, h lives in shared memory and is broadcast.
+//        The same kernel with T = 1 and h0/hlast is the streaming step (D11).
+// The input projections (W_ih x + b_ih) are hoisted out as one implicit GEMM.
+// Forward stores r, z, n and hn = W_hn h + b_hn so that backward-through-time only
+// needs one mat-vec per step (dGh @ W_hh).
+#include "net_kernels.cuh"
+
+namespace tru {
+namespace {
+
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg((const float4*)p); }
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// =============================== FGRU ========================================
+constexpr int FH = 64, FL = 16, FSEQ = 64, FNT = 256;
+constexpr int F_WT_LD = 3 * FH + 4;      // forward: WT[k][j]
+constexpr int F_H_LD = FH + 4;
+constexpr int F_W_LD = FH + 4;           // backward: W[j][k]
+constexpr int F_G_LD = 3 * FH + 4;
+
+__global__ void __launch_bounds__(FNT) fgru_fwd_kernel(const __grid_constant__ GruParams p) {
+  extern __shared__ __align__(16) float smem[];
+  float* WT = smem;                       // [64][196]
+  float* hs = WT + FH * F_WT_LD;          // [64][68]
+  const int tid = threadIdx.x, dir = blockIdx.y;
+  const float* whh = p.whh[dir];
+  for (int i = tid; i < 3 * FH * FH; i += FNT) {
+    const int j = i / FH, k = i % FH;
+    WT[k * F_WT_LD + j] = __ldg(whh + i);
+  }
+  for (int i = tid; i < FSEQ * F_H_LD; i += FNT) hs[i] = 0.f;
+  const int ts = tid >> 4, tu = tid & 15;
+  const int seq0 = blockIdx.x * FSEQ + ts * 4;
+  float4 bh[3];
+#pragma unroll
+  for (int g = 0; g < 3; ++g) bh[g] = ld4(p.bhh[dir] + g * FH + tu * 4);
+  float hown[4][4];
+#pragma unroll
+  for (int s = 0; s < 4; ++s)
+#pragma unroll
+    for (int u = 0; u < 4; ++u) hown[s][u] = 0.f;
+  __syncthreads();
+
+  for (int step = 0; step < FL; ++step) {
+    const int l = dir ? FL - 1 - step : step;
+    float4 gi[4][3];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const bool ok = seq0 + s < p.nseq;
+      const float* g = p.G + ((long)(seq0 + s) * FL + l) * (6 * FH) + dir * 3 * FH + tu * 4;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) gi[s][q] = ok ? ld4(g + q * FH) : make_float4(0, 0, 0, 0);
+    }
+    float acc[4][3][4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+#pragma unroll
+      for (int g = 0; g < 3; ++g) { acc[s][g][0] = bh[g].x; acc[s][g][1] = bh[g].y; acc[s][g][2] = bh[g].z; acc[s][g][3] = bh[g].w; }
+#pragma unroll 4
+    for (int k4 = 0; k4 < FH / 4; ++k4) {
+      float4 hv[4];
+#pragma unroll
+      for (int s = 0; s < 4; ++s) hv[s] = *(const float4*)(hs + (ts * 4 + s) * F_H_LD + k4 * 4);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          const float4 w = *(const float4*)(WT + (k4 * 4 + kk) * F_WT_LD + g * FH + tu * 4);
+#pragma unroll
+          for (int s = 0; s < 4; ++s) {
+            const float h = kk == 0 ? hv[s].x : kk == 1 ? hv[s].y : kk == 2 ? hv[s].z : hv[s].w;
+            acc[s][g][0] = fmaf(h, w.x, acc[s][g][0]); acc[s][g][1] = fmaf(h, w.y, acc[s][g][1]);
+            acc[s][g][2] = fmaf(h, w.z, acc[s][g][2]); acc[s][g][3] = fmaf(h, w.w, acc[s][g][3]);
+          }
+        }
+      }
+    }
+    __syncthreads();                      // everyone has read hs
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const float gr[4] = {gi[s][0].x, gi[s][0].y, gi[s][0].z, gi[s][0].w};
+      const float gz[4] = {gi[s][1].x, gi[s][1].y, gi[s][1].z, gi[s][1].w};
+      const float gn[4] = {gi[s][2].x, gi[s][2].y, gi[s][2].z, gi[s][2].w};
+      float r[4], z[4], n[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        r[u] = sigmoidf_(gr[u] + acc[s][0][u]);
+        z[u] = sigmoidf_(gz[u] + acc[s][1][u]);
+        n[u] = tanhf(gn[u] + r[u] * acc[s][2][u]);
+        hown[s][u] = (1.0f - z[u]) * n[u] + z[u] * hown[s][u];
+      }
+      const float4 hv = make_float4(hown[s][0], hown[s][1], hown[s][2], hown[s][3]);
+      *(float4*)(hs + (ts * 4 + s) * F_H_LD + tu * 4) = hv;
+      if (seq0 + s < p.nseq) {
+        const long row = (long)(seq0 + s) * FL + l;
+        *(float4*)(p.H + row * (2 * FH) + dir * FH + tu * 4) = hv;
+        if (p.cache) {
+          float* c = p.cache + row * (8 * FH) + dir * 4 * FH + tu * 4;
+          *(float4*)(c) = make_float4(r[0], r[1], r[2], r[3]);
+          *(float4*)(c + FH) = make_float4(z[0], z[1], z[2], z[3]);
+          *(float4*)(c + 2 * FH) = make_float4(n[0], n[1], n[2], n[3]);
+          *(float4*)(c + 3 * FH) = make_float4(acc[s][2][0], acc[s][2][1], acc[s][2][2], acc[s][2][3]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(FNT) fgru_bwd_kernel(const __grid_constant__ GruParams p) {
+  extern __shared__ __align__(16) float smem[];
+  float* W = smem;                        // [192][68]
+  float* dg = W + 3 * FH * F_W_LD;        // [64][196]
+  const int tid = threadIdx.x, dir = blockIdx.y;
+  const float* whh = p.whh[dir];
+  for (int i = tid; i < 3 * FH * FH; i += FNT) W[(i / FH) * F_W_LD + (i % FH)] = __ldg(whh + i);
+  const int ts = tid >> 4, tu = tid & 15;
+  const int seq0 = blockIdx.x * FSEQ + ts * 4;
+  float carry[4][4];
+#pragma unroll
+  for (int s = 0; s < 4; ++s)
+#pragma unroll
+    for (int u = 0; u < 4; ++u) carry[s][u] = 0.f;
+  __syncthreads();
+
+  for (int step = 0; step < FL; ++step) {
+    const int l = dir ? step : FL - 1 - step;           // reverse of the forward order
+    const int lp = dir ? l + 1 : l - 1;                 // position of h_prev
+    float dd[4][4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      float4 dr = make_float4(0, 0, 0, 0), dz = dr, dn = dr, dhn = dr;
+      if (seq0 + s < p.nseq) {
+        const long row = (long)(seq0 + s) * FL + l;
+        const float4 dh4 = ld4(p.dH + row * (2 * FH) + dir * FH + tu * 4);
+        const float* c = p.cache + row * (8 * FH) + dir * 4 * FH + tu * 4;
+        const float4 r4 = ld4(c), z4 = ld4(c + FH), n4 = ld4(c + 2 * FH), hn4 = ld4(c + 3 * FH);
+        float4 hp4 = make_float4(0, 0, 0, 0);
+        if (lp >= 0 && lp < FL) hp4 = ld4(p.H + ((long)(seq0 + s) * FL + lp) * (2 * FH) + dir * FH + tu * 4);
+        const float dh[4] = {dh4.x + carry[s][0], dh4.y + carry[s][1], dh4.z + carry[s][2], dh4.w + carry[s][3]};
+        const float r[4] = {r4.x, r4.y, r4.z, r4.w}, z[4] = {z4.x, z4.y, z4.z, z4.w};
+        const float n[4] = {n4.x, n4.y, n4.z, n4.w}, hn[4] = {hn4.x, hn4.y, hn4.z, hn4.w};
+        const float hp[4] = {hp4.x, hp4.y, hp4.z, hp4.w};
+        float o[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float dnu = dh[u] * (1.0f - z[u]) * (1.0f - n[u] * n[u]);
+          o[0][u] = dnu * hn[u] * r[u] * (1.0f - r[u]);             // d pre-activation r
+          o[1][u] = dh[u] * (hp[u] - n[u]) * z[u] * (1.0f - z[u]);  // d pre-activation z
+          o[2][u] = dnu;                                            // d (gi_n)
+          o[3][u] = dnu * r[u];                                     // d (hn)
+          dd[s][u] = dh[u] * z[u];
+        }
+        dr = make_float4(o[0][0], o[0][1], o[0][2], o[0][3]);
+        dz = make_float4(o[1][0], o[1][1], o[1][2], o[1][3]);
+        dn = make_float4(o[2][0], o[2][1], o[2][2], o[2][3]);
+        dhn = make_float4(o[3][0], o[3][1], o[3][2], o[3][3]);
+        float* gi = p.dGi + row * (6 * FH) + dir * 3 * FH + tu * 4;
+        float* gh = p.dGh + row * (6 * FH) + dir * 3 * FH + tu * 4;
+        *(float4*)(gi) = dr; *(float4*)(gi + FH) = dz; *(float4*)(gi + 2 * FH) = dn;
+        *(float4*)(gh) = dr; *(float4*)(gh + FH) = dz; *(float4*)(gh + 2 * FH) = dhn;
+      } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dd[s][u] = 0.f;
+      }
+      float* d = dg + (ts * 4 + s) * F_G_LD + tu * 4;
+      *(float4*)(d) = dr; *(float4*)(d + FH) = dz; *(float4*)(d + 2 * FH) = dhn;
+    }
+    __syncthreads();
+    float acc[4][4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[s][u] = 0.f;
+#pragma unroll 4
+    for (int j4 = 0; j4 < 3 * FH / 4; ++j4) {
+      float4 gv[4];
+#pragma unroll
+      for (int s = 0; s < 4; ++s) gv[s] = *(const float4*)(dg + (ts * 4 + s) * F_G_LD + j4 * 4);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const float4 w = *(const float4*)(W + (j4 * 4 + jj) * F_W_LD + tu * 4);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          const float g = jj == 0 ? gv[s].x : jj == 1 ? gv[s].y : jj == 2 ? gv[s].z : gv[s].w;
+          acc[s][0] = fmaf(g, w.x, acc[s][0]); acc[s][1] = fmaf(g, w.y, acc[s][1]);
+          acc[s][2] = fmaf(g, w.z, acc[s][2]); acc[s][3] = fmaf(g, w.w, acc[s][3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) carry[s][u] = dd[s][u] + acc[s][u];
+    __syncthreads();
+  }
+}
+
+// =============================== TGRU ========================================
+constexpr int TH = 128, TL = 16, TNT = 384;
+
+template <int SC>
+__global__ void __launch_bounds__(TNT, 1) tgru_fwd_kernel(const __grid_constant__ GruParams p, int B, int T) {
+  constexpr int NI = (SC * TH + TNT - 1) / TNT;        // (s,u) items per thread
+  __shared__ __align__(16) float hs[SC][TH];
+  __shared__ __align__(16) float hid[SC][3 * TH];
+  const int tid = threadIdx.x;
+  float w[TH];
+#pragma unroll
+  for (int k4 = 0; k4 < TH / 4; ++k4) {
+    const float4 v = ld4(p.whh[0] + (long)tid * TH + k4 * 4);
+    w[k4 * 4] = v.x; w[k4 * 4 + 1] = v.y; w[k4 * 4 + 2] = v.z; w[k4 * 4 + 3] = v.w;
+  }
+  const float bj = __ldg(p.bhh[0] + tid);
+  const int nseq = B * TL;
+  const int sbase = blockIdx.x * SC;
+  int is[NI], iu[NI]; long ibase[NI]; bool iok[NI]; float hprev[NI];
+#pragma unroll
+  for (int r = 0; r < NI; ++r) {
+    const int it = tid + r * TNT;
+    is[r] = it / TH; iu[r] = it % TH;
+    const int sidx = sbase + is[r];
+    iok[r] = it < SC * TH && sidx < nseq;
+    const int b = iok[r] ? sidx / TL : 0, l = iok[r] ? sidx % TL : 0;
+    ibase[r] = ((long)b * T) * TL + l;                  // row(t) = ibase + t*16
+    hprev[r] = (iok[r] && p.h0) ? __ldg(p.h0 + (long)sidx * TH + iu[r]) : 0.f;
+    if (it < SC * TH) hs[is[r]][iu[r]] = hprev[r];
+  }
+  float gi[NI][3];
+#pragma unroll
+  for (int r = 0; r < NI; ++r)
+#pragma unroll
+    for (int g = 0; g < 3; ++g) gi[r][g] = iok[r] ? __ldg(p.G + ibase[r] * (3 * TH) + g * TH + iu[r]) : 0.f;
+  __syncthreads();
+
+  for (int t = 0; t < T; ++t) {
+    float acc[SC];
+#pragma unroll
+    for (int s = 0; s < SC; ++s) acc[s] = bj;
+#pragma unroll
+    for (int k4 = 0; k4 < TH / 4; ++k4) {
+#pragma unroll
+      for (int s = 0; s < SC; ++s) {
+        const float4 h = *(const float4*)&hs[s][k4 * 4];
+        acc[s] = fmaf(w[k4 * 4], h.x, acc[s]); acc[s] = fmaf(w[k4 * 4 + 1], h.y, acc[s]);
+        acc[s] = fmaf(w[k4 * 4 + 2], h.z, acc[s]); acc[s] = fmaf(w[k4 * 4 + 3], h.w, acc[s]);
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < SC; ++s) hid[s][tid] = acc[s];
+    __syncthreads();
+    float gcur[NI][3];
+#pragma unroll
+    for (int r = 0; r < NI; ++r)
+#pragma unroll
+      for (int g = 0; g < 3; ++g) gcur[r][g] = gi[r][g];
+    if (t + 1 < T) {                                    // prefetch next step's input gates
+#pragma unroll
+      for (int r = 0; r < NI; ++r)
+#pragma unroll
+        for (int g = 0; g < 3; ++g)
+          gi[r][g] = iok[r] ? __ldg(p.G + (ibase[r] + (long)(t + 1) * TL) * (3 * TH) + g * TH + iu[r]) : 0.f;
+    }
+#pragma unroll
+    for (int r = 0; r < NI; ++r) {
+      if (tid + r * TNT < SC * TH) {
+        const int s = is[r], u = iu[r];
+        const float hn = hid[s][2 * TH + u];
+        const float rr = sigmoidf_(gcur[r][0] + hid[s][u]);
+        const float zz = sigmoidf_(gcur[r][1] + hid[s][TH + u]);
+        const float nn = tanhf(gcur[r][2] + rr * hn);
+        const float hnew = (1.0f - zz) * nn + zz * hprev[r];
+        hprev[r] = hnew;
+        hs[s][u] = hnew;
+        if (iok[r]) {
+          const long row = ibase[r] + (long)t * TL;
+          p.H[row * TH + u] = hnew;
+          if (p.cache) {
+            float* c = p.cache + row * (4 * TH) + u;
+            c[0] = rr; c[TH] = zz; c[2 * TH] = nn; c[3 * TH] = hn;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (p.hlast) {
+#pragma unroll
+    for (int r = 0; r < NI; ++r)
+      if (iok[r]) p.hlast[(long)(sbase + is[r]) * TH + iu[r]] = hprev[r];
+  }
+}
+
+template <int SC>
+__global__ void __launch_bounds__(TNT, 1) tgru_bwd_kernel(const __grid_constant__ GruParams p, int B, int T) {
+  constexpr int NI = (SC * TH + TNT - 1) / TNT;
+  __shared__ __align__(16) float dgs[SC][3 * TH];
+  __shared__ float part[3][SC][TH];
+  const int tid = threadIdx.x, k = tid & (TH - 1), prt = tid >> 7;
+  float w[TH];                                          // w[jj] = W_hh[prt*128 + jj][k]
+#pragma unroll
+  for (int jj = 0; jj < TH; ++jj) w[jj] = __ldg(p.whh[0] + (long)(prt * TH + jj) * TH + k);
+  const int nseq = B * TL;
+  const int sbase = blockIdx.x * SC;
+  int is[NI], iu[NI]; long ibase[NI]; bool iok[NI]; float carry[NI];
+#pragma unroll
+  for (int r = 0; r < NI; ++r) {
+    const int it = tid + r * TNT;
+    is[r] = it / TH; iu[r] = it % TH;
+    const int sidx = sbase + is[r];
+    iok[r] = it < SC * TH && sidx < nseq;
+    const int b = iok[r] ? sidx / TL : 0, l = iok[r] ? sidx % TL : 0;
+    ibase[r] = ((long)b * T) * TL + l;
+    carry[r] = 0.f;
+  }
+  // software pipeline: values of step t are loaded one step ahead
+  float v_dh[NI], v_r[NI], v_z[NI], v_n[NI], v_hn[NI], v_hp[NI];
+  auto fetch = [&](int t) {
+#pragma unroll
+    for (int r = 0; r < NI; ++r) {
+      if (iok[r]) {
+        const long row = ibase[r] + (long)t * TL;
+        v_dh[r] = __ldg(p.dH + row * TH + iu[r]);
+        const float* c = p.cache + row * (4 * TH) + iu[r];
+        v_r[r] = __ldg(c); v_z[r] = __ldg(c + TH); v_n[r] = __ldg(c + 2 * TH); v_hn[r] = __ldg(c + 3 * TH);
+        v_hp[r] = t > 0 ? __ldg(p.H + (row - TL) * TH + iu[r])
+                        : (p.h0 ? __ldg(p.h0 + (long)(sbase + is[r]) * TH + iu[r]) : 0.f);
+      } else {
+        v_dh[r] = v_r[r] = v_z[r] = v_n[r] = v_hn[r] = v_hp[r] = 0.f;
+      }
+    }
+  };
+  fetch(T - 1);
+
+  for (int t = T - 1; t >= 0; --t) {
+    float dd[NI];
+#pragma unroll
+    for (int r = 0; r < NI; ++r) {
+      dd[r] = 0.f;
+      if (tid + r * TNT < SC * TH) {
+        const int s = is[r], u = iu[r];
+        const float dh = v_dh[r] + carry[r];
+        const float dn = dh * (1.0f - v_z[r]) * (1.0f - v_n[r] * v_n[r]);
+        const float dr = dn * v_hn[r] * v_r[r] * (1.0f - v_r[r]);
+        const float dz = dh * (v_hp[r] - v_n[r]) * v_z[r] * (1.0f - v_z[r]);
+        const float dhn = dn * v_r[r];
+        dd[r] = dh * v_z[r];
+        dgs[s][u] = dr; dgs[s][TH + u] = dz; dgs[s][2 * TH + u] = dhn;
+        if (iok[r]) {
+          const long row = ibase[r] + (long)t * TL;
+          float* gi = p.dGi + row * (3 * TH) + u;
+          float* gh = p.dGh + row * (3 * TH) + u;
+          gi[0] = dr; gi[TH] = dz; gi[2 * TH] = dn;
+          gh[0] = dr; gh[TH] = dz; gh[2 * TH] = dhn;
+        }
+      }
+    }
+    __syncthreads();
+    if (t > 0) fetch(t - 1);
+    float acc[SC];
+#pragma unroll
+    for (int s = 0; s < SC; ++s) acc[s] = 0.f;
+#pragma unroll
+    for (int j4 = 0; j4 < TH / 4; ++j4) {
+#pragma unroll
+      for (int s = 0; s < SC; ++s) {
+        const float4 g = *(const float4*)&dgs[s][prt * TH + j4 * 4];
+        acc[s] = fmaf(w[j4 * 4], g.x, acc[s]); acc[s] = fmaf(w[j4 * 4 + 1], g.y, acc[s]);
+        acc[s] = fmaf(w[j4 * 4 + 2], g.z, acc[s]); acc[s] = fmaf(w[j4 * 4 + 3], g.w, acc[s]);
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < SC; ++s) part[prt][s][k] = acc[s];
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < NI; ++r)
+      if (tid + r * TNT < SC * TH)
+        carry[r] = dd[r] + part[0][is[r]][iu[r]] + part[1][is[r]][iu[r]] + part[2][is[r]][iu[r]];
+  }
+}
+
+}  // namespace
+
+int launch_fgru_fwd(const GruParams& p, cudaStream_t st) {
+  const size_t smem = (size_t)(FH * F_WT_LD + FSEQ * F_H_LD) * 4;
+  TRU_CUDA(cudaFuncSetAttribute(fgru_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((p.nseq + FSEQ - 1) / FSEQ, 2);
+  fgru_fwd_kernel<<<grid, FNT, smem, st>>>(p);
+  TRU_LAUNCH_CHECK();
+  return TRU_OK;
+}
+
+int launch_fgru_bwd(const GruParams& p, cudaStream_t st) {
+  const size_t smem = (size_t)(3 * FH * F_W_LD + FSEQ * F_G_LD) * 4;
+  TRU_CUDA(cudaFuncSetAttribute(fgru_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((p.nseq + FSEQ - 1) / FSEQ, 2);
+  fgru_bwd_kernel<<<grid, FNT, smem, st>>>(p);
+  TRU_LAUNCH_CHECK();
+  return TRU_OK;
+}
+
+int launch_tgru_fwd(const GruParams& p, int B, int T, cudaStream_t st) {
+  const int nseq = B * TL;
+  if (nseq <= 4 * sm_count()) tgru_fwd_kernel<4><<<(nseq + 3) / 4, TNT, 0, st>>>(p, B, T);
+  else tgru_fwd_kernel<8><<<(nseq + 7) / 8, TNT, 0, st>>>(p, B, T);
+  TRU_LAUNCH_CHECK();
+  return TRU_OK;
+}
+
+int launch_tgru_bwd(const GruParams& p, int B, int T, cudaStream_t st) {
+  const int nseq = B * TL;
+  if (nseq <= 4 * sm_count()) tgru_bwd_kernel<4><<<(nseq + 3) / 4, TNT, 0, st>>>(p, B, T);
+  else tgru_bwd_kernel<8><<<(nseq + 7) / 8, TNT, 0, st>>>(p, B, T);
+  TRU_LAUNCH_CHECK();
+  return TRU_OK;
+}
+
+}  // namespace tru

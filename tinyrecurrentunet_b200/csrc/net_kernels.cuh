@@ -1,0 +1,104 @@
+// Internal launch API of the TRU-Net layer kernels (channels-last activations
+// [B*T][L][C], fp32).  See DESIGN.md "network kernels" for the scheme:
+//   * every conv layer stores its PRE-BatchNorm output Z; BN + ReLU of the
+//     producer is applied by the consumer while loading (a = relu(p0*z + p2)),
+//     so each activation is written once and read once per consumer;
+//   * BN batch statistics are accumulated by the producing kernel's epilogue
+//     (fp64 atomics) and turned into (p0, p2) by a tiny finalize kernel;
+//   * the backward mirrors this: a layer's incoming gradient dY (w.r.t. the BN
+//     output, already ReLU-masked) is turned into dZ = q0*dY + q1*Z + q2 on load.
+#pragma once
+#include "tru_common.cuh"
+
+namespace tru {
+
+// ---- implicit GEMM over channels with gathered rows --------------------------
+struct Seg {
+  const float* src;      // values (Z for a forward load, dY for a backward load)
+  const float* src2;     // backward load: Z of the same layer (else null)
+  const float* p0; const float* p1; const float* p2;   // per-channel coefficients, p0 == null: identity
+  const float* W;        // weights of this segment: W[wbase + c*wsc + n*wsn]
+  int Lsrc, ld, coff, C; // rows per frame, row stride (floats), first channel, channels
+  int smul, sadd;        // source row li = q*smul + sadd (must satisfy 0 <= li < Lsrc, else zero row)
+  int relu;
+  int wbase, wsc, wsn;
+};
+
+struct IgemmParams {
+  Seg seg[5]; int nseg;
+  int BT, Lq, N;               // rows m = bt*Lq + q, output channels
+  const float* bias;
+  float* out; int Lout, ldo, ocoff, omul, oadd, planar;
+  double* stats;               // forward: [2N] sum, sum of squares of the output (null: none)
+  const float* extra; int ext_ld;                 // backward: gradient to add (skip connections)
+  const float* zmask; const float* mp0; const float* mp2; int use_mask;   // ReLU mask of the layer receiving the gradient
+  const float* bmean; const float* binv; double* bstats;                  // backward BN sums: sum g, sum g*xhat
+};
+int launch_igemm(const IgemmParams& p, cudaStream_t st);
+
+struct WgradJob {
+  const float* a_src; const float* a_p0; const float* a_p2; int a_relu;
+  int a_L, a_ld, a_coff, a_mul, a_add, C;
+  const float* z_src; const float* z_src2; const float* z_p0; const float* z_p1; const float* z_p2;
+  int z_L, z_ld, z_coff, z_mul, z_add, N;
+  float* dW; int wbase, wsc, wsn;
+  float* db;
+};
+struct WgradParams { WgradJob job[8]; int njobs; int BT, Lq; };
+int launch_wgrad(const WgradParams& p, cudaStream_t st);
+
+// ---- BatchNorm bookkeeping -----------------------------------------------------
+struct BnFwdParams {
+  const double* stats; double count; int C; int training;
+  const float* gamma; const float* beta; float* running_mean; float* running_var; long long* nbt;
+  float eps, momentum;
+  float* p0; float* p2; float* mean; float* invstd;
+};
+int launch_bn_finalize(const BnFwdParams& p, cudaStream_t st);
+struct BnBwdParams {
+  const double* bstats; double count; int C;
+  const float* gamma; const float* mean; const float* invstd;
+  float* q0; float* q1; float* q2; float* dgamma; float* dbeta;
+};
+int launch_bn_bwd_finalize(const BnBwdParams& p, cudaStream_t st);
+
+// ---- encoder stem (network.py:9-21) ---------------------------------------------
+int launch_enc0_fwd(const float* x, const float* w, const float* b, float* out, int BT, cudaStream_t st);
+int launch_enc0_wgrad(const float* x, const float* dy, float* dw, float* db, int BT, cudaStream_t st);
+
+// ---- depthwise conv (network.py:33-40), C = 128 ----------------------------------
+struct DwParams {
+  const float* src; const float* src2; const float* p0; const float* p1; const float* p2;  // loader (fwd or bwd)
+  const float* w; const float* bias;    // (C,1,k), (C)
+  float* out;
+  int BT, Lin, Lout, C, k, stride, pad;
+  double* stats;
+  // backward-data epilogue
+  const float* zmask; const float* mp0; const float* mp2; const float* bmean; const float* binv; double* bstats;
+  // backward-weight
+  const float* a_src; const float* a_p0; const float* a_p2; float* dw; float* db;
+};
+int launch_dw_fwd(const DwParams& p, cudaStream_t st);
+int launch_dw_bwd_data(const DwParams& p, cudaStream_t st);
+int launch_dw_wgrad(const DwParams& p, cudaStream_t st);
+
+// planar (BT, C, L) <-> channels-last (BT, L, C), small C
+int launch_planar_to_cl(const float* src, float* dst, int BT, int C, int L, cudaStream_t st);
+
+// ---- GRUs (network.py:45-58; torch.nn.GRU gate order r,z,n) ----------------------
+struct GruParams {
+  const float* G;          // input projections [rows][ldg] (b_ih already added)
+  const float* whh[2]; const float* bhh[2];
+  float* H;                // [rows][ldh] hidden outputs
+  float* cache;            // [rows][ndir*4*Hd]: r, z, n, hn   (null in inference)
+  const float* h0; float* hlast;      // TGRU only: [nseq][Hd] (nullable)
+  int nseq, steps;
+  // backward
+  const float* dH; float* dGi; float* dGh;
+};
+int launch_fgru_fwd(const GruParams& p, cudaStream_t st);   // nseq = B*T, steps = 16, Hd = 64, 2 directions
+int launch_fgru_bwd(const GruParams& p, cudaStream_t st);
+int launch_tgru_fwd(const GruParams& p, int B, int T, cudaStream_t st);   // sequences (b,l), l<16, Hd = 128
+int launch_tgru_bwd(const GruParams& p, int B, int T, cudaStream_t st);
+
+}  // namespace tru

@@ -1,0 +1,539 @@
+// TRU-Net forward / backward orchestration (network.py:122-171 repaired per
+// SURVEY D4/D10/D11) on top of the layer kernels, exported through the C ABI.
+//
+// Activations are channels-last [B*T][L][C]; each conv stores its pre-BN output Z
+// in the caller-provided workspace (saved for the backward), BN+ReLU is applied by
+// consumers on load.  The host code below is the only "runtime": one C call walks
+// the whole layer list and enqueues every kernel on the caller's stream.
+#include <algorithm>
+#include <string>
+#include "net_kernels.cuh"
+
+namespace tru {
+namespace {
+
+constexpr int NBN = TRU_NET_NBN, NPARAM = TRU_NET_NPARAMS;
+
+// geometry
+const int ENC_K[6] = {5, 3, 5, 3, 5, 3}, ENC_S[6] = {2, 1, 2, 1, 2, 2};
+const int ENC_L[6] = {128, 128, 64, 64, 32, 16};      // output length of encoder block i
+const int ENC_CIN[6] = {4, 64, 128, 128, 128, 128};
+const int DEC_K[6] = {3, 5, 3, 5, 3, 5}, DEC_S[6] = {2, 2, 1, 2, 1, 2};
+const int DEC_LP[6] = {16, 32, 64, 64, 128, 128};     // rows of the pointwise conv (= skip length)
+const int DEC_LT[6] = {31, 65, 66, 129, 130, 257};    // rows after the transposed conv
+const int DEC_CIN[6] = {64, 192, 192, 192, 192, 128};
+const int DEC_COUT[6] = {64, 64, 64, 64, 64, 8};
+const int DEC_SKIP[6] = {-1, 4, 3, 2, 1, 0};          // encoder block feeding decoder d
+
+// canonical parameter order (Python side: network.PARAM_ORDER)
+inline int P_ENC(int i, int j) { return i == 0 ? j : 2 + 8 * (i - 1) + j; }   // i>=1: pw.w pw.b bn1.w bn1.b dw.w dw.b bn2.w bn2.b
+inline int P_DEC(int d, int j) { return 42 + 8 * d + j; }                    // pw.w pw.b bn1.w bn1.b ct.w ct.b [bn2.w bn2.b]
+constexpr int P_FGRU = 88, P_TGRU = 100;
+inline int BN_ENC(int i, int which) { return 2 * (i - 1) + which; }
+inline int BN_DEC(int d, int which) { return 10 + 2 * d + which; }
+constexpr int BN_FGRU = 21, BN_TGRU = 22;
+
+struct BnSlot { double* stats; double* bstats; float *p0, *p2, *mean, *inv, *q0, *q1, *q2; };
+
+struct Plan {
+  size_t total = 0;
+  size_t take(size_t bytes) { size_t o = total; total += align_up(bytes, 256); return o; }
+  // offsets (bytes)
+  size_t A0, Zp[6], Zd[6], GF, HF, CF, ZFp, GT, HT, CT, ZTp, ZDp[6], ZDt[5];
+  size_t stats, bstats, small;
+  // backward
+  size_t dA0, dZp[6], dZd[6], dGFi, dGFh, dHF, dZFp, dGTi, dGTh, dHT, dZTp, dZDp[6], dZDt[5], dOUT, dSkip[5];
+  void build(long BT, bool bwd) {
+    auto f = [&](long per_frame) { return take((size_t)BT * per_frame * 4); };
+    A0 = f(128 * 64);
+    for (int i = 1; i <= 5; ++i) { Zp[i] = f((long)ENC_L[i - 1] * 128); Zd[i] = f((long)ENC_L[i] * 128); }
+    GF = f(16 * 384); HF = f(16 * 128); CF = f(16 * 512); ZFp = f(16 * 64);
+    GT = f(16 * 384); HT = f(16 * 128); CT = f(16 * 512); ZTp = f(16 * 64);
+    for (int d = 0; d <= 5; ++d) { ZDp[d] = f((long)DEC_LP[d] * DEC_COUT[d]); if (d < 5) ZDt[d] = f((long)DEC_LT[d] * 64); }
+    stats = take(NBN * 256 * 8); bstats = take(NBN * 256 * 8); small = take(NBN * 7 * 128 * 4);
+    if (!bwd) return;
+    dA0 = f(128 * 64);
+    for (int i = 1; i <= 5; ++i) { dZp[i] = f((long)ENC_L[i - 1] * 128); dZd[i] = f((long)ENC_L[i] * 128); }
+    dGFi = f(16 * 384); dGFh = f(16 * 384); dHF = f(16 * 128); dZFp = f(16 * 64);
+    dGTi = f(16 * 384); dGTh = f(16 * 384); dHT = f(16 * 128); dZTp = f(16 * 64);
+    for (int d = 0; d <= 5; ++d) { dZDp[d] = f((long)DEC_LP[d] * DEC_COUT[d]); if (d < 5) dZDt[d] = f((long)DEC_LT[d] * 64); }
+    dOUT = f(257 * 8);
+    dSkip[0] = f(128 * 64); dSkip[1] = f(128 * 128); dSkip[2] = f(64 * 128); dSkip[3] = f(64 * 128); dSkip[4] = f(32 * 128);
+  }
+};
+
+// an activation: pre-BN tensor + the affine that turns it into the post-BN-ReLU value
+struct Act { const float* z; int L, C; const float* p0; const float* p2; int bn; };
+// a gradient w.r.t. a layer output: dY (BN output grad, ReLU-masked) + what turns it into dZ
+struct Grad { const float* dy; const float* z; const float* q0; const float* q1; const float* q2; int L, C; };
+
+struct Ctx {
+  const TruNetDesc* d; cudaStream_t st; char* ws; Plan plan; long BT; int B, T;
+  const float* const* prm; float* const* grd;
+  float* const* rmean; float* const* rvar; long long* const* nbt;
+  BnSlot bn[NBN];
+  float* F(size_t off) const { return (float*)(ws + off); }
+  void slots() {
+    for (int i = 0; i < NBN; ++i) {
+      bn[i].stats = (double*)(ws + plan.stats) + i * 256;
+      bn[i].bstats = (double*)(ws + plan.bstats) + i * 256;
+      float* s = (float*)(ws + plan.small) + (size_t)i * 7 * 128;
+      bn[i].p0 = s; bn[i].p2 = s + 128; bn[i].mean = s + 256; bn[i].inv = s + 384;
+      bn[i].q0 = s + 512; bn[i].q1 = s + 640; bn[i].q2 = s + 768;
+    }
+  }
+  Act act(size_t off, int L, int C, int bnidx) const {
+    Act a{F(off), L, C, nullptr, nullptr, bnidx};
+    if (bnidx >= 0) { a.p0 = bn[bnidx].p0; a.p2 = bn[bnidx].p2; }
+    return a;
+  }
+  Grad grad(size_t doff, size_t zoff, int L, int C, int bnidx) const {
+    Grad g{F(doff), F(zoff), nullptr, nullptr, nullptr, L, C};
+    if (bnidx >= 0) { g.q0 = bn[bnidx].q0; g.q1 = bn[bnidx].q1; g.q2 = bn[bnidx].q2; }
+    return g;
+  }
+};
+
+#define TRY(x) do { int rc__ = (x); if (rc__) return rc__; } while (0)
+
+Seg fwd_seg(const Act& a, const float* W, int wbase, int wsc, int wsn, int smul, int sadd) {
+  Seg s{};
+  s.src = a.z; s.p0 = a.p0; s.p2 = a.p2; s.relu = 1; s.W = W;
+  s.Lsrc = a.L; s.ld = a.C; s.coff = 0; s.C = a.C; s.smul = smul; s.sadd = sadd;
+  s.wbase = wbase; s.wsc = wsc; s.wsn = wsn;
+  return s;
+}
+Seg bwd_seg(const Grad& g, int coff, int C, int ld, const float* W, int wbase, int wsc, int wsn, int smul, int sadd) {
+  Seg s{};
+  s.src = g.dy; s.src2 = g.q0 ? g.z : nullptr; s.p0 = g.q0; s.p1 = g.q1; s.p2 = g.q2; s.relu = 0; s.W = W;
+  s.Lsrc = g.L; s.ld = ld; s.coff = coff; s.C = C; s.smul = smul; s.sadd = sadd;
+  s.wbase = wbase; s.wsc = wsc; s.wsn = wsn;
+  return s;
+}
+
+int bn_fin(Ctx& c, int idx, int C, long rows, const float* gamma, const float* beta) {
+  BnFwdParams p{};
+  p.stats = c.bn[idx].stats; p.count = (double)rows; p.C = C; p.training = c.d->training;
+  p.gamma = gamma; p.beta = beta; p.running_mean = c.rmean[idx]; p.running_var = c.rvar[idx];
+  p.nbt = c.nbt ? c.nbt[idx] : nullptr;
+  p.eps = (float)c.d->bn_eps; p.momentum = (float)c.d->bn_momentum;
+  p.p0 = c.bn[idx].p0; p.p2 = c.bn[idx].p2; p.mean = c.bn[idx].mean; p.invstd = c.bn[idx].inv;
+  return launch_bn_finalize(p, c.st);
+}
+int bn_bfin(Ctx& c, int idx, int C, long rows, int pgamma) {
+  BnBwdParams p{};
+  p.bstats = c.bn[idx].bstats; p.count = (double)rows; p.C = C;
+  p.gamma = c.prm[pgamma]; p.mean = c.bn[idx].mean; p.invstd = c.bn[idx].inv;
+  p.q0 = c.bn[idx].q0; p.q1 = c.bn[idx].q1; p.q2 = c.bn[idx].q2;
+  p.dgamma = c.grd[pgamma]; p.dbeta = c.grd[pgamma + 1];
+  return launch_bn_bwd_finalize(p, c.st);
+}
+
+// ---- forward building blocks ---------------------------------------------------
+// pointwise conv over [x1 (shifted by padL) ; skip] -> out [BT][Lq][N]
+int pw_fwd(Ctx& c, const Act& x1, int padL, const Act* skip, const float* W, const float* bias, int N, int Lq,
+           float* out, int ldo, int ocoff, double* stats) {
+  IgemmParams p{};
+  const int K = x1.C + (skip ? skip->C : 0);
+  p.seg[0] = fwd_seg(x1, W, 0, 1, K, 1, -padL);
+  p.nseg = 1;
+  if (skip) { p.seg[1] = fwd_seg(*skip, W, x1.C, 1, K, 1, 0); p.nseg = 2; }
+  p.BT = (int)c.BT; p.Lq = Lq; p.N = N; p.bias = bias;
+  p.out = out; p.Lout = Lq; p.ldo = ldo; p.ocoff = ocoff; p.omul = 1; p.oadd = 0;
+  p.stats = stats;
+  return launch_igemm(p, c.st);
+}
+
+// transposed conv (weight (Cin,Cout,k), stride s, pad s/2): x [BT][L][Cin] -> out [BT][Lout][Cout]
+int convt_fwd(Ctx& c, const Act& x, const float* W, const float* bias, int Cout, int k, int s, int Lout, float* out,
+              double* stats, int planar) {
+  const int pad = s / 2;
+  for (int par = 0; par < s; ++par) {
+    IgemmParams p{};
+    p.nseg = 0;
+    for (int j = 0; j < k; ++j) {
+      if (((par + pad - j) % s + s) % s != 0) continue;
+      // lo = s*q + par ; li = (lo + pad - j)/s = q + (par + pad - j)/s   (exact division)
+      const int num = par + pad - j;
+      const int add = num >= 0 ? num / s : -((-num) / s);
+      p.seg[p.nseg++] = fwd_seg(x, W, j, Cout * k, k, 1, add);
+    }
+    p.BT = (int)c.BT; p.Lq = (Lout - par + s - 1) / s; p.N = Cout; p.bias = bias;
+    p.out = out; p.Lout = Lout; p.ldo = Cout; p.ocoff = 0; p.omul = s; p.oadd = par; p.planar = planar;
+    p.stats = stats;
+    if (p.Lq > 0 && p.nseg > 0) TRY(launch_igemm(p, c.st));
+  }
+  return TRU_OK;
+}
+
+int forward(Ctx& c, const float* x, const float* h0, float* out, float* hlast) {
+  const Plan& P = c.plan;
+  const long BT = c.BT;
+  TRU_CUDA(cudaMemsetAsync(c.ws + P.stats, 0, NBN * 256 * 8, c.st));
+  // encoder stem
+  TRY(launch_enc0_fwd(x, c.prm[0], c.prm[1], c.F(P.A0), (int)BT, c.st));
+  Act cur = c.act(P.A0, 128, 64, -1);
+  for (int i = 1; i <= 5; ++i) {
+    const int Lin = ENC_L[i - 1], Lo = ENC_L[i];
+    const int b1 = BN_ENC(i, 0), b2 = BN_ENC(i, 1);
+    TRY(pw_fwd(c, cur, 0, nullptr, c.prm[P_ENC(i, 0)], c.prm[P_ENC(i, 1)], 128, Lin, c.F(P.Zp[i]), 128, 0, c.bn[b1].stats));
+    TRY(bn_fin(c, b1, 128, BT * Lin, c.prm[P_ENC(i, 2)], c.prm[P_ENC(i, 3)]));
+    DwParams dp{};
+    dp.src = c.F(P.Zp[i]); dp.p0 = c.bn[b1].p0; dp.p2 = c.bn[b1].p2;
+    dp.w = c.prm[P_ENC(i, 4)]; dp.bias = c.prm[P_ENC(i, 5)]; dp.out = c.F(P.Zd[i]);
+    dp.BT = (int)BT; dp.Lin = Lin; dp.Lout = Lo; dp.C = 128; dp.k = ENC_K[i]; dp.stride = ENC_S[i]; dp.pad = ENC_K[i] / 2;
+    dp.stats = c.bn[b2].stats;
+    TRY(launch_dw_fwd(dp, c.st));
+    TRY(bn_fin(c, b2, 128, BT * Lo, c.prm[P_ENC(i, 6)], c.prm[P_ENC(i, 7)]));
+    cur = c.act(P.Zd[i], Lo, 128, b2);
+  }
+  // FGRU (network.py:149): input projection for both directions, recurrence, pw conv
+  for (int dir = 0; dir < 2; ++dir)
+    TRY(pw_fwd(c, cur, 0, nullptr, c.prm[P_FGRU + 4 * dir], c.prm[P_FGRU + 4 * dir + 2], 192, 16, c.F(P.GF), 384, 192 * dir, nullptr));
+  {
+    GruParams g{};
+    g.G = c.F(P.GF); g.whh[0] = c.prm[P_FGRU + 1]; g.whh[1] = c.prm[P_FGRU + 5];
+    g.bhh[0] = c.prm[P_FGRU + 3]; g.bhh[1] = c.prm[P_FGRU + 7];
+    g.H = c.F(P.HF); g.cache = c.F(P.CF); g.nseq = (int)BT; g.steps = 16;
+    TRY(launch_fgru_fwd(g, c.st));
+  }
+  Act hf = c.act(P.HF, 16, 128, -1);
+  TRY(pw_fwd(c, hf, 0, nullptr, c.prm[P_FGRU + 8], c.prm[P_FGRU + 9], 64, 16, c.F(P.ZFp), 64, 0, c.bn[BN_FGRU].stats));
+  TRY(bn_fin(c, BN_FGRU, 64, BT * 16, c.prm[P_FGRU + 10], c.prm[P_FGRU + 11]));
+  Act fo = c.act(P.ZFp, 16, 64, BN_FGRU);
+  // TGRU (network.py:150, wiring D4): sequences (b, l) over t
+  TRY(pw_fwd(c, fo, 0, nullptr, c.prm[P_TGRU], c.prm[P_TGRU + 2], 384, 16, c.F(P.GT), 384, 0, nullptr));
+  {
+    GruParams g{};
+    g.G = c.F(P.GT); g.whh[0] = c.prm[P_TGRU + 1]; g.bhh[0] = c.prm[P_TGRU + 3];
+    g.H = c.F(P.HT); g.cache = c.F(P.CT); g.h0 = h0; g.hlast = hlast; g.nseq = c.B * 16; g.steps = c.T;
+    TRY(launch_tgru_fwd(g, c.B, c.T, c.st));
+  }
+  Act ht = c.act(P.HT, 16, 128, -1);
+  TRY(pw_fwd(c, ht, 0, nullptr, c.prm[P_TGRU + 4], c.prm[P_TGRU + 5], 64, 16, c.F(P.ZTp), 64, 0, c.bn[BN_TGRU].stats));
+  TRY(bn_fin(c, BN_TGRU, 64, BT * 16, c.prm[P_TGRU + 6], c.prm[P_TGRU + 7]));
+  cur = c.act(P.ZTp, 16, 64, BN_TGRU);
+  // decoder (network.py:141-146, skip concat :95-98)
+  for (int d = 0; d <= 5; ++d) {
+    const int Lp = DEC_LP[d], Co = DEC_COUT[d];
+    const int b1 = BN_DEC(d, 0);
+    Act skip{};
+    const Act* sp = nullptr;
+    int padL = 0;
+    if (d >= 1) {
+      const int e = DEC_SKIP[d];
+      skip = e == 0 ? c.act(P.A0, 128, 64, -1) : c.act(P.Zd[e], ENC_L[e], 128, BN_ENC(e, 1));
+      sp = &skip;
+      const int diff = Lp - cur.L;
+      padL = diff >= 0 ? diff / 2 : -((-diff + 1) / 2);       // Python floor division (network.py:97)
+    }
+    TRY(pw_fwd(c, cur, padL, sp, c.prm[P_DEC(d, 0)], c.prm[P_DEC(d, 1)], Co, Lp, c.F(P.ZDp[d]), Co, 0, c.bn[b1].stats));
+    TRY(bn_fin(c, b1, Co, BT * Lp, c.prm[P_DEC(d, 2)], c.prm[P_DEC(d, 3)]));
+    Act pw = c.act(P.ZDp[d], Lp, Co, b1);
+    if (d < 5) {
+      const int b2 = BN_DEC(d, 1);
+      TRY(convt_fwd(c, pw, c.prm[P_DEC(d, 4)], c.prm[P_DEC(d, 5)], Co, DEC_K[d], DEC_S[d], DEC_LT[d], c.F(P.ZDt[d]),
+                    c.bn[b2].stats, 0));
+      TRY(bn_fin(c, b2, Co, BT * DEC_LT[d], c.prm[P_DEC(d, 6)], c.prm[P_DEC(d, 7)]));
+      cur = c.act(P.ZDt[d], DEC_LT[d], Co, b2);
+    } else {
+      TRY(convt_fwd(c, pw, c.prm[P_DEC(d, 4)], c.prm[P_DEC(d, 5)], Co, DEC_K[d], DEC_S[d], DEC_LT[d], out, nullptr, 1));
+    }
+  }
+  return TRU_OK;
+}
+
+// ---- backward building blocks ------------------------------------------------------
+void set_mask(IgemmParams& p, Ctx& c, const Act& a, bool stats) {
+  p.use_mask = 1; p.zmask = a.z; p.mp0 = a.p0; p.mp2 = a.p2;
+  if (stats && a.bn >= 0) { p.bstats = c.bn[a.bn].bstats; p.bmean = c.bn[a.bn].mean; p.binv = c.bn[a.bn].inv; }
+}
+
+// pointwise conv backward: weight grads (+bias), data grads to x1 (masked, BN sums) and to skip (raw)
+int pw_bwd(Ctx& c, const Grad& g, const Act& x1, int padL, const Act* skip, int pw_param, float* dX1, bool mask_x1,
+           const float* extra, float* dSkip) {
+  const float* W = c.prm[pw_param];
+  const int N = g.C, K = x1.C + (skip ? skip->C : 0);
+  {
+    WgradParams w{};
+    WgradJob& j0 = w.job[0];
+    j0.a_src = x1.z; j0.a_p0 = x1.p0; j0.a_p2 = x1.p2; j0.a_relu = 1; j0.a_L = x1.L; j0.a_ld = x1.C; j0.a_coff = 0;
+    j0.a_mul = 1; j0.a_add = -padL; j0.C = x1.C;
+    j0.z_src = g.dy; j0.z_src2 = g.q0 ? g.z : nullptr; j0.z_p0 = g.q0; j0.z_p1 = g.q1; j0.z_p2 = g.q2;
+    j0.z_L = g.L; j0.z_ld = N; j0.z_coff = 0; j0.z_mul = 1; j0.z_add = 0; j0.N = N;
+    j0.dW = c.grd[pw_param]; j0.wbase = 0; j0.wsc = 1; j0.wsn = K; j0.db = skip ? nullptr : c.grd[pw_param + 1];
+    w.njobs = 1;
+    if (skip) {
+      WgradJob& j1 = w.job[1];
+      j1 = j0;
+      j1.a_src = skip->z; j1.a_p0 = skip->p0; j1.a_p2 = skip->p2; j1.a_L = skip->L; j1.a_ld = skip->C; j1.a_add = 0; j1.C = skip->C;
+      j1.wbase = x1.C; j1.db = c.grd[pw_param + 1];
+      w.njobs = 2;
+    }
+    w.BT = (int)c.BT; w.Lq = g.L;
+    TRY(launch_wgrad(w, c.st));
+  }
+  {
+    IgemmParams p{};
+    p.seg[0] = bwd_seg(g, 0, N, N, W, 0, K, 1, 1, padL);
+    p.nseg = 1; p.BT = (int)c.BT; p.Lq = x1.L; p.N = x1.C;
+    p.out = dX1; p.Lout = x1.L; p.ldo = x1.C; p.omul = 1;
+    p.extra = extra; p.ext_ld = x1.C;
+    if (mask_x1) set_mask(p, c, x1, true);
+    TRY(launch_igemm(p, c.st));
+  }
+  if (skip) {
+    IgemmParams p{};
+    p.seg[0] = bwd_seg(g, 0, N, N, W, x1.C, K, 1, 1, 0);
+    p.nseg = 1; p.BT = (int)c.BT; p.Lq = skip->L; p.N = skip->C;
+    p.out = dSkip; p.Lout = skip->L; p.ldo = skip->C; p.omul = 1;
+    TRY(launch_igemm(p, c.st));
+  }
+  return TRU_OK;
+}
+
+// transposed conv backward: g = grad of the convT output (Lout rows, Cout ch), x = its input activation
+int convt_bwd(Ctx& c, const Grad& g, const Act& x, int ct_param, int k, int s, float* dX) {
+  const float* W = c.prm[ct_param];
+  const int Cout = g.C, Cin = x.C, pad = s / 2;
+  {
+    WgradParams w{};
+    for (int j = 0; j < k; ++j) {
+      WgradJob& J = w.job[j];
+      J.a_src = x.z; J.a_p0 = x.p0; J.a_p2 = x.p2; J.a_relu = 1; J.a_L = x.L; J.a_ld = Cin; J.a_mul = 1; J.a_add = 0; J.C = Cin;
+      J.z_src = g.dy; J.z_src2 = g.q0 ? g.z : nullptr; J.z_p0 = g.q0; J.z_p1 = g.q1; J.z_p2 = g.q2;
+      J.z_L = g.L; J.z_ld = Cout; J.z_mul = s; J.z_add = j - pad; J.N = Cout;
+      J.dW = c.grd[ct_param]; J.wbase = j; J.wsc = Cout * k; J.wsn = k; J.db = nullptr;
+    }
+    w.njobs = k; w.BT = (int)c.BT; w.Lq = x.L;
+    TRY(launch_wgrad(w, c.st));
+    WgradParams b{};
+    WgradJob& J = b.job[0];
+    J.a_src = nullptr; J.C = 4; J.a_ld = 4;
+    J.z_src = g.dy; J.z_src2 = g.q0 ? g.z : nullptr; J.z_p0 = g.q0; J.z_p1 = g.q1; J.z_p2 = g.q2;
+    J.z_L = g.L; J.z_ld = Cout; J.z_mul = 1; J.z_add = 0; J.N = Cout; J.dW = nullptr; J.db = c.grd[ct_param + 1];
+    b.njobs = 1; b.BT = (int)c.BT; b.Lq = g.L;
+    TRY(launch_wgrad(b, c.st));
+  }
+  IgemmParams p{};
+  for (int j = 0; j < k; ++j) p.seg[j] = bwd_seg(g, 0, Cout, Cout, W, j, k, Cout * k, s, j - pad);
+  p.nseg = k; p.BT = (int)c.BT; p.Lq = x.L; p.N = Cin;
+  p.out = dX; p.Lout = x.L; p.ldo = Cin; p.omul = 1;
+  set_mask(p, c, x, true);
+  return launch_igemm(p, c.st);
+}
+
+int backward(Ctx& c, const float* x, const float* gout) {
+  const Plan& P = c.plan;
+  const long BT = c.BT;
+  TRU_CUDA(cudaMemsetAsync(c.ws + P.bstats, 0, NBN * 256 * 8, c.st));
+  TRY(launch_planar_to_cl(gout, c.F(P.dOUT), (int)BT, 8, 257, c.st));
+
+  // ---- decoder, last block first ----
+  for (int d = 5; d >= 0; --d) {
+    const int Lp = DEC_LP[d], Co = DEC_COUT[d];
+    const int b1 = BN_DEC(d, 0);
+    Act pw = c.act(P.ZDp[d], Lp, Co, b1);
+    Grad gt = d == 5 ? Grad{c.F(P.dOUT), nullptr, nullptr, nullptr, nullptr, 257, 8}
+                     : c.grad(P.dZDt[d], P.ZDt[d], DEC_LT[d], Co, BN_DEC(d, 1));
+    if (d < 5) TRY(bn_bfin(c, BN_DEC(d, 1), Co, BT * DEC_LT[d], P_DEC(d, 6)));
+    TRY(convt_bwd(c, gt, pw, P_DEC(d, 4), DEC_K[d], DEC_S[d], c.F(P.dZDp[d])));
+    TRY(bn_bfin(c, b1, Co, BT * Lp, P_DEC(d, 2)));
+    Grad gp = c.grad(P.dZDp[d], P.ZDp[d], Lp, Co, b1);
+    if (d >= 1) {
+      const int e = DEC_SKIP[d];
+      Act skip = e == 0 ? c.act(P.A0, 128, 64, -1) : c.act(P.Zd[e], ENC_L[e], 128, BN_ENC(e, 1));
+      Act x1 = c.act(P.ZDt[d - 1], DEC_LT[d - 1], 64, BN_DEC(d - 1, 1));
+      const int diff = Lp - x1.L;
+      const int padL = diff >= 0 ? diff / 2 : -((-diff + 1) / 2);
+      TRY(pw_bwd(c, gp, x1, padL, &skip, P_DEC(d, 0), c.F(P.dZDt[d - 1]), true, nullptr, c.F(P.dSkip[e])));
+    } else {
+      Act x1 = c.act(P.ZTp, 16, 64, BN_TGRU);
+      TRY(pw_bwd(c, gp, x1, 0, nullptr, P_DEC(0, 0), c.F(P.dZTp), true, nullptr, nullptr));
+    }
+  }
+  // ---- TGRU block ----
+  TRY(bn_bfin(c, BN_TGRU, 64, BT * 16, P_TGRU + 6));
+  {
+    Grad gp = c.grad(P.dZTp, P.ZTp, 16, 64, BN_TGRU);
+    Act ht = c.act(P.HT, 16, 128, -1);
+    TRY(pw_bwd(c, gp, ht, 0, nullptr, P_TGRU + 4, c.F(P.dHT), false, nullptr, nullptr));
+    GruParams g{};
+    g.whh[0] = c.prm[P_TGRU + 1]; g.H = c.F(P.HT); g.cache = c.F(P.CT); g.nseq = c.B * 16; g.steps = c.T;
+    g.dH = c.F(P.dHT); g.dGi = c.F(P.dGTi); g.dGh = c.F(P.dGTh);
+    TRY(launch_tgru_bwd(g, c.B, c.T, c.st));
+    Act fo = c.act(P.ZFp, 16, 64, BN_FGRU);
+    WgradParams w{};
+    {   // W_ih, b_ih
+      WgradJob& J = w.job[0];
+      J.a_src = fo.z; J.a_p0 = fo.p0; J.a_p2 = fo.p2; J.a_relu = 1; J.a_L = c.T * 16; J.a_ld = 64; J.a_mul = 1; J.C = 64;
+      J.z_src = c.F(P.dGTi); J.z_L = c.T * 16; J.z_ld = 384; J.z_mul = 1; J.N = 384;
+      J.dW = c.grd[P_TGRU]; J.wsc = 1; J.wsn = 64; J.db = c.grd[P_TGRU + 2];
+    }
+    {   // W_hh: h_{t-1} rows are 16 rows up inside a clip
+      WgradJob& J = w.job[1];
+      J.a_src = c.F(P.HT); J.a_L = c.T * 16; J.a_ld = 128; J.a_mul = 1; J.a_add = -16; J.C = 128;
+      J.z_src = c.F(P.dGTh); J.z_L = c.T * 16; J.z_ld = 384; J.z_mul = 1; J.N = 384;
+      J.dW = c.grd[P_TGRU + 1]; J.wsc = 1; J.wsn = 128;
+    }
+    {   // b_hh
+      WgradJob& J = w.job[2];
+      J.C = 4; J.a_ld = 4;
+      J.z_src = c.F(P.dGTh); J.z_L = c.T * 16; J.z_ld = 384; J.z_mul = 1; J.N = 384; J.db = c.grd[P_TGRU + 3];
+    }
+    w.njobs = 3; w.BT = c.B; w.Lq = c.T * 16;
+    TRY(launch_wgrad(w, c.st));
+    IgemmParams p{};
+    Grad gi{c.F(P.dGTi), nullptr, nullptr, nullptr, nullptr, 16, 384};
+    p.seg[0] = bwd_seg(gi, 0, 384, 384, c.prm[P_TGRU], 0, 64, 1, 1, 0);
+    p.nseg = 1; p.BT = (int)BT; p.Lq = 16; p.N = 64; p.out = c.F(P.dZFp); p.Lout = 16; p.ldo = 64; p.omul = 1;
+    set_mask(p, c, fo, true);
+    TRY(launch_igemm(p, c.st));
+  }
+  // ---- FGRU block ----
+  TRY(bn_bfin(c, BN_FGRU, 64, BT * 16, P_FGRU + 10));
+  Act e5 = c.act(P.Zd[5], 16, 128, BN_ENC(5, 1));
+  {
+    Grad gp = c.grad(P.dZFp, P.ZFp, 16, 64, BN_FGRU);
+    Act hf = c.act(P.HF, 16, 128, -1);
+    TRY(pw_bwd(c, gp, hf, 0, nullptr, P_FGRU + 8, c.F(P.dHF), false, nullptr, nullptr));
+    GruParams g{};
+    g.whh[0] = c.prm[P_FGRU + 1]; g.whh[1] = c.prm[P_FGRU + 5]; g.H = c.F(P.HF); g.cache = c.F(P.CF);
+    g.nseq = (int)BT; g.steps = 16; g.dH = c.F(P.dHF); g.dGi = c.F(P.dGFi); g.dGh = c.F(P.dGFh);
+    TRY(launch_fgru_bwd(g, c.st));
+    WgradParams w{};
+    for (int dir = 0; dir < 2; ++dir) {
+      WgradJob& Ji = w.job[dir];          // W_ih, b_ih
+      Ji.a_src = e5.z; Ji.a_p0 = e5.p0; Ji.a_p2 = e5.p2; Ji.a_relu = 1; Ji.a_L = 16; Ji.a_ld = 128; Ji.a_mul = 1; Ji.C = 128;
+      Ji.z_src = c.F(P.dGFi); Ji.z_L = 16; Ji.z_ld = 384; Ji.z_coff = 192 * dir; Ji.z_mul = 1; Ji.N = 192;
+      Ji.dW = c.grd[P_FGRU + 4 * dir]; Ji.wsc = 1; Ji.wsn = 128; Ji.db = c.grd[P_FGRU + 4 * dir + 2];
+      WgradJob& Jh = w.job[2 + dir];      // W_hh: h_prev is the neighbouring frequency position
+      Jh.a_src = c.F(P.HF); Jh.a_L = 16; Jh.a_ld = 128; Jh.a_coff = 64 * dir; Jh.a_mul = 1; Jh.a_add = dir ? 1 : -1; Jh.C = 64;
+      Jh.z_src = c.F(P.dGFh); Jh.z_L = 16; Jh.z_ld = 384; Jh.z_coff = 192 * dir; Jh.z_mul = 1; Jh.N = 192;
+      Jh.dW = c.grd[P_FGRU + 4 * dir + 1]; Jh.wsc = 1; Jh.wsn = 64;
+      WgradJob& Jb = w.job[4 + dir];      // b_hh
+      Jb.C = 4; Jb.a_ld = 4;
+      Jb.z_src = c.F(P.dGFh); Jb.z_L = 16; Jb.z_ld = 384; Jb.z_coff = 192 * dir; Jb.z_mul = 1; Jb.N = 192;
+      Jb.db = c.grd[P_FGRU + 4 * dir + 3];
+    }
+    w.njobs = 6; w.BT = (int)BT; w.Lq = 16;
+    TRY(launch_wgrad(w, c.st));
+    IgemmParams p{};
+    Grad gi{c.F(P.dGFi), nullptr, nullptr, nullptr, nullptr, 16, 384};
+    p.seg[0] = bwd_seg(gi, 0, 192, 384, c.prm[P_FGRU], 0, 128, 1, 1, 0);
+    p.seg[1] = bwd_seg(gi, 192, 192, 384, c.prm[P_FGRU + 4], 0, 128, 1, 1, 0);
+    p.nseg = 2; p.BT = (int)BT; p.Lq = 16; p.N = 128; p.out = c.F(P.dZd[5]); p.Lout = 16; p.ldo = 128; p.omul = 1;
+    set_mask(p, c, e5, true);
+    TRY(launch_igemm(p, c.st));
+  }
+  // ---- encoder blocks 5..1 ----
+  for (int i = 5; i >= 1; --i) {
+    const int Lin = ENC_L[i - 1], Lo = ENC_L[i];
+    const int b1 = BN_ENC(i, 0), b2 = BN_ENC(i, 1);
+    TRY(bn_bfin(c, b2, 128, BT * Lo, P_ENC(i, 6)));
+    DwParams dp{};
+    dp.src = c.F(P.dZd[i]); dp.src2 = c.F(P.Zd[i]); dp.p0 = c.bn[b2].q0; dp.p1 = c.bn[b2].q1; dp.p2 = c.bn[b2].q2;
+    dp.w = c.prm[P_ENC(i, 4)]; dp.out = c.F(P.dZp[i]);
+    dp.BT = (int)BT; dp.Lin = Lin; dp.Lout = Lo; dp.C = 128; dp.k = ENC_K[i]; dp.stride = ENC_S[i]; dp.pad = ENC_K[i] / 2;
+    dp.zmask = c.F(P.Zp[i]); dp.mp0 = c.bn[b1].p0; dp.mp2 = c.bn[b1].p2;
+    dp.bmean = c.bn[b1].mean; dp.binv = c.bn[b1].inv; dp.bstats = c.bn[b1].bstats;
+    dp.a_src = c.F(P.Zp[i]); dp.a_p0 = c.bn[b1].p0; dp.a_p2 = c.bn[b1].p2;
+    dp.dw = c.grd[P_ENC(i, 4)]; dp.db = c.grd[P_ENC(i, 5)];
+    TRY(launch_dw_wgrad(dp, c.st));
+    TRY(launch_dw_bwd_data(dp, c.st));
+    TRY(bn_bfin(c, b1, 128, BT * Lin, P_ENC(i, 2)));
+    Grad gp = c.grad(P.dZp[i], P.Zp[i], Lin, 128, b1);
+    if (i >= 2) {
+      Act xin = c.act(P.Zd[i - 1], Lin, 128, BN_ENC(i - 1, 1));
+      // encoder output i-1 also feeds a decoder skip (blocks 1..4): add that gradient
+      const float* extra = (i - 1 >= 1 && i - 1 <= 4) ? c.F(P.dSkip[i - 1]) : nullptr;
+      TRY(pw_bwd(c, gp, xin, 0, nullptr, P_ENC(i, 0), c.F(P.dZd[i - 1]), true, extra, nullptr));
+    } else {
+      Act a0 = c.act(P.A0, 128, 64, -1);
+      TRY(pw_bwd(c, gp, a0, 0, nullptr, P_ENC(1, 0), c.F(P.dA0), true, c.F(P.dSkip[0]), nullptr));
+    }
+  }
+  // ---- stem ----
+  return launch_enc0_wgrad(x, c.F(P.dA0), c.grd[0], c.grd[1], (int)BT, c.st);
+}
+
+int make_ctx(Ctx& c, const TruNetDesc* d, void* ws, size_t ws_bytes, bool bwd, void* stream) {
+  TRU_REQUIRE(d && d->batch > 0 && d->n_frames > 0, TRU_ERR_ARG, "trunet: bad descriptor");
+  TRU_REQUIRE(ws && aligned16(ws), TRU_ERR_ALIGN, "trunet: workspace must be 16-byte aligned");
+  c.d = d; c.st = (cudaStream_t)stream; c.ws = (char*)ws; c.B = d->batch; c.T = d->n_frames; c.BT = (long)d->batch * d->n_frames;
+  TRU_REQUIRE(c.BT * 257 < (1L << 31) / 8, TRU_ERR_ARG, "trunet: B*T too large for 32-bit row indices");
+  c.plan.build(c.BT, bwd);
+  TRU_REQUIRE(ws_bytes >= c.plan.total, TRU_ERR_WORKSPACE, "trunet: workspace too small (%zu < %zu)", ws_bytes, c.plan.total);
+  c.slots();
+  return TRU_OK;
+}
+
+}  // namespace
+}  // namespace tru
+
+using namespace tru;
+
+extern "C" size_t tru_trunet_workspace_bytes(const TruNetDesc* d, int with_backward) {
+  if (!d || d->batch <= 0 || d->n_frames <= 0) return 0;
+  Plan p;
+  p.build((long)d->batch * d->n_frames, with_backward != 0);
+  return p.total;
+}
+
+extern "C" int tru_trunet_forward(const TruNetDesc* d, const float* const* params, float* const* bn_running_mean,
+                                  float* const* bn_running_var, long long* const* bn_num_batches, const float* x,
+                                  const float* h0, float* out, float* h_last, void* ws, size_t ws_bytes, void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  TRU_REQUIRE(params && bn_running_mean && bn_running_var && x && out, TRU_ERR_ARG, "trunet_forward: null pointer");
+  for (int i = 0; i < NPARAM; ++i) TRU_REQUIRE(params[i] && aligned16(params[i]), TRU_ERR_ALIGN, "trunet_forward: parameter %d null/unaligned", i);
+  Ctx c{};
+  if ((rc = make_ctx(c, d, ws, ws_bytes, false, stream))) return rc;
+  c.prm = params; c.rmean = bn_running_mean; c.rvar = bn_running_var; c.nbt = bn_num_batches;
+  return forward(c, x, h0, out, h_last);
+}
+
+extern "C" int tru_trunet_backward(const TruNetDesc* d, const float* const* params, const float* x,
+                                   const float* grad_out, float* const* grads, void* ws, size_t ws_bytes, void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  TRU_REQUIRE(params && grads && x && grad_out, TRU_ERR_ARG, "trunet_backward: null pointer");
+  TRU_REQUIRE(d && d->training, TRU_ERR_ARG, "trunet_backward: needs a training-mode forward (batch statistics)");
+  for (int i = 0; i < NPARAM; ++i) TRU_REQUIRE(params[i] && grads[i], TRU_ERR_ARG, "trunet_backward: parameter/grad %d null", i);
+  Ctx c{};
+  if ((rc = make_ctx(c, d, ws, ws_bytes, true, stream))) return rc;
+  c.prm = params; c.grd = grads;
+  return backward(c, x, grad_out);
+}
+
+// Debug/test aid: byte offset of a named workspace buffer (see tests/test_gpu_network.py).
+extern "C" long long tru_trunet_buffer_offset(const TruNetDesc* d, const char* name, int index) {
+  if (!d || !name) return -1;
+  Plan p;
+  p.build((long)d->batch * d->n_frames, true);
+  const std::string n(name);
+  if (n == "A0") return p.A0;   if (n == "Zp") return p.Zp[index];   if (n == "Zd") return p.Zd[index];
+  if (n == "GF") return p.GF;   if (n == "HF") return p.HF;   if (n == "ZFp") return p.ZFp;
+  if (n == "GT") return p.GT;   if (n == "HT") return p.HT;   if (n == "ZTp") return p.ZTp;
+  if (n == "ZDp") return p.ZDp[index];   if (n == "ZDt") return p.ZDt[index];
+  if (n == "dA0") return p.dA0; if (n == "dZp") return p.dZp[index]; if (n == "dZd") return p.dZd[index];
+  if (n == "dHF") return p.dHF; if (n == "dHT") return p.dHT; if (n == "dZFp") return p.dZFp; if (n == "dZTp") return p.dZTp;
+  if (n == "dZDp") return p.dZDp[index]; if (n == "dZDt") return p.dZDt[index];
+  if (n == "dGFi") return p.dGFi; if (n == "dGTi") return p.dGTi; if (n == "dSkip") return p.dSkip[index];
+  if (n == "small") return p.small;
+  return -1;
+}
+
+// Test aid: raw transposed-conv data gradient through the implicit-GEMM path.
+// dy (BT, Lout, Cout) channels-last, w (Cin, Cout, k) -> dx (BT, L, Cin); no BN, no mask.
+extern "C" int tru_debug_convt_bwd_data(const float* dy, const float* w, float* dx, int BT, int L, int Lout,
+                                        int Cin, int Cout, int k, int s, void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  IgemmParams p{};
+  Grad g{dy, nullptr, nullptr, nullptr, nullptr, Lout, Cout};
+  for (int j = 0; j < k; ++j) p.seg[j] = bwd_seg(g, 0, Cout, Cout, w, j, k, Cout * k, s, j - s / 2);
+  p.nseg = k; p.BT = BT; p.Lq = L; p.N = Cin;
+  p.out = dx; p.Lout = L; p.ldo = Cin; p.omul = 1;
+  return launch_igemm(p, (cudaStream_t)stream);
+}
