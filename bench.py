@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""bench.py - TRU-Net training-step throughput (BASELINE.json: "train 4-s clips/sec").
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...  # reference algorithm on host CPU
+
+A "step" = one pass of the hot path over one batch of synthetic 16 kHz clips:
+front end -> TRU-Net -> mask + iSTFT -> L1 + multi-resolution STFT loss -> backward ->
+(N > 1: one NCCL all-reduce of the flat gradient bucket) -> AdamW step.
+Workload = BASELINE.json configs[1]: tiny.json, 32 clean/noisy 4-s pairs per GPU
+(weak scaling: global batch 32*N).  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "train_4s_clips_per_sec"
+UNIT = "clips/s"
+CLIP_SAMPLES = 64000           # 4 s at 16 kHz
+STFT_CFG = dict(fft_sizes=[512, 1024, 2048], hop_sizes=[50, 120, 240], win_lengths=[240, 600, 1200],
+                sc_lambda=0.5, mag_lambda=0.5)          # config/tiny.json:30-37
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="clips per GPU")
+    ap.add_argument("--cpu-batch", type=int, default=2, help="clips per CPU step (bounded sample)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------ CPU arm (oracle)
+def cpu_training_clips_per_sec(batch, steps, warmup):
+    """The reference algorithm (oracle restatement, SURVEY section 8c: the reference itself does
+    not run) on the host cores with every thread torch can use.  Returns (clips/s, cores)."""
+    import torch
+    from oracle import tru_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    net = O.randomize_bn(O.TRUNet()).train()
+    opt = torch.optim.AdamW(net.parameters(), lr=4e-4)
+    clean, noisy = O.synthetic_batch(batch, n=CLIP_SAMPLES)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        loss, _, _ = O.loss_fn(net, clean, noisy)
+        loss.backward()
+        opt.step()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return batch * len(times) / sum(times), torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 5))
+    warm = max(1, min(args.warmup, 2))
+    v, cores = cpu_training_clips_per_sec(args.cpu_batch, steps, warm)
+    sample = "%d clips/step x %d steps of the tiny.json training step (fwd+bwd+AdamW), torch CPU, %d threads" % (
+        args.cpu_batch, steps, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": round(1000.0 * args.cpu_batch / v, 2),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "tiny.json training step, 4-s 16 kHz clips (BASELINE.json configs[1])",
+                       "clips_per_step": args.cpu_batch, "device": "host CPU"},
+            "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": round(v, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ helpers
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in open(self.path):
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.path)
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------ native arm
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun exactly like the driver does
+        port = 29500 + (os.getpid() % 2000)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", init_method="env://", world_size=world, rank=rank,
+                                device_id=dev)
+    from oracle import tru_oracle as O                      # synthetic data generator + cpu_baseline only
+    from tinyrecurrentunet_b200 import _lib as L, network, stft_loss, util
+    from tinyrecurrentunet_b200 import distributed as tdist
+
+    B = args.batch
+    torch.manual_seed(0)
+    net = network.TRUNet(3, 64, 3, 128, [5, 3], [2, 1], 192).to(dev).train()
+    mr = stft_loss.MultiResolutionSTFTLoss(**STFT_CFG).to(dev)
+    if world > 1:
+        tdist.apply_gradient_allreduce(net)
+    opt = torch.optim.AdamW(net.parameters(), lr=4e-4, fused=True)       # train.py:68
+
+    # synthetic clips: a pool of distinct clips, rank-dependent, tiled to the batch
+    pool = min(B, 8)
+    clean_h, noisy_h = O.synthetic_batch(pool, n=CLIP_SAMPLES, first=rank * pool)
+    reps = (B + pool - 1) // pool
+    clean_h = clean_h.repeat(reps, 1)[:B].contiguous().pin_memory()
+    noisy_h = noisy_h.repeat(reps, 1)[:B].contiguous().pin_memory()
+    clean_d = clean_h.to(dev)
+    noisy_d = noisy_h.to(dev)
+
+    def step(clean, noisy):
+        opt.zero_grad(set_to_none=True)
+        loss, _ = util.loss_fn(net, (clean, noisy), ell_p=1, ell_p_lambda=1, stft_lambda=1, mrstftloss=mr)
+        loss.backward()                  # N>1: the all-reduce fires from the engine callback
+        opt.step()
+        return loss
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(nsteps, fn):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(nsteps):
+            fn()
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for _ in range(max(args.warmup, 3)):
+        step(clean_d, noisy_d)
+    sync_all()
+
+    # ---- (1) device-resident throughput -------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = L.lib.tru_launch_count()
+    ms = timed(args.steps, lambda: step(clean_d, noisy_d))
+    launches = L.lib.tru_launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else {}
+    value = world * B * args.steps / (ms / 1000.0)
+
+    # ---- (2) end to end: pinned host buffers in, loss read back, every step ----------
+    e2e = None
+    if not args.no_e2e:
+        def e2e_step():
+            c = clean_h.to(dev, non_blocking=True)
+            n = noisy_h.to(dev, non_blocking=True)
+            return step(c, n).item()
+        e2e_step()
+        ms_e = timed(args.steps, e2e_step)
+        e2e = {"value": round(world * B * args.steps / (ms_e / 1000.0), 2), "unit": UNIT,
+               "h2d_bytes_per_step": 2 * B * CLIP_SAMPLES * 4 * world, "d2h_bytes_per_step": 4 * world}
+
+    # ---- (3) per-kernel CUDA-event profile over a second timed region ---------------
+    L.profile_enable(True)
+    ms_p = timed(args.steps, lambda: step(clean_d, noisy_d))
+    prof = L.profile_report()
+    L.profile_enable(False)
+    peak, peak_src = measured_peaks()
+    total_kernel_ms = sum(v["ms"] for v in prof.values()) or 1.0
+    top = max(prof.items(), key=lambda kv: kv[1]["ms"])
+    tname, t = top
+    ach = t["bytes"] / (t["ms"] / 1000.0) / 1e9
+    roofline = {"kernel": tname, "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                "launches_per_step": t["launches"] / args.steps,
+                "avg_launch_ms": round(t["ms"] / t["launches"], 4),
+                "share_of_kernel_time": round(t["ms"] / total_kernel_ms, 4),
+                "tflops_fp32": round(t["flops"] / (t["ms"] / 1000.0) / 1e12, 2),
+                "ms_per_step_profiled": round(ms_p / args.steps, 3)}
+    kernels = {k: {"ms_per_step": round(v["ms"] / args.steps, 4), "launches_per_step": v["launches"] / args.steps,
+                   "GBps": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1),
+                   "TFLOPs": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 2)}
+               for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+
+    # ---- (4) CPU baseline on this box's host cores (rank 0, N = 1 only) ---------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cores = cpu_training_clips_per_sec(args.cpu_batch, 3, 1)
+        cpu = {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "%d clips/step x 3 steps of the same training step (oracle, torch CPU)" % args.cpu_batch}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "tiny.json training step (BASELINE.json configs[1]): %d clean/noisy 4-s 16 kHz "
+                                       "pairs per GPU, front end + TRU-Net + mask/iSTFT + L1/MRSTFT loss, fwd+bwd, "
+                                       "flat-bucket NCCL all-reduce (N>1), AdamW" % B,
+                           "clips_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world,
+                           "l2": "no explicit flush: one step streams >10 GB of activations through the 126 MB L2"},
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+                "cpu_baseline": cpu, "kernels": kernels}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -46,6 +46,14 @@ const char* tru_last_error(void);
  * every entry point; call it explicitly before CUDA-graph capture. */
 int tru_init(void);
 
+/* Optional per-kernel profiler used by bench.py for the roofline numbers: when
+ * enabled every kernel launch is bracketed by CUDA events on its stream.
+ * tru_profile_report synchronises the device and writes one line per kernel:
+ * "name launches total_ms algorithmic_bytes flops". */
+long long tru_launch_count(void);   /* kernels launched by this library so far (this process) */
+int tru_profile_enable(int on);
+int tru_profile_report(char* buf, size_t cap);
+
 /* ------------------------------------------------------------------ *
  * Front end: dataset.py:246-272 (ProcessAudio.forward), :56-76 (pcenfunc)
  * audio (B,N) -> feats (B,T',4,257), T' = 1 + N/128.

@@ -73,7 +73,11 @@ _sig("tru_trunet_backward", C.c_int, [C.POINTER(TruNetDesc), _PP, c_float_p, c_f
                                      C.c_size_t, c_stream])
 _sig("tru_trunet_buffer_offset", C.c_longlong, [C.POINTER(TruNetDesc), C.c_char_p, C.c_int])
 
-EXPORTS = ["tru_abi_version", "tru_last_error", "tru_init", "tru_frontend_workspace_bytes",
+_sig("tru_launch_count", C.c_longlong, [])
+_sig("tru_profile_enable", C.c_int, [C.c_int])
+_sig("tru_profile_report", C.c_int, [C.c_char_p, C.c_size_t])
+
+EXPORTS = ["tru_launch_count", "tru_profile_enable", "tru_profile_report", "tru_abi_version", "tru_last_error", "tru_init", "tru_frontend_workspace_bytes",
            "tru_frontend_fwd", "tru_frontend_step", "tru_backend_fwd", "tru_backend_bwd",
            "tru_loss_fwd", "tru_loss_bwd", "tru_trunet_workspace_bytes", "tru_trunet_forward",
            "tru_trunet_backward", "tru_trunet_buffer_offset"]
@@ -87,6 +91,21 @@ def check(rc, what=""):
     if rc != 0:
         msg = lib.tru_last_error()
         raise TruError("%s failed (%d): %s" % (what or "libtru_b200", rc, msg.decode() if msg else "?"))
+
+
+def profile_enable(on=True):
+    check(lib.tru_profile_enable(int(bool(on))), "tru_profile_enable")
+
+
+def profile_report():
+    """{kernel: dict(launches, ms, bytes, flops)} since the last report (synchronises)."""
+    buf = C.create_string_buffer(1 << 16)
+    check(lib.tru_profile_report(buf, len(buf)), "tru_profile_report")
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, n, ms, b, f = line.split()
+        out[name] = dict(launches=int(n), ms=float(ms), bytes=float(b), flops=float(f))
+    return out
 
 
 def ptr(t):

@@ -237,6 +237,8 @@ extern "C" int tru_backend_fwd(const TruBackendDesc* d, const float* net_out, fl
   p.net = net_out; p.audio = audio;
   p.nchunks = (p.T - 1 + JC - 1) / JC;
   TRU_CUDA(cudaFuncSetAttribute(backend_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM));
+  ProfScope prof("backend_fwd", 4.0 * p.B * ((double)p.C * NB * p.T + (double)HOP * (p.T - 1)), 0.5 * p.B * p.T * 5.0 * NFFT * 9,
+                 (cudaStream_t)stream);
   backend_fwd_kernel<<<p.B * p.nchunks, NT, FWD_SMEM, (cudaStream_t)stream>>>(p);
   TRU_LAUNCH_CHECK();
   return TRU_OK;
@@ -251,6 +253,8 @@ extern "C" int tru_backend_bwd(const TruBackendDesc* d, const float* net_out, co
   TRU_REQUIRE(net_out && grad_audio && grad_net_out, TRU_ERR_ARG, "backend_bwd: null pointer");
   p.net = net_out; p.gaudio = grad_audio; p.gnet = grad_net_out;
   p.nchunks = (p.T + TCB - 1) / TCB;
+  ProfScope prof("backend_bwd", 4.0 * p.B * (2.0 * p.C * NB * p.T + (double)HOP * (p.T - 1)), 0.5 * p.B * p.T * 5.0 * NFFT * 9,
+                 (cudaStream_t)stream);
   backend_bwd_kernel<<<p.B * p.nchunks, NT, BWD_SMEM, (cudaStream_t)stream>>>(p);
   TRU_LAUNCH_CHECK();
   return TRU_OK;

@@ -1,5 +1,6 @@
 // Library-wide state: error string, per-device init (twiddle table, arch check).
 #include <mutex>
+#include <vector>
 #include <string.h>
 #include "tru_common.cuh"
 
@@ -67,8 +68,65 @@ int sm_count() {
   return g_sms[dev] > 0 ? g_sms[dev] : 148;
 }
 
+// ---------------------------------------------------------------------------------
+struct ProfRec { const char* name; double bytes, flops; cudaEvent_t e0, e1; };
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_pool;
+static bool g_prof_on = false;
+
+static long long g_launches = 0;
+void count_launch() { ++g_launches; }
+bool prof_enabled() { return g_prof_on; }
+
+static cudaEvent_t prof_event() {
+  if (!g_pool.empty()) { cudaEvent_t e = g_pool.back(); g_pool.pop_back(); return e; }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+void prof_begin(const char* name, double bytes, double flops, cudaStream_t st) {
+  ProfRec r{name, bytes, flops, prof_event(), prof_event()};
+  cudaEventRecord(r.e0, st);
+  g_prof.push_back(r);
+}
+void prof_end(cudaStream_t st) { cudaEventRecord(g_prof.back().e1, st); }
+
 }  // namespace tru
 
+extern "C" int tru_profile_enable(int on) {
+  tru::g_prof_on = on != 0;
+  return TRU_OK;
+}
+
+// Synchronises the device, aggregates the recorded launches per kernel name into
+// "name count total_ms total_bytes total_flops\n" lines, clears the records.
+extern "C" int tru_profile_report(char* buf, size_t cap) {
+  using namespace tru;
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return set_error(-1000 - (int)e, "profile_report: %s", cudaGetErrorString(e));
+  struct Agg { const char* name; long n; double ms, bytes, flops; };
+  std::vector<Agg> agg;
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    g_pool.push_back(r.e0); g_pool.push_back(r.e1);
+    Agg* a = nullptr;
+    for (auto& x : agg) if (x.name == r.name || strcmp(x.name, r.name) == 0) { a = &x; break; }
+    if (!a) { agg.push_back(Agg{r.name, 0, 0, 0, 0}); a = &agg.back(); }
+    a->n++; a->ms += ms; a->bytes += r.bytes; a->flops += r.flops;
+  }
+  g_prof.clear();
+  size_t off = 0;
+  if (buf && cap) buf[0] = 0;
+  for (auto& a : agg) {
+    int w = snprintf(buf + off, off < cap ? cap - off : 0, "%s %ld %.6f %.0f %.0f\n", a.name, a.n, a.ms, a.bytes, a.flops);
+    if (w < 0 || off + (size_t)w >= cap) break;
+    off += (size_t)w;
+  }
+  return TRU_OK;
+}
+
+extern "C" long long tru_launch_count(void) { return tru::g_launches; }
 extern "C" int tru_abi_version(void) { return TRU_ABI_VERSION; }
 extern "C" const char* tru_last_error(void) { return tru::last_error_buf(); }
 extern "C" int tru_init(void) { return tru::ensure_init(); }

@@ -278,45 +278,53 @@ int dw_grid(long rows) { return (int)std::min<long>((rows + DW_ROWS - 1) / DW_RO
 }  // namespace
 
 int launch_bn_finalize(const BnFwdParams& p, cudaStream_t st) {
+  ProfScope prof("bn_finalize", 0, 0, st);
   bn_finalize_kernel<<<(p.C + 127) / 128, 128, 0, st>>>(p);
   TRU_LAUNCH_CHECK();
   return TRU_OK;
 }
 int launch_bn_bwd_finalize(const BnBwdParams& p, cudaStream_t st) {
+  ProfScope prof("bn_bwd_finalize", 0, 0, st);
   bn_bwd_finalize_kernel<<<(p.C + 127) / 128, 128, 0, st>>>(p);
   TRU_LAUNCH_CHECK();
   return TRU_OK;
 }
 int launch_enc0_fwd(const float* x, const float* w, const float* b, float* out, int BT, cudaStream_t st) {
+  ProfScope prof("enc0_fwd", 4.0 * BT * (4 * 257 + 128 * 64), 2.0 * BT * 128 * 64 * 20, st);
   enc0_fwd_kernel<<<std::min(BT, sm_count() * 4), 256, 0, st>>>(x, w, b, out, BT);
   TRU_LAUNCH_CHECK();
   return TRU_OK;
 }
 int launch_enc0_wgrad(const float* x, const float* dy, float* dw, float* db, int BT, cudaStream_t st) {
+  ProfScope prof("enc0_wgrad", 4.0 * BT * (4 * 257 + 128 * 64), 2.0 * BT * 128 * 64 * 20, st);
   enc0_wgrad_kernel<<<std::min(BT, sm_count() * 2), 256, 0, st>>>(x, dy, dw, db, BT);
   TRU_LAUNCH_CHECK();
   return TRU_OK;
 }
 int launch_dw_fwd(const DwParams& p, cudaStream_t st) {
   TRU_REQUIRE(p.C == DW_C && p.k <= 5, TRU_ERR_ARG, "depthwise kernel supports C=128, k<=5");
+  ProfScope prof("dw_fwd", 4.0 * p.BT * ((double)p.Lin + p.Lout) * p.C, 2.0 * p.k * p.BT * p.Lout * p.C, st);
   dw_fwd_kernel<<<dw_grid((long)p.BT * p.Lout), 256, 0, st>>>(p);
   TRU_LAUNCH_CHECK();
   return TRU_OK;
 }
 int launch_dw_bwd_data(const DwParams& p, cudaStream_t st) {
   TRU_REQUIRE(p.C == DW_C && p.k <= 5, TRU_ERR_ARG, "depthwise kernel supports C=128, k<=5");
+  ProfScope prof("dw_bwd_data", 4.0 * p.BT * (2.0 * p.Lin + 2.0 * p.Lout) * p.C, 2.0 * p.k * p.BT * p.Lout * p.C, st);
   dw_bwd_data_kernel<<<dw_grid((long)p.BT * p.Lin), 256, 0, st>>>(p);
   TRU_LAUNCH_CHECK();
   return TRU_OK;
 }
 int launch_dw_wgrad(const DwParams& p, cudaStream_t st) {
   TRU_REQUIRE(p.C == DW_C && p.k <= 5, TRU_ERR_ARG, "depthwise kernel supports C=128, k<=5");
+  ProfScope prof("dw_wgrad", 4.0 * p.BT * ((double)p.Lin + 2.0 * p.Lout) * p.C, 2.0 * p.k * p.BT * p.Lout * p.C, st);
   dw_wgrad_kernel<<<std::min(dw_grid((long)p.BT * p.Lout), sm_count() * 2), 256, 0, st>>>(p);
   TRU_LAUNCH_CHECK();
   return TRU_OK;
 }
 int launch_planar_to_cl(const float* src, float* dst, int BT, int C, int L, cudaStream_t st) {
   const long total = (long)BT * C * L;
+  ProfScope prof("planar_to_cl", 8.0 * total, 0, st);
   planar_to_cl_kernel<<<(int)std::min<long>((total + 255) / 256, (long)sm_count() * 8), 256, 0, st>>>(src, dst, BT, C, L);
   TRU_LAUNCH_CHECK();
   return TRU_OK;

@@ -218,6 +218,7 @@ extern "C" int tru_frontend_fwd(const TruFrontendDesc* d, const float* audio, co
     TRU_CUDA(cudaFuncSetAttribute(frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FRONT_SMEM));
     attr_set = true;
   }
+  ProfScope prof("frontend", 4.0 * p.B * ((double)p.N + 4.0 * NB * p.T), 0.5 * p.B * p.T * 5.0 * NFFT * 9, st);
   frontend_kernel<<<p.B * p.nchunks, NT, FRONT_SMEM, st>>>(p);
   TRU_LAUNCH_CHECK();
   return TRU_OK;

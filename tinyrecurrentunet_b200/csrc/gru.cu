@@ -394,6 +394,7 @@ int launch_fgru_fwd(const GruParams& p, cudaStream_t st) {
   const size_t smem = (size_t)(FH * F_WT_LD + FSEQ * F_H_LD) * 4;
   TRU_CUDA(cudaFuncSetAttribute(fgru_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((p.nseq + FSEQ - 1) / FSEQ, 2);
+  ProfScope prof("fgru_fwd", 4.0 * p.nseq * FL * (384 + 128 + 512), 2.0 * p.nseq * FL * 2 * FH * 3 * FH, st);
   fgru_fwd_kernel<<<grid, FNT, smem, st>>>(p);
   TRU_LAUNCH_CHECK();
   return TRU_OK;
@@ -403,6 +404,7 @@ int launch_fgru_bwd(const GruParams& p, cudaStream_t st) {
   const size_t smem = (size_t)(3 * FH * F_W_LD + FSEQ * F_G_LD) * 4;
   TRU_CUDA(cudaFuncSetAttribute(fgru_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((p.nseq + FSEQ - 1) / FSEQ, 2);
+  ProfScope prof("fgru_bwd", 4.0 * p.nseq * FL * (128 + 512 + 128 + 768), 2.0 * p.nseq * FL * 2 * FH * 3 * FH, st);
   fgru_bwd_kernel<<<grid, FNT, smem, st>>>(p);
   TRU_LAUNCH_CHECK();
   return TRU_OK;
@@ -410,6 +412,7 @@ int launch_fgru_bwd(const GruParams& p, cudaStream_t st) {
 
 int launch_tgru_fwd(const GruParams& p, int B, int T, cudaStream_t st) {
   const int nseq = B * TL;
+  ProfScope prof("tgru_fwd", 4.0 * nseq * T * (384 + 128 + 512), 2.0 * nseq * T * TH * 3 * TH, st);
   if (nseq <= 4 * sm_count()) tgru_fwd_kernel<4><<<(nseq + 3) / 4, TNT, 0, st>>>(p, B, T);
   else tgru_fwd_kernel<8><<<(nseq + 7) / 8, TNT, 0, st>>>(p, B, T);
   TRU_LAUNCH_CHECK();
@@ -418,6 +421,7 @@ int launch_tgru_fwd(const GruParams& p, int B, int T, cudaStream_t st) {
 
 int launch_tgru_bwd(const GruParams& p, int B, int T, cudaStream_t st) {
   const int nseq = B * TL;
+  ProfScope prof("tgru_bwd", 4.0 * nseq * T * (128 + 512 + 128 + 768), 2.0 * nseq * T * TH * 3 * TH, st);
   if (nseq <= 4 * sm_count()) tgru_bwd_kernel<4><<<(nseq + 3) / 4, TNT, 0, st>>>(p, B, T);
   else tgru_bwd_kernel<8><<<(nseq + 7) / 8, TNT, 0, st>>>(p, B, T);
   TRU_LAUNCH_CHECK();

@@ -314,6 +314,21 @@ int launch_igemm(const IgemmParams& p, cudaStream_t st) {
   const int ntiles = (int)((M + BM - 1) / BM);
   const int per_sm = smem > 100 * 1024 ? 1 : 2;
   dim3 grid(std::min(ntiles, sm_count() * per_sm), (p.N + BN - 1) / BN);
+  double bytes = 0, flops = 2.0 * (double)M * ktot * p.N;
+  if (prof_enabled()) {
+    const float* seen[5]; int ns = 0;
+    for (int s = 0; s < p.nseg; ++s) {
+      bool dup = false;
+      for (int t = 0; t < ns; ++t) dup |= (seen[t] == p.seg[s].src + p.seg[s].coff);
+      if (!dup) {
+        seen[ns++] = p.seg[s].src + p.seg[s].coff;
+        bytes += 4.0 * p.BT * p.seg[s].Lsrc * p.seg[s].C * (p.seg[s].src2 ? 2 : 1) * (p.src_frac > 0 ? p.src_frac : 1.0f);
+      }
+      bytes += 4.0 * p.seg[s].C * p.N;
+    }
+    bytes += 4.0 * M * p.N * (1 + (p.use_mask ? 1 : 0) + (p.extra ? 1 : 0));
+  }
+  ProfScope prof("igemm", bytes, flops, st);
   igemm_kernel<<<grid, NT, smem, st>>>(p, ktot_pad);
   TRU_LAUNCH_CHECK();
   return TRU_OK;
@@ -334,6 +349,14 @@ int launch_wgrad(const WgradParams& p, cudaStream_t st) {
   long rows = std::max<long>(256, (M + target - 1) / target);
   rows = (rows + WR - 1) / WR * WR;
   dim3 grid((unsigned)((M + rows - 1) / rows), maxt, p.njobs);
+  double bytes = 0, flops = 0;
+  if (prof_enabled())
+    for (int j = 0; j < p.njobs; ++j) {
+      const WgradJob& J = p.job[j];
+      bytes += 4.0 * M * ((J.a_src ? J.C : 0) + J.N * (J.z_src2 ? 2 : 1)) + 4.0 * (J.a_src ? J.C : 0) * J.N;
+      flops += J.a_src ? 2.0 * M * J.C * J.N : 0.0;
+    }
+  ProfScope prof("wgrad", bytes, flops, st);
   wgrad_kernel<<<grid, NT, 0, st>>>(p, (int)rows);
   TRU_LAUNCH_CHECK();
   return TRU_OK;

@@ -285,7 +285,12 @@ extern "C" int tru_loss_fwd(const TruLossDesc* d, const float* x, const float* y
   cudaStream_t st = (cudaStream_t)stream;
   TRU_CUDA(cudaMemsetAsync(sums, 0, 16 * sizeof(double), st));
   TRU_CUDA(cudaFuncSetAttribute(loss_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LOSS_FWD_SMEM));
-  loss_fwd_kernel<<<p.seg[4], NT, LOSS_FWD_SMEM, st>>>(p);
+  double fl = 0;
+  for (int r = 0; r < p.nres; ++r) fl += (double)p.B * p.T[r] * 5.0 * p.nfft[r] * log2((double)p.nfft[r]);
+  {
+    ProfScope prof("loss_fwd", 8.0 * p.B * p.N, fl, st);
+    loss_fwd_kernel<<<p.seg[4], NT, LOSS_FWD_SMEM, st>>>(p);
+  }
   TRU_LAUNCH_CHECK();
   loss_finalize_kernel<<<1, 32, 0, st>>>(p);
   TRU_LAUNCH_CHECK();
@@ -303,6 +308,9 @@ extern "C" int tru_loss_bwd(const TruLossDesc* d, const float* x, const float* y
   cudaStream_t st = (cudaStream_t)stream;
   TRU_CUDA(cudaMemsetAsync(grad_x, 0, (size_t)p.B * p.N * sizeof(float), st));
   TRU_CUDA(cudaFuncSetAttribute(loss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LOSS_BWD_SMEM));
+  double fl = 0;
+  for (int r = 0; r < p.nres; ++r) fl += 1.5 * p.B * p.T[r] * 5.0 * p.nfft[r] * log2((double)p.nfft[r]);
+  ProfScope prof("loss_bwd", 12.0 * p.B * p.N, fl, st);
   loss_bwd_kernel<<<p.seg[4], NT, LOSS_BWD_SMEM, st>>>(p);
   TRU_LAUNCH_CHECK();
   return TRU_OK;

@@ -33,6 +33,7 @@ struct IgemmParams {
   const float* extra; int ext_ld;                 // backward: gradient to add (skip connections)
   const float* zmask; const float* mp0; const float* mp2; int use_mask;   // ReLU mask of the layer receiving the gradient
   const float* bmean; const float* binv; double* bstats;                  // backward BN sums: sum g, sum g*xhat
+  float src_frac;              // profiler only: fraction of each source this launch needs (0 -> 1)
 };
 int launch_igemm(const IgemmParams& p, cudaStream_t st);
 

@@ -36,6 +36,21 @@ int sm_count();
     if (!(cond)) return tru::set_error(code, __VA_ARGS__);                     \
   } while (0)
 
+// ---- optional per-kernel event profiler (bench.py roofline; off by default) -----
+// prof_begin/prof_end bracket one kernel launch with CUDA events on its stream.
+bool prof_enabled();
+void prof_begin(const char* name, double bytes, double flops, cudaStream_t st);
+void prof_end(cudaStream_t st);
+void count_launch();
+struct ProfScope {
+  cudaStream_t st; bool on;
+  ProfScope(const char* name, double bytes, double flops, cudaStream_t s) : st(s), on(prof_enabled()) {
+    count_launch();
+    if (on) prof_begin(name, bytes, flops, st);
+  }
+  ~ProfScope() { if (on) prof_end(st); }
+};
+
 static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -160,7 +160,7 @@ int convt_fwd(Ctx& c, const Act& x, const float* W, const float* bias, int Cout,
     }
     p.BT = (int)c.BT; p.Lq = (Lout - par + s - 1) / s; p.N = Cout; p.bias = bias;
     p.out = out; p.Lout = Lout; p.ldo = Cout; p.ocoff = 0; p.omul = s; p.oadd = par; p.planar = planar;
-    p.stats = stats;
+    p.stats = stats; p.src_frac = 1.0f / s;
     if (p.Lq > 0 && p.nseg > 0) TRY(launch_igemm(p, c.st));
   }
   return TRU_OK;
