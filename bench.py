@@ -239,8 +239,18 @@ def run_native(args):
     # ---- (3) per-kernel CUDA-event profile over a second timed region ---------------
     L.profile_enable(True)
     ms_p = timed(args.steps, lambda: step(clean_d, noisy_d))
-    prof = L.profile_report()
+    prof_detail = L.profile_report()
     L.profile_enable(False)
+    prof = {}
+    for k, v in prof_detail.items():               # "igemm_tc:M=..,K=.." -> "igemm_tc"
+        a = prof.setdefault(k.split(":")[0], dict(launches=0, ms=0.0, bytes=0.0, flops=0.0))
+        for f in a:
+            a[f] += v[f]
+    if os.environ.get("TRU_BENCH_DETAIL") and rank == 0:
+        for k, v in sorted(prof_detail.items(), key=lambda kv: -kv[1]["ms"])[:60]:
+            print("# %-60s n=%5.1f %8.3f ms/step %7.1f GB/s %7.1f TF" % (
+                k, v["launches"] / args.steps, v["ms"] / args.steps, v["bytes"] / max(v["ms"], 1e-9) / 1e6,
+                v["flops"] / max(v["ms"], 1e-9) / 1e9), file=sys.stderr)
     peak, peak_src = measured_peaks()
     total_kernel_ms = sum(v["ms"] for v in prof.values()) or 1.0
     top = max(prof.items(), key=lambda kv: kv[1]["ms"])

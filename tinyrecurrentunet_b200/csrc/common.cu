@@ -91,6 +91,7 @@ void prof_begin(const char* name, double bytes, double flops, cudaStream_t st) {
 }
 void prof_end(cudaStream_t st) { cudaEventRecord(g_prof.back().e1, st); }
 
+
 }  // namespace tru
 
 extern "C" int tru_profile_enable(int on) {

@@ -9,6 +9,9 @@
 // or (backward) adds the skip gradient, applies the ReLU mask and accumulates the
 // two BN-backward sums.  Weights for the CTA's 64 output columns stay resident in
 // shared memory while the CTA walks over row tiles.
+#include <map>
+#include <string>
+#include <string.h>
 #include "net_kernels.cuh"
 
 namespace tru {
@@ -294,7 +297,53 @@ __global__ void __launch_bounds__(NT) wgrad_kernel(const __grid_constant__ Wgrad
 
 }  // namespace
 
+static bool g_tc_on = true;
+void set_tc_enabled(bool on) { g_tc_on = on; }
+bool tc_enabled() { return g_tc_on; }
+
+static void igemm_cost(const IgemmParams& p, double& bytes, double& flops) {
+  const long M = (long)p.BT * p.Lq;
+  int ktot = 0;
+  bytes = 0;
+  const float* seen[5]; int ns = 0;
+  for (int s = 0; s < p.nseg; ++s) {
+    ktot += p.seg[s].C;
+    bool dup = false;
+    for (int t = 0; t < ns; ++t) dup |= (seen[t] == p.seg[s].src + p.seg[s].coff);
+    if (!dup) {
+      seen[ns++] = p.seg[s].src + p.seg[s].coff;
+      bytes += 4.0 * p.BT * p.seg[s].Lsrc * p.seg[s].C * (p.seg[s].src2 ? 2 : 1) * (p.src_frac > 0 ? p.src_frac : 1.0f);
+    }
+    bytes += 4.0 * p.seg[s].C * p.N;
+  }
+  bytes += 4.0 * M * p.N * (1 + (p.use_mask ? 1 : 0) + (p.extra ? 1 : 0));
+  flops = 2.0 * (double)M * ktot * p.N;
+}
+
+// interned "<kind>:M=..,K=..,N=..,seg=..[,bwd]" strings for the profiler (bench.py groups by prefix)
+static const char* shape_name(const char* kind, const IgemmParams& p) {
+  static std::map<std::string, const char*> names;
+  int ktot = 0;
+  for (int s = 0; s < p.nseg; ++s) ktot += p.seg[s].C;
+  char buf[128];
+  snprintf(buf, sizeof(buf), "%s:M=%ld,K=%d,N=%d,seg=%d%s%s", kind, (long)p.BT * p.Lq, ktot, p.N, p.nseg,
+           p.seg[0].src2 ? ",bnload" : "", p.use_mask ? ",mask" : "");
+  auto it = names.find(buf);
+  if (it == names.end()) it = names.emplace(buf, strdup(buf)).first;
+  return it->second;
+}
+
 int launch_igemm(const IgemmParams& p, cudaStream_t st) {
+  if (g_tc_on && igemm_tc_eligible(p)) {
+    double bytes = 0, flops = 0;
+    if (prof_enabled()) igemm_cost(p, bytes, flops);
+    ProfScope prof(prof_enabled() ? shape_name("igemm_tc", p) : "igemm_tc", bytes, flops, st);
+    return launch_igemm_tc(p, st);
+  }
+  return launch_igemm_simt(p, st);
+}
+
+int launch_igemm_simt(const IgemmParams& p, cudaStream_t st) {
   TRU_REQUIRE(p.nseg >= 1 && p.nseg <= 5 && p.N % 4 == 0 && p.BT > 0 && p.Lq > 0, TRU_ERR_ARG, "igemm: bad params");
   int ktot = 0;
   for (int s = 0; s < p.nseg; ++s) {
@@ -314,20 +363,8 @@ int launch_igemm(const IgemmParams& p, cudaStream_t st) {
   const int ntiles = (int)((M + BM - 1) / BM);
   const int per_sm = smem > 100 * 1024 ? 1 : 2;
   dim3 grid(std::min(ntiles, sm_count() * per_sm), (p.N + BN - 1) / BN);
-  double bytes = 0, flops = 2.0 * (double)M * ktot * p.N;
-  if (prof_enabled()) {
-    const float* seen[5]; int ns = 0;
-    for (int s = 0; s < p.nseg; ++s) {
-      bool dup = false;
-      for (int t = 0; t < ns; ++t) dup |= (seen[t] == p.seg[s].src + p.seg[s].coff);
-      if (!dup) {
-        seen[ns++] = p.seg[s].src + p.seg[s].coff;
-        bytes += 4.0 * p.BT * p.seg[s].Lsrc * p.seg[s].C * (p.seg[s].src2 ? 2 : 1) * (p.src_frac > 0 ? p.src_frac : 1.0f);
-      }
-      bytes += 4.0 * p.seg[s].C * p.N;
-    }
-    bytes += 4.0 * M * p.N * (1 + (p.use_mask ? 1 : 0) + (p.extra ? 1 : 0));
-  }
+  double bytes = 0, flops = 0;
+  if (prof_enabled()) igemm_cost(p, bytes, flops);
   ProfScope prof("igemm", bytes, flops, st);
   igemm_kernel<<<grid, NT, smem, st>>>(p, ktot_pad);
   TRU_LAUNCH_CHECK();

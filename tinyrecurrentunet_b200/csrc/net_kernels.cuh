@@ -35,7 +35,12 @@ struct IgemmParams {
   const float* bmean; const float* binv; double* bstats;                  // backward BN sums: sum g, sum g*xhat
   float src_frac;              // profiler only: fraction of each source this launch needs (0 -> 1)
 };
-int launch_igemm(const IgemmParams& p, cudaStream_t st);
+int launch_igemm(const IgemmParams& p, cudaStream_t st);       // tensor-core path when eligible, else FFMA
+bool igemm_tc_eligible(const IgemmParams& p);
+int launch_igemm_tc(const IgemmParams& p, cudaStream_t st);    // 0 launched, 1 not eligible, <0 error
+int launch_igemm_simt(const IgemmParams& p, cudaStream_t st);
+void set_tc_enabled(bool on);
+bool tc_enabled();
 
 struct WgradJob {
   const float* a_src; const float* a_p0; const float* a_p2; int a_relu;

@@ -537,3 +537,21 @@ extern "C" int tru_debug_convt_bwd_data(const float* dy, const float* w, float* 
   p.out = dx; p.Lout = L; p.ldo = Cin; p.omul = 1;
   return launch_igemm(p, (cudaStream_t)stream);
 }
+
+// Test aid: pointwise conv y = act(x) W^T + b through either GEMM path.  x (M,K), w (N,K), out (M,N).
+extern "C" int tru_debug_pw(const float* x, const float* p0, const float* p2, const float* w, const float* bias,
+                            float* out, double* stats, int M, int K, int N, int use_tc, void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  IgemmParams p{};
+  Act a{x, 1, K, p0, p2, -1};
+  p.seg[0] = fwd_seg(a, w, 0, 1, K, 1, 0);
+  p.nseg = 1; p.BT = M; p.Lq = 1; p.N = N; p.bias = bias;
+  p.out = out; p.Lout = 1; p.ldo = N; p.omul = 1; p.stats = stats;
+  if (use_tc) {
+    rc = launch_igemm_tc(p, (cudaStream_t)stream);
+    return rc == 1 ? set_error(TRU_ERR_ARG, "debug_pw: shape not eligible for the tensor-core path") : rc;
+  }
+  return launch_igemm_simt(p, (cudaStream_t)stream);
+}
+extern "C" int tru_set_tensor_cores(int on) { set_tc_enabled(on != 0); return TRU_OK; }
