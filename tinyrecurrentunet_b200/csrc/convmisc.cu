@@ -262,6 +262,46 @@ __global__ void __launch_bounds__(256) dw_wgrad_kernel(const __grid_constant__ D
   }
 }
 
+// db[n] += sum over rows of dz(row, n), dz = q0*dY + q1*Z + q2 (or dY): bias gradients that cannot
+// ride on a weight-gradient pass (transposed convs, GRU hidden biases).
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ src, const float* __restrict__ src2,
+                                                     const float* __restrict__ q0, const float* __restrict__ q1,
+                                                     const float* __restrict__ q2, float* __restrict__ db, long rows,
+                                                     int ld, int coff, int N) {
+  __shared__ float red[256][4];
+  const int cpl = N >> 2;                       // float4 columns per row
+  const int rlanes = 256 / cpl;                 // rows handled per pass by this block
+  const int col = threadIdx.x % cpl, rl = threadIdx.x / cpl;
+  const bool active = rl < rlanes;
+  float4 a0 = make_float4(1, 1, 1, 1), a1 = make_float4(0, 0, 0, 0), a2 = a1;
+  if (q0 && active) { a0 = ld4(q0 + coff + col * 4); a2 = ld4(q2 + coff + col * 4); if (q1) a1 = ld4(q1 + coff + col * 4); }
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  if (active) {
+    for (long r = (long)blockIdx.x * rlanes + rl; r < rows; r += (long)gridDim.x * rlanes) {
+      float4 v = ld4(src + r * ld + coff + col * 4);
+      if (q0) {
+        v.x = a0.x * v.x + a2.x; v.y = a0.y * v.y + a2.y; v.z = a0.z * v.z + a2.z; v.w = a0.w * v.w + a2.w;
+        if (q1) {
+          const float4 z = ld4(src2 + r * ld + coff + col * 4);
+          v.x += a1.x * z.x; v.y += a1.y * z.y; v.z += a1.z * z.z; v.w += a1.w * z.w;
+        }
+      }
+      s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) red[threadIdx.x][e] = s[e];
+  __syncthreads();
+  if (threadIdx.x < cpl) {
+    float t[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int r = 0; r < rlanes; ++r)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) t[e] += red[r * cpl + threadIdx.x][e];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) atomicAdd(db + threadIdx.x * 4 + e, t[e]);
+  }
+}
+
 __global__ void planar_to_cl_kernel(const float* __restrict__ src, float* __restrict__ dst, int BT, int C, int L) {
   const long total = (long)BT * C * L;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -319,6 +359,16 @@ int launch_dw_wgrad(const DwParams& p, cudaStream_t st) {
   TRU_REQUIRE(p.C == DW_C && p.k <= 5, TRU_ERR_ARG, "depthwise kernel supports C=128, k<=5");
   ProfScope prof("dw_wgrad", 4.0 * p.BT * ((double)p.Lin + 2.0 * p.Lout) * p.C, 2.0 * p.k * p.BT * p.Lout * p.C, st);
   dw_wgrad_kernel<<<std::min(dw_grid((long)p.BT * p.Lout), sm_count() * 2), 256, 0, st>>>(p);
+  TRU_LAUNCH_CHECK();
+  return TRU_OK;
+}
+int launch_colsum(const float* src, const float* src2, const float* q0, const float* q1, const float* q2, float* db,
+                  long rows, int ld, int coff, int N, cudaStream_t st) {
+  TRU_REQUIRE(N % 4 == 0 && N >= 4 && N <= 1024 && ld % 4 == 0 && coff % 4 == 0, TRU_ERR_ARG, "colsum: bad shape");
+  const int rlanes = 256 / (N / 4);
+  ProfScope prof("colsum", 4.0 * rows * N * (q1 ? 2 : 1), 0, st);
+  colsum_kernel<<<(int)std::min<long>((rows + rlanes - 1) / rlanes, (long)sm_count() * 8), 256, 0, st>>>(
+      src, src2, q0, q1, q2, db, rows, ld, coff, N);
   TRU_LAUNCH_CHECK();
   return TRU_OK;
 }

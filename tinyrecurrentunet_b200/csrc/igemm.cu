@@ -371,7 +371,60 @@ int launch_igemm_simt(const IgemmParams& p, cudaStream_t st) {
   return TRU_OK;
 }
 
+static void wgrad_cost(const WgradParams& p, double& bytes, double& flops) {
+  const long M = (long)p.BT * p.Lq;
+  bytes = 0; flops = 0;
+  for (int j = 0; j < p.njobs; ++j) {
+    const WgradJob& J = p.job[j];
+    bytes += 4.0 * M * ((J.a_src ? J.C : 0) + J.N * (J.z_src2 ? 2 : 1)) + 4.0 * (J.a_src ? J.C : 0) * J.N;
+    flops += J.a_src ? 2.0 * M * J.C * J.N : 0.0;
+  }
+}
+
 int launch_wgrad(const WgradParams& p, cudaStream_t st) {
+  if (!tc_enabled()) return launch_wgrad_simt(p, st);
+  WgradParams tcp{}, rest{};
+  tcp.BT = rest.BT = p.BT; tcp.Lq = rest.Lq = p.Lq;
+  for (int j = 0; j < p.njobs; ++j) {
+    if (p.job[j].a_src) tcp.job[tcp.njobs++] = p.job[j]; else rest.job[rest.njobs++] = p.job[j];
+  }
+  if (tcp.njobs) {
+    double bytes = 0, flops = 0;
+    if (prof_enabled()) wgrad_cost(tcp, bytes, flops);
+    int rc;
+    {
+      const char* nm = "wgrad_tc";
+      if (prof_enabled()) {
+        static std::map<std::string, const char*> names;
+        char buf[128];
+        snprintf(buf, sizeof(buf), "wgrad_tc:M=%ld,jobs=%d,C=%d,N=%d%s", (long)p.BT * p.Lq, tcp.njobs, tcp.job[0].C, tcp.job[0].N,
+                 tcp.job[0].z_src2 ? ",bnload" : "");
+        auto it = names.find(buf);
+        if (it == names.end()) it = names.emplace(buf, strdup(buf)).first;
+        nm = it->second;
+      }
+      ProfScope prof(nm, bytes, flops, st);
+      rc = launch_wgrad_tc(tcp, st);
+    }
+    if (rc == 1) return launch_wgrad_simt(p, st);      // (records an empty wgrad_tc interval; harmless)
+    if (rc) return rc;
+  }
+  WgradParams left{};
+  left.BT = p.BT; left.Lq = p.Lq;
+  for (int j = 0; j < rest.njobs; ++j) {
+    const WgradJob& J = rest.job[j];
+    if (!J.a_src && J.db && J.z_mul == 1 && J.z_add == 0 && J.z_L == p.Lq) {
+      const int rc = launch_colsum(J.z_src, J.z_src2, J.z_p0, J.z_p1, J.z_p2, J.db, (long)p.BT * p.Lq, J.z_ld, J.z_coff, J.N, st);
+      if (rc) return rc;
+    } else {
+      left.job[left.njobs++] = J;
+    }
+  }
+  if (left.njobs) return launch_wgrad_simt(left, st);
+  return TRU_OK;
+}
+
+int launch_wgrad_simt(const WgradParams& p, cudaStream_t st) {
   TRU_REQUIRE(p.njobs >= 1 && p.njobs <= 8 && p.BT > 0 && p.Lq > 0, TRU_ERR_ARG, "wgrad: bad params");
   int maxt = 1;
   for (int j = 0; j < p.njobs; ++j) {
@@ -387,12 +440,7 @@ int launch_wgrad(const WgradParams& p, cudaStream_t st) {
   rows = (rows + WR - 1) / WR * WR;
   dim3 grid((unsigned)((M + rows - 1) / rows), maxt, p.njobs);
   double bytes = 0, flops = 0;
-  if (prof_enabled())
-    for (int j = 0; j < p.njobs; ++j) {
-      const WgradJob& J = p.job[j];
-      bytes += 4.0 * M * ((J.a_src ? J.C : 0) + J.N * (J.z_src2 ? 2 : 1)) + 4.0 * (J.a_src ? J.C : 0) * J.N;
-      flops += J.a_src ? 2.0 * M * J.C * J.N : 0.0;
-    }
+  if (prof_enabled()) wgrad_cost(p, bytes, flops);
   ProfScope prof("wgrad", bytes, flops, st);
   wgrad_kernel<<<grid, NT, 0, st>>>(p, (int)rows);
   TRU_LAUNCH_CHECK();

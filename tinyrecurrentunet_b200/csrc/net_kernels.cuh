@@ -51,7 +51,9 @@ struct WgradJob {
   float* db;
 };
 struct WgradParams { WgradJob job[8]; int njobs; int BT, Lq; };
-int launch_wgrad(const WgradParams& p, cudaStream_t st);
+int launch_wgrad(const WgradParams& p, cudaStream_t st);        // tensor-core path for eligible jobs, FFMA for the rest
+int launch_wgrad_tc(const WgradParams& p, cudaStream_t st);     // 0 launched, 1 not eligible
+int launch_wgrad_simt(const WgradParams& p, cudaStream_t st);
 
 // ---- BatchNorm bookkeeping -----------------------------------------------------
 struct BnFwdParams {
@@ -88,6 +90,8 @@ int launch_dw_fwd(const DwParams& p, cudaStream_t st);
 int launch_dw_bwd_data(const DwParams& p, cudaStream_t st);
 int launch_dw_wgrad(const DwParams& p, cudaStream_t st);
 
+int launch_colsum(const float* src, const float* src2, const float* q0, const float* q1, const float* q2, float* db,
+                  long rows, int ld, int coff, int N, cudaStream_t st);
 // planar (BT, C, L) <-> channels-last (BT, L, C), small C
 int launch_planar_to_cl(const float* src, float* dst, int BT, int C, int L, cudaStream_t st);
 

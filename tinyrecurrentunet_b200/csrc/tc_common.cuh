@@ -76,6 +76,12 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) /* descriptor version (Blackwell) */ |
          (2ull << 61) /* SWIZZLE_128B */;
 }
+// MN-major tf32 operands: the only legal swizzle is SWIZZLE_128B_BASE32B (layout type 1): atoms of
+// 4 K-rows x 128 B, the four 32-byte chunks of a row XOR-ed with the row index (Swizzle<2,5,2>).
+__device__ __forceinline__ uint64_t smem_desc_sw128_32b(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (1ull << 61) /* SWIZZLE_128B_BASE32B */;
+}
 // Instruction descriptor: kind::tf32, fp32 accumulator, M x N, operand majors (0 = K-major, 1 = MN-major).
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4) /* D = f32 */ | (2u << 7) /* A = tf32 */ | (2u << 10) /* B = tf32 */ |

@@ -1,0 +1,265 @@
+// Tensor-core weight gradient (tcgen05 / TMEM, 3xTF32):  dW[c][n] += sum_m a(m,c) * dz(m,n).
+//
+// The reduction runs over ROWS, so both operands are consumed "MN-major": a k-block is
+// 32 consecutive rows of the two row-major activation tensors, written as-is (channels
+// contiguous) into SWIZZLE_128B_BASE32B shared-memory atoms of 4 rows x 32 channels.  One
+// side ("P", 128 channels, zero padded) becomes the M dimension of the MMA, the other
+// ("Q", 32..128 channels) the N dimension; the roles are chosen per job so that the
+// wider tensor sits on P.  A CTA owns a contiguous range of rows and keeps ONE fp32
+// accumulator (128 x Q) in TMEM for its whole range; at the end the accumulator is
+// added to dW with atomics.  a() is the forward activation (BN + ReLU applied on load),
+// dz() the BN-backward-transformed gradient, exactly as in wgrad_kernel (igemm.cu).
+//
+// 17 warps: warp 0 MMA issuer, warps 1-8 P loaders, warps 9-16 Q loaders; the bias
+// gradient (column sums of dz) is accumulated by the dz-side loaders on the fly.
+#include <algorithm>
+#include "net_kernels.cuh"
+#include "tc_common.cuh"
+
+namespace tru {
+namespace {
+using namespace tc;
+
+constexpr int KROWS = 32;                       // rows per k-block
+constexpr int NT = 32 * 17;
+constexpr int PW = 128;                         // P tile width (channels)
+constexpr int P_TILE = KROWS * PW * 4;          // 16 KB per hi (or lo)
+constexpr int NSTAGE = 3;
+
+struct Side {          // one operand of a job, as seen by its loaders
+  const float* src; const float* src2; const float* p0; const float* p1; const float* p2;
+  int L, ld, coff, mul, add, C;      // rows per frame, row stride, first channel, row map, channels
+  int relu, c0;                      // c0: first channel of this CTA's tile
+};
+struct TcWJob {
+  Side P, Q;
+  float* dW; int wbase, sp, sq;      // dW[wbase + p*sp + q*sq]
+  float* db; int db_on_p;            // bias gradient = column sums of the dz side
+  int ptiles, qtiles, QW;            // tiles along P (128 wide) and Q (QW wide)
+};
+struct TcWParams { TcWJob job[8]; int njobs, BT, Lq, nsplit; };
+
+struct WMisc { uint64_t full[NSTAGE], empty[NSTAGE], done; uint32_t tmem_base; };
+
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg((const float4*)p); }
+
+// Loader of one side.  W = tile width in channels (128 for P, QW for Q).  256 threads.
+template <bool IS_P>
+__device__ __forceinline__ void side_loader(const TcWParams& P, const TcWJob& J, const Side& S, int W, int lt, int lane,
+                                            uint8_t* ring, int side_off, int tile_bytes, WMisc& mi, unsigned kb0,
+                                            unsigned kb1, bool want_db) {
+  const int cpr = W >> 2;                        // 16-byte chunks per row
+  const int cidx = lt % cpr, rsub = lt / cpr, rstep = 256 / cpr, npass = KROWS / rstep;   // npass = W/32
+  const int mb = cidx >> 3, ch = cidx & 7, NB = W >> 5;
+  const int c = S.c0 + cidx * 4;                 // channel inside the tensor (before coff)
+  const bool c_ok = c < S.C;
+  float4 p0 = make_float4(1, 1, 1, 1), p1 = make_float4(0, 0, 0, 0), p2 = p1;
+  if (S.p0 && c_ok) {
+    p0 = ld4(S.p0 + S.coff + c); p2 = ld4(S.p2 + S.coff + c);
+    if (S.p1) p1 = ld4(S.p1 + S.coff + c);
+  }
+  float bs[4] = {0.f, 0.f, 0.f, 0.f};
+  // row cursor: m = kb*32 + rsub + rstep*i  ->  (bt, q) kept incrementally for i = 0
+  const unsigned Lq = (unsigned)P.Lq, Mrows = (unsigned)P.BT * Lq;
+  float4 va[2][4], vb[2][4];
+  unsigned msk[2] = {0, 0};
+  auto issue = [&](unsigned kb, float4 (&a)[4], float4 (&b)[4], unsigned& mk) {
+    mk = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (i < npass) {
+        const unsigned m = kb * KROWS + rsub + rstep * i;
+        if (m < Mrows && c_ok) {
+          const unsigned bt = m / Lq, q = m - bt * Lq;
+          const int l = (int)q * S.mul + S.add;
+          if (l >= 0 && l < S.L) {
+            const unsigned off = (bt * S.L + l) * S.ld + S.coff + c;
+            a[i] = ld4(S.src + off);
+            if (S.src2) b[i] = ld4(S.src2 + off);
+            mk |= 1u << i;
+          }
+        }
+      }
+    }
+  };
+  int st = 0;
+  uint32_t ph = 0;
+  if (kb0 < kb1) issue(kb0, va[0], vb[0], msk[0]);
+  for (unsigned kb = kb0; kb < kb1; kb += 2) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const unsigned k = kb + u;
+      if (k < kb1) {
+        if (k + 1 < kb1) issue(k + 1, va[u ^ 1], vb[u ^ 1], msk[u ^ 1]);
+        mbar_wait(&mi.empty[st], ph ^ 1);
+        uint8_t* base = ring + st * (2 * P_TILE + 2 * P_TILE) + side_off;     // stage = [P hi | P lo | Q hi | Q lo], each 16 KB max
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (i < npass) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (msk[u] & (1u << i)) {
+              v = va[u][i];
+              if (S.p0) {
+                v.x = p0.x * v.x + p2.x; v.y = p0.y * v.y + p2.y; v.z = p0.z * v.z + p2.z; v.w = p0.w * v.w + p2.w;
+                if (S.p1) { v.x += p1.x * vb[u][i].x; v.y += p1.y * vb[u][i].y; v.z += p1.z * vb[u][i].z; v.w += p1.w * vb[u][i].w; }
+                if (S.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+              }
+              bs[0] += v.x; bs[1] += v.y; bs[2] += v.z; bs[3] += v.w;
+            }
+            uint4 hi, lo;
+            split_tf32(v, hi, lo);
+            const int r = rsub + rstep * i;
+            // atom = 4 rows x 128 B; 32-byte chunk index (ch>>1) XOR row-in-atom (Swizzle<2,5,2>)
+            const uint32_t off = ((r >> 2) * NB + mb) * 512 + (r & 3) * 128 + ((((ch >> 1) ^ (r & 3)) << 5) | ((ch & 1) << 4));
+            *(uint4*)(base + off) = hi;
+            *(uint4*)(base + tile_bytes + off) = lo;
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&mi.full[st]);
+        if (++st == NSTAGE) { st = 0; ph ^= 1; }
+      }
+    }
+  }
+  if (want_db && c_ok) {
+    // threads with the same cidx hold partial column sums: reduce the rstep row-lanes through atomics
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (c + e < S.C) atomicAdd(J.db + c + e, bs[e]);
+  }
+  (void)IS_P;
+}
+
+__global__ void __launch_bounds__(NT, 1) tc_wgrad_kernel(const __grid_constant__ TcWParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const TcWJob& J0 = P.job[blockIdx.z];
+  const int ntile = J0.ptiles * J0.qtiles;
+  if ((int)blockIdx.y >= ntile) return;
+  TcWJob J = J0;
+  const int pt = blockIdx.y % J.ptiles, qt = blockIdx.y / J.ptiles;
+  J.P.c0 = pt * PW;
+  J.Q.c0 = qt * J.QW;
+  const int QW = J.QW;
+  uint8_t* ring = smem;                                       // NSTAGE x 64 KB
+  WMisc& mi = *(WMisc*)(smem + NSTAGE * 4 * P_TILE);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const unsigned Mrows = (unsigned)P.BT * (unsigned)P.Lq;
+  const unsigned nkb = (Mrows + KROWS - 1) / KROWS;
+  const unsigned per = (nkb + P.nsplit - 1) / P.nsplit;
+  const unsigned kb0 = min(nkb, blockIdx.x * per), kb1 = min(nkb, kb0 + per);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int s = 0; s < NSTAGE; ++s) { mbar_init(&mi.full[s], 16); mbar_init(&mi.empty[s], 1); }
+      mbar_init(&mi.done, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(&mi.tmem_base, 128);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = mi.tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0 && kb0 < kb1) {
+      const uint32_t idesc = idesc_tf32(128, QW, 1, 1);
+      // MN-major SW128_32B: LBO = 512 B between 32-channel blocks, SBO = distance between 4-row groups
+      const uint64_t dP = ((smem_desc_sw128_32b(0, 512, (PW / 32) * 512) >> 16) << 16);
+      const uint64_t dQ = ((smem_desc_sw128_32b(0, 512, (QW / 32) * 512) >> 16) << 16);
+      const uint32_t rbase = smem_u32(ring) >> 4;
+      int st = 0;
+      uint32_t ph = 0;
+      for (unsigned kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&mi.full[st], ph);
+        tc_fence_after();
+        const uint32_t p_hi = rbase + st * ((4 * P_TILE) >> 4), p_lo = p_hi + (P_TILE >> 4);
+        const uint32_t q_hi = p_hi + ((2 * P_TILE) >> 4), q_lo = q_hi + (P_TILE >> 4);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {                         // 4 groups of 8 rows = 4 k-steps
+          const uint32_t po = g * (PW / 32) * 64, qo = g * (QW / 32) * 64;     // (blocks * 1024 B) >> 4
+          mma_tf32(tmem, dP | (p_lo + po), dQ | (q_hi + qo), idesc, (kb != kb0) || g != 0);
+          mma_tf32(tmem, dP | (p_hi + po), dQ | (q_lo + qo), idesc, 1);
+          mma_tf32(tmem, dP | (p_hi + po), dQ | (q_hi + qo), idesc, 1);
+        }
+        mma_commit(&mi.empty[st]);
+        if (++st == NSTAGE) { st = 0; ph ^= 1; }
+      }
+      mma_commit(&mi.done);
+    }
+  } else if (warp <= 8) {
+    side_loader<true>(P, J, J.P, PW, tid - 32, lane, ring, 0, P_TILE, mi, kb0, kb1, J.db && J.db_on_p && qt == 0);
+  } else {
+    side_loader<false>(P, J, J.Q, QW, tid - 288, lane, ring, 2 * P_TILE, P_TILE, mi, kb0, kb1, J.db && !J.db_on_p && pt == 0);
+  }
+
+  // ---- epilogue: warps 1-4 drain the accumulator and add it to dW ---------------------
+  if (warp >= 1 && warp <= 4 && kb0 < kb1) {
+    mbar_wait(&mi.done, 0);
+    tc_fence_after();
+    const int lgrp = warp & 3;
+    const int p = J.P.c0 + lgrp * 32 + lane;
+    for (int cc = 0; cc * 32 < QW; ++cc) {
+      uint32_t v[32];
+      tmem_ld32(tmem + ((uint32_t)(lgrp * 32) << 16) + cc * 32, v);
+      if (p < J.P.C) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int q = J.Q.c0 + cc * 32 + j;
+          if (q < J.Q.C) atomicAdd(J.dW + J.wbase + (long)p * J.sp + (long)q * J.sq, __uint_as_float(v[j]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 128);
+  }
+}
+
+}  // namespace
+
+// Converts the generic wgrad jobs into tensor-core jobs.  Returns 1 if some job is not eligible.
+int launch_wgrad_tc(const WgradParams& p, cudaStream_t st) {
+  TcWParams T{};
+  T.njobs = 0; T.BT = p.BT; T.Lq = p.Lq;
+  int maxt = 1;
+  for (int j = 0; j < p.njobs; ++j) {
+    const WgradJob& J = p.job[j];
+    if (!J.a_src) return 1;                                          // bias-only jobs stay on the FFMA kernel
+    if (J.C % 32 || J.N % 32 || J.a_ld % 4 || J.z_ld % 4 || J.a_coff % 4 || J.z_coff % 4) return 1;
+    if ((double)p.BT * J.a_L * J.a_ld >= 4294967296.0 || (double)p.BT * J.z_L * J.z_ld >= 4294967296.0) return 1;
+    if (J.db && !(J.z_mul == 1 && J.z_add == 0 && J.z_L == p.Lq)) return 1;   // db needs every dz row exactly once
+    Side A{J.a_src, nullptr, J.a_p0, nullptr, J.a_p2, J.a_L, J.a_ld, J.a_coff, J.a_mul, J.a_add, J.C, J.a_relu, 0};
+    Side Z{J.z_src, J.z_src2, J.z_p0, J.z_p1, J.z_p2, J.z_L, J.z_ld, J.z_coff, J.z_mul, J.z_add, J.N, 0, 0};
+    TcWJob& O = T.job[T.njobs++];
+    const bool a_on_p = J.C >= J.N;                                  // wider tensor on the 128-wide P side
+    O.P = a_on_p ? A : Z; O.Q = a_on_p ? Z : A;
+    O.dW = J.dW; O.wbase = J.wbase; O.sp = a_on_p ? J.wsc : J.wsn; O.sq = a_on_p ? J.wsn : J.wsc;
+    O.db = J.db; O.db_on_p = a_on_p ? 0 : 1;
+    O.QW = std::min(128, O.Q.C);
+    if (O.Q.C % O.QW) O.QW = O.Q.C % 64 == 0 ? 64 : 32;
+    O.ptiles = (O.P.C + PW - 1) / PW; O.qtiles = O.Q.C / O.QW;
+    maxt = std::max(maxt, O.ptiles * O.qtiles);
+  }
+  const long M = (long)p.BT * p.Lq;
+  const long nkb = (M + KROWS - 1) / KROWS;
+  T.nsplit = (int)std::max<long>(1, std::min<long>(nkb, sm_count() / (maxt * T.njobs)));
+  const size_t smem = 1024 + (size_t)NSTAGE * 4 * P_TILE + sizeof(WMisc) + 64;
+  static bool attr = false;
+  if (!attr) {
+    TRU_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  dim3 grid(T.nsplit, maxt, T.njobs);
+  tc_wgrad_kernel<<<grid, NT, smem, st>>>(T);
+  TRU_LAUNCH_CHECK();
+  return TRU_OK;
+}
+
+}  // namespace tru

@@ -555,3 +555,21 @@ extern "C" int tru_debug_pw(const float* x, const float* p0, const float* p2, co
   return launch_igemm_simt(p, (cudaStream_t)stream);
 }
 extern "C" int tru_set_tensor_cores(int on) { set_tc_enabled(on != 0); return TRU_OK; }
+
+// Test aid: dW (N,C) += z^T a for a (M,C), z (M,N) through either weight-gradient path.
+extern "C" int tru_debug_wgrad(const float* a, const float* z, float* dw, float* db, int M, int C, int N, int use_tc,
+                               void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  WgradParams w{};
+  WgradJob& J = w.job[0];
+  J.a_src = a; J.a_L = 1; J.a_ld = C; J.a_mul = 1; J.C = C;
+  J.z_src = z; J.z_L = 1; J.z_ld = N; J.z_mul = 1; J.N = N;
+  J.dW = dw; J.wsc = 1; J.wsn = C; J.db = db;
+  w.njobs = 1; w.BT = M; w.Lq = 1;
+  if (use_tc) {
+    rc = launch_wgrad_tc(w, (cudaStream_t)stream);
+    return rc == 1 ? set_error(TRU_ERR_ARG, "debug_wgrad: not eligible for the tensor-core path") : rc;
+  }
+  return launch_wgrad_simt(w, (cudaStream_t)stream);
+}
