@@ -26,7 +26,7 @@ def run(M, K, N, affine, stats, use_tc):
         s1 = ref.sum(0); s2 = (ref*ref).sum(0)
         serr = max(((st[:N]-s1).abs().max()/s1.abs().max()).item(), ((st[N:]-s2).abs().max()/s2.abs().max()).item())
     return err, serr
-for shape in [(128,32,32),(128,64,64),(256,64,128),(1000,128,128),(128*300+17,128,128),(5000,192,64),(4097,64,384),(3000,128,192),(777,384,128),(2048,320,64)]:
+for shape in [(1000,128,8),(3000,8,64),(5000,40,8),(128,32,32),(128,64,64),(256,64,128),(1000,128,128),(128*300+17,128,128),(5000,192,64),(4097,64,384),(3000,128,192),(777,384,128),(2048,320,64)]:
     for affine, stats in ((False, False), (True, True)):
         try:
             e_tc = run(*shape, affine, stats, 1)

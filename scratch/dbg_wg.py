@@ -21,7 +21,7 @@ dw, ref, db, dbr = run(64, 128, 128, 1, "ones")
 print("ones: dw[0,:8]", dw[0,:8].tolist(), "expected", ref[0,0].item(), "nonzero frac", (dw!=0).float().mean().item())
 dw, ref, db, dbr = run(64, 128, 128, 1, "idx")
 print("idx: dw[0,:8]", dw[0,:8].tolist(), " dw[1,:4]", dw[1,:4].tolist(), "expected", ref[0,:8].tolist())
-for shape in [(32,128,128),(64,128,128),(1000,128,128),(5000,64,128),(5000,128,64),(4097,64,64),(3000,128,384),(3000,64,192),(100000,128,128)]:
+for shape in [(5000,128,8),(5000,8,8),(32,128,128),(64,128,128),(1000,128,128),(5000,64,128),(5000,128,64),(4097,64,64),(3000,128,384),(3000,64,192),(100000,128,128)]:
     for tc in (1,0):
         dw, ref, db, dbr = run(*shape, tc)
         print(shape, "tc" if tc else "simt", "dW rel err", ((dw.double()-ref).abs().max()/ref.abs().max()).item(), "db rel err", ((db.double()-dbr).abs().max()/dbr.abs().max()).item(), flush=True)

@@ -295,7 +295,89 @@ __global__ void __launch_bounds__(NT) wgrad_kernel(const __grid_constant__ Wgrad
   }
 }
 
+// ---- weight gradient for tiny channel counts (C*N <= 1024, e.g. the 8-channel output block) ----
+// One thread per output element (up to 4 per thread); 32-row chunks staged in shared memory.
+constexpr int SW_ROWS = 32;
+__global__ void __launch_bounds__(256) wgrad_small_kernel(const __grid_constant__ WgradParams P) {
+  __shared__ float As[SW_ROWS][64 + 1];
+  __shared__ float Zs[SW_ROWS][64 + 1];
+  const WgradJob& J = P.job[blockIdx.y];
+  const int tid = threadIdx.x;
+  const int nout = J.C * J.N;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  int oc[4], on[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { const int o = tid + 256 * k; oc[k] = o % J.C; on[k] = o / J.C; }
+  const long M = (long)P.BT * P.Lq;
+  for (long mb = (long)blockIdx.x * SW_ROWS; mb < M; mb += (long)gridDim.x * SW_ROWS) {
+    __syncthreads();
+    for (int i = tid; i < SW_ROWS * J.C; i += 256) {
+      const int r = i / J.C, c = i % J.C;
+      const long m = mb + r;
+      float v = 0.f;
+      if (m < M) {
+        const int bt = (int)(m / P.Lq), q = (int)(m - (long)bt * P.Lq);
+        const int la = q * J.a_mul + J.a_add;
+        if (la >= 0 && la < J.a_L) {
+          v = __ldg(J.a_src + ((long)bt * J.a_L + la) * J.a_ld + J.a_coff + c);
+          if (J.a_p0) {
+            v = __ldg(J.a_p0 + J.a_coff + c) * v + __ldg(J.a_p2 + J.a_coff + c);
+            if (J.a_relu) v = fmaxf(v, 0.f);
+          }
+        }
+      }
+      As[r][c] = v;
+    }
+    for (int i = tid; i < SW_ROWS * J.N; i += 256) {
+      const int r = i / J.N, n = i % J.N;
+      const long m = mb + r;
+      float v = 0.f;
+      if (m < M) {
+        const int bt = (int)(m / P.Lq), q = (int)(m - (long)bt * P.Lq);
+        const int lz = q * J.z_mul + J.z_add;
+        if (lz >= 0 && lz < J.z_L) {
+          const long zo = ((long)bt * J.z_L + lz) * J.z_ld + J.z_coff + n;
+          v = __ldg(J.z_src + zo);
+          if (J.z_p0) {
+            v = __ldg(J.z_p0 + J.z_coff + n) * v + __ldg(J.z_p2 + J.z_coff + n);
+            if (J.z_p1) v += __ldg(J.z_p1 + J.z_coff + n) * __ldg(J.z_src2 + zo);
+          }
+        }
+      }
+      Zs[r][n] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (tid + 256 * k < nout) {
+        float a = acc[k];
+#pragma unroll 8
+        for (int r = 0; r < SW_ROWS; ++r) a = fmaf(As[r][oc[k]], Zs[r][on[k]], a);
+        acc[k] = a;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (tid + 256 * k < nout) atomicAdd(J.dW + J.wbase + (long)oc[k] * J.wsc + (long)on[k] * J.wsn, acc[k]);
+}
+
 }  // namespace
+
+static bool small_wgrad_job(const WgradJob& J) {
+  return J.a_src && !J.db && J.C <= 64 && J.N <= 64 && J.C * J.N <= 1024 && (J.C < 32 || J.N < 32);
+}
+static int launch_wgrad_small(const WgradParams& p, cudaStream_t st) {
+  const long M = (long)p.BT * p.Lq;
+  double bytes = 0, flops = 0;
+  if (prof_enabled())
+    for (int j = 0; j < p.njobs; ++j) { bytes += 4.0 * M * (p.job[j].C + p.job[j].N * (p.job[j].z_src2 ? 2 : 1)); flops += 2.0 * M * p.job[j].C * p.job[j].N; }
+  ProfScope prof("wgrad_small", bytes, flops, st);
+  dim3 grid((unsigned)std::min<long>((M + SW_ROWS - 1) / SW_ROWS, (long)sm_count() * 8 / p.njobs + 1), p.njobs);
+  wgrad_small_kernel<<<grid, 256, 0, st>>>(p);
+  TRU_LAUNCH_CHECK();
+  return TRU_OK;
+}
 
 static bool g_tc_on = true;
 void set_tc_enabled(bool on) { g_tc_on = on; }
@@ -385,8 +467,16 @@ int launch_wgrad(const WgradParams& p, cudaStream_t st) {
   if (!tc_enabled()) return launch_wgrad_simt(p, st);
   WgradParams tcp{}, rest{};
   tcp.BT = rest.BT = p.BT; tcp.Lq = rest.Lq = p.Lq;
+  WgradParams small{};
+  small.BT = p.BT; small.Lq = p.Lq;
   for (int j = 0; j < p.njobs; ++j) {
-    if (p.job[j].a_src) tcp.job[tcp.njobs++] = p.job[j]; else rest.job[rest.njobs++] = p.job[j];
+    if (small_wgrad_job(p.job[j])) small.job[small.njobs++] = p.job[j];
+    else if (p.job[j].a_src) tcp.job[tcp.njobs++] = p.job[j];
+    else rest.job[rest.njobs++] = p.job[j];
+  }
+  if (small.njobs) {
+    const int rc = launch_wgrad_small(small, st);
+    if (rc) return rc;
   }
   if (tcp.njobs) {
     double bytes = 0, flops = 0;

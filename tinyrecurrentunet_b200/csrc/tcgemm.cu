@@ -25,6 +25,7 @@ using namespace tc;
 
 constexpr int BM = 128, KBLK = 32;
 constexpr int LOAD_WARPS = 8, EPI_WARPS = 4;
+constexpr int RPT = BM * 8 / (32 * LOAD_WARPS);           // rows per loader thread and k-block (4)
 constexpr int NT = 32 * (1 + LOAD_WARPS + EPI_WARPS);    // 416
 constexpr int NLOAD = 32 * LOAD_WARPS, NEPI = 32 * EPI_WARPS;
 constexpr int A_TILE = BM * 128;                          // bytes of one hi (or lo) operand tile
@@ -66,23 +67,27 @@ __global__ void __launch_bounds__(NT, 1) tc_igemm_kernel(const __grid_constant__
 
   // ---- one-time setup -------------------------------------------------------------
   {
-    int kbase = 0;
+    // segments whose channel count is not a multiple of 32 are zero padded to whole k-blocks
+    for (uint32_t i = tid; i < (uint32_t)nkb * BN * 64; i += NT) ((uint32_t*)Wsm)[i] = 0u;
+    __syncthreads();
+    int kbb = 0;                                  // first k-block of the segment
     for (int s = 0; s < P.nseg; ++s) {
       const Seg& sg = P.seg[s];
+      const int skb = (sg.C + KBLK - 1) / KBLK;
       if (tid == 0)
-        for (int c0 = 0; c0 < sg.C; c0 += KBLK) { mi.kb_seg[(kbase + c0) / KBLK] = s; mi.kb_c0[(kbase + c0) / KBLK] = c0; }
+        for (int b = 0; b < skb; ++b) { mi.kb_seg[kbb + b] = s; mi.kb_c0[kbb + b] = b * KBLK; }
       for (int i = tid; i < sg.C * BN; i += NT) {
         int c, n;
         if (sg.wsc == 1) { c = i % sg.C; n = i / sg.C; } else { n = i % BN; c = i / BN; }
         float v = 0.f;
         if (n0 + n < P.N) v = __ldg(sg.W + sg.wbase + (long)c * sg.wsc + (long)(n0 + n) * sg.wsn);
-        const int k = kbase + c, kb = k >> 5, kk = k & 31;
+        const int kb = kbb + (c >> 5), kk = c & 31;
         const uint32_t off = (uint32_t)kb * BN * 128 + n * 128 + ((((kk >> 2) ^ (n & 7)) << 4) | ((kk & 3) << 2));
         const uint32_t hi = f2tf32(v);
         *(uint32_t*)(Wsm + off) = hi;
         *(float*)(Wsm + (uint32_t)nkb * BN * 128 + off) = v - __uint_as_float(hi);
       }
-      kbase += sg.C;
+      kbb += skb;
     }
     for (int i = tid; i < BN; i += NT) {
       const bool in = n0 + i < P.N;
@@ -148,18 +153,19 @@ __global__ void __launch_bounds__(NT, 1) tc_igemm_kernel(const __grid_constant__
     const int total = n_my * nkb;
     const unsigned Mu = (unsigned)M, Lq = (unsigned)P.Lq;
     constexpr int NS = LD2 ? 2 : 3;                     // register slots; prefetch distance NS-1 k-blocks
-    float4 va[NS][4], vb[LD2 ? NS : 1][4];
+    constexpr int RSTEP = BM / RPT;
+    float4 va[NS][RPT], vb[LD2 ? NS : 1][RPT];
     unsigned vmask[NS];
     // issue-side cursor (runs two k-blocks ahead of the commit-side cursor)
     int i_kb = 0, i_ti = 0, i_seg = -1;
-    unsigned rbt[4], rq[4];
-    bool rok[4];
-    int roff[4] = {-1, -1, -1, -1};
+    unsigned rbt[RPT], rq[RPT];
+    bool rok[RPT];
+    int roff[RPT];
     auto decode_rows = [&]() {
       const unsigned m0 = ((unsigned)blockIdx.x + (unsigned)i_ti * gridDim.x) * BM;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const unsigned m = m0 + r0 + 32 * i;
+      for (int i = 0; i < RPT; ++i) {
+        const unsigned m = m0 + r0 + RSTEP * i;
         rok[i] = m < Mu;
         rbt[i] = rok[i] ? m / Lq : 0u;
         rq[i] = rok[i] ? m - rbt[i] * Lq : 0u;
@@ -167,12 +173,12 @@ __global__ void __launch_bounds__(NT, 1) tc_igemm_kernel(const __grid_constant__
       i_seg = -1;
     };
     decode_rows();
-    auto issue = [&](float4 (&a)[4], float4 (&b)[4], unsigned& msk) {
+    auto issue = [&](float4 (&a)[RPT], float4 (&b)[RPT], unsigned& msk) {
       const int s = mi.kb_seg[i_kb];
       const Seg& sg = P.seg[s];
       if (s != i_seg) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < RPT; ++i) {
           const int li = (int)rq[i] * sg.smul + sg.sadd;
           roff[i] = (rok[i] && li >= 0 && li < sg.Lsrc) ? ((int)rbt[i] * sg.Lsrc + li) * sg.ld + sg.coff : -1;
         }
@@ -181,8 +187,8 @@ __global__ void __launch_bounds__(NT, 1) tc_igemm_kernel(const __grid_constant__
       const int c = mi.kb_c0[i_kb] + chunk * 4;
       msk = 0;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (roff[i] >= 0) {
+      for (int i = 0; i < RPT; ++i) {
+        if (roff[i] >= 0 && c < sg.C) {
           a[i] = ld4(sg.src + (unsigned)(roff[i] + c));
           if (LD2 && sg.src2) b[i] = ld4(sg.src2 + (unsigned)(roff[i] + c));
           msk |= 1u << i;
@@ -193,18 +199,18 @@ __global__ void __launch_bounds__(NT, 1) tc_igemm_kernel(const __grid_constant__
     // commit-side cursor
     int c_kb = 0, c_st = 0;
     uint32_t c_ph = 0;
-    auto commit = [&](float4 (&a)[4], float4 (&b)[4], unsigned msk) {
+    auto commit = [&](float4 (&a)[RPT], float4 (&b)[RPT], unsigned msk) {
       const Seg& sg = P.seg[mi.kb_seg[c_kb]];
       const int c = sg.coff + mi.kb_c0[c_kb] + chunk * 4;
       float4 p0 = make_float4(1, 1, 1, 1), p1 = make_float4(0, 0, 0, 0), p2 = p1;
-      if (sg.p0) {
+      if (sg.p0 && mi.kb_c0[c_kb] + chunk * 4 < sg.C) {
         p0 = ld4(sg.p0 + c); p2 = ld4(sg.p2 + c);
         if (LD2 && sg.p1) p1 = ld4(sg.p1 + c);
       }
       mbar_wait(&mi.empty[c_st], c_ph ^ 1);
       uint8_t* ah = Asm + c_st * STAGE;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < RPT; ++i) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (msk & (1u << i)) {
           v = a[i];
@@ -216,7 +222,7 @@ __global__ void __launch_bounds__(NT, 1) tc_igemm_kernel(const __grid_constant__
         }
         uint4 hi, lo;
         split_tf32(v, hi, lo);
-        const int row = r0 + 32 * i;
+        const int row = r0 + RSTEP * i;
         const uint32_t off = row * 128 + ((chunk ^ (row & 7)) << 4);
         *(uint4*)(ah + off) = hi;
         *(uint4*)(ah + A_TILE + off) = lo;
@@ -302,7 +308,7 @@ __global__ void __launch_bounds__(NT, 1) tc_igemm_kernel(const __grid_constant__
               for (int i = 0; i < 4; ++i) {
                 const int r = orow[h * 4 + i];
                 zv[i] = make_float4(0.f, 0.f, 0.f, 0.f); xv[i] = zv[i];
-                if (r >= 0) {
+                if (r >= 0 && n0 + col < P.N) {
                   if (P.use_mask) zv[i] = ld4(P.zmask + (unsigned)r * (unsigned)P.ldo + P.ocoff + n0 + col);
                   if (P.extra) xv[i] = ld4(P.extra + (unsigned)r * (unsigned)P.ext_ld + n0 + col);
                 }
@@ -332,7 +338,15 @@ __global__ void __launch_bounds__(NT, 1) tc_igemm_kernel(const __grid_constant__
                 st1[cc][0] += o.x; st1[cc][1] += o.y; st1[cc][2] += o.z; st1[cc][3] += o.w;
                 st2[cc][0] += o.x * o.x; st2[cc][1] += o.y * o.y; st2[cc][2] += o.z * o.z; st2[cc][3] += o.w * o.w;
               }
-              *(float4*)(P.out + gofs) = o;
+              if (n0 + col < P.N) {
+                if (P.planar) {                       // (BT, N, Lout) layout of the network output
+                  const unsigned bt = (unsigned)r / (unsigned)P.Lout, lo = (unsigned)r - bt * P.Lout;
+                  float* op = P.out + ((size_t)bt * P.N + n0 + col) * P.Lout + lo;
+                  op[0] = o.x; op[P.Lout] = o.y; op[2 * (size_t)P.Lout] = o.z; op[3 * (size_t)P.Lout] = o.w;
+                } else {
+                  *(float4*)(P.out + gofs) = o;
+                }
+              }
             }
           }
         }
@@ -368,13 +382,13 @@ __global__ void __launch_bounds__(NT, 1) tc_igemm_kernel(const __grid_constant__
 constexpr size_t SMEM_MAX = 227 * 1024;
 
 bool plan(const IgemmParams& p, TcLayout& L, dim3& grid, size_t& smem_bytes) {
-  if (p.planar || p.N % 32 != 0 || p.ldo % 4 != 0 || p.ocoff % 4 != 0) return false;
-  int ktot = 0;
+  if ((p.N % 32 != 0 && p.N > 32) || p.N % 4 != 0 || p.ldo % 4 != 0 || p.ocoff % 4 != 0) return false;
+  if (p.planar && p.N > 32) return false;
+  int nkb = 0;
   for (int s = 0; s < p.nseg; ++s) {
-    if (p.seg[s].C % KBLK != 0 || p.seg[s].ld % 4 != 0 || p.seg[s].coff % 4 != 0) return false;
-    ktot += p.seg[s].C;
+    if (p.seg[s].C % 4 != 0 || p.seg[s].ld % 4 != 0 || p.seg[s].coff % 4 != 0) return false;
+    nkb += (p.seg[s].C + KBLK - 1) / KBLK;
   }
-  const int nkb = ktot / KBLK;
   if (nkb > MAXKB) return false;
   // 32-bit element offsets inside the kernel
   for (int s = 0; s < p.nseg; ++s)
@@ -382,7 +396,7 @@ bool plan(const IgemmParams& p, TcLayout& L, dim3& grid, size_t& smem_bytes) {
   if ((double)p.BT * p.Lout * p.ldo >= 4294967296.0 || (double)p.BT * p.Lq + BM >= 4294967296.0) return false;
   const size_t fixed = 1024 /* alignment slack */ + EPI_BYTES + sizeof(Misc) + 256;
   for (int BN : {128, 64, 32}) {
-    if (p.N % BN != 0) continue;
+    if (p.N % BN != 0 && !(BN == 32 && p.N < 32)) continue;
     const size_t w = (size_t)2 * nkb * BN * 128;
     if (fixed + w + 2 * STAGE > SMEM_MAX) continue;
     int nstage = (int)std::min<size_t>(8, (SMEM_MAX - fixed - w) / STAGE);
@@ -392,7 +406,7 @@ bool plan(const IgemmParams& p, TcLayout& L, dim3& grid, size_t& smem_bytes) {
     L.epi_off = L.a_off + nstage * STAGE;
     L.misc_off = L.epi_off + EPI_BYTES;
     smem_bytes = 1024 + L.misc_off + sizeof(Misc);
-    const int ny = p.N / BN;
+    const int ny = (p.N + BN - 1) / BN;
     const long M = (long)p.BT * p.Lq;
     const int ntiles = (int)((M + BM - 1) / BM);
     grid = dim3(std::max(1, std::min(ntiles, sm_count() / ny)), ny);

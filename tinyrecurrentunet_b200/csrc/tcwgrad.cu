@@ -10,8 +10,9 @@
 // added to dW with atomics.  a() is the forward activation (BN + ReLU applied on load),
 // dz() the BN-backward-transformed gradient, exactly as in wgrad_kernel (igemm.cu).
 //
-// 17 warps: warp 0 MMA issuer, warps 1-8 P loaders, warps 9-16 Q loaders; the bias
-// gradient (column sums of dz) is accumulated by the dz-side loaders on the fly.
+// 25 warps: warp 0 MMA issuer, warps 1-8 load the activation side, warps 9-24 the dz side
+// (which reads two tensors when a BatchNorm sits behind the layer); the bias gradient
+// (column sums of dz) is accumulated by the dz-side loaders on the fly.
 #include <algorithm>
 #include "net_kernels.cuh"
 #include "tc_common.cuh"
@@ -21,7 +22,7 @@ namespace {
 using namespace tc;
 
 constexpr int KROWS = 32;                       // rows per k-block
-constexpr int NT = 32 * 17;
+constexpr int NT = 32 * 17;                     // 1 MMA warp + 8 loader warps (activation side) + 16 (dz side)
 constexpr int PW = 128;                         // P tile width (channels)
 constexpr int P_TILE = KROWS * PW * 4;          // 16 KB per hi (or lo)
 constexpr int NSTAGE = 3;
@@ -43,30 +44,32 @@ struct WMisc { uint64_t full[NSTAGE], empty[NSTAGE], done; uint32_t tmem_base; }
 
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldg((const float4*)p); }
 
-// Loader of one side.  W = tile width in channels (128 for P, QW for Q).  256 threads.
-template <bool IS_P>
-__device__ __forceinline__ void side_loader(const TcWParams& P, const TcWJob& J, const Side& S, int W, int lt, int lane,
-                                            uint8_t* ring, int side_off, int tile_bytes, WMisc& mi, unsigned kb0,
-                                            unsigned kb1, bool want_db) {
+// Loader of one side.  W = tile width in channels (128 for P, QW for Q); NTHR threads cooperate,
+// each handling at most MAXPASS rows of the 32-row k-block; NS-1 k-blocks are kept in flight.
+template <int NTHR, int MAXPASS, int NS, bool HAS2>
+__device__ __forceinline__ void side_loader(const TcWParams& P, const TcWJob& J, const Side& S, int c0, int W, int lt, int lane,
+                                            uint8_t* ring, int side_off, WMisc& mi, unsigned kb0, unsigned kb1,
+                                            bool want_db) {
   const int cpr = W >> 2;                        // 16-byte chunks per row
-  const int cidx = lt % cpr, rsub = lt / cpr, rstep = 256 / cpr, npass = KROWS / rstep;   // npass = W/32
+  const int cidx = lt % cpr, rsub = lt / cpr, rstep = NTHR / cpr;
+  const int npass = rstep >= KROWS ? 1 : KROWS / rstep;
+  const bool t_ok = rsub < KROWS;                // (W = 32 with 512 threads: half of them idle)
   const int mb = cidx >> 3, ch = cidx & 7, NB = W >> 5;
-  const int c = S.c0 + cidx * 4;                 // channel inside the tensor (before coff)
-  const bool c_ok = c < S.C;
+  const int c = c0 + cidx * 4;                   // channel inside the tensor (before coff)
+  const bool c_ok = c < S.C && t_ok;
   float4 p0 = make_float4(1, 1, 1, 1), p1 = make_float4(0, 0, 0, 0), p2 = p1;
   if (S.p0 && c_ok) {
     p0 = ld4(S.p0 + S.coff + c); p2 = ld4(S.p2 + S.coff + c);
     if (S.p1) p1 = ld4(S.p1 + S.coff + c);
   }
   float bs[4] = {0.f, 0.f, 0.f, 0.f};
-  // row cursor: m = kb*32 + rsub + rstep*i  ->  (bt, q) kept incrementally for i = 0
   const unsigned Lq = (unsigned)P.Lq, Mrows = (unsigned)P.BT * Lq;
-  float4 va[2][4], vb[2][4];
-  unsigned msk[2] = {0, 0};
-  auto issue = [&](unsigned kb, float4 (&a)[4], float4 (&b)[4], unsigned& mk) {
+  float4 va[NS][MAXPASS], vb[HAS2 ? NS : 1][HAS2 ? MAXPASS : 1];
+  unsigned msk[NS];
+  auto issue = [&](unsigned kb, float4 (&a)[MAXPASS], float4 (&b)[HAS2 ? MAXPASS : 1], unsigned& mk) {
     mk = 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < MAXPASS; ++i) {
       if (i < npass) {
         const unsigned m = kb * KROWS + rsub + rstep * i;
         if (m < Mrows && c_ok) {
@@ -75,7 +78,7 @@ __device__ __forceinline__ void side_loader(const TcWParams& P, const TcWJob& J,
           if (l >= 0 && l < S.L) {
             const unsigned off = (bt * S.L + l) * S.ld + S.coff + c;
             a[i] = ld4(S.src + off);
-            if (S.src2) b[i] = ld4(S.src2 + off);
+            if (HAS2 && S.src2) b[HAS2 ? i : 0] = ld4(S.src2 + off);
             mk |= 1u << i;
           }
         }
@@ -84,35 +87,42 @@ __device__ __forceinline__ void side_loader(const TcWParams& P, const TcWJob& J,
   };
   int st = 0;
   uint32_t ph = 0;
-  if (kb0 < kb1) issue(kb0, va[0], vb[0], msk[0]);
-  for (unsigned kb = kb0; kb < kb1; kb += 2) {
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+  for (int u = 0; u < NS - 1; ++u)
+    if (kb0 + u < kb1) issue(kb0 + u, va[u], vb[HAS2 ? u : 0], msk[u]);
+  for (unsigned kb = kb0; kb < kb1; kb += NS) {
+#pragma unroll
+    for (int u = 0; u < NS; ++u) {
       const unsigned k = kb + u;
       if (k < kb1) {
-        if (k + 1 < kb1) issue(k + 1, va[u ^ 1], vb[u ^ 1], msk[u ^ 1]);
+        if (k + NS - 1 < kb1) issue(k + NS - 1, va[(u + NS - 1) % NS], vb[HAS2 ? (u + NS - 1) % NS : 0], msk[(u + NS - 1) % NS]);
         mbar_wait(&mi.empty[st], ph ^ 1);
-        uint8_t* base = ring + st * (2 * P_TILE + 2 * P_TILE) + side_off;     // stage = [P hi | P lo | Q hi | Q lo], each 16 KB max
+        uint8_t* base = ring + st * (4 * P_TILE) + side_off;     // stage = [P hi | P lo | Q hi | Q lo], 16 KB slots
+        if (t_ok) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (i < npass) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (msk[u] & (1u << i)) {
-              v = va[u][i];
-              if (S.p0) {
-                v.x = p0.x * v.x + p2.x; v.y = p0.y * v.y + p2.y; v.z = p0.z * v.z + p2.z; v.w = p0.w * v.w + p2.w;
-                if (S.p1) { v.x += p1.x * vb[u][i].x; v.y += p1.y * vb[u][i].y; v.z += p1.z * vb[u][i].z; v.w += p1.w * vb[u][i].w; }
-                if (S.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+          for (int i = 0; i < MAXPASS; ++i) {
+            if (i < npass) {
+              float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (msk[u] & (1u << i)) {
+                v = va[u][i];
+                if (S.p0) {
+                  v.x = p0.x * v.x + p2.x; v.y = p0.y * v.y + p2.y; v.z = p0.z * v.z + p2.z; v.w = p0.w * v.w + p2.w;
+                  if (HAS2 && S.p1) {
+                    const float4 z = vb[HAS2 ? u : 0][HAS2 ? i : 0];
+                    v.x += p1.x * z.x; v.y += p1.y * z.y; v.z += p1.z * z.z; v.w += p1.w * z.w;
+                  }
+                  if (S.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                }
+                bs[0] += v.x; bs[1] += v.y; bs[2] += v.z; bs[3] += v.w;
               }
-              bs[0] += v.x; bs[1] += v.y; bs[2] += v.z; bs[3] += v.w;
+              uint4 hi, lo;
+              split_tf32(v, hi, lo);
+              const int r = rsub + rstep * i;
+              // atom = 4 rows x 128 B; 32-byte chunk index (ch>>1) XOR row-in-atom (Swizzle<2,5,2>)
+              const uint32_t off = ((r >> 2) * NB + mb) * 512 + (r & 3) * 128 + ((((ch >> 1) ^ (r & 3)) << 5) | ((ch & 1) << 4));
+              *(uint4*)(base + off) = hi;
+              *(uint4*)(base + P_TILE + off) = lo;
             }
-            uint4 hi, lo;
-            split_tf32(v, hi, lo);
-            const int r = rsub + rstep * i;
-            // atom = 4 rows x 128 B; 32-byte chunk index (ch>>1) XOR row-in-atom (Swizzle<2,5,2>)
-            const uint32_t off = ((r >> 2) * NB + mb) * 512 + (r & 3) * 128 + ((((ch >> 1) ^ (r & 3)) << 5) | ((ch & 1) << 4));
-            *(uint4*)(base + off) = hi;
-            *(uint4*)(base + tile_bytes + off) = lo;
           }
         }
         fence_proxy_async();
@@ -123,25 +133,21 @@ __device__ __forceinline__ void side_loader(const TcWParams& P, const TcWJob& J,
     }
   }
   if (want_db && c_ok) {
-    // threads with the same cidx hold partial column sums: reduce the rstep row-lanes through atomics
 #pragma unroll
     for (int e = 0; e < 4; ++e)
       if (c + e < S.C) atomicAdd(J.db + c + e, bs[e]);
   }
-  (void)IS_P;
 }
 
 __global__ void __launch_bounds__(NT, 1) tc_wgrad_kernel(const __grid_constant__ TcWParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const TcWJob& J0 = P.job[blockIdx.z];
-  const int ntile = J0.ptiles * J0.qtiles;
+  const TcWJob& J = P.job[blockIdx.z];
+  const int ntile = J.ptiles * J.qtiles;
   if ((int)blockIdx.y >= ntile) return;
-  TcWJob J = J0;
   const int pt = blockIdx.y % J.ptiles, qt = blockIdx.y / J.ptiles;
-  J.P.c0 = pt * PW;
-  J.Q.c0 = qt * J.QW;
   const int QW = J.QW;
+  const int pc0 = pt * PW, qc0 = qt * QW;                     // first channel of this CTA's P / Q tile
   uint8_t* ring = smem;                                       // NSTAGE x 64 KB
   WMisc& mi = *(WMisc*)(smem + NSTAGE * 4 * P_TILE);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -190,10 +196,17 @@ __global__ void __launch_bounds__(NT, 1) tc_wgrad_kernel(const __grid_constant__
       }
       mma_commit(&mi.done);
     }
-  } else if (warp <= 8) {
-    side_loader<true>(P, J, J.P, PW, tid - 32, lane, ring, 0, P_TILE, mi, kb0, kb1, J.db && J.db_on_p && qt == 0);
   } else {
-    side_loader<false>(P, J, J.Q, QW, tid - 288, lane, ring, 2 * P_TILE, P_TILE, mi, kb0, kb1, J.db && !J.db_on_p && pt == 0);
+    // the dz side (two tensors when a BN sits behind the layer) gets the 16-warp group
+    const bool p_is_dz = J.db_on_p != 0;
+    const bool big = warp > 8;                                   // warps 9..16
+    const bool do_p = (big == p_is_dz);
+    const Side& S = do_p ? J.P : J.Q;
+    const int W = do_p ? PW : QW, soff = do_p ? 0 : 2 * P_TILE;
+    const bool wdb = J.db && (do_p ? (J.db_on_p && qt == 0) : (!J.db_on_p && pt == 0));
+    const int c0 = do_p ? pc0 : qc0;
+    if (big) side_loader<256, 4, 2, true>(P, J, S, c0, W, tid - 288, lane, ring, soff, mi, kb0, kb1, wdb);
+    else side_loader<256, 4, 3, false>(P, J, S, c0, W, tid - 32, lane, ring, soff, mi, kb0, kb1, wdb);
   }
 
   // ---- epilogue: warps 1-4 drain the accumulator and add it to dW ---------------------
@@ -201,14 +214,14 @@ __global__ void __launch_bounds__(NT, 1) tc_wgrad_kernel(const __grid_constant__
     mbar_wait(&mi.done, 0);
     tc_fence_after();
     const int lgrp = warp & 3;
-    const int p = J.P.c0 + lgrp * 32 + lane;
+    const int p = pc0 + lgrp * 32 + lane;
     for (int cc = 0; cc * 32 < QW; ++cc) {
       uint32_t v[32];
       tmem_ld32(tmem + ((uint32_t)(lgrp * 32) << 16) + cc * 32, v);
       if (p < J.P.C) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const int q = J.Q.c0 + cc * 32 + j;
+          const int q = qc0 + cc * 32 + j;
           if (q < J.Q.C) atomicAdd(J.dW + J.wbase + (long)p * J.sp + (long)q * J.sq, __uint_as_float(v[j]));
         }
       }
@@ -232,7 +245,7 @@ int launch_wgrad_tc(const WgradParams& p, cudaStream_t st) {
   for (int j = 0; j < p.njobs; ++j) {
     const WgradJob& J = p.job[j];
     if (!J.a_src) return 1;                                          // bias-only jobs stay on the FFMA kernel
-    if (J.C % 32 || J.N % 32 || J.a_ld % 4 || J.z_ld % 4 || J.a_coff % 4 || J.z_coff % 4) return 1;
+    if (J.C % 4 || J.N % 4 || J.a_ld % 4 || J.z_ld % 4 || J.a_coff % 4 || J.z_coff % 4) return 1;
     if ((double)p.BT * J.a_L * J.a_ld >= 4294967296.0 || (double)p.BT * J.z_L * J.z_ld >= 4294967296.0) return 1;
     if (J.db && !(J.z_mul == 1 && J.z_add == 0 && J.z_L == p.Lq)) return 1;   // db needs every dz row exactly once
     Side A{J.a_src, nullptr, J.a_p0, nullptr, J.a_p2, J.a_L, J.a_ld, J.a_coff, J.a_mul, J.a_add, J.C, J.a_relu, 0};
@@ -242,9 +255,8 @@ int launch_wgrad_tc(const WgradParams& p, cudaStream_t st) {
     O.P = a_on_p ? A : Z; O.Q = a_on_p ? Z : A;
     O.dW = J.dW; O.wbase = J.wbase; O.sp = a_on_p ? J.wsc : J.wsn; O.sq = a_on_p ? J.wsn : J.wsc;
     O.db = J.db; O.db_on_p = a_on_p ? 0 : 1;
-    O.QW = std::min(128, O.Q.C);
-    if (O.Q.C % O.QW) O.QW = O.Q.C % 64 == 0 ? 64 : 32;
-    O.ptiles = (O.P.C + PW - 1) / PW; O.qtiles = O.Q.C / O.QW;
+    O.QW = O.Q.C % 128 == 0 ? 128 : (O.Q.C % 64 == 0 ? 64 : 32);
+    O.ptiles = (O.P.C + PW - 1) / PW; O.qtiles = (O.Q.C + O.QW - 1) / O.QW;
     maxt = std::max(maxt, O.ptiles * O.qtiles);
   }
   const long M = (long)p.BT * p.Lq;

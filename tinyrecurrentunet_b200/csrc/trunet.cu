@@ -270,6 +270,13 @@ int pw_bwd(Ctx& c, const Grad& g, const Act& x1, int padL, const Act* skip, int 
       j1.wbase = x1.C; j1.db = c.grd[pw_param + 1];
       w.njobs = 2;
     }
+    if (N < 32) {     // tiny output width: weight grads on the small-shape kernel, bias grad as a column sum
+      float* db = c.grd[pw_param + 1];
+      for (int j = 0; j < w.njobs; ++j) w.job[j].db = nullptr;
+      WgradJob& jb = w.job[w.njobs++];
+      jb = w.job[0];
+      jb.a_src = nullptr; jb.C = 4; jb.a_ld = 4; jb.dW = nullptr; jb.db = db;
+    }
     w.BT = (int)c.BT; w.Lq = g.L;
     TRY(launch_wgrad(w, c.st));
   }
