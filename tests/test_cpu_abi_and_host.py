@@ -1,0 +1,105 @@
+"""CPU-only: the C-ABI library loads and exports every symbol include/tru_b200.h declares;
+host-side logic (module tree, state-dict keys, parameter order, error paths)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ensure_built():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("tru_build", os.path.join(ROOT, "tinyrecurrentunet_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.build_library()
+
+
+def test_library_exports_every_declared_symbol():
+    lib_path = _ensure_built()
+    lib = ctypes.CDLL(lib_path)
+    header = open(os.path.join(ROOT, "include", "tru_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(tru_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 15
+    for name in sorted(declared):
+        assert hasattr(lib, name), "missing export: %s" % name
+    lib.tru_abi_version.restype = ctypes.c_int
+    assert lib.tru_abi_version() == 1
+
+
+def test_binding_table_matches_header():
+    from tinyrecurrentunet_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "tru_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(tru_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS)
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    """Without a CUDA device every hot-path op must raise (no CPU path)."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from tinyrecurrentunet_b200 import _lib, dataset, network, ops, stft_loss
+    with pytest.raises(Exception):
+        ops.frontend(torch.zeros(1, 4096))
+    with pytest.raises(Exception):
+        network.TRUNet()(torch.zeros(3, 4, 257))
+    with pytest.raises(Exception):
+        dataset.ProcessAudio()(torch.zeros(1, 1, 4096))
+    with pytest.raises(Exception):
+        stft_loss.MultiResolutionSTFTLoss()(torch.zeros(1, 4096), torch.zeros(1, 4096))
+    assert _lib.lib.tru_init() != 0            # no device: error code, message set, no crash
+    assert _lib.lib.tru_last_error()
+
+
+def test_module_tree_matches_reference_schema():
+    """State-dict keys / shapes of SURVEY Appendix C; the 7 reference kwargs are accepted."""
+    from oracle import tru_oracle as O
+    from tinyrecurrentunet_b200 import network
+    net = network.TRUNet(input_size=3, channels_input=64, channels_output=3, channels_hidden=128,
+                         kernel_sizes=[5, 3], strides=[2, 1], tr_channels_input=192)
+    ref = O.TRUNet()
+    sd, sr = net.state_dict(), ref.state_dict()
+    assert list(sd) == list(sr) and len(sd) == 177
+    assert all(sd[k].shape == sr[k].shape for k in sd)
+    assert sum(p.numel() for p in net.parameters()) == 381472
+    assert [k for k, _ in net.named_parameters()] == network.PARAM_ORDER
+    bns = dict(net.named_modules())
+    assert all(isinstance(bns[n], torch.nn.BatchNorm1d) for n in network.BN_ORDER)
+    net.load_state_dict(sr)                      # checkpoints are interchangeable
+    with pytest.raises(NotImplementedError):
+        network.TRUNet(in_channels=3)
+
+
+def test_reference_api_names_exist():
+    from tinyrecurrentunet_b200 import dataset, distributed, network, phm, stft_loss, util
+    for mod, names in ((network, ["StandardConv1d", "DepthwiseSeparableConv1d", "GRUBlock", "FirstTrCNN", "TrCNN",
+                                  "LastTrCNN", "TRUNet"]),
+                       (phm, ["PhaseAwareMask"]),
+                       (stft_loss, ["stft", "SpectralConvergenceLoss", "LogSTFTMagnitudeLoss", "STFTLoss",
+                                    "MultiResolutionSTFTLoss"]),
+                       (dataset, ["ProcessAudio", "pcenfunc", "unwrap", "diff"]),
+                       (util, ["loss_fn", "sampling"]),
+                       (distributed, ["init_distributed", "apply_gradient_allreduce", "reduce_tensor"])):
+        for n in names:
+            assert hasattr(mod, n), (mod.__name__, n)
+
+
+def test_cpu_helpers_match_oracle():
+    """The small elementwise helpers kept for API compatibility (not the hot path)."""
+    from oracle import tru_oracle as O
+    from tinyrecurrentunet_b200 import dataset, phm
+    dp = dataset.ProcessAudio()
+    m, s, c = torch.rand(257, 5) * 2.4 - 1.2, torch.randn(257, 5), torch.randn(257, 5)
+    assert torch.equal(dp.mod_phase(m, s, c)[0], O.mod_phase(m, s, c))
+    x = torch.rand(1, 9, 257)
+    torch.testing.assert_close(dataset.pcenfunc(x.clone()), O.pcen(x)[0])
+    a = torch.randn(1, 257, 4, dtype=torch.complex64)
+    b = torch.randn(1, 257, 4, dtype=torch.complex64)
+    torch.testing.assert_close(phm.PhaseAwareMask(0.5)(a, b), O.phase_aware_mask(a, b, 0.5))
+    with pytest.raises(NotImplementedError):
+        dataset.ProcessAudio(n_fft=1024)
