@@ -167,6 +167,8 @@ def run_native(args):
     from tinyrecurrentunet_b200 import _lib as L, network, stft_loss, util
     from tinyrecurrentunet_b200 import distributed as tdist
 
+    if os.environ.get("TRU_LOADER_WARPS"):                 # tuning aid (8 or 16 loader warps in the GEMM kernels)
+        L.lib.tru_debug_set_loader_warps(int(os.environ["TRU_LOADER_WARPS"]))
     B = args.batch
     torch.manual_seed(0)
     net = network.TRUNet(3, 64, 3, 128, [5, 3], [2, 1], 192).to(dev).train()

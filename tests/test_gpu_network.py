@@ -215,11 +215,19 @@ def test_backward_matches_oracle():
     gref = dict(ref.named_parameters())
     rows = []
     gmax = max(p.grad.abs().max().item() for p in gref.values())
+    zero_bias = {"encoder.%d.DepthwiseSeparableConv1d.%d.bias" % (i, j) for i in range(1, 6) for j in (0, 3)}
+    zero_bias |= {"decoder.%d.%s.0.bias" % (d, c) for d, c in enumerate(["FirstTrCNN"] + ["TrCNN"] * 4 + ["LastTrCNN"])}
+    zero_bias |= {"decoder.%d.%s.3.bias" % (d, c) for d, c in enumerate(["FirstTrCNN"] + ["TrCNN"] * 4)}
+    zero_bias |= {"FGRU.conv.0.bias", "TGRU.conv.0.bias"}
     for k, p in net.named_parameters():
         assert p.grad is not None, k
         g, r = p.grad.cpu(), gref[k].grad
-        # conv biases in front of a training-mode BN have an exactly-zero true gradient;
-        # both sides only hold rounding noise there, so scale by the global gradient size.
+        if k in zero_bias:
+            # A conv bias in front of a training-mode BN has an exactly-zero true gradient: what both
+            # sides hold is the rounding noise of a fully cancelling sum (eps * sum|dz|), which cannot
+            # agree digit for digit.  Require both to be noise-sized relative to the largest gradient.
+            rows.append((k, max(g.abs().max().item(), r.abs().max().item()) / (2e-5 * gmax) * GRAD_TOL))
+            continue
         scale = max(r.abs().max().item(), 1e-3 * gmax)
         rows.append((k, (g - r).abs().max().item() / scale))
     print("\n".join("%-55s %.3e" % r for r in rows))

@@ -43,6 +43,7 @@ __global__ void bn_bwd_finalize_kernel(BnBwdParams p) {
   p.q2[c] = (float)(g * inv * (mean * inv * s2 - s1) / p.count);
   p.dgamma[c] += (float)s2;
   p.dbeta[c] += (float)s1;
+  if (p.db_acc) p.db_out[c] += (float)p.db_acc[c];
 }
 
 // ---- encoder stem: Conv1d(4->64, k5, s2, p1) + ReLU; planar (BT,4,257) in, CL (BT,128,64) out ----
@@ -217,6 +218,75 @@ __global__ void __launch_bounds__(256) dw_bwd_data_kernel(const __grid_constant_
   if (p.bstats) block_chan_reduce(s1, s2, p.bstats, p.bstats + DW_C, c4);
 }
 
+// fused backward (data + weight + bias): one pass over the input rows.  For row (bt, li) the taps
+// t with lo*s - pad + t == li give  dA += w[c][t]*dz(lo)  and  dw[c][t] += dz(lo)*a(li); the centre tap
+// (t == pad, li == lo*s) visits every output row exactly once, so it also carries db.  a() is the same
+// tensor as the ReLU mask (Zp with BN1's affine), so every operand is read once per use site and the
+// weight-gradient pass over dY / Zd / Zp of dw_wgrad_kernel disappears.  db (whose true value is 0 in
+// front of a training-mode BN: pure cancellation) is summed in fp64 next to the BN sums.
+__global__ void __launch_bounds__(256, 2) dw_bwd_fused_kernel(const __grid_constant__ DwParams p) {
+  __shared__ float red[DW_ROWS][DW_C];
+  const int c4 = (threadIdx.x & 31) * 4, rl = threadIdx.x >> 5;
+  float4 p0 = make_float4(1, 1, 1, 1), p2 = make_float4(0, 0, 0, 0), p1 = p2;
+  if (p.p0) { p0 = ld4(p.p0 + c4); p2 = ld4(p.p2 + c4); if (p.p1) p1 = ld4(p.p1 + c4); }
+  const float4 mp0 = ld4(p.mp0 + c4), mp2 = ld4(p.mp2 + c4), bmean = ld4(p.bmean + c4), binv = ld4(p.binv + c4);
+  float w[4][5];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int t = 0; t < 5; ++t) w[j][t] = t < p.k ? __ldg(p.w + (c4 + j) * p.k + t) : 0.f;
+  float acc[8][4];                 // 0-4: dw taps, 5: db, 6: sum g, 7: sum g*xhat
+#pragma unroll
+  for (int t = 0; t < 8; ++t)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[t][j] = 0.f;
+  const long M = (long)p.BT * p.Lin;
+  for (long m = (long)blockIdx.x * DW_ROWS + rl; m < M; m += (long)gridDim.x * DW_ROWS) {
+    const int bt = (int)(m / p.Lin), li = (int)(m - (long)bt * p.Lin);
+    const float4 z = ld4(p.zmask + m * DW_C + c4);
+    float4 a;
+    a.x = fmaxf(z.x * mp0.x + mp2.x, 0.f); a.y = fmaxf(z.y * mp0.y + mp2.y, 0.f);
+    a.z = fmaxf(z.z * mp0.z + mp2.z, 0.f); a.w = fmaxf(z.w * mp0.w + mp2.w, 0.f);
+    float4 g = make_float4(0, 0, 0, 0);
+#pragma unroll
+    for (int t = 0; t < 5; ++t) {
+      const int num = li + p.pad - t;
+      if (t < p.k && num >= 0 && num % p.stride == 0) {
+        const int lo = num / p.stride;
+        if (lo < p.Lout) {
+          const float4 v = dw_load(p, ((long)bt * p.Lout + lo) * DW_C, c4, p0, p1, p2, false);
+          g.x = fmaf(w[0][t], v.x, g.x); g.y = fmaf(w[1][t], v.y, g.y);
+          g.z = fmaf(w[2][t], v.z, g.z); g.w = fmaf(w[3][t], v.w, g.w);
+          acc[t][0] = fmaf(v.x, a.x, acc[t][0]); acc[t][1] = fmaf(v.y, a.y, acc[t][1]);
+          acc[t][2] = fmaf(v.z, a.z, acc[t][2]); acc[t][3] = fmaf(v.w, a.w, acc[t][3]);
+          if (t == p.pad) { acc[5][0] += v.x; acc[5][1] += v.y; acc[5][2] += v.z; acc[5][3] += v.w; }
+        }
+      }
+    }
+    g.x = (z.x * mp0.x + mp2.x > 0.f) ? g.x : 0.f; g.y = (z.y * mp0.y + mp2.y > 0.f) ? g.y : 0.f;
+    g.z = (z.z * mp0.z + mp2.z > 0.f) ? g.z : 0.f; g.w = (z.w * mp0.w + mp2.w > 0.f) ? g.w : 0.f;
+    *(float4*)(p.out + m * DW_C + c4) = g;
+    acc[6][0] += g.x; acc[6][1] += g.y; acc[6][2] += g.z; acc[6][3] += g.w;
+    acc[7][0] += g.x * (z.x - bmean.x) * binv.x; acc[7][1] += g.y * (z.y - bmean.y) * binv.y;
+    acc[7][2] += g.z * (z.z - bmean.z) * binv.z; acc[7][3] += g.w * (z.w - bmean.w) * binv.w;
+  }
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    if (t < 5 && t >= p.k) continue;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[rl][c4 + j] = acc[t][j];
+    __syncthreads();
+    if (threadIdx.x < DW_C) {
+      double s = 0.0;
+      for (int r = 0; r < DW_ROWS; ++r) s += (double)red[r][threadIdx.x];
+      if (t < 5) atomicAdd(p.dw + threadIdx.x * p.k + t, (float)s);
+      else if (t == 5) atomicAdd(p.bstats + 2 * DW_C + threadIdx.x, s);     // db: fp64 scratch, folded in by bn_bwd_finalize
+      else atomicAdd(p.bstats + (t - 6) * DW_C + threadIdx.x, s);
+    }
+  }
+}
+
 // backward weight: dw[c][j] = sum dz(bt,lo,c) * a(bt, lo*s-pad+j, c); db[c] = sum dz
 __global__ void __launch_bounds__(256) dw_wgrad_kernel(const __grid_constant__ DwParams p) {
   __shared__ float red[DW_ROWS][DW_C];
@@ -352,6 +422,17 @@ int launch_dw_bwd_data(const DwParams& p, cudaStream_t st) {
   TRU_REQUIRE(p.C == DW_C && p.k <= 5, TRU_ERR_ARG, "depthwise kernel supports C=128, k<=5");
   ProfScope prof("dw_bwd_data", 4.0 * p.BT * (2.0 * p.Lin + 2.0 * p.Lout) * p.C, 2.0 * p.k * p.BT * p.Lout * p.C, st);
   dw_bwd_data_kernel<<<dw_grid((long)p.BT * p.Lin), 256, 0, st>>>(p);
+  TRU_LAUNCH_CHECK();
+  return TRU_OK;
+}
+int launch_dw_bwd_fused(const DwParams& p, cudaStream_t st) {
+  TRU_REQUIRE(p.C == DW_C && p.k <= 5, TRU_ERR_ARG, "depthwise kernel supports C=128, k<=5");
+  TRU_REQUIRE(p.zmask && p.mp0 && p.bstats && p.dw && p.db && p.a_src == p.zmask && p.a_p0 == p.mp0 && p.a_p2 == p.mp2,
+              TRU_ERR_ARG, "dw_bwd_fused: the activation and the ReLU mask must be the same tensor");
+  ProfScope prof("dw_bwd_fused", 4.0 * p.BT * (2.0 * p.Lin + 2.0 * p.Lout) * p.C, 4.0 * p.k * p.BT * p.Lout * p.C, st);
+  // 2 resident CTAs per SM (122 registers): a grid-stride loop over exactly that many CTAs also keeps the
+  // number of float atomics per weight-gradient element small
+  dw_bwd_fused_kernel<<<std::min(dw_grid((long)p.BT * p.Lin), sm_count() * 2), 256, 0, st>>>(p);
   TRU_LAUNCH_CHECK();
   return TRU_OK;
 }

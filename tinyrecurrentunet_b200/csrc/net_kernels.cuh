@@ -40,6 +40,7 @@ bool igemm_tc_eligible(const IgemmParams& p);
 int launch_igemm_tc(const IgemmParams& p, cudaStream_t st);    // 0 launched, 1 not eligible, <0 error
 int launch_igemm_simt(const IgemmParams& p, cudaStream_t st);
 void set_tc_enabled(bool on);
+void set_tc_loader_warps(int n);   // 8 or 16 (tuning aid)
 bool tc_enabled();
 
 struct WgradJob {
@@ -67,6 +68,7 @@ struct BnBwdParams {
   const double* bstats; double count; int C;
   const float* gamma; const float* mean; const float* invstd;
   float* q0; float* q1; float* q2; float* dgamma; float* dbeta;
+  const double* db_acc; float* db_out;      // optional: fp64 bias-gradient sums to add to a bias gradient
 };
 int launch_bn_bwd_finalize(const BnBwdParams& p, cudaStream_t st);
 
@@ -89,6 +91,7 @@ struct DwParams {
 int launch_dw_fwd(const DwParams& p, cudaStream_t st);
 int launch_dw_bwd_data(const DwParams& p, cudaStream_t st);
 int launch_dw_wgrad(const DwParams& p, cudaStream_t st);
+int launch_dw_bwd_fused(const DwParams& p, cudaStream_t st);   // bwd_data + wgrad in one pass
 
 int launch_colsum(const float* src, const float* src2, const float* q0, const float* q1, const float* q2, float* db,
                   long rows, int ld, int coff, int N, cudaStream_t st);

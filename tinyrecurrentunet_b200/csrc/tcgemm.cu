@@ -1,21 +1,33 @@
 // Tensor-core implicit GEMM (tcgen05 / TMEM), fp32-accurate via the 3xTF32 split.
 //
 // Same contract as igemm.cu (gathered rows x resident weights, BN/ReLU applied on
-// load, bias / BN statistics / ReLU mask / skip-gradient epilogue), for the shapes
-// where every K-segment has a multiple of 32 channels and N is a multiple of 32.
+// load, bias / BN statistics / ReLU mask / skip-gradient epilogue).
 //
-// One persistent CTA per SM, 13 warps:
-//   warp 0      MMA issuer (one elected thread) + TMEM allocation
-//   warps 1-8   loaders: gather 128 rows x 32 channels from HBM, apply the affine
-//               (+ReLU or BN-backward) transform, split into tf32 hi/lo and write both
-//               into the 128B-swizzled K-major operand tiles of a shared-memory ring
-//   warps 9-12  epilogue: TMEM -> registers -> 16-byte stores (one accumulator row =
-//               one 128-byte line per thread), BN statistics by a shuffle butterfly
-// The CTA's slice of the weights (hi and lo) stays resident in shared memory.
+// The product is computed TRANSPOSED: the CTA's weight slice is the M operand of the
+// MMA (M = 64 or 128 output channels, resident in shared memory as hi/lo tf32 tiles)
+// and a tile of 128 gathered activation rows is the N operand, so the accumulator in
+// TMEM holds  D[channel][row].  An epilogue thread therefore owns ONE output channel
+// (TMEM lane) and walks over rows: bias, BN scale/shift of the ReLU mask and the BN
+// statistics are per-thread scalars, a warp stores 32 consecutive channels of one row
+// with one coalesced instruction, and no shared-memory transpose is needed.
+//
+// One persistent CTA per SM:
+//   warp 0            MMA issuer (one elected thread) + TMEM allocation (warps 1-3 idle: register
+//                     budgets are re-balanced per 4-warp group with setmaxnreg)
+//   warps 4..3+LW     loaders: gather 128 rows x 32 channels from HBM (float4, NS
+//                     k-blocks kept in flight in registers), apply the affine (+ReLU or
+//                     BN-backward) transform, split into tf32 hi/lo and write both into
+//                     the 128B-swizzled K-major operand tiles of a shared-memory ring
+//   last 8 warps      epilogue: tcgen05.ld (32 lanes x 32 columns) -> registers -> HBM
 // For every 32-wide k-block the MMA thread issues 4 k-steps x 3 products
-// (lo*hi + hi*lo + hi*hi) of tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) into one of
+// (lo*hi + hi*lo + hi*hi) of tcgen05.mma.kind::tf32 (M=64|128, N=128, K=8) into one of
 // two TMEM accumulators, so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Split: weights are rounded to tf32 (cvt.rna) once per CTA; activations use the cheap
+// truncating split hi = x & ~0x1fff, lo = x - hi (exact), 2 instructions per element.
+// The dropped lo*lo term is <= 2^-21 relative per product.
 #include <algorithm>
+#include <string.h>
 #include "net_kernels.cuh"
 #include "tc_common.cuh"
 
@@ -24,88 +36,104 @@ namespace {
 using namespace tc;
 
 constexpr int BM = 128, KBLK = 32;
-constexpr int LOAD_WARPS = 8, EPI_WARPS = 4;
-constexpr int RPT = BM * 8 / (32 * LOAD_WARPS);           // rows per loader thread and k-block (4)
-constexpr int NT = 32 * (1 + LOAD_WARPS + EPI_WARPS);    // 416
-constexpr int NLOAD = 32 * LOAD_WARPS, NEPI = 32 * EPI_WARPS;
-constexpr int A_TILE = BM * 128;                          // bytes of one hi (or lo) operand tile
+constexpr int EW = 8;                                     // epilogue warps
+constexpr int A_TILE = BM * 128;                          // bytes of one hi (or lo) activation tile
 constexpr int STAGE = 2 * A_TILE;
-constexpr int MAXKB = 16;
-constexpr int EPI_LD = 36;                                // floats per staged row (conflict-free 16-byte accesses)
-constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_LD * 4;
+constexpr int MAXKB = 16, MAXCOEF = 12;
+constexpr int COEF_FLOATS = 96;                           // p0[32] p2[32] p1[32]
 
-struct TcLayout { int BN, nkb, nstage; uint32_t w_off, a_off, epi_off, misc_off; };
+struct TcLayout {
+  int MW;                       // MMA M = weight rows (output channels) per CTA: 64 or 128
+  int nkb, nstage, ncoef;
+  uint32_t a_off, coef_off, misc_off;                      // W tiles at offset 0
+  int8_t kb_seg[MAXKB], kb_coef[MAXKB], kb_relu[MAXKB];
+  int16_t kb_c0[MAXKB], kb_valid[MAXKB];
+  int8_t coef_seg[MAXCOEF];
+  int16_t coef_c0[MAXCOEF];
+};
 
 struct Misc {
   uint64_t full[8], empty[8], tfull[2], tempty[2];
   uint32_t tmem_base;
-  int kb_seg[MAXKB], kb_c0[MAXKB];
-  alignas(16) float bias[128];
-  alignas(16) float mp0[128];
-  alignas(16) float mp2[128];
-  alignas(16) float bmean[128];
-  alignas(16) float binv[128];
 };
 
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldg((const float4*)p); }
 
-// LD2: loaders read two tensors (dY and Z) and apply the BN-backward affine; EPI: the epilogue adds the
-// skip gradient / applies the ReLU mask / accumulates the BN-backward sums.
-template <bool LD2, bool EPI>
-__global__ void __launch_bounds__(NT, 1) tc_igemm_kernel(const __grid_constant__ IgemmParams P, const TcLayout Lo) {
+// LW: loader warps (8 or 16).  LD2: loaders read two tensors (dY and Z) and apply the BN-backward
+// affine.  EPI: the epilogue adds the skip gradient / applies the ReLU mask / accumulates the
+// BN-backward sums.
+template <int LW, bool LD2, bool EPI>
+__global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const __grid_constant__ IgemmParams P,
+                                                                        const __grid_constant__ TcLayout Lo) {
+  constexpr int NT = 32 * (4 + LW + EW);
+  // register budgets per role (launch value: 72 for 28 warps, 96 for 20 warps)
+  constexpr int REG_MMA = LW == 16 ? 24 : 32, REG_LOAD = LW == 16 ? 72 : 112, REG_EPI = LW == 16 ? 96 : 112;   // sums: 64512 of 64512, 61440 of 61440
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* Wsm = smem + Lo.w_off;                      // [hi|lo][nkb][BN rows][128 B], swizzled
+  uint8_t* Wsm = smem;                                 // [hi|lo][nkb][MW rows][128 B], swizzled
   uint8_t* Asm = smem + Lo.a_off;                      // ring: [stage][hi|lo][128 rows][128 B]
+  float* coef = (float*)(smem + Lo.coef_off);          // [ncoef][p0 | p2 | p1][32]
   Misc& mi = *(Misc*)(smem + Lo.misc_off);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int BN = Lo.BN, nkb = Lo.nkb, nstage = Lo.nstage;
-  const int n0 = blockIdx.y * BN;
+  const int MW = Lo.MW, nkb = Lo.nkb, nstage = Lo.nstage;
+  const int n0 = blockIdx.y * MW;
   const long M = (long)P.BT * P.Lq;
   const int ntiles = (int)((M + BM - 1) / BM);
   const int n_my = ((int)blockIdx.x < ntiles) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
-  // ---- one-time setup -------------------------------------------------------------
+  // ---- one-time setup: resident weight slice (hi/lo), affine coefficient table, barriers, TMEM ------
   {
-    // segments whose channel count is not a multiple of 32 are zero padded to whole k-blocks
-    for (uint32_t i = tid; i < (uint32_t)nkb * BN * 64; i += NT) ((uint32_t*)Wsm)[i] = 0u;
+    const uint32_t wwords = (uint32_t)nkb * MW * 64;    // hi + lo, in 32-bit words
+    for (uint32_t i = tid; i < wwords / 4; i += NT) ((uint4*)Wsm)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
-    int kbb = 0;                                  // first k-block of the segment
+    const uint32_t lo_off = (uint32_t)nkb * MW * 128;
+    int kbb = 0;
     for (int s = 0; s < P.nseg; ++s) {
       const Seg& sg = P.seg[s];
-      const int skb = (sg.C + KBLK - 1) / KBLK;
-      if (tid == 0)
-        for (int b = 0; b < skb; ++b) { mi.kb_seg[kbb + b] = s; mi.kb_c0[kbb + b] = b * KBLK; }
-      for (int i = tid; i < sg.C * BN; i += NT) {
-        int c, n;
-        if (sg.wsc == 1) { c = i % sg.C; n = i / sg.C; } else { n = i % BN; c = i / BN; }
-        float v = 0.f;
-        if (n0 + n < P.N) v = __ldg(sg.W + sg.wbase + (long)c * sg.wsc + (long)(n0 + n) * sg.wsn);
-        const int kb = kbb + (c >> 5), kk = c & 31;
-        const uint32_t off = (uint32_t)kb * BN * 128 + n * 128 + ((((kk >> 2) ^ (n & 7)) << 4) | ((kk & 3) << 2));
-        const uint32_t hi = f2tf32(v);
-        *(uint32_t*)(Wsm + off) = hi;
-        *(float*)(Wsm + (uint32_t)nkb * BN * 128 + off) = v - __uint_as_float(hi);
+      const int tot = sg.C * MW;
+      for (int i0 = tid; i0 < tot; i0 += NT * 4) {
+        float v[4];
+        int cc[4], nn[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * NT;
+          int c = 0, n = MW;
+          if (i < tot) { if (sg.wsc == 1) { c = i % sg.C; n = i / sg.C; } else { n = i % MW; c = i / MW; } }
+          cc[u] = c; nn[u] = n;
+          v[u] = (n < MW && n0 + n < P.N) ? __ldg(sg.W + sg.wbase + (long)c * sg.wsc + (long)(n0 + n) * sg.wsn) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (nn[u] < MW) {
+            const int c = cc[u], n = nn[u];
+            const int kb = kbb + (c >> 5), kk = c & 31;
+            const uint32_t off = (uint32_t)kb * MW * 128 + n * 128 + ((((kk >> 2) ^ (n & 7)) << 4) | ((kk & 3) << 2));
+            const uint32_t hi = f2tf32(v[u]);
+            *(uint32_t*)(Wsm + off) = hi;
+            *(float*)(Wsm + lo_off + off) = v[u] - __uint_as_float(hi);
+          }
+        }
       }
-      kbb += skb;
+      kbb += (sg.C + KBLK - 1) / KBLK;
     }
-    for (int i = tid; i < BN; i += NT) {
-      const bool in = n0 + i < P.N;
-      mi.bias[i] = (P.bias && in) ? __ldg(P.bias + n0 + i) : 0.f;
-      mi.mp0[i] = (P.use_mask && P.mp0 && in) ? __ldg(P.mp0 + n0 + i) : 1.f;
-      mi.mp2[i] = (P.use_mask && P.mp0 && in) ? __ldg(P.mp2 + n0 + i) : 0.f;
-      mi.bmean[i] = (P.bstats && in) ? __ldg(P.bmean + n0 + i) : 0.f;
-      mi.binv[i] = (P.bstats && in) ? __ldg(P.binv + n0 + i) : 0.f;
+    for (int i = tid; i < Lo.ncoef * 32; i += NT) {
+      const int e = i >> 5, j = i & 31;
+      const Seg& sg = P.seg[Lo.coef_seg[e]];
+      const int c = Lo.coef_c0[e] + j;
+      const bool ok = c < sg.C;
+      coef[e * COEF_FLOATS + j] = ok ? __ldg(sg.p0 + sg.coff + c) : 1.f;
+      coef[e * COEF_FLOATS + 32 + j] = ok ? __ldg(sg.p2 + sg.coff + c) : 0.f;
+      coef[e * COEF_FLOATS + 64 + j] = (ok && sg.p1) ? __ldg(sg.p1 + sg.coff + c) : 0.f;
     }
   }
   if (warp == 0) {
     if (lane == 0) {
-      for (int s = 0; s < nstage; ++s) { mbar_init(&mi.full[s], LOAD_WARPS); mbar_init(&mi.empty[s], 1); }
-      for (int a = 0; a < 2; ++a) { mbar_init(&mi.tfull[a], 1); mbar_init(&mi.tempty[a], NEPI); }
+      for (int s = 0; s < nstage; ++s) { mbar_init(&mi.full[s], LW); mbar_init(&mi.empty[s], 1); }
+      for (int a = 0; a < 2; ++a) { mbar_init(&mi.tfull[a], 1); mbar_init(&mi.tempty[a], 32 * EW); }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(&mi.tmem_base, 2 * BN);
+    tmem_alloc(&mi.tmem_base, 2 * BM);
   }
   fence_proxy_async();
   tc_fence_before();
@@ -113,33 +141,34 @@ __global__ void __launch_bounds__(NT, 1) tc_igemm_kernel(const __grid_constant__
   tc_fence_after();
   const uint32_t tmem = mi.tmem_base;
 
-  if (warp == 0) {
+  if (warp < 4) {
     // ================================ MMA issuer ==================================
-    if (lane == 0) {
-      const uint32_t idesc = idesc_tf32(BM, BN, 0, 0);
+    reg_dec<REG_MMA>();
+    if (tid == 0) {
+      const uint32_t idesc = idesc_tf32(MW, BM, 0, 0);
       // descriptor = constant high word | 14-bit (address >> 4); K-steps advance the address by 32 B
       const uint64_t dhi = (uint64_t)(smem_desc_sw128(0, 16, 1024) >> 32) << 32 | (1ull << 16);
       const uint32_t a_base = smem_u32(Asm) >> 4, w_base = smem_u32(Wsm) >> 4;
-      const uint32_t w_lo_off = ((uint32_t)nkb * BN * 128) >> 4;
+      const uint32_t w_lo_off = ((uint32_t)nkb * MW * 128) >> 4, w_kb = ((uint32_t)MW * 128) >> 4;
       int st = 0;
       uint32_t ph = 0;
       for (int ti = 0; ti < n_my; ++ti) {
         const int acc = ti & 1;
         mbar_wait(&mi.tempty[acc], ((ti >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d = tmem + acc * BN;
+        const uint32_t d = tmem + acc * BM;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&mi.full[st], ph);
           tc_fence_after();
-          const uint32_t a_hi = a_base + st * (STAGE >> 4), a_lo = a_hi + (A_TILE >> 4);
-          const uint32_t w_hi = w_base + (((uint32_t)kb * BN * 128) >> 4), w_lo = w_hi + w_lo_off;
+          const uint32_t x_hi = a_base + st * (STAGE >> 4), x_lo = x_hi + (A_TILE >> 4);
+          const uint32_t w_hi = w_base + (uint32_t)kb * w_kb, w_lo = w_hi + w_lo_off;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const uint64_t dah = dhi | (a_hi + 2 * j), dal = dhi | (a_lo + 2 * j);
-            const uint64_t dbh = dhi | (w_hi + 2 * j), dbl = dhi | (w_lo + 2 * j);
-            mma_tf32(d, dal, dbh, idesc, (kb | j) != 0);
-            mma_tf32(d, dah, dbl, idesc, 1);
-            mma_tf32(d, dah, dbh, idesc, 1);
+            const uint64_t dxh = dhi | (x_hi + 2 * j), dxl = dhi | (x_lo + 2 * j);
+            const uint64_t dwh = dhi | (w_hi + 2 * j), dwl = dhi | (w_lo + 2 * j);
+            mma_tf32(d, dwl, dxh, idesc, (kb | j) != 0);
+            mma_tf32(d, dwh, dxl, idesc, 1);
+            mma_tf32(d, dwh, dxh, idesc, 1);
           }
           mma_commit(&mi.empty[st]);
           if (++st == nstage) { st = 0; ph ^= 1; }
@@ -147,17 +176,22 @@ __global__ void __launch_bounds__(NT, 1) tc_igemm_kernel(const __grid_constant__
         mma_commit(&mi.tfull[acc]);
       }
     }
-  } else if (warp <= LOAD_WARPS) {
+  } else if (warp < 4 + LW) {
     // ================================== loaders ====================================
-    const int lt = tid - 32, chunk = lt & 7, r0 = lt >> 3;
+    if (LW == 8) reg_inc<REG_LOAD>();
+    constexpr int RPT = 32 / LW;                        // rows per thread and k-block
+    constexpr int RSTEP = 4 * LW;                       // row distance between a thread's rows
+    constexpr int NS = LD2 ? 2 : (LW == 8 ? 3 : 4);     // register slots; prefetch distance NS-1 k-blocks
+    const int lt = tid - 128, chunk = lt & 7, r0 = lt >> 3;
+    const uint32_t st_off = (uint32_t)r0 * 128 + ((uint32_t)(chunk ^ (r0 & 7)) << 4);
     const int total = n_my * nkb;
     const unsigned Mu = (unsigned)M, Lq = (unsigned)P.Lq;
-    constexpr int NS = LD2 ? 2 : 3;                     // register slots; prefetch distance NS-1 k-blocks
-    constexpr int RSTEP = BM / RPT;
     float4 va[NS][RPT], vb[LD2 ? NS : 1][RPT];
     unsigned vmask[NS];
-    // issue-side cursor (runs two k-blocks ahead of the commit-side cursor)
+    // issue-side cursor (runs NS-1 k-blocks ahead of the commit-side cursor)
     int i_kb = 0, i_ti = 0, i_seg = -1;
+    const float* i_src = nullptr;
+    const float* i_src2 = nullptr;
     unsigned rbt[RPT], rq[RPT];
     bool rok[RPT];
     int roff[RPT];
@@ -174,23 +208,25 @@ __global__ void __launch_bounds__(NT, 1) tc_igemm_kernel(const __grid_constant__
     };
     decode_rows();
     auto issue = [&](float4 (&a)[RPT], float4 (&b)[RPT], unsigned& msk) {
-      const int s = mi.kb_seg[i_kb];
-      const Seg& sg = P.seg[s];
+      const int s = Lo.kb_seg[i_kb];
       if (s != i_seg) {
+        const Seg& sg = P.seg[s];
+        const int Lsrc = sg.Lsrc, ld = sg.ld, coff = sg.coff, smul = sg.smul, sadd = sg.sadd;
 #pragma unroll
         for (int i = 0; i < RPT; ++i) {
-          const int li = (int)rq[i] * sg.smul + sg.sadd;
-          roff[i] = (rok[i] && li >= 0 && li < sg.Lsrc) ? ((int)rbt[i] * sg.Lsrc + li) * sg.ld + sg.coff : -1;
+          const int li = (int)rq[i] * smul + sadd;
+          roff[i] = (rok[i] && (unsigned)li < (unsigned)Lsrc) ? ((int)rbt[i] * Lsrc + li) * ld + coff : -1;
         }
-        i_seg = s;
+        i_seg = s; i_src = sg.src; i_src2 = sg.src2;
       }
-      const int c = mi.kb_c0[i_kb] + chunk * 4;
+      const int c = Lo.kb_c0[i_kb] + chunk * 4;
+      const bool cok = chunk * 4 < Lo.kb_valid[i_kb];
       msk = 0;
 #pragma unroll
       for (int i = 0; i < RPT; ++i) {
-        if (roff[i] >= 0 && c < sg.C) {
-          a[i] = ld4(sg.src + (unsigned)(roff[i] + c));
-          if (LD2 && sg.src2) b[i] = ld4(sg.src2 + (unsigned)(roff[i] + c));
+        if (cok && roff[i] >= 0) {
+          a[i] = ld4(i_src + (unsigned)(roff[i] + c));
+          if (LD2) b[i] = i_src2 ? ld4(i_src2 + (unsigned)(roff[i] + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
           msk |= 1u << i;
         }
       }
@@ -200,32 +236,36 @@ __global__ void __launch_bounds__(NT, 1) tc_igemm_kernel(const __grid_constant__
     int c_kb = 0, c_st = 0;
     uint32_t c_ph = 0;
     auto commit = [&](float4 (&a)[RPT], float4 (&b)[RPT], unsigned msk) {
-      const Seg& sg = P.seg[mi.kb_seg[c_kb]];
-      const int c = sg.coff + mi.kb_c0[c_kb] + chunk * 4;
+      const int e = Lo.kb_coef[c_kb];
       float4 p0 = make_float4(1, 1, 1, 1), p1 = make_float4(0, 0, 0, 0), p2 = p1;
-      if (sg.p0 && mi.kb_c0[c_kb] + chunk * 4 < sg.C) {
-        p0 = ld4(sg.p0 + c); p2 = ld4(sg.p2 + c);
-        if (LD2 && sg.p1) p1 = ld4(sg.p1 + c);
+      if (e >= 0) {
+        const float* ce = coef + e * COEF_FLOATS + chunk * 4;
+        p0 = *(const float4*)ce; p2 = *(const float4*)(ce + 32);
+        if (LD2) p1 = *(const float4*)(ce + 64);
       }
+      const float fl = Lo.kb_relu[c_kb] ? 0.f : -__int_as_float(0x7f800000);
       mbar_wait(&mi.empty[c_st], c_ph ^ 1);
-      uint8_t* ah = Asm + c_st * STAGE;
+      uint8_t* ah = Asm + c_st * STAGE + st_off;
 #pragma unroll
       for (int i = 0; i < RPT; ++i) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (msk & (1u << i)) {
-          v = a[i];
-          if (sg.p0) {
-            v.x = p0.x * v.x + p2.x; v.y = p0.y * v.y + p2.y; v.z = p0.z * v.z + p2.z; v.w = p0.w * v.w + p2.w;
-            if (LD2 && sg.p1) { v.x += p1.x * b[i].x; v.y += p1.y * b[i].y; v.z += p1.z * b[i].z; v.w += p1.w * b[i].w; }
-            if (sg.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        float4 v = a[i];
+        if (e >= 0) {
+          if (LD2) {
+            v.x = fmaf(p1.x, b[i].x, fmaf(p0.x, v.x, p2.x)); v.y = fmaf(p1.y, b[i].y, fmaf(p0.y, v.y, p2.y));
+            v.z = fmaf(p1.z, b[i].z, fmaf(p0.z, v.z, p2.z)); v.w = fmaf(p1.w, b[i].w, fmaf(p0.w, v.w, p2.w));
+          } else {
+            v.x = fmaf(p0.x, v.x, p2.x); v.y = fmaf(p0.y, v.y, p2.y); v.z = fmaf(p0.z, v.z, p2.z); v.w = fmaf(p0.w, v.w, p2.w);
           }
+          v.x = fmaxf(v.x, fl); v.y = fmaxf(v.y, fl); v.z = fmaxf(v.z, fl); v.w = fmaxf(v.w, fl);
         }
+        if (!(msk & (1u << i))) v = make_float4(0.f, 0.f, 0.f, 0.f);
         uint4 hi, lo;
-        split_tf32(v, hi, lo);
-        const int row = r0 + RSTEP * i;
-        const uint32_t off = row * 128 + ((chunk ^ (row & 7)) << 4);
-        *(uint4*)(ah + off) = hi;
-        *(uint4*)(ah + A_TILE + off) = lo;
+        hi.x = __float_as_uint(v.x) & 0xffffe000u; hi.y = __float_as_uint(v.y) & 0xffffe000u;
+        hi.z = __float_as_uint(v.z) & 0xffffe000u; hi.w = __float_as_uint(v.w) & 0xffffe000u;
+        lo.x = __float_as_uint(v.x - __uint_as_float(hi.x)); lo.y = __float_as_uint(v.y - __uint_as_float(hi.y));
+        lo.z = __float_as_uint(v.z - __uint_as_float(hi.z)); lo.w = __float_as_uint(v.w - __uint_as_float(hi.w));
+        *(uint4*)(ah + i * (RSTEP * 128)) = hi;
+        *(uint4*)(ah + A_TILE + i * (RSTEP * 128)) = lo;
       }
       fence_proxy_async();
       __syncwarp();
@@ -242,7 +282,6 @@ __global__ void __launch_bounds__(NT, 1) tc_igemm_kernel(const __grid_constant__
       for (int u = 0; u < NS; ++u) {
         const int ww = w + u;
         if (ww < total) {
-          constexpr int dummy = 0; (void)dummy;
           if (ww + NS - 1 < total) issue(va[(u + NS - 1) % NS], vb[LD2 ? (u + NS - 1) % NS : 0], vmask[(u + NS - 1) % NS]);
           commit(va[u], vb[LD2 ? u : 0], vmask[u]);
         }
@@ -250,124 +289,114 @@ __global__ void __launch_bounds__(NT, 1) tc_igemm_kernel(const __grid_constant__
     }
   } else {
     // ================================== epilogue ===================================
-    // Each warp drains its 32 accumulator rows in 32-column chunks: TMEM -> registers
-    // (+bias) -> warp-private padded smem tile -> transposed read so that every global
-    // access (store, ReLU-mask load, skip-gradient load) covers whole 128-byte lines.
-    // BN statistics: a lane keeps the same 4 columns for all rows, sums stay in registers.
-    const int lgrp = warp & 3;                          // TMEM lane group this warp may read
-    float* tile = (float*)(smem + Lo.epi_off) + (warp - 1 - LOAD_WARPS) * (32 * EPI_LD);
-    const int c4 = (lane & 7) * 4, rsub = lane >> 3;
+    // Thread = one output channel (TMEM lane); per tile a warp drains 2 chunks of 32 tile rows
+    // (TMEM columns), each as two sub-chunks of 16 rows.  M = 64: the accumulator occupies lanes
+    // 0-15 of every 32-lane quadrant (rows 16q..16q+15).  The ReLU-mask values (Z of the layer that
+    // receives the gradient) do not depend on the accumulator, so they are fetched one sub-chunk
+    // ahead - across tile boundaries too - and their latency hides behind the previous sub-chunk.
+    reg_inc<REG_EPI>();
+    const int ew = warp - 4 - LW, lg = warp & 3, half = ew >> 2;
+    const int nl = MW == 128 ? lg * 32 + lane : lg * 16 + lane;
+    const int n = n0 + nl;
+    const bool nok = (MW == 128 || lane < 16) && n < P.N;
     const unsigned Mu = (unsigned)M, Lq = (unsigned)P.Lq;
-    float st1[4][4], st2[4][4];
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) { st1[a][b] = 0.f; st2[a][b] = 0.f; }
+    const float bias = (P.bias && nok) ? __ldg(P.bias + n) : 0.f;
+    float mp0 = 1.f, mp2 = 0.f;
+    const bool use_mask = EPI && P.use_mask, has_extra = EPI && P.extra != nullptr;
+    if (use_mask && P.mp0 && nok) { mp0 = __ldg(P.mp0 + n); mp2 = __ldg(P.mp2 + n); }
     const bool do_stats = P.stats != nullptr, do_bstats = EPI && P.bstats != nullptr;
-    for (int ti = 0; ti < n_my; ++ti) {
-      const int acc = ti & 1;
-      const unsigned mw = ((unsigned)blockIdx.x + (unsigned)ti * gridDim.x) * BM + lgrp * 32;   // first row of this warp
-      // output row index of the 8 rows this lane touches in the transposed phase: rows rsub + 4*i
-      int orow[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const unsigned m = mw + rsub + 4 * i;
-        orow[i] = -1;
+    const float bmean = (do_bstats && nok) ? __ldg(P.bmean + n) : 0.f;
+    float s1 = 0.f, s2 = 0.f;      // stats: sum o, sum o*o;  bstats: sum g, sum g*(z - mean) (scaled at the end)
+    // per-thread base element offset; per-row offsets are computed by lane j for row j of a chunk
+    const size_t obase = P.planar ? (size_t)n * P.Lout : (size_t)n;
+    const float* zbase = use_mask ? P.zmask + obase : nullptr;
+    const float* xbase = has_extra ? P.extra + n : nullptr;
+    float* outb = P.out + obase;
+
+    // lane j: element offsets of tile row cc*32 + j of tile ti (0xffffffff: row does not exist)
+    auto row_offsets = [&](int ti, int cc, unsigned& ooff, unsigned& eoff) {
+      ooff = 0xffffffffu; eoff = 0u;
+      if (ti < n_my) {
+        const unsigned m = ((unsigned)blockIdx.x + (unsigned)ti * gridDim.x) * BM + cc * 32 + lane;
         if (m < Mu) {
           const unsigned bt = m / Lq, q = m - bt * Lq;
-          orow[i] = (int)(bt * P.Lout + q * P.omul + P.oadd);
+          const unsigned lo = q * P.omul + P.oadd, r = bt * P.Lout + lo;
+          ooff = P.planar ? bt * (unsigned)P.N * (unsigned)P.Lout + lo : r * (unsigned)P.ldo + P.ocoff;
+          eoff = r * (unsigned)P.ext_ld;
         }
       }
+    };
+    auto zfetch = [&](float (&z)[16], float (&x)[EPI ? 16 : 1], unsigned ooff, unsigned eoff, int h) {
+      if (EPI && use_mask) {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const unsigned off = __shfl_sync(0xffffffffu, ooff, h * 16 + r);
+          z[r] = (nok && off != 0xffffffffu) ? __ldg(zbase + off) : 0.f;
+        }
+      }
+      if (EPI && has_extra) {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const unsigned off = __shfl_sync(0xffffffffu, ooff, h * 16 + r);
+          const unsigned eo = __shfl_sync(0xffffffffu, eoff, h * 16 + r);
+          x[EPI ? r : 0] = (nok && off != 0xffffffffu) ? __ldg(xbase + eo) : 0.f;
+        }
+      }
+    };
+    auto process = [&](const uint32_t (&v)[16], int h, const float (&z)[16], const float (&x)[EPI ? 16 : 1], unsigned ooff) {
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const unsigned off = __shfl_sync(0xffffffffu, ooff, h * 16 + r);
+        const bool ok = nok && off != 0xffffffffu;
+        float o = __uint_as_float(v[r]) + bias;
+        if (EPI) {
+          if (has_extra) o += x[EPI ? r : 0];
+          if (use_mask) o = (fmaf(z[r], mp0, mp2) > 0.f) ? o : 0.f;
+        }
+        if (ok) {
+          outb[off] = o;
+          if (do_stats) { s1 += o; s2 = fmaf(o, o, s2); }
+          if (EPI && do_bstats) { s1 += o; s2 = fmaf(o, z[r] - bmean, s2); }
+        }
+      }
+    };
+
+    float za[16], zb[16], xa[EPI ? 16 : 1], xb[EPI ? 16 : 1];
+    unsigned oa, ea, ob, eb;
+    row_offsets(0, half * 2, oa, ea);
+    zfetch(za, xa, oa, ea, 0);
+    for (int ti = 0; ti < n_my; ++ti) {
+      const int acc = ti & 1;
+      row_offsets(ti, half * 2 + 1, ob, eb);
       mbar_wait(&mi.tfull[acc], (ti >> 1) & 1);
       tc_fence_after();
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        if (cc * 32 < BN) {
-          uint32_t v[32];
-          tmem_ld32(tmem + ((uint32_t)(lgrp * 32) << 16) + acc * BN + cc * 32, v);
-          if ((cc + 1) * 32 >= BN) { tc_fence_before(); mbar_arrive(&mi.tempty[acc]); }
-          __syncwarp();                                 // previous chunk's readers are done
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4)
-            *(float4*)(tile + lane * EPI_LD + j4 * 4) =
-                make_float4(__uint_as_float(v[j4 * 4]), __uint_as_float(v[j4 * 4 + 1]), __uint_as_float(v[j4 * 4 + 2]),
-                            __uint_as_float(v[j4 * 4 + 3]));
-          __syncwarp();
-          const int col = cc * 32 + c4;                 // column inside the CTA's N tile
-          const float4 bias = *(const float4*)&mi.bias[col];
-          float4 mp0 = make_float4(1, 1, 1, 1), mp2 = make_float4(0, 0, 0, 0), bmean = mp2, binv = mp2;
-          if (EPI && P.use_mask) { mp0 = *(const float4*)&mi.mp0[col]; mp2 = *(const float4*)&mi.mp2[col]; }
-          if (do_bstats) { bmean = *(const float4*)&mi.bmean[col]; binv = *(const float4*)&mi.binv[col]; }
-          // two half-chunks of 4 rows; the global loads of a half are issued before its stores
-          // (a load cannot be hoisted above a store the compiler cannot prove disjoint)
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            float4 zv[4], xv[4];
-            if (EPI) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int r = orow[h * 4 + i];
-                zv[i] = make_float4(0.f, 0.f, 0.f, 0.f); xv[i] = zv[i];
-                if (r >= 0 && n0 + col < P.N) {
-                  if (P.use_mask) zv[i] = ld4(P.zmask + (unsigned)r * (unsigned)P.ldo + P.ocoff + n0 + col);
-                  if (P.extra) xv[i] = ld4(P.extra + (unsigned)r * (unsigned)P.ext_ld + n0 + col);
-                }
-              }
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int r = orow[h * 4 + i];
-              if (r < 0) continue;
-              float4 o = *(const float4*)(tile + (rsub + 4 * (h * 4 + i)) * EPI_LD + c4);
-              o.x += bias.x; o.y += bias.y; o.z += bias.z; o.w += bias.w;
-              const unsigned gofs = (unsigned)r * (unsigned)P.ldo + P.ocoff + n0 + col;
-              if (EPI) {
-                o.x += xv[i].x; o.y += xv[i].y; o.z += xv[i].z; o.w += xv[i].w;
-                if (P.use_mask) {
-                  const float4 z = zv[i];
-                  o.x = (z.x * mp0.x + mp2.x > 0.f) ? o.x : 0.f; o.y = (z.y * mp0.y + mp2.y > 0.f) ? o.y : 0.f;
-                  o.z = (z.z * mp0.z + mp2.z > 0.f) ? o.z : 0.f; o.w = (z.w * mp0.w + mp2.w > 0.f) ? o.w : 0.f;
-                  if (do_bstats) {
-                    st1[cc][0] += o.x; st1[cc][1] += o.y; st1[cc][2] += o.z; st1[cc][3] += o.w;
-                    st2[cc][0] += o.x * (z.x - bmean.x) * binv.x; st2[cc][1] += o.y * (z.y - bmean.y) * binv.y;
-                    st2[cc][2] += o.z * (z.z - bmean.z) * binv.z; st2[cc][3] += o.w * (z.w - bmean.w) * binv.w;
-                  }
-                }
-              }
-              if (do_stats) {
-                st1[cc][0] += o.x; st1[cc][1] += o.y; st1[cc][2] += o.z; st1[cc][3] += o.w;
-                st2[cc][0] += o.x * o.x; st2[cc][1] += o.y * o.y; st2[cc][2] += o.z * o.z; st2[cc][3] += o.w * o.w;
-              }
-              if (n0 + col < P.N) {
-                if (P.planar) {                       // (BT, N, Lout) layout of the network output
-                  const unsigned bt = (unsigned)r / (unsigned)P.Lout, lo = (unsigned)r - bt * P.Lout;
-                  float* op = P.out + ((size_t)bt * P.N + n0 + col) * P.Lout + lo;
-                  op[0] = o.x; op[P.Lout] = o.y; op[2 * (size_t)P.Lout] = o.z; op[3 * (size_t)P.Lout] = o.w;
-                } else {
-                  *(float4*)(P.out + gofs) = o;
-                }
-              }
-            }
-          }
-        }
-      }
+      const uint32_t taddr = tmem + ((uint32_t)(lg * 32) << 16) + acc * BM + half * 64;
+      uint32_t v[16];
+      tmem_ld16(taddr, v);
+      zfetch(zb, xb, oa, ea, 1);
+      process(v, 0, za, xa, oa);
+      tmem_ld16(taddr + 16, v);
+      zfetch(za, xa, ob, eb, 0);
+      process(v, 1, zb, xb, oa);
+      tmem_ld16(taddr + 32, v);
+      zfetch(zb, xb, ob, eb, 1);
+      process(v, 0, za, xa, ob);
+      tmem_ld16(taddr + 48, v);
+      tc_fence_before();
+      mbar_arrive(&mi.tempty[acc]);
+      row_offsets(ti + 1, half * 2, oa, ea);
+      zfetch(za, xa, oa, ea, 0);
+      process(v, 1, zb, xb, ob);
     }
     double* gst = P.stats ? P.stats : (EPI ? P.bstats : nullptr);
-    if (gst) {
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc)
-        if (cc * 32 < BN)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float a = st1[cc][j], b = st2[cc][j];
-            a += __shfl_xor_sync(0xffffffffu, a, 8); a += __shfl_xor_sync(0xffffffffu, a, 16);
-            b += __shfl_xor_sync(0xffffffffu, b, 8); b += __shfl_xor_sync(0xffffffffu, b, 16);
-            const int n = n0 + cc * 32 + c4 + j;
-            if (lane < 8 && n < P.N) {
-              atomicAdd(gst + n, (double)a);
-              atomicAdd(gst + P.N + n, (double)b);
-            }
-          }
+    if (gst && nok) {
+      if (EPI && do_bstats) {       // sum g*xhat = invstd * sum g*(z - mean)
+        atomicAdd(gst + n, (double)s1);
+        atomicAdd(gst + P.N + n, (double)s2 * (double)__ldg(P.binv + n));
+      } else {
+        atomicAdd(gst + n, (double)s1);
+        atomicAdd(gst + P.N + n, (double)s2);
+      }
     }
   }
 
@@ -375,77 +404,165 @@ __global__ void __launch_bounds__(NT, 1) tc_igemm_kernel(const __grid_constant__
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem, 2 * BN);
+    tmem_dealloc(tmem, 2 * BM);
   }
 }
 
 constexpr size_t SMEM_MAX = 227 * 1024;
 
-bool plan(const IgemmParams& p, TcLayout& L, dim3& grid, size_t& smem_bytes) {
-  if ((p.N % 32 != 0 && p.N > 32) || p.N % 4 != 0 || p.ldo % 4 != 0 || p.ocoff % 4 != 0) return false;
-  if (p.planar && p.N > 32) return false;
+int total_kblocks(const IgemmParams& p) {
   int nkb = 0;
+  for (int s = 0; s < p.nseg; ++s) nkb += (p.seg[s].C + KBLK - 1) / KBLK;
+  return nkb;
+}
+
+bool shape_ok(const IgemmParams& p) {
+  if (p.nseg < 1 || p.nseg > 5 || p.N < 1) return false;
   for (int s = 0; s < p.nseg; ++s) {
     if (p.seg[s].C % 4 != 0 || p.seg[s].ld % 4 != 0 || p.seg[s].coff % 4 != 0) return false;
-    nkb += (p.seg[s].C + KBLK - 1) / KBLK;
-  }
-  if (nkb > MAXKB) return false;
-  // 32-bit element offsets inside the kernel
-  for (int s = 0; s < p.nseg; ++s)
+    // 32-bit element offsets inside the kernel
     if ((double)p.BT * p.seg[s].Lsrc * p.seg[s].ld >= 2147483648.0) return false;
-  if ((double)p.BT * p.Lout * p.ldo >= 4294967296.0 || (double)p.BT * p.Lq + BM >= 4294967296.0) return false;
-  const size_t fixed = 1024 /* alignment slack */ + EPI_BYTES + sizeof(Misc) + 256;
-  for (int BN : {128, 64, 32}) {
-    if (p.N % BN != 0 && !(BN == 32 && p.N < 32)) continue;
-    const size_t w = (size_t)2 * nkb * BN * 128;
-    if (fixed + w + 2 * STAGE > SMEM_MAX) continue;
-    int nstage = (int)std::min<size_t>(8, (SMEM_MAX - fixed - w) / STAGE);
-    L.BN = BN; L.nkb = nkb; L.nstage = nstage;
-    L.w_off = 0;
-    L.a_off = (uint32_t)((w + 1023) / 1024 * 1024);
-    L.epi_off = L.a_off + nstage * STAGE;
-    L.misc_off = L.epi_off + EPI_BYTES;
-    smem_bytes = 1024 + L.misc_off + sizeof(Misc);
-    const int ny = (p.N + BN - 1) / BN;
-    const long M = (long)p.BT * p.Lq;
-    const int ntiles = (int)((M + BM - 1) / BM);
-    grid = dim3(std::max(1, std::min(ntiles, sm_count() / ny)), ny);
-    return smem_bytes <= SMEM_MAX;
   }
-  return false;
+  if ((double)p.BT * p.Lout * std::max(p.ldo, 1) >= 4294967296.0 || (double)p.BT * p.Lq + BM >= 4294967296.0) return false;
+  if (p.planar && (double)p.BT * p.N * p.Lout >= 4294967296.0) return false;
+  if (p.extra && (double)p.BT * p.Lout * p.ext_ld >= 4294967296.0) return false;
+  return true;
 }
 
-}  // namespace
+int weight_rows(const IgemmParams& p) { return p.N <= 64 ? 64 : 128; }
 
-bool igemm_tc_eligible(const IgemmParams& p) {
-  TcLayout L{};
-  dim3 grid;
-  size_t smem = 0;
-  return plan(p, L, grid, smem);
+// the most k-blocks one launch can keep resident next to a 2-stage ring
+int max_kblocks(int MW) {
+  const size_t fixed = 1024 + 2 * STAGE + sizeof(Misc) + 64 + (size_t)MAXCOEF * COEF_FLOATS * 4;
+  return (int)std::min<size_t>(MAXKB, (SMEM_MAX - fixed) / ((size_t)MW * 256));
 }
 
-// returns TRU_OK if launched, 1 if the shape is not eligible (caller falls back to the FFMA kernel)
-int launch_igemm_tc(const IgemmParams& p, cudaStream_t st) {
-  TcLayout L{};
-  dim3 grid;
-  size_t smem = 0;
-  if (!plan(p, L, grid, smem)) return 1;
+bool plan(const IgemmParams& p, TcLayout& L, dim3& grid, size_t& smem_bytes) {
+  if (!shape_ok(p)) return false;
+  memset(&L, 0, sizeof(L));
+  L.MW = weight_rows(p);
+  int nkb = 0, ncoef = 0;
+  for (int s = 0; s < p.nseg; ++s) {
+    const Seg& sg = p.seg[s];
+    for (int c0 = 0; c0 < sg.C; c0 += KBLK) {
+      if (nkb >= MAXKB) return false;
+      L.kb_seg[nkb] = (int8_t)s; L.kb_c0[nkb] = (int16_t)c0; L.kb_valid[nkb] = (int16_t)std::min(KBLK, sg.C - c0);
+      L.kb_relu[nkb] = (int8_t)(sg.p0 && sg.relu);
+      L.kb_coef[nkb] = -1;
+      if (sg.p0) {
+        int e = -1;
+        for (int t = 0; t < ncoef && e < 0; ++t) {
+          const Seg& o = p.seg[L.coef_seg[t]];
+          if (o.p0 == sg.p0 && o.p1 == sg.p1 && o.p2 == sg.p2 && o.coff + L.coef_c0[t] == sg.coff + c0 &&
+              std::min(KBLK, o.C - L.coef_c0[t]) == L.kb_valid[nkb]) e = t;
+        }
+        if (e < 0) {
+          if (ncoef >= MAXCOEF) return false;
+          e = ncoef++;
+          L.coef_seg[e] = (int8_t)s; L.coef_c0[e] = (int16_t)c0;
+        }
+        L.kb_coef[nkb] = (int8_t)e;
+      }
+      ++nkb;
+    }
+  }
+  L.nkb = nkb; L.ncoef = ncoef;
+  const size_t w = (size_t)2 * nkb * L.MW * 128;
+  const size_t coefb = (size_t)ncoef * COEF_FLOATS * 4;
+  const size_t fixed = 1024 + coefb + sizeof(Misc) + 64;
+  if (fixed + w + 2 * STAGE > SMEM_MAX) return false;
+  L.nstage = (int)std::min<size_t>(6, (SMEM_MAX - fixed - w) / STAGE);
+  L.a_off = (uint32_t)w;                                   // multiple of 1024
+  L.coef_off = L.a_off + L.nstage * STAGE;
+  L.misc_off = (uint32_t)align_up(L.coef_off + coefb, 16);
+  smem_bytes = 1024 + L.misc_off + sizeof(Misc);
+  const int ny = (p.N + L.MW - 1) / L.MW;
+  const long M = (long)p.BT * p.Lq;
+  const int ntiles = (int)((M + BM - 1) / BM);
+  grid = dim3(std::max(1, std::min(ntiles, sm_count() / ny)), ny);
+  return smem_bytes <= SMEM_MAX;
+}
+
+int g_loader_warps = 8;
+
+template <int LW>
+int launch_one(const IgemmParams& p, const TcLayout& L, dim3 grid, size_t smem, cudaStream_t st) {
   const bool epi = p.use_mask || p.extra != nullptr || p.bstats != nullptr;
   bool ld2 = false;
   for (int s = 0; s < p.nseg; ++s) ld2 |= (p.seg[s].src2 != nullptr);
   static bool attr_done = false;
   if (!attr_done) {
-    TRU_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
-    TRU_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
-    TRU_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
-    TRU_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+    TRU_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<LW, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+    TRU_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<LW, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+    TRU_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<LW, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+    TRU_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<LW, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
     attr_done = true;
   }
-  if (ld2 && epi) tc_igemm_kernel<true, true><<<grid, NT, smem, st>>>(p, L);
-  else if (ld2) tc_igemm_kernel<true, false><<<grid, NT, smem, st>>>(p, L);
-  else if (epi) tc_igemm_kernel<false, true><<<grid, NT, smem, st>>>(p, L);
-  else tc_igemm_kernel<false, false><<<grid, NT, smem, st>>>(p, L);
+  constexpr int NT = 32 * (4 + LW + EW);
+  if (ld2 && epi) tc_igemm_kernel<LW, true, true><<<grid, NT, smem, st>>>(p, L);
+  else if (ld2) tc_igemm_kernel<LW, true, false><<<grid, NT, smem, st>>>(p, L);
+  else if (epi) tc_igemm_kernel<LW, false, true><<<grid, NT, smem, st>>>(p, L);
+  else tc_igemm_kernel<LW, false, false><<<grid, NT, smem, st>>>(p, L);
   TRU_LAUNCH_CHECK();
+  return TRU_OK;
+}
+
+int launch_planned(const IgemmParams& p, cudaStream_t st) {
+  TcLayout L;
+  dim3 grid;
+  size_t smem = 0;
+  if (!plan(p, L, grid, smem)) return 1;
+  return g_loader_warps == 8 ? launch_one<8>(p, L, grid, smem, st) : launch_one<16>(p, L, grid, smem, st);
+}
+
+// k-blocks [k0, k1) of p as a launch of their own
+IgemmParams slice_kblocks(const IgemmParams& p, int k0, int k1) {
+  IgemmParams q = p;
+  q.nseg = 0;
+  int kb = 0;
+  for (int s = 0; s < p.nseg; ++s) {
+    const Seg& sg = p.seg[s];
+    const int skb = (sg.C + KBLK - 1) / KBLK;
+    const int a = std::max(k0, kb), b = std::min(k1, kb + skb);
+    if (a < b) {
+      Seg t = sg;
+      const int c0 = (a - kb) * KBLK, c1 = std::min(sg.C, (b - kb) * KBLK);
+      t.coff = sg.coff + c0; t.C = c1 - c0; t.wbase = sg.wbase + c0 * sg.wsc;
+      q.seg[q.nseg++] = t;
+    }
+    kb += skb;
+  }
+  return q;
+}
+
+}  // namespace
+
+void set_tc_loader_warps(int n) { g_loader_warps = (n == 8) ? 8 : 16; }
+
+bool igemm_tc_eligible(const IgemmParams& p) {
+  if (!shape_ok(p)) return false;
+  const int nkb = total_kblocks(p), cap = max_kblocks(weight_rows(p));
+  if (nkb <= cap) { TcLayout L; dim3 g; size_t s = 0; return plan(p, L, g, s); }
+  return !p.planar && cap >= 1 && (nkb + cap - 1) / cap <= 4;
+}
+
+// returns TRU_OK if launched, 1 if the shape is not eligible (caller falls back to the FFMA kernel).
+// When the weight slice does not fit in shared memory the reduction is split into passes over
+// k-block ranges: pass 0 writes the partial product (+bias, +skip gradient), later passes add to it
+// in place, and the last one applies the mask / accumulates the statistics.
+int launch_igemm_tc(const IgemmParams& p, cudaStream_t st) {
+  if (!igemm_tc_eligible(p)) return 1;
+  const int nkb = total_kblocks(p), cap = max_kblocks(weight_rows(p));
+  if (nkb <= cap) return launch_planned(p, st);
+  const int npass = (nkb + cap - 1) / cap, per = (nkb + npass - 1) / npass;
+  for (int i = 0; i < npass; ++i) {
+    IgemmParams q = slice_kblocks(p, i * per, std::min(nkb, (i + 1) * per));
+    const bool first = i == 0, last = i == npass - 1;
+    if (!first) { q.bias = nullptr; q.extra = p.out + p.ocoff; q.ext_ld = p.ldo; }
+    if (!last) { q.stats = nullptr; q.use_mask = 0; q.zmask = nullptr; q.bstats = nullptr; }
+    const int rc = launch_planned(q, st);
+    if (rc) return rc < 0 ? rc : set_error(TRU_ERR_ARG, "igemm_tc: k-split pass %d not plannable", i);
+  }
   return TRU_OK;
 }
 

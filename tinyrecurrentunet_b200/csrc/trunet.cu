@@ -50,7 +50,8 @@ struct Plan {
     GF = f(16 * 384); HF = f(16 * 128); CF = f(16 * 512); ZFp = f(16 * 64);
     GT = f(16 * 384); HT = f(16 * 128); CT = f(16 * 512); ZTp = f(16 * 64);
     for (int d = 0; d <= 5; ++d) { ZDp[d] = f((long)DEC_LP[d] * DEC_COUT[d]); if (d < 5) ZDt[d] = f((long)DEC_LT[d] * 64); }
-    stats = take(NBN * 256 * 8); bstats = take(NBN * 256 * 8); small = take(NBN * 7 * 128 * 4);
+    // bstats slot: sum g, sum g*xhat, fp64 bias-gradient scratch
+    stats = take(NBN * 256 * 8); bstats = take(NBN * 384 * 8); small = take(NBN * 7 * 128 * 4);
     if (!bwd) return;
     dA0 = f(128 * 64);
     for (int i = 1; i <= 5; ++i) { dZp[i] = f((long)ENC_L[i - 1] * 128); dZd[i] = f((long)ENC_L[i] * 128); }
@@ -76,7 +77,7 @@ struct Ctx {
   void slots() {
     for (int i = 0; i < NBN; ++i) {
       bn[i].stats = (double*)(ws + plan.stats) + i * 256;
-      bn[i].bstats = (double*)(ws + plan.bstats) + i * 256;
+      bn[i].bstats = (double*)(ws + plan.bstats) + i * 384;
       float* s = (float*)(ws + plan.small) + (size_t)i * 7 * 128;
       bn[i].p0 = s; bn[i].p2 = s + 128; bn[i].mean = s + 256; bn[i].inv = s + 384;
       bn[i].q0 = s + 512; bn[i].q1 = s + 640; bn[i].q2 = s + 768;
@@ -120,8 +121,9 @@ int bn_fin(Ctx& c, int idx, int C, long rows, const float* gamma, const float* b
   p.p0 = c.bn[idx].p0; p.p2 = c.bn[idx].p2; p.mean = c.bn[idx].mean; p.invstd = c.bn[idx].inv;
   return launch_bn_finalize(p, c.st);
 }
-int bn_bfin(Ctx& c, int idx, int C, long rows, int pgamma) {
+int bn_bfin(Ctx& c, int idx, int C, long rows, int pgamma, int pbias_acc = -1) {
   BnBwdParams p{};
+  if (pbias_acc >= 0) { p.db_acc = c.bn[idx].bstats + 256; p.db_out = c.grd[pbias_acc]; }
   p.bstats = c.bn[idx].bstats; p.count = (double)rows; p.C = C;
   p.gamma = c.prm[pgamma]; p.mean = c.bn[idx].mean; p.invstd = c.bn[idx].inv;
   p.q0 = c.bn[idx].q0; p.q1 = c.bn[idx].q1; p.q2 = c.bn[idx].q2;
@@ -333,7 +335,7 @@ int convt_bwd(Ctx& c, const Grad& g, const Act& x, int ct_param, int k, int s, f
 int backward(Ctx& c, const float* x, const float* gout) {
   const Plan& P = c.plan;
   const long BT = c.BT;
-  TRU_CUDA(cudaMemsetAsync(c.ws + P.bstats, 0, NBN * 256 * 8, c.st));
+  TRU_CUDA(cudaMemsetAsync(c.ws + P.bstats, 0, NBN * 384 * 8, c.st));
   TRY(launch_planar_to_cl(gout, c.F(P.dOUT), (int)BT, 8, 257, c.st));
 
   // ---- decoder, last block first ----
@@ -446,9 +448,8 @@ int backward(Ctx& c, const float* x, const float* gout) {
     dp.bmean = c.bn[b1].mean; dp.binv = c.bn[b1].inv; dp.bstats = c.bn[b1].bstats;
     dp.a_src = c.F(P.Zp[i]); dp.a_p0 = c.bn[b1].p0; dp.a_p2 = c.bn[b1].p2;
     dp.dw = c.grd[P_ENC(i, 4)]; dp.db = c.grd[P_ENC(i, 5)];
-    TRY(launch_dw_wgrad(dp, c.st));
-    TRY(launch_dw_bwd_data(dp, c.st));
-    TRY(bn_bfin(c, b1, 128, BT * Lin, P_ENC(i, 2)));
+    TRY(launch_dw_bwd_fused(dp, c.st));
+    TRY(bn_bfin(c, b1, 128, BT * Lin, P_ENC(i, 2), P_ENC(i, 5)));   // also folds the fp64 depthwise-bias sums into db
     Grad gp = c.grad(P.dZp[i], P.Zp[i], Lin, 128, b1);
     if (i >= 2) {
       Act xin = c.act(P.Zd[i - 1], Lin, 128, BN_ENC(i - 1, 1));
@@ -562,6 +563,7 @@ extern "C" int tru_debug_pw(const float* x, const float* p0, const float* p2, co
   return launch_igemm_simt(p, (cudaStream_t)stream);
 }
 extern "C" int tru_set_tensor_cores(int on) { set_tc_enabled(on != 0); return TRU_OK; }
+extern "C" int tru_debug_set_loader_warps(int n) { set_tc_loader_warps(n); return TRU_OK; }
 
 // Test aid: dW (N,C) += z^T a for a (M,C), z (M,N) through either weight-gradient path.
 extern "C" int tru_debug_wgrad(const float* a, const float* z, float* dw, float* db, int M, int C, int N, int use_tc,
