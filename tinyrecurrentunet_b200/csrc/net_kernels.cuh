@@ -56,6 +56,18 @@ int launch_wgrad(const WgradParams& p, cudaStream_t st);        // tensor-core p
 int launch_wgrad_tc(const WgradParams& p, cudaStream_t st);     // 0 launched, 1 not eligible
 int launch_wgrad_simt(const WgradParams& p, cudaStream_t st);
 
+// Streaming weight gradient of a conv layer (tcwgrad2.cu): up to two activation sources (skip concat) or up
+// to five taps (transposed conv) in one pass.  dW[wbase[s] + tap*wtap + c*wsc + n*wsn] += sum_m a_s(m,c) dz(zs*m + tap - zpad, n)
+struct WgStream {
+  int nsrc; const float* a_src[2]; const float* a_p0[2]; const float* a_p2[2];     // a = relu(p0*src + p2) (p0 null: src)
+  int a_L[2], a_ld[2], a_add[2], a_C[2], wbase[2];                                  // source row l = q + a_add
+  const float* z_src; const float* z_src2; const float* z_p0; const float* z_p1; const float* z_p2;   // dz = p0*src + p1*src2 + p2
+  int z_L, z_ld, N, ntap, zs, zpad;
+  float* dW; int wsc, wsn, wtap; float* db;
+  int BT, Lq;
+};
+int launch_wgrad_stream(const WgStream& w, cudaStream_t st);     // 0 launched, 1 not eligible
+
 // ---- BatchNorm bookkeeping -----------------------------------------------------
 struct BnFwdParams {
   const double* stats; double count; int C; int training;

@@ -22,7 +22,8 @@ namespace {
 using namespace tc;
 
 constexpr int KROWS = 32;                       // rows per k-block
-constexpr int NT = 32 * 17;                     // 1 MMA warp + 8 loader warps (activation side) + 16 (dz side)
+constexpr int NT = 32 * 20;                     // 4-warp MMA group (warp 0 issues) + 8 loader warps per side
+constexpr int REG_MMA = 32, REG_LOAD = 112;     // setmaxnreg budgets: 4*32*32 + 16*32*112 = 61440 = 640 threads x 96
 constexpr int PW = 128;                         // P tile width (channels)
 constexpr int P_TILE = KROWS * PW * 4;          // 16 KB per hi (or lo)
 constexpr int NSTAGE = 3;
@@ -44,60 +45,81 @@ struct WMisc { uint64_t full[NSTAGE], empty[NSTAGE], done; uint32_t tmem_base; }
 
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldg((const float4*)p); }
 
-// Loader of one side.  W = tile width in channels (128 for P, QW for Q); NTHR threads cooperate,
-// each handling at most MAXPASS rows of the 32-row k-block; NS-1 k-blocks are kept in flight.
-template <int NTHR, int MAXPASS, int NS, bool HAS2>
+// Loader of one side.  W = tile width in channels (128 for P, QW for Q); NTHR threads cooperate.
+// The unit of the software pipeline is UR rows (32 = a whole k-block, or 16 = half of one, which
+// halves the registers a two-tensor side needs for the same number of bytes in flight); NS-1 units
+// are kept in flight.  Rows are decoded incrementally (one division per thread and pass at the
+// start, none per unit); the tf32 split is the truncating one (hi = x & ~0x1fff, lo = x - hi).
+template <int NTHR, int UR, int MAXPASS, int NS, bool HAS2>
 __device__ __forceinline__ void side_loader(const TcWParams& P, const TcWJob& J, const Side& S, int c0, int W, int lt, int lane,
                                             uint8_t* ring, int side_off, WMisc& mi, unsigned kb0, unsigned kb1,
                                             bool want_db) {
+  constexpr int UPK = KROWS / UR;                // units per k-block
   const int cpr = W >> 2;                        // 16-byte chunks per row
   const int cidx = lt % cpr, rsub = lt / cpr, rstep = NTHR / cpr;
-  const int npass = rstep >= KROWS ? 1 : KROWS / rstep;
-  const bool t_ok = rsub < KROWS;                // (W = 32 with 512 threads: half of them idle)
+  const int npass = rstep >= UR ? 1 : UR / rstep;
+  const bool t_ok = rsub < UR;
   const int mb = cidx >> 3, ch = cidx & 7, NB = W >> 5;
   const int c = c0 + cidx * 4;                   // channel inside the tensor (before coff)
   const bool c_ok = c < S.C && t_ok;
   float4 p0 = make_float4(1, 1, 1, 1), p1 = make_float4(0, 0, 0, 0), p2 = p1;
-  if (S.p0 && c_ok) {
+  const bool affine = S.p0 != nullptr;
+  if (affine && c_ok) {
     p0 = ld4(S.p0 + S.coff + c); p2 = ld4(S.p2 + S.coff + c);
-    if (S.p1) p1 = ld4(S.p1 + S.coff + c);
+    if (HAS2 && S.p1) p1 = ld4(S.p1 + S.coff + c);
   }
+  const float fl = S.relu ? 0.f : -__int_as_float(0x7f800000);
   float bs[4] = {0.f, 0.f, 0.f, 0.f};
   const unsigned Lq = (unsigned)P.Lq, Mrows = (unsigned)P.BT * Lq;
+  const unsigned dq = UR % Lq, dbt = UR / Lq;                  // row advance per unit, as (frames, rows)
+  const float* src = S.src + S.coff + c;
+  const float* src2 = (HAS2 && S.src2) ? S.src2 + S.coff + c : nullptr;
+  const int mul = S.mul, add = S.add, SL = S.L, ld = S.ld;
+  // issue-side row cursor of every pass: row m = unit*UR + rsub + rstep*i = bt*Lq + q
+  unsigned rm0 = kb0 * KROWS + rsub, rbt[MAXPASS], rq[MAXPASS];
+#pragma unroll
+  for (int i = 0; i < MAXPASS; ++i) {
+    const unsigned m = rm0 + rstep * i;
+    rbt[i] = m / Lq; rq[i] = m - rbt[i] * Lq;
+  }
+  // shared-memory offset of (row rsub, this thread's chunk); pass i adds i*rstep rows = i*(rstep/4) atoms
+  const uint32_t st_off = (uint32_t)((rsub >> 2) * NB + mb) * 512 + (rsub & 3) * 128 + ((((ch >> 1) ^ (rsub & 3)) << 5) | ((ch & 1) << 4));
+  const uint32_t st_step = (uint32_t)(rstep >> 2) * NB * 512, st_unit = (uint32_t)(UR >> 2) * NB * 512;
   float4 va[NS][MAXPASS], vb[HAS2 ? NS : 1][HAS2 ? MAXPASS : 1];
   unsigned msk[NS];
-  auto issue = [&](unsigned kb, float4 (&a)[MAXPASS], float4 (&b)[HAS2 ? MAXPASS : 1], unsigned& mk) {
+  auto issue = [&](float4 (&a)[MAXPASS], float4 (&b)[HAS2 ? MAXPASS : 1], unsigned& mk) {
     mk = 0;
 #pragma unroll
     for (int i = 0; i < MAXPASS; ++i) {
       if (i < npass) {
-        const unsigned m = kb * KROWS + rsub + rstep * i;
-        if (m < Mrows && c_ok) {
-          const unsigned bt = m / Lq, q = m - bt * Lq;
-          const int l = (int)q * S.mul + S.add;
-          if (l >= 0 && l < S.L) {
-            const unsigned off = (bt * S.L + l) * S.ld + S.coff + c;
-            a[i] = ld4(S.src + off);
-            if (HAS2 && S.src2) b[HAS2 ? i : 0] = ld4(S.src2 + off);
-            mk |= 1u << i;
-          }
+        const int l = (int)rq[i] * mul + add;
+        if (c_ok && rm0 + rstep * i < Mrows && (unsigned)l < (unsigned)SL) {
+          const unsigned off = (rbt[i] * SL + l) * ld;
+          a[i] = ld4(src + off);
+          if (HAS2) b[HAS2 ? i : 0] = src2 ? ld4(src2 + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+          mk |= 1u << i;
         }
+        rq[i] += dq; rbt[i] += dbt;
+        if (rq[i] >= Lq) { rq[i] -= Lq; ++rbt[i]; }
       }
     }
+    rm0 += UR;
   };
   int st = 0;
   uint32_t ph = 0;
+  const unsigned u1 = (kb1 - kb0) * UPK;        // units of this CTA
 #pragma unroll
   for (int u = 0; u < NS - 1; ++u)
-    if (kb0 + u < kb1) issue(kb0 + u, va[u], vb[HAS2 ? u : 0], msk[u]);
-  for (unsigned kb = kb0; kb < kb1; kb += NS) {
+    if ((unsigned)u < u1) issue(va[u], vb[HAS2 ? u : 0], msk[u]);
+  for (unsigned ub = 0; ub < u1; ub += NS) {
 #pragma unroll
     for (int u = 0; u < NS; ++u) {
-      const unsigned k = kb + u;
-      if (k < kb1) {
-        if (k + NS - 1 < kb1) issue(k + NS - 1, va[(u + NS - 1) % NS], vb[HAS2 ? (u + NS - 1) % NS : 0], msk[(u + NS - 1) % NS]);
-        mbar_wait(&mi.empty[st], ph ^ 1);
-        uint8_t* base = ring + st * (4 * P_TILE) + side_off;     // stage = [P hi | P lo | Q hi | Q lo], 16 KB slots
+      const unsigned k = ub + u;
+      if (k < u1) {
+        if (k + NS - 1 < u1) issue(va[(u + NS - 1) % NS], vb[HAS2 ? (u + NS - 1) % NS : 0], msk[(u + NS - 1) % NS]);
+        const unsigned sub = UPK == 1 ? 0u : (k & (UPK - 1));
+        if (sub == 0) mbar_wait(&mi.empty[st], ph ^ 1);
+        uint8_t* base = ring + st * (4 * P_TILE) + side_off + st_off + sub * st_unit;   // stage = [P hi | P lo | Q hi | Q lo]
         if (t_ok) {
 #pragma unroll
           for (int i = 0; i < MAXPASS; ++i) {
@@ -105,30 +127,34 @@ __device__ __forceinline__ void side_loader(const TcWParams& P, const TcWJob& J,
               float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
               if (msk[u] & (1u << i)) {
                 v = va[u][i];
-                if (S.p0) {
-                  v.x = p0.x * v.x + p2.x; v.y = p0.y * v.y + p2.y; v.z = p0.z * v.z + p2.z; v.w = p0.w * v.w + p2.w;
-                  if (HAS2 && S.p1) {
+                if (affine) {
+                  if (HAS2) {
                     const float4 z = vb[HAS2 ? u : 0][HAS2 ? i : 0];
-                    v.x += p1.x * z.x; v.y += p1.y * z.y; v.z += p1.z * z.z; v.w += p1.w * z.w;
+                    v.x = fmaf(p1.x, z.x, fmaf(p0.x, v.x, p2.x)); v.y = fmaf(p1.y, z.y, fmaf(p0.y, v.y, p2.y));
+                    v.z = fmaf(p1.z, z.z, fmaf(p0.z, v.z, p2.z)); v.w = fmaf(p1.w, z.w, fmaf(p0.w, v.w, p2.w));
+                  } else {
+                    v.x = fmaf(p0.x, v.x, p2.x); v.y = fmaf(p0.y, v.y, p2.y); v.z = fmaf(p0.z, v.z, p2.z); v.w = fmaf(p0.w, v.w, p2.w);
                   }
-                  if (S.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                  v.x = fmaxf(v.x, fl); v.y = fmaxf(v.y, fl); v.z = fmaxf(v.z, fl); v.w = fmaxf(v.w, fl);
                 }
                 bs[0] += v.x; bs[1] += v.y; bs[2] += v.z; bs[3] += v.w;
               }
               uint4 hi, lo;
-              split_tf32(v, hi, lo);
-              const int r = rsub + rstep * i;
-              // atom = 4 rows x 128 B; 32-byte chunk index (ch>>1) XOR row-in-atom (Swizzle<2,5,2>)
-              const uint32_t off = ((r >> 2) * NB + mb) * 512 + (r & 3) * 128 + ((((ch >> 1) ^ (r & 3)) << 5) | ((ch & 1) << 4));
-              *(uint4*)(base + off) = hi;
-              *(uint4*)(base + P_TILE + off) = lo;
+              hi.x = __float_as_uint(v.x) & 0xffffe000u; hi.y = __float_as_uint(v.y) & 0xffffe000u;
+              hi.z = __float_as_uint(v.z) & 0xffffe000u; hi.w = __float_as_uint(v.w) & 0xffffe000u;
+              lo.x = __float_as_uint(v.x - __uint_as_float(hi.x)); lo.y = __float_as_uint(v.y - __uint_as_float(hi.y));
+              lo.z = __float_as_uint(v.z - __uint_as_float(hi.z)); lo.w = __float_as_uint(v.w - __uint_as_float(hi.w));
+              *(uint4*)(base + i * st_step) = hi;
+              *(uint4*)(base + P_TILE + i * st_step) = lo;
             }
           }
         }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&mi.full[st]);
-        if (++st == NSTAGE) { st = 0; ph ^= 1; }
+        if (sub == UPK - 1) {
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&mi.full[st]);
+          if (++st == NSTAGE) { st = 0; ph ^= 1; }
+        }
       }
     }
   }
@@ -170,8 +196,9 @@ __global__ void __launch_bounds__(NT, 1) tc_wgrad_kernel(const __grid_constant__
   tc_fence_after();
   const uint32_t tmem = mi.tmem_base;
 
-  if (warp == 0) {
-    if (lane == 0 && kb0 < kb1) {
+  if (warp < 4) {
+    reg_dec<REG_MMA>();
+    if (tid == 0 && kb0 < kb1) {
       const uint32_t idesc = idesc_tf32(128, QW, 1, 1);
       // MN-major SW128_32B: LBO = 512 B between 32-channel blocks, SBO = distance between 4-row groups
       const uint64_t dP = ((smem_desc_sw128_32b(0, 512, (PW / 32) * 512) >> 16) << 16);
@@ -197,36 +224,37 @@ __global__ void __launch_bounds__(NT, 1) tc_wgrad_kernel(const __grid_constant__
       mma_commit(&mi.done);
     }
   } else {
-    // the dz side (two tensors when a BN sits behind the layer) gets the 16-warp group
+    // warps 4-11 load the activation side, warps 12-19 the dz side (two tensors when a BN sits behind the layer)
+    reg_inc<REG_LOAD>();
     const bool p_is_dz = J.db_on_p != 0;
-    const bool big = warp > 8;                                   // warps 9..16
+    const bool big = warp >= 12;
     const bool do_p = (big == p_is_dz);
     const Side& S = do_p ? J.P : J.Q;
     const int W = do_p ? PW : QW, soff = do_p ? 0 : 2 * P_TILE;
     const bool wdb = J.db && (do_p ? (J.db_on_p && qt == 0) : (!J.db_on_p && pt == 0));
     const int c0 = do_p ? pc0 : qc0;
-    if (big) side_loader<256, 4, 2, true>(P, J, S, c0, W, tid - 288, lane, ring, soff, mi, kb0, kb1, wdb);
-    else side_loader<256, 4, 3, false>(P, J, S, c0, W, tid - 32, lane, ring, soff, mi, kb0, kb1, wdb);
-  }
-
-  // ---- epilogue: warps 1-4 drain the accumulator and add it to dW ---------------------
-  if (warp >= 1 && warp <= 4 && kb0 < kb1) {
-    mbar_wait(&mi.done, 0);
-    tc_fence_after();
-    const int lgrp = warp & 3;
-    const int p = pc0 + lgrp * 32 + lane;
-    for (int cc = 0; cc * 32 < QW; ++cc) {
-      uint32_t v[32];
-      tmem_ld32(tmem + ((uint32_t)(lgrp * 32) << 16) + cc * 32, v);
-      if (p < J.P.C) {
+    if (big) side_loader<256, 16, 2, 3, true>(P, J, S, c0, W, tid - 384, lane, ring, soff, mi, kb0, kb1, wdb);
+    else side_loader<256, 32, 4, 3, false>(P, J, S, c0, W, tid - 128, lane, ring, soff, mi, kb0, kb1, wdb);
+    // ---- epilogue: warps 4-7 drain the accumulator and add it to dW ---------------------
+    if (warp >= 4 && warp <= 7 && kb0 < kb1) {
+      mbar_wait(&mi.done, 0);
+      tc_fence_after();
+      const int lgrp = warp & 3;
+      const int p = pc0 + lgrp * 32 + lane;
+      for (int cc = 0; cc * 32 < QW; ++cc) {
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(lgrp * 32) << 16) + cc * 32, v);
+        if (p < J.P.C) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int q = qc0 + cc * 32 + j;
-          if (q < J.Q.C) atomicAdd(J.dW + J.wbase + (long)p * J.sp + (long)q * J.sq, __uint_as_float(v[j]));
+          for (int j = 0; j < 32; ++j) {
+            const int q = qc0 + cc * 32 + j;
+            if (q < J.Q.C) atomicAdd(J.dW + J.wbase + (long)p * J.sp + (long)q * J.sq, __uint_as_float(v[j]));
+          }
         }
       }
     }
   }
+
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {

@@ -1,0 +1,425 @@
+// Streaming tensor-core weight gradient (tcgen05 / TMEM, 3xTF32) for the conv layers:
+//
+//   dW[s][c][j][n] += sum_m  a_s(m, c) * dz(zs*m + j - zpad, n)
+//
+// for up to two activation sources s (the two halves of a skip concat) and up to five taps
+// j (a transposed conv), all in ONE pass over the rows: every operand row is read from HBM
+// exactly once per 16-row unit (plus the k-s halo rows of a transposed conv).
+//
+// A weight gradient is a pure streaming reduction (M ~ 10^6 rows, a 64..320 x 64..192 result),
+// so the kernel is organised around keeping ~100 KB of loads in flight per SM:
+//   warp 1       producer: per 16-row unit, one cp.async.bulk (TMA, no tensor map) per operand
+//                (the rows of a unit that exist are one contiguous run in memory) into a ring of
+//                RAW fp32 stages, completion on an mbarrier (expect_tx); rows that fall outside
+//                their frame are skipped and flagged
+//   warps 4-19   transform: raw stage -> BN/ReLU (activations) or BN-backward affine (dz, applied
+//                ONCE per row, then scattered to every tap slot it feeds) -> truncating tf32
+//                split -> MN-major SWIZZLE_128B_BASE32B operand tiles (2 stages)
+//   warp 0       MMA issuer: per unit 2 k-steps x 3 products of tcgen05.mma.kind::tf32 into ONE
+//                fp32 accumulator (P channels x Q columns) that lives in TMEM for the CTA's
+//                whole row range; warps 4-7 add it to dW with atomics at the end.
+// P (the MMA M side, 64 or 128 channels) is the activation tile when there are several taps and
+// the dz tile when there are two sources; Q (up to 384 columns) is the other one.
+#include <algorithm>
+#include <map>
+#include <string>
+#include <string.h>
+#include "net_kernels.cuh"
+#include "tc_common.cuh"
+
+namespace tru {
+namespace {
+using namespace tc;
+
+constexpr int UR = 16;                          // rows per unit (2 k-steps of 8)
+constexpr int TRW = 16;                         // transform warps
+constexpr int NTR = 32 * TRW;
+constexpr int NT = 32 * (4 + TRW);
+constexpr int MAXRAW = 8;
+constexpr int IA = 3, IZ = 4;                   // per-thread item slots (activation / dz float4s per unit)
+
+struct WgK {
+  int nsrc; const float* a_src[2]; const float* a_p0[2]; const float* a_p2[2];
+  int a_L[2], a_ld[2], a_add[2], a_C[2], a_c0[2], Ca;
+  const float* z_src; const float* z_src2; const float* z_p0; const float* z_p1; const float* z_p2;
+  int z_L, z_ld, N, ntap, zs, zpad, NZ;
+  int p_is_z, PWt, QWt, Mmma, Pvalid, Qvalid, tmem_cols;
+  uint32_t op_stage, p_tile, q_tile, raw_off, raw_stage, raw_a[2], raw_dy, raw_z, coef_off, misc_off;
+  int nraw;
+  float* dW; int wbase[2], wsc, wsn, wtap; float* db;
+  int BT, Lq; unsigned units_total, units_per_cta;
+};
+
+struct StageFlags { uint32_t amask[2]; uint32_t zmask[2]; };
+struct WMisc2 {
+  uint64_t raw_full[MAXRAW], raw_empty[MAXRAW], op_full[2], op_empty[2], done;
+  StageFlags flags[MAXRAW];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// byte offset of (k-row r, channel c) in an MN-major SWIZZLE_128B_BASE32B tile of NB 32-channel blocks
+__device__ __forceinline__ uint32_t tile_off(int r, int c, int NB) {
+  return (uint32_t)((r >> 2) * NB + (c >> 5)) * 512u + (uint32_t)(r & 3) * 128u +
+         ((((uint32_t)(c >> 3) & 3u) ^ (uint32_t)(r & 3)) << 5) + (uint32_t)(c & 7) * 4u;
+}
+__device__ __forceinline__ void split_store(uint8_t* hi_ptr, uint32_t lo_delta, const float4& v) {
+  uint4 hi, lo;
+  hi.x = __float_as_uint(v.x) & 0xffffe000u; hi.y = __float_as_uint(v.y) & 0xffffe000u;
+  hi.z = __float_as_uint(v.z) & 0xffffe000u; hi.w = __float_as_uint(v.w) & 0xffffe000u;
+  lo.x = __float_as_uint(v.x - __uint_as_float(hi.x)); lo.y = __float_as_uint(v.y - __uint_as_float(hi.y));
+  lo.z = __float_as_uint(v.z - __uint_as_float(hi.z)); lo.w = __float_as_uint(v.w - __uint_as_float(hi.w));
+  *(uint4*)hi_ptr = hi;
+  *(uint4*)(hi_ptr + lo_delta) = lo;
+}
+
+__global__ void __launch_bounds__(NT, 1) tc_wgrad_stream_kernel(const __grid_constant__ WgK K) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* ops = smem;                                   // 2 x [P hi | P lo | Q hi | Q lo]
+  uint8_t* raws = smem + K.raw_off;                      // nraw x [A rows | dY rows | Z rows]
+  float* coef = (float*)(smem + K.coef_off);             // A: p0[Ca] p2[Ca] floor[Ca]; Z: q0[N] q1[N] q2[N]
+  WMisc2& mi = *(WMisc2*)(smem + K.misc_off);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const unsigned u0 = min(K.units_total, blockIdx.x * K.units_per_cta), u1 = min(K.units_total, u0 + K.units_per_cta);
+  const unsigned nun = u1 - u0;
+  const int nraw = K.nraw;
+
+  // ---- setup: coefficient tables, barriers, TMEM -----------------------------------------
+  for (int i = tid; i < K.Ca; i += NT) {
+    const int s = (K.nsrc == 2 && i >= K.a_c0[1]) ? 1 : 0, c = i - K.a_c0[s];
+    const bool aff = K.a_p0[s] != nullptr;
+    coef[i] = aff ? __ldg(K.a_p0[s] + c) : 1.f;
+    coef[K.Ca + i] = aff ? __ldg(K.a_p2[s] + c) : 0.f;
+    coef[2 * K.Ca + i] = aff ? 0.f : -__int_as_float(0x7f800000);     // ReLU only behind a BN (trunet.cu: fwd_seg)
+  }
+  float* zc = coef + 3 * K.Ca;
+  for (int i = tid; i < K.N; i += NT) {
+    zc[i] = K.z_p0 ? __ldg(K.z_p0 + i) : 1.f;
+    zc[K.N + i] = (K.z_p0 && K.z_p1) ? __ldg(K.z_p1 + i) : 0.f;
+    zc[2 * K.N + i] = K.z_p0 ? __ldg(K.z_p2 + i) : 0.f;
+  }
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int s = 0; s < nraw; ++s) { mbar_init(&mi.raw_full[s], 1); mbar_init(&mi.raw_empty[s], TRW); }
+      for (int s = 0; s < 2; ++s) { mbar_init(&mi.op_full[s], TRW); mbar_init(&mi.op_empty[s], 1); }
+      mbar_init(&mi.done, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(&mi.tmem_base, K.tmem_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = mi.tmem_base;
+  const int NBp = K.PWt >> 5, NBq = K.QWt >> 5;
+
+  if (warp < 4) {
+  reg_dec<48>();                               // 4*32*48 + 16*32*104 = 59392 <= 640 threads x 96 registers
+  if (warp == 0) {
+    // ================================ MMA issuer ==================================
+    if (lane == 0 && nun > 0) {
+      const uint64_t dP = ((smem_desc_sw128_32b(0, 512, NBp * 512) >> 16) << 16);
+      const uint64_t dQ = ((smem_desc_sw128_32b(0, 512, NBq * 512) >> 16) << 16);
+      const int nsplit = (K.QWt + 255) / 256, per = (NBq + nsplit - 1) / nsplit;     // Q blocks per MMA
+      const uint32_t obase = smem_u32(ops) >> 4;
+      for (unsigned u = 0; u < nun; ++u) {
+        const int os = u & 1;
+        mbar_wait(&mi.op_full[os], (u >> 1) & 1);
+        tc_fence_after();
+        const uint32_t p_hi = obase + os * (K.op_stage >> 4), p_lo = p_hi + (K.p_tile >> 4);
+        const uint32_t q_hi = p_lo + (K.p_tile >> 4), q_lo = q_hi + (K.q_tile >> 4);
+        for (int sp = 0; sp < nsplit; ++sp) {
+          const int b0 = sp * per, nb = min(per, NBq - b0);
+          const uint32_t idesc = idesc_tf32(K.Mmma, nb * 32, 1, 1);
+          const uint32_t d = tmem + b0 * 32;
+#pragma unroll
+          for (int g = 0; g < UR / 8; ++g) {                    // k-steps of 8 rows = 2 atoms
+            const uint32_t po = g * NBp * 64, qo = g * NBq * 64 + b0 * 32;     // (bytes >> 4)
+            mma_tf32(d, dP | (p_lo + po), dQ | (q_hi + qo), idesc, (u | g) != 0);
+            mma_tf32(d, dP | (p_hi + po), dQ | (q_lo + qo), idesc, 1);
+            mma_tf32(d, dP | (p_hi + po), dQ | (q_hi + qo), idesc, 1);
+          }
+        }
+        mma_commit(&mi.op_empty[os]);
+      }
+      mma_commit(&mi.done);
+    }
+  } else if (warp == 1) {
+    // ================================ producer (TMA bulk copies) =====================
+    // Rows of a unit that exist are one contiguous run in their frame and (ld == channels) in memory,
+    // so each operand needs ONE bulk copy per unit: lane 0/1 = activation sources, lane 2 = dY, lane 3 = Z.
+    const unsigned Lq = (unsigned)K.Lq;
+    int rs = 0;
+    uint32_t ph = 0;
+    for (unsigned u = 0; u < nun; ++u) {
+      const unsigned m0 = (u0 + u) * UR, bt = m0 / Lq, q0 = m0 - bt * Lq;
+      int lo = 0, hi = 0;                       // valid run [lo, hi) of this lane's operand, in raw-stage rows
+      const float* src = nullptr;
+      uint32_t dst = 0, rowb = 0;
+      if (lane < K.nsrc) {
+        const int l0 = (int)q0 + K.a_add[lane];
+        lo = max(0, -l0); hi = min(UR, K.a_L[lane] - l0);
+        rowb = (uint32_t)K.a_C[lane] * 4u;
+        src = K.a_src[lane] + ((size_t)bt * K.a_L[lane] + (l0 + lo)) * K.a_C[lane];
+        dst = K.raw_a[lane] + (uint32_t)lo * rowb;
+      } else if (lane == 2 || (lane == 3 && K.z_src2)) {
+        const int r0 = K.zs * (int)q0 - K.zpad;
+        lo = max(0, -r0); hi = min(K.NZ, K.z_L - r0);
+        rowb = (uint32_t)K.N * 4u;
+        src = (lane == 2 ? K.z_src : K.z_src2) + ((size_t)bt * K.z_L + (r0 + lo)) * K.N;
+        dst = (lane == 2 ? K.raw_dy : K.raw_z) + (uint32_t)lo * rowb;
+      }
+      const bool has = hi > lo;
+      uint32_t bytes = has ? (uint32_t)(hi - lo) * rowb : 0u;
+      const uint32_t mybytes = bytes;
+      bytes += __shfl_xor_sync(0xffffffffu, bytes, 1);
+      bytes += __shfl_xor_sync(0xffffffffu, bytes, 2);
+      const unsigned long long run = has ? (((hi >= 64 ? ~0ull : (1ull << hi) - 1ull)) & ~((1ull << lo) - 1ull)) : 0ull;
+      const unsigned long long r0m = __shfl_sync(0xffffffffu, run, 0), r1m = __shfl_sync(0xffffffffu, run, 1), r2m = __shfl_sync(0xffffffffu, run, 2);
+      mbar_wait(&mi.raw_empty[rs], ph ^ 1);
+      uint8_t* st = raws + (size_t)rs * K.raw_stage;
+      if (lane == 0) {
+        mi.flags[rs].amask[0] = (uint32_t)r0m; mi.flags[rs].amask[1] = (uint32_t)r1m;
+        mi.flags[rs].zmask[0] = (uint32_t)r2m; mi.flags[rs].zmask[1] = (uint32_t)(r2m >> 32);
+        mbar_arrive_expect_tx(&mi.raw_full[rs], bytes);
+      }
+      __syncwarp();
+      if (has) bulk_g2s(st + dst, src, mybytes, &mi.raw_full[rs]);
+      if (++rs == nraw) { rs = 0; ph ^= 1; }
+    }
+  }
+  } else {
+    // ================================ transform =======================================
+    reg_inc<104>();
+    const int tt = tid - 128;
+    const int NBa = K.Ca >> 5, NBz = K.N >> 5;
+    // Per-thread item slots, fully decoded once: raw-stage byte offset, operand-stage byte offset(s), channel and
+    // validity bit.  Lane = (row & 3) * 8 + 16-byte chunk, so a quarter warp reads 128 contiguous bytes of a raw
+    // row and writes 128 bytes of one swizzle atom (conflict-free both ways).
+    const uint32_t a_tile = K.p_is_z ? 2 * K.p_tile : 0u, a_lo = K.p_is_z ? K.q_tile : K.p_tile;
+    const uint32_t z_tile = K.p_is_z ? 0u : 2 * K.p_tile, z_lo = K.p_is_z ? K.p_tile : K.q_tile;
+    const int NBat = K.p_is_z ? NBq : NBp, NBzt = K.p_is_z ? NBp : NBq;
+    constexpr uint32_t NONE = 0xffffffffu;
+    uint32_t a_raw[IA], a_dst[IA], a_cb[IA];          // a_cb: channel | row << 16 | source << 24
+    uint32_t z_raw[IZ], z_cb[IZ], z_dst[IZ][5];       // z_cb: channel | t << 16
+    const int nA = UR * (K.Ca >> 2), nZ = ((K.NZ + 3) & ~3) * (K.N >> 2);
+#pragma unroll
+    for (int k = 0; k < IA; ++k) {
+      const int it = tt + k * NTR;
+      a_raw[k] = NONE; a_dst[k] = 0; a_cb[k] = 0;
+      if (it < nA) {
+        const int blk = (it >> 5) % NBa, rg = (it >> 5) / NBa, r = rg * 4 + ((it >> 3) & 3), c = blk * 32 + (it & 7) * 4;
+        const int s = (K.nsrc == 2 && c >= K.a_c0[1]) ? 1 : 0;
+        a_raw[k] = K.raw_a[s] + (uint32_t)(r * K.a_C[s] + c - K.a_c0[s]) * 4u;
+        a_dst[k] = a_tile + tile_off(r, c, NBat);
+        a_cb[k] = (uint32_t)c | ((uint32_t)r << 16) | ((uint32_t)s << 24);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < IZ; ++k) {
+      const int it = tt + k * NTR;
+      z_raw[k] = NONE; z_cb[k] = 0;
+#pragma unroll
+      for (int j = 0; j < 5; ++j) z_dst[k][j] = NONE;
+      if (it < nZ) {
+        const int blk = (it >> 5) % NBz, rg = (it >> 5) / NBz, t = rg * 4 + ((it >> 3) & 3), c = blk * 32 + (it & 7) * 4;
+        if (t < K.NZ) {
+          z_raw[k] = (uint32_t)(t * K.N + c) * 4u;
+          z_cb[k] = (uint32_t)c | ((uint32_t)t << 16);
+          // row t of the unit's dz window feeds tap j at unit row (t - j) / zs
+#pragma unroll
+          for (int j = 0; j < 5; ++j) {
+            const int d = t - j;
+            if (j < K.ntap && d >= 0 && d % K.zs == 0 && d / K.zs < UR) z_dst[k][j] = z_tile + tile_off(d / K.zs, j * K.N + c, NBzt);
+          }
+        }
+      }
+    }
+    const bool has_z2 = K.z_src2 != nullptr;
+    float bs[4] = {0.f, 0.f, 0.f, 0.f};
+    int rs = 0;
+    uint32_t ph = 0;
+    for (unsigned u = 0; u < nun; ++u) {
+      const int os = u & 1;
+      mbar_wait(&mi.raw_full[rs], ph);
+      const uint32_t am0 = mi.flags[rs].amask[0], am1 = mi.flags[rs].amask[1];
+      const uint32_t zm0 = mi.flags[rs].zmask[0], zm1 = mi.flags[rs].zmask[1];
+      const uint8_t* st = raws + (size_t)rs * K.raw_stage;
+      // raw loads first (independent of the operand stage), then wait for the stage to be free
+      float4 xa[IA], xy[IZ], xz[IZ];
+#pragma unroll
+      for (int k = 0; k < IA; ++k)
+        if (a_raw[k] != NONE) xa[k] = *(const float4*)(st + a_raw[k]);
+#pragma unroll
+      for (int k = 0; k < IZ; ++k)
+        if (z_raw[k] != NONE) {
+          xy[k] = *(const float4*)(st + K.raw_dy + z_raw[k]);
+          xz[k] = has_z2 ? *(const float4*)(st + K.raw_z + z_raw[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      mbar_wait(&mi.op_empty[os], ((u >> 1) & 1) ^ 1);
+      uint8_t* op = ops + (size_t)os * K.op_stage;
+#pragma unroll
+      for (int k = 0; k < IA; ++k) {
+        if (a_raw[k] != NONE) {
+          const int c = a_cb[k] & 0xffff, r = (a_cb[k] >> 16) & 0xff;
+          const bool ok = (((a_cb[k] >> 24) ? am1 : am0) >> r) & 1u;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok) {
+            const float4 p0 = *(const float4*)(coef + c), p2 = *(const float4*)(coef + K.Ca + c), fl = *(const float4*)(coef + 2 * K.Ca + c);
+            v.x = fmaxf(fmaf(p0.x, xa[k].x, p2.x), fl.x); v.y = fmaxf(fmaf(p0.y, xa[k].y, p2.y), fl.y);
+            v.z = fmaxf(fmaf(p0.z, xa[k].z, p2.z), fl.z); v.w = fmaxf(fmaf(p0.w, xa[k].w, p2.w), fl.w);
+          }
+          split_store(op + a_dst[k], a_lo, v);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < IZ; ++k) {
+        if (z_raw[k] != NONE) {
+          const int c = z_cb[k] & 0xffff, t = z_cb[k] >> 16;
+          const bool ok = ((t < 32 ? zm0 >> t : zm1 >> (t - 32)) & 1u) != 0;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok) {
+            const float4 q0 = *(const float4*)(zc + c), q1 = *(const float4*)(zc + K.N + c), q2 = *(const float4*)(zc + 2 * K.N + c);
+            v.x = fmaf(q1.x, xz[k].x, fmaf(q0.x, xy[k].x, q2.x)); v.y = fmaf(q1.y, xz[k].y, fmaf(q0.y, xy[k].y, q2.y));
+            v.z = fmaf(q1.z, xz[k].z, fmaf(q0.z, xy[k].z, q2.z)); v.w = fmaf(q1.w, xz[k].w, fmaf(q0.w, xy[k].w, q2.w));
+            if (k == 0) { bs[0] += v.x; bs[1] += v.y; bs[2] += v.z; bs[3] += v.w; }
+          }
+          uint4 hi, lo;
+          hi.x = __float_as_uint(v.x) & 0xffffe000u; hi.y = __float_as_uint(v.y) & 0xffffe000u;
+          hi.z = __float_as_uint(v.z) & 0xffffe000u; hi.w = __float_as_uint(v.w) & 0xffffe000u;
+          lo.x = __float_as_uint(v.x - __uint_as_float(hi.x)); lo.y = __float_as_uint(v.y - __uint_as_float(hi.y));
+          lo.z = __float_as_uint(v.z - __uint_as_float(hi.z)); lo.w = __float_as_uint(v.w - __uint_as_float(hi.w));
+#pragma unroll
+          for (int j = 0; j < 5; ++j)
+            if (z_dst[k][j] != NONE) { *(uint4*)(op + z_dst[k][j]) = hi; *(uint4*)(op + z_dst[k][j] + z_lo) = lo; }
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&mi.op_full[os]); mbar_arrive(&mi.raw_empty[rs]); }
+      if (++rs == nraw) { rs = 0; ph ^= 1; }
+    }
+    if (K.db && z_raw[0] != NONE) {                      // (eligibility: one dz item per thread, one tap)
+      const int c = z_cb[0] & 0xffff;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) atomicAdd(K.db + c + e, bs[e]);
+    }
+    // ---- epilogue: warps 4-7 add the accumulator to dW -----------------------------------
+    if (warp <= 7 && nun > 0) {
+      mbar_wait(&mi.done, 0);
+      tc_fence_after();
+      const int lg = warp & 3;
+      const int p = K.Mmma == 128 ? lg * 32 + lane : lg * 16 + lane;
+      const bool pok = (K.Mmma == 128 || lane < 16) && p < K.Pvalid;
+      for (int cb = 0; cb < NBq; ++cb) {
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(lg * 32) << 16) + cb * 32, v);
+        if (pok) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int q = cb * 32 + j;
+            if (q < K.Qvalid) {
+              const int acol = K.p_is_z ? q : p, zcol = K.p_is_z ? p : q;
+              const int s = (K.nsrc == 2 && acol >= K.a_c0[1]) ? 1 : 0, c = acol - K.a_c0[s];
+              const int tap = zcol / K.N, n = zcol - tap * K.N;
+              atomicAdd(K.dW + K.wbase[s] + (long)tap * K.wtap + (long)c * K.wsc + (long)n * K.wsn, __uint_as_float(v[j]));
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, K.tmem_cols);
+  }
+}
+
+constexpr size_t SMEM_MAX = 227 * 1024;
+
+}  // namespace
+
+// returns TRU_OK if launched, 1 if the job does not fit this kernel (caller uses the per-job kernels)
+int launch_wgrad_stream(const WgStream& w, cudaStream_t st) {
+  WgK K{};
+  if (w.nsrc < 1 || w.nsrc > 2 || w.ntap < 1 || w.ntap > 5 || w.Lq % UR != 0 || w.N % 32 != 0 || w.N > 128) return 1;
+  if (w.nsrc == 2 && w.ntap > 1) return 1;
+  int Ca = 0;
+  for (int s = 0; s < w.nsrc; ++s) {
+    if (w.a_C[s] % 32 != 0 || w.a_ld[s] % 4 != 0 || !aligned16(w.a_src[s])) return 1;
+    K.a_src[s] = w.a_src[s]; K.a_p0[s] = w.a_p0[s]; K.a_p2[s] = w.a_p2[s];
+    K.a_L[s] = w.a_L[s]; K.a_ld[s] = w.a_ld[s]; K.a_add[s] = w.a_add[s]; K.a_C[s] = w.a_C[s]; K.a_c0[s] = Ca;
+    K.wbase[s] = w.wbase[s];
+    Ca += w.a_C[s];
+  }
+  if (w.z_ld % 4 != 0 || !aligned16(w.z_src) || (w.z_src2 && !aligned16(w.z_src2))) return 1;
+  K.nsrc = w.nsrc; K.Ca = Ca;
+  K.z_src = w.z_src; K.z_src2 = w.z_p0 ? w.z_src2 : nullptr; K.z_p0 = w.z_p0; K.z_p1 = w.z_p1; K.z_p2 = w.z_p2;
+  K.z_L = w.z_L; K.z_ld = w.z_ld; K.N = w.N; K.ntap = w.ntap; K.zs = w.zs; K.zpad = w.zpad;
+  K.NZ = (UR - 1) * w.zs + w.ntap;
+  if (K.NZ > 64) return 1;
+  const int Zcols = w.ntap * w.N;
+  K.p_is_z = (w.ntap == 1 && (Ca > 128 || w.N > Ca)) ? 1 : 0;
+  const int Pc = K.p_is_z ? w.N : Ca, Qc = K.p_is_z ? Ca : Zcols;
+  if (Pc > 128 || Qc > 384) return 1;
+  K.Mmma = Pc <= 64 ? 64 : 128; K.PWt = K.Mmma; K.QWt = Qc; K.Pvalid = Pc; K.Qvalid = Qc;
+  K.tmem_cols = Qc <= 32 ? 32 : Qc <= 64 ? 64 : Qc <= 128 ? 128 : Qc <= 256 ? 256 : 512;
+  const int nA = UR * (Ca / 4), nZ = ((K.NZ + 3) & ~3) * (w.N / 4);
+  if (nA > IA * NTR || nZ > IZ * NTR) return 1;
+  if (w.db && (w.ntap != 1 || nZ > NTR)) return 1;
+  K.db = w.db;
+  K.p_tile = (uint32_t)UR * K.PWt * 4; K.q_tile = (uint32_t)UR * K.QWt * 4;
+  K.op_stage = (uint32_t)align_up(2 * K.p_tile + 2 * K.q_tile, 1024);
+  if (w.z_ld != w.N) return 1;                          // rows must be contiguous in memory (one bulk copy per run)
+  for (int s = 0; s < w.nsrc; ++s) if (w.a_ld[s] != w.a_C[s]) return 1;
+  K.raw_a[0] = 0; K.raw_a[1] = (uint32_t)UR * K.a_C[0] * 4;
+  K.raw_dy = (uint32_t)align_up((size_t)UR * Ca * 4, 128);
+  K.raw_z = K.raw_dy + (uint32_t)align_up((size_t)K.NZ * w.N * 4, 128);
+  K.raw_stage = (uint32_t)align_up(K.raw_z + (K.z_src2 ? (size_t)K.NZ * w.N * 4 : 0), 1024);
+  const size_t coefb = align_up((size_t)(3 * Ca + 3 * w.N) * 4, 128), miscb = align_up(sizeof(WMisc2), 128);
+  const size_t fixed = 1024 + 2 * (size_t)K.op_stage + coefb + miscb;
+  if (fixed + 2 * (size_t)K.raw_stage > SMEM_MAX) return 1;
+  K.nraw = (int)std::min<size_t>(MAXRAW, (SMEM_MAX - fixed) / K.raw_stage);
+  K.raw_off = 2 * K.op_stage;
+  K.coef_off = K.raw_off + (uint32_t)K.nraw * K.raw_stage;
+  K.misc_off = K.coef_off + (uint32_t)coefb;
+  const size_t smem = 1024 + K.misc_off + miscb;
+  K.dW = w.dW; K.wsc = w.wsc; K.wsn = w.wsn; K.wtap = w.wtap;
+  K.BT = w.BT; K.Lq = w.Lq;
+  const long M = (long)w.BT * w.Lq;
+  if ((double)w.BT * w.z_L * w.z_ld >= 1.8e19) return 1;
+  K.units_total = (unsigned)(M / UR);
+  const int grid = (int)std::min<long>(sm_count(), K.units_total);
+  K.units_per_cta = (K.units_total + grid - 1) / grid;
+  static bool attr = false;
+  if (!attr) {
+    TRU_CUDA(cudaFuncSetAttribute(tc_wgrad_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+    attr = true;
+  }
+  const char* nm = "wgrad_stream";
+  if (prof_enabled()) {
+    static std::map<std::string, const char*> names;
+    char buf[128];
+    snprintf(buf, sizeof(buf), "wgrad_stream:M=%ld,Ca=%d,N=%d,taps=%d,s=%d%s", M, Ca, w.N, w.ntap, w.zs, K.z_src2 ? ",bnload" : "");
+    auto it = names.find(buf);
+    if (it == names.end()) it = names.emplace(buf, strdup(buf)).first;
+    nm = it->second;
+  }
+  ProfScope prof(nm, 4.0 * M * (Ca + (double)w.N * w.zs * (K.z_src2 ? 2 : 1)), 2.0 * M * Ca * (double)w.N * w.ntap, st);
+  tc_wgrad_stream_kernel<<<grid, NT, smem, st>>>(K);
+  TRU_LAUNCH_CHECK();
+  return TRU_OK;
+}
+
+}  // namespace tru

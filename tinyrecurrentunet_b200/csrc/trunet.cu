@@ -256,7 +256,23 @@ int pw_bwd(Ctx& c, const Grad& g, const Act& x1, int padL, const Act* skip, int 
            const float* extra, float* dSkip) {
   const float* W = c.prm[pw_param];
   const int N = g.C, K = x1.C + (skip ? skip->C : 0);
+  int streamed = 1;
   {
+    WgStream w{};
+    w.nsrc = skip ? 2 : 1;
+    w.a_src[0] = x1.z; w.a_p0[0] = x1.p0; w.a_p2[0] = x1.p2; w.a_L[0] = x1.L; w.a_ld[0] = x1.C; w.a_add[0] = -padL; w.a_C[0] = x1.C; w.wbase[0] = 0;
+    if (skip) {
+      w.a_src[1] = skip->z; w.a_p0[1] = skip->p0; w.a_p2[1] = skip->p2; w.a_L[1] = skip->L; w.a_ld[1] = skip->C; w.a_add[1] = 0;
+      w.a_C[1] = skip->C; w.wbase[1] = x1.C;
+    }
+    w.z_src = g.dy; w.z_src2 = g.q0 ? g.z : nullptr; w.z_p0 = g.q0; w.z_p1 = g.q1; w.z_p2 = g.q2;
+    w.z_L = g.L; w.z_ld = N; w.N = N; w.ntap = 1; w.zs = 1; w.zpad = 0;
+    w.dW = c.grd[pw_param]; w.wsc = 1; w.wsn = K; w.wtap = 0; w.db = c.grd[pw_param + 1];
+    w.BT = (int)c.BT; w.Lq = g.L;
+    streamed = launch_wgrad_stream(w, c.st);
+    if (streamed < 0) return streamed;
+  }
+  if (streamed == 1) {
     WgradParams w{};
     WgradJob& j0 = w.job[0];
     j0.a_src = x1.z; j0.a_p0 = x1.p0; j0.a_p2 = x1.p2; j0.a_relu = 1; j0.a_L = x1.L; j0.a_ld = x1.C; j0.a_coff = 0;
@@ -306,6 +322,16 @@ int convt_bwd(Ctx& c, const Grad& g, const Act& x, int ct_param, int k, int s, f
   const float* W = c.prm[ct_param];
   const int Cout = g.C, Cin = x.C, pad = s / 2;
   {
+    WgStream ws{};
+    ws.nsrc = 1;
+    ws.a_src[0] = x.z; ws.a_p0[0] = x.p0; ws.a_p2[0] = x.p2; ws.a_L[0] = x.L; ws.a_ld[0] = Cin; ws.a_add[0] = 0; ws.a_C[0] = Cin; ws.wbase[0] = 0;
+    ws.z_src = g.dy; ws.z_src2 = g.q0 ? g.z : nullptr; ws.z_p0 = g.q0; ws.z_p1 = g.q1; ws.z_p2 = g.q2;
+    ws.z_L = g.L; ws.z_ld = Cout; ws.N = Cout; ws.ntap = k; ws.zs = s; ws.zpad = pad;
+    ws.dW = c.grd[ct_param]; ws.wsc = Cout * k; ws.wsn = k; ws.wtap = 1; ws.db = nullptr;
+    ws.BT = (int)c.BT; ws.Lq = x.L;
+    const int streamed = launch_wgrad_stream(ws, c.st);
+    if (streamed < 0) return streamed;
+    if (streamed == 1) {
     WgradParams w{};
     for (int j = 0; j < k; ++j) {
       WgradJob& J = w.job[j];
@@ -316,6 +342,7 @@ int convt_bwd(Ctx& c, const Grad& g, const Act& x, int ct_param, int k, int s, f
     }
     w.njobs = k; w.BT = (int)c.BT; w.Lq = x.L;
     TRY(launch_wgrad(w, c.st));
+    }
     WgradParams b{};
     WgradJob& J = b.job[0];
     J.a_src = nullptr; J.C = 4; J.a_ld = 4;
@@ -581,4 +608,18 @@ extern "C" int tru_debug_wgrad(const float* a, const float* z, float* dw, float*
     return rc == 1 ? set_error(TRU_ERR_ARG, "debug_wgrad: not eligible for the tensor-core path") : rc;
   }
   return launch_wgrad_simt(w, (cudaStream_t)stream);
+}
+
+// Test aid: the streaming weight-gradient kernel on plain operands.  a (M,C), dy/z (M,N) with dz = q0*dy + q1*z + q2
+// (q0 null: dz = dy); rows are grouped in frames of Lq.  dW (N,C), db (N).
+extern "C" int tru_debug_wgrad_stream(const float* a, const float* dy, const float* z, const float* q0, const float* q1,
+                                      const float* q2, float* dw, float* db, int M, int Lq, int C, int N, void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  WgStream w{};
+  w.nsrc = 1; w.a_src[0] = a; w.a_L[0] = Lq; w.a_ld[0] = C; w.a_C[0] = C;
+  w.z_src = dy; w.z_src2 = z; w.z_p0 = q0; w.z_p1 = q1; w.z_p2 = q2; w.z_L = Lq; w.z_ld = N; w.N = N; w.ntap = 1; w.zs = 1;
+  w.dW = dw; w.wsc = 1; w.wsn = C; w.db = db; w.BT = M / Lq; w.Lq = Lq;
+  rc = launch_wgrad_stream(w, (cudaStream_t)stream);
+  return rc == 1 ? set_error(TRU_ERR_ARG, "debug_wgrad_stream: not eligible") : rc;
 }
