@@ -413,6 +413,7 @@ int launch_enc0_wgrad(const float* x, const float* dy, float* dw, float* db, int
 }
 int launch_dw_fwd(const DwParams& p, cudaStream_t st) {
   TRU_REQUIRE(p.C == DW_C && p.k <= 5, TRU_ERR_ARG, "depthwise kernel supports C=128, k<=5");
+  { const int rc = launch_dw_fwd_stream(p, st); if (rc != 1) return rc; }
   ProfScope prof("dw_fwd", 4.0 * p.BT * ((double)p.Lin + p.Lout) * p.C, 2.0 * p.k * p.BT * p.Lout * p.C, st);
   dw_fwd_kernel<<<dw_grid((long)p.BT * p.Lout), 256, 0, st>>>(p);
   TRU_LAUNCH_CHECK();
@@ -429,6 +430,7 @@ int launch_dw_bwd_fused(const DwParams& p, cudaStream_t st) {
   TRU_REQUIRE(p.C == DW_C && p.k <= 5, TRU_ERR_ARG, "depthwise kernel supports C=128, k<=5");
   TRU_REQUIRE(p.zmask && p.mp0 && p.bstats && p.dw && p.db && p.a_src == p.zmask && p.a_p0 == p.mp0 && p.a_p2 == p.mp2,
               TRU_ERR_ARG, "dw_bwd_fused: the activation and the ReLU mask must be the same tensor");
+  { const int rc = launch_dw_bwd_stream(p, st); if (rc != 1) return rc; }
   ProfScope prof("dw_bwd_fused", 4.0 * p.BT * (2.0 * p.Lin + 2.0 * p.Lout) * p.C, 4.0 * p.k * p.BT * p.Lout * p.C, st);
   // 2 resident CTAs per SM (122 registers): a grid-stride loop over exactly that many CTAs also keeps the
   // number of float atomics per weight-gradient element small

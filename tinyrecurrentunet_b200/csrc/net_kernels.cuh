@@ -104,6 +104,8 @@ int launch_dw_fwd(const DwParams& p, cudaStream_t st);
 int launch_dw_bwd_data(const DwParams& p, cudaStream_t st);
 int launch_dw_wgrad(const DwParams& p, cudaStream_t st);
 int launch_dw_bwd_fused(const DwParams& p, cudaStream_t st);   // bwd_data + wgrad in one pass
+int launch_dw_fwd_stream(const DwParams& p, cudaStream_t st);  // dwstream.cu: TMA-fed versions; 1 = shape not covered
+int launch_dw_bwd_stream(const DwParams& p, cudaStream_t st);
 
 int launch_colsum(const float* src, const float* src2, const float* q0, const float* q1, const float* q2, float* db,
                   long rows, int ld, int coff, int N, cudaStream_t st);
