@@ -36,7 +36,6 @@ constexpr int TRW = 16;                         // transform warps
 constexpr int NTR = 32 * TRW;
 constexpr int NT = 32 * (4 + TRW);
 constexpr int MAXRAW = 8;
-constexpr int IA = 3, IZ = 4;                   // per-thread item slots (activation / dz float4s per unit)
 
 struct WgK {
   int nsrc; const float* a_src[2]; const float* a_p0[2]; const float* a_p2[2];
@@ -79,6 +78,9 @@ __device__ __forceinline__ void split_store(uint8_t* hi_ptr, uint32_t lo_delta, 
   *(uint4*)(hi_ptr + lo_delta) = lo;
 }
 
+// IA / IZ: per-thread item slots (activation / dz float4s per unit), NTAP: taps (compile-time so that unused
+// slots and taps cost nothing; with one slot each the BN coefficients live in registers)
+template <int IA, int IZ, int NTAP>
 __global__ void __launch_bounds__(NT, 1) tc_wgrad_stream_kernel(const __grid_constant__ WgK K) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -99,6 +101,7 @@ __global__ void __launch_bounds__(NT, 1) tc_wgrad_stream_kernel(const __grid_con
     coef[K.Ca + i] = aff ? __ldg(K.a_p2[s] + c) : 0.f;
     coef[2 * K.Ca + i] = aff ? 0.f : -__int_as_float(0x7f800000);     // ReLU only behind a BN (trunet.cu: fwd_seg)
   }
+  for (uint32_t i = tid; i < 2 * K.op_stage / 16; i += NT) ((uint4*)ops)[i] = make_uint4(0u, 0u, 0u, 0u);   // pad columns stay zero
   float* zc = coef + 3 * K.Ca;
   for (int i = tid; i < K.N; i += NT) {
     zc[i] = K.z_p0 ? __ldg(K.z_p0 + i) : 1.f;
@@ -115,6 +118,7 @@ __global__ void __launch_bounds__(NT, 1) tc_wgrad_stream_kernel(const __grid_con
     __syncwarp();
     tmem_alloc(&mi.tmem_base, K.tmem_cols);
   }
+  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -200,7 +204,7 @@ __global__ void __launch_bounds__(NT, 1) tc_wgrad_stream_kernel(const __grid_con
     // ================================ transform =======================================
     reg_inc<104>();
     const int tt = tid - 128;
-    const int NBa = K.Ca >> 5, NBz = K.N >> 5;
+    const int NBa = (K.Ca + 31) >> 5, NBz = (K.N + 31) >> 5;     // item grids are padded to 32 channels; pad slots stay idle
     // Per-thread item slots, fully decoded once: raw-stage byte offset, operand-stage byte offset(s), channel and
     // validity bit.  Lane = (row & 3) * 8 + 16-byte chunk, so a quarter warp reads 128 contiguous bytes of a raw
     // row and writes 128 bytes of one swizzle atom (conflict-free both ways).
@@ -209,8 +213,8 @@ __global__ void __launch_bounds__(NT, 1) tc_wgrad_stream_kernel(const __grid_con
     const int NBat = K.p_is_z ? NBq : NBp, NBzt = K.p_is_z ? NBp : NBq;
     constexpr uint32_t NONE = 0xffffffffu;
     uint32_t a_raw[IA], a_dst[IA], a_cb[IA];          // a_cb: channel | row << 16 | source << 24
-    uint32_t z_raw[IZ], z_cb[IZ], z_dst[IZ][5];       // z_cb: channel | t << 16
-    const int nA = UR * (K.Ca >> 2), nZ = ((K.NZ + 3) & ~3) * (K.N >> 2);
+    uint32_t z_raw[IZ], z_cb[IZ], z_dst[IZ][NTAP];    // z_cb: channel | t << 16
+    const int nA = UR * NBa * 8, nZ = ((K.NZ + 3) & ~3) * NBz * 8;
 #pragma unroll
     for (int k = 0; k < IA; ++k) {
       const int it = tt + k * NTR;
@@ -218,9 +222,11 @@ __global__ void __launch_bounds__(NT, 1) tc_wgrad_stream_kernel(const __grid_con
       if (it < nA) {
         const int blk = (it >> 5) % NBa, rg = (it >> 5) / NBa, r = rg * 4 + ((it >> 3) & 3), c = blk * 32 + (it & 7) * 4;
         const int s = (K.nsrc == 2 && c >= K.a_c0[1]) ? 1 : 0;
-        a_raw[k] = K.raw_a[s] + (uint32_t)(r * K.a_C[s] + c - K.a_c0[s]) * 4u;
-        a_dst[k] = a_tile + tile_off(r, c, NBat);
-        a_cb[k] = (uint32_t)c | ((uint32_t)r << 16) | ((uint32_t)s << 24);
+        if (c < K.Ca) {
+          a_raw[k] = K.raw_a[s] + (uint32_t)(r * K.a_C[s] + c - K.a_c0[s]) * 4u;
+          a_dst[k] = a_tile + tile_off(r, c, NBat);
+          a_cb[k] = (uint32_t)c | ((uint32_t)r << 16) | ((uint32_t)s << 24);
+        }
       }
     }
 #pragma unroll
@@ -228,22 +234,29 @@ __global__ void __launch_bounds__(NT, 1) tc_wgrad_stream_kernel(const __grid_con
       const int it = tt + k * NTR;
       z_raw[k] = NONE; z_cb[k] = 0;
 #pragma unroll
-      for (int j = 0; j < 5; ++j) z_dst[k][j] = NONE;
+      for (int j = 0; j < NTAP; ++j) z_dst[k][j] = NONE;
       if (it < nZ) {
         const int blk = (it >> 5) % NBz, rg = (it >> 5) / NBz, t = rg * 4 + ((it >> 3) & 3), c = blk * 32 + (it & 7) * 4;
-        if (t < K.NZ) {
+        if (t < K.NZ && c < K.N) {
           z_raw[k] = (uint32_t)(t * K.N + c) * 4u;
           z_cb[k] = (uint32_t)c | ((uint32_t)t << 16);
           // row t of the unit's dz window feeds tap j at unit row (t - j) / zs
 #pragma unroll
-          for (int j = 0; j < 5; ++j) {
+          for (int j = 0; j < NTAP; ++j) {
             const int d = t - j;
-            if (j < K.ntap && d >= 0 && d % K.zs == 0 && d / K.zs < UR) z_dst[k][j] = z_tile + tile_off(d / K.zs, j * K.N + c, NBzt);
+            if (d >= 0 && d % K.zs == 0 && d / K.zs < UR) z_dst[k][j] = z_tile + tile_off(d / K.zs, j * K.N + c, NBzt);
           }
         }
       }
     }
     const bool has_z2 = K.z_src2 != nullptr;
+    constexpr bool CREG = IA == 1 && IZ == 1;
+    float4 rp0, rp2, rfl, rq0, rq1, rq2;
+    if (CREG) {
+      const int ca = a_cb[0] & 0xffff, cz = z_cb[0] & 0xffff;
+      rp0 = *(const float4*)(coef + ca); rp2 = *(const float4*)(coef + K.Ca + ca); rfl = *(const float4*)(coef + 2 * K.Ca + ca);
+      rq0 = *(const float4*)(zc + cz); rq1 = *(const float4*)(zc + K.N + cz); rq2 = *(const float4*)(zc + 2 * K.N + cz);
+    }
     float bs[4] = {0.f, 0.f, 0.f, 0.f};
     int rs = 0;
     uint32_t ph = 0;
@@ -273,7 +286,8 @@ __global__ void __launch_bounds__(NT, 1) tc_wgrad_stream_kernel(const __grid_con
           const bool ok = (((a_cb[k] >> 24) ? am1 : am0) >> r) & 1u;
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
           if (ok) {
-            const float4 p0 = *(const float4*)(coef + c), p2 = *(const float4*)(coef + K.Ca + c), fl = *(const float4*)(coef + 2 * K.Ca + c);
+            const float4 p0 = CREG ? rp0 : *(const float4*)(coef + c), p2 = CREG ? rp2 : *(const float4*)(coef + K.Ca + c);
+            const float4 fl = CREG ? rfl : *(const float4*)(coef + 2 * K.Ca + c);
             v.x = fmaxf(fmaf(p0.x, xa[k].x, p2.x), fl.x); v.y = fmaxf(fmaf(p0.y, xa[k].y, p2.y), fl.y);
             v.z = fmaxf(fmaf(p0.z, xa[k].z, p2.z), fl.z); v.w = fmaxf(fmaf(p0.w, xa[k].w, p2.w), fl.w);
           }
@@ -287,7 +301,8 @@ __global__ void __launch_bounds__(NT, 1) tc_wgrad_stream_kernel(const __grid_con
           const bool ok = ((t < 32 ? zm0 >> t : zm1 >> (t - 32)) & 1u) != 0;
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
           if (ok) {
-            const float4 q0 = *(const float4*)(zc + c), q1 = *(const float4*)(zc + K.N + c), q2 = *(const float4*)(zc + 2 * K.N + c);
+            const float4 q0 = CREG ? rq0 : *(const float4*)(zc + c), q1 = CREG ? rq1 : *(const float4*)(zc + K.N + c);
+            const float4 q2 = CREG ? rq2 : *(const float4*)(zc + 2 * K.N + c);
             v.x = fmaf(q1.x, xz[k].x, fmaf(q0.x, xy[k].x, q2.x)); v.y = fmaf(q1.y, xz[k].y, fmaf(q0.y, xy[k].y, q2.y));
             v.z = fmaf(q1.z, xz[k].z, fmaf(q0.z, xy[k].z, q2.z)); v.w = fmaf(q1.w, xz[k].w, fmaf(q0.w, xy[k].w, q2.w));
             if (k == 0) { bs[0] += v.x; bs[1] += v.y; bs[2] += v.z; bs[3] += v.w; }
@@ -298,8 +313,8 @@ __global__ void __launch_bounds__(NT, 1) tc_wgrad_stream_kernel(const __grid_con
           lo.x = __float_as_uint(v.x - __uint_as_float(hi.x)); lo.y = __float_as_uint(v.y - __uint_as_float(hi.y));
           lo.z = __float_as_uint(v.z - __uint_as_float(hi.z)); lo.w = __float_as_uint(v.w - __uint_as_float(hi.w));
 #pragma unroll
-          for (int j = 0; j < 5; ++j)
-            if (z_dst[k][j] != NONE) { *(uint4*)(op + z_dst[k][j]) = hi; *(uint4*)(op + z_dst[k][j] + z_lo) = lo; }
+          for (int j = 0; j < NTAP; ++j)
+            if (NTAP == 1 || z_dst[k][j] != NONE) { *(uint4*)(op + z_dst[k][j]) = hi; *(uint4*)(op + z_dst[k][j] + z_lo) = lo; }
         }
       }
       fence_proxy_async();
@@ -348,16 +363,28 @@ __global__ void __launch_bounds__(NT, 1) tc_wgrad_stream_kernel(const __grid_con
 
 constexpr size_t SMEM_MAX = 227 * 1024;
 
+template <int IA, int IZ, int NTAP>
+int launch_variant(const WgK& K, int grid, size_t smem, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    TRU_CUDA(cudaFuncSetAttribute(tc_wgrad_stream_kernel<IA, IZ, NTAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+    attr = true;
+  }
+  tc_wgrad_stream_kernel<IA, IZ, NTAP><<<grid, NT, smem, st>>>(K);
+  TRU_LAUNCH_CHECK();
+  return TRU_OK;
+}
+
 }  // namespace
 
 // returns TRU_OK if launched, 1 if the job does not fit this kernel (caller uses the per-job kernels)
 int launch_wgrad_stream(const WgStream& w, cudaStream_t st) {
   WgK K{};
-  if (w.nsrc < 1 || w.nsrc > 2 || w.ntap < 1 || w.ntap > 5 || w.Lq % UR != 0 || w.N % 32 != 0 || w.N > 128) return 1;
+  if (w.nsrc < 1 || w.nsrc > 2 || w.ntap < 1 || w.ntap > 5 || w.Lq % UR != 0 || w.N % 4 != 0 || w.N > 128) return 1;
   if (w.nsrc == 2 && w.ntap > 1) return 1;
   int Ca = 0;
   for (int s = 0; s < w.nsrc; ++s) {
-    if (w.a_C[s] % 32 != 0 || w.a_ld[s] % 4 != 0 || !aligned16(w.a_src[s])) return 1;
+    if (w.a_C[s] % 4 != 0 || (w.nsrc == 2 && w.a_C[s] % 32 != 0) || w.a_ld[s] % 4 != 0 || !aligned16(w.a_src[s])) return 1;
     K.a_src[s] = w.a_src[s]; K.a_p0[s] = w.a_p0[s]; K.a_p2[s] = w.a_p2[s];
     K.a_L[s] = w.a_L[s]; K.a_ld[s] = w.a_ld[s]; K.a_add[s] = w.a_add[s]; K.a_C[s] = w.a_C[s]; K.a_c0[s] = Ca;
     K.wbase[s] = w.wbase[s];
@@ -373,10 +400,11 @@ int launch_wgrad_stream(const WgStream& w, cudaStream_t st) {
   K.p_is_z = (w.ntap == 1 && (Ca > 128 || w.N > Ca)) ? 1 : 0;
   const int Pc = K.p_is_z ? w.N : Ca, Qc = K.p_is_z ? Ca : Zcols;
   if (Pc > 128 || Qc > 384) return 1;
-  K.Mmma = Pc <= 64 ? 64 : 128; K.PWt = K.Mmma; K.QWt = Qc; K.Pvalid = Pc; K.Qvalid = Qc;
-  K.tmem_cols = Qc <= 32 ? 32 : Qc <= 64 ? 64 : Qc <= 128 ? 128 : Qc <= 256 ? 256 : 512;
-  const int nA = UR * (Ca / 4), nZ = ((K.NZ + 3) & ~3) * (w.N / 4);
-  if (nA > IA * NTR || nZ > IZ * NTR) return 1;
+  K.Mmma = Pc <= 64 ? 64 : 128; K.PWt = K.Mmma; K.QWt = (Qc + 31) / 32 * 32; K.Pvalid = Pc; K.Qvalid = Qc;
+  K.tmem_cols = K.QWt <= 32 ? 32 : K.QWt <= 64 ? 64 : K.QWt <= 128 ? 128 : K.QWt <= 256 ? 256 : 512;
+  const int nA = UR * ((Ca + 31) / 32) * 8, nZ = ((K.NZ + 3) & ~3) * ((w.N + 31) / 32) * 8;
+  const int ia = (nA + NTR - 1) / NTR, iz = (nZ + NTR - 1) / NTR, nt = w.ntap == 1 ? 1 : (w.ntap <= 3 ? 3 : 5);
+  if (ia > 2 || iz > 2) return 1;
   if (w.db && (w.ntap != 1 || nZ > NTR)) return 1;
   K.db = w.db;
   K.p_tile = (uint32_t)UR * K.PWt * 4; K.q_tile = (uint32_t)UR * K.QWt * 4;
@@ -402,11 +430,6 @@ int launch_wgrad_stream(const WgStream& w, cudaStream_t st) {
   K.units_total = (unsigned)(M / UR);
   const int grid = (int)std::min<long>(sm_count(), K.units_total);
   K.units_per_cta = (K.units_total + grid - 1) / grid;
-  static bool attr = false;
-  if (!attr) {
-    TRU_CUDA(cudaFuncSetAttribute(tc_wgrad_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
-    attr = true;
-  }
   const char* nm = "wgrad_stream";
   if (prof_enabled()) {
     static std::map<std::string, const char*> names;
@@ -417,9 +440,19 @@ int launch_wgrad_stream(const WgStream& w, cudaStream_t st) {
     nm = it->second;
   }
   ProfScope prof(nm, 4.0 * M * (Ca + (double)w.N * w.zs * (K.z_src2 ? 2 : 1)), 2.0 * M * Ca * (double)w.N * w.ntap, st);
-  tc_wgrad_stream_kernel<<<grid, NT, smem, st>>>(K);
-  TRU_LAUNCH_CHECK();
-  return TRU_OK;
+  const int key = ia * 100 + iz * 10 + nt;
+  switch (key) {
+    case 111: return launch_variant<1, 1, 1>(K, grid, smem, st);
+    case 113: return launch_variant<1, 1, 3>(K, grid, smem, st);
+    case 115: return launch_variant<1, 1, 5>(K, grid, smem, st);
+    case 123: return launch_variant<1, 2, 3>(K, grid, smem, st);
+    case 125: return launch_variant<1, 2, 5>(K, grid, smem, st);
+    case 211: return launch_variant<2, 1, 1>(K, grid, smem, st);
+    case 121: return launch_variant<1, 2, 1>(K, grid, smem, st);
+    case 221: return launch_variant<2, 2, 1>(K, grid, smem, st);
+    default: break;
+  }
+  return set_error(TRU_ERR_ARG, "wgrad_stream: no kernel variant for slots (%d,%d) taps %d", ia, iz, w.ntap);
 }
 
 }  // namespace tru
