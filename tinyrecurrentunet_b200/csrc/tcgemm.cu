@@ -291,14 +291,17 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
     // ================================== epilogue ===================================
     // Thread = one output channel (TMEM lane); per tile a warp drains 2 chunks of 32 tile rows
     // (TMEM columns), each as two sub-chunks of 16 rows.  M = 64: the accumulator occupies lanes
-    // 0-15 of every 32-lane quadrant (rows 16q..16q+15).  The ReLU-mask values (Z of the layer that
+    // 0-15 of every 32-lane quadrant (rows 16q..16q+15); a 16x32bx2 load hands lanes 16-31 the
+    // second 16 columns of a chunk, so a chunk is one sub-step and no lane idles.  The ReLU-mask values (Z of the layer that
     // receives the gradient) do not depend on the accumulator, so they are fetched one sub-chunk
     // ahead - across tile boundaries too - and their latency hides behind the previous sub-chunk.
     reg_inc<REG_EPI>();
     const int ew = warp - 4 - LW, lg = warp & 3, half = ew >> 2;
-    const int nl = MW == 128 ? lg * 32 + lane : lg * 16 + lane;
+    const bool m64 = MW == 64;
+    const int nl = m64 ? lg * 16 + (lane & 15) : lg * 32 + lane;
     const int n = n0 + nl;
-    const bool nok = (MW == 128 || lane < 16) && n < P.N;
+    const bool nok = n < P.N;
+    const int src64 = lane & 16;                        // M = 64: lanes 16-31 hold the second 16 rows of a chunk
     const unsigned Mu = (unsigned)M, Lq = (unsigned)P.Lq;
     const float bias = (P.bias && nok) ? __ldg(P.bias + n) : 0.f;
     float mp0 = 1.f, mp2 = 0.f;
@@ -326,27 +329,27 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
         }
       }
     };
-    auto zfetch = [&](float (&z)[16], float (&x)[EPI ? 16 : 1], unsigned ooff, unsigned eoff, int h) {
+    auto zfetch = [&](float (&z)[16], float (&x)[EPI ? 16 : 1], unsigned ooff, unsigned eoff, int src0) {
       if (EPI && use_mask) {
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
-          const unsigned off = __shfl_sync(0xffffffffu, ooff, h * 16 + r);
+          const unsigned off = __shfl_sync(0xffffffffu, ooff, src0 + r);
           z[r] = (nok && off != 0xffffffffu) ? __ldg(zbase + off) : 0.f;
         }
       }
       if (EPI && has_extra) {
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
-          const unsigned off = __shfl_sync(0xffffffffu, ooff, h * 16 + r);
-          const unsigned eo = __shfl_sync(0xffffffffu, eoff, h * 16 + r);
+          const unsigned off = __shfl_sync(0xffffffffu, ooff, src0 + r);
+          const unsigned eo = __shfl_sync(0xffffffffu, eoff, src0 + r);
           x[EPI ? r : 0] = (nok && off != 0xffffffffu) ? __ldg(xbase + eo) : 0.f;
         }
       }
     };
-    auto process = [&](const uint32_t (&v)[16], int h, const float (&z)[16], const float (&x)[EPI ? 16 : 1], unsigned ooff) {
+    auto process = [&](const uint32_t (&v)[16], int src0, const float (&z)[16], const float (&x)[EPI ? 16 : 1], unsigned ooff) {
 #pragma unroll
       for (int r = 0; r < 16; ++r) {
-        const unsigned off = __shfl_sync(0xffffffffu, ooff, h * 16 + r);
+        const unsigned off = __shfl_sync(0xffffffffu, ooff, src0 + r);
         const bool ok = nok && off != 0xffffffffu;
         float o = __uint_as_float(v[r]) + bias;
         if (EPI) {
@@ -364,7 +367,7 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
     float za[16], zb[16], xa[EPI ? 16 : 1], xb[EPI ? 16 : 1];
     unsigned oa, ea, ob, eb;
     row_offsets(0, half * 2, oa, ea);
-    zfetch(za, xa, oa, ea, 0);
+    zfetch(za, xa, oa, ea, m64 ? src64 : 0);
     for (int ti = 0; ti < n_my; ++ti) {
       const int acc = ti & 1;
       row_offsets(ti, half * 2 + 1, ob, eb);
@@ -372,21 +375,33 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
       tc_fence_after();
       const uint32_t taddr = tmem + ((uint32_t)(lg * 32) << 16) + acc * BM + half * 64;
       uint32_t v[16];
-      tmem_ld16(taddr, v);
-      zfetch(zb, xb, oa, ea, 1);
-      process(v, 0, za, xa, oa);
-      tmem_ld16(taddr + 16, v);
-      zfetch(za, xa, ob, eb, 0);
-      process(v, 1, zb, xb, oa);
-      tmem_ld16(taddr + 32, v);
-      zfetch(zb, xb, ob, eb, 1);
-      process(v, 0, za, xa, ob);
-      tmem_ld16(taddr + 48, v);
-      tc_fence_before();
-      mbar_arrive(&mi.tempty[acc]);
-      row_offsets(ti + 1, half * 2, oa, ea);
-      zfetch(za, xa, oa, ea, 0);
-      process(v, 1, zb, xb, ob);
+      if (m64) {                       // 2 sub-steps of 32 columns, all 32 lanes busy
+        tmem_ld16x2(taddr, v);
+        zfetch(zb, xb, ob, eb, src64);
+        process(v, src64, za, xa, oa);
+        tmem_ld16x2(taddr + 32, v);
+        tc_fence_before();
+        mbar_arrive(&mi.tempty[acc]);
+        row_offsets(ti + 1, half * 2, oa, ea);
+        zfetch(za, xa, oa, ea, src64);
+        process(v, src64, zb, xb, ob);
+      } else {                         // 4 sub-steps of 16 columns
+        tmem_ld16(taddr, v);
+        zfetch(zb, xb, oa, ea, 16);
+        process(v, 0, za, xa, oa);
+        tmem_ld16(taddr + 16, v);
+        zfetch(za, xa, ob, eb, 0);
+        process(v, 16, zb, xb, oa);
+        tmem_ld16(taddr + 32, v);
+        zfetch(zb, xb, ob, eb, 16);
+        process(v, 0, za, xa, ob);
+        tmem_ld16(taddr + 48, v);
+        tc_fence_before();
+        mbar_arrive(&mi.tempty[acc]);
+        row_offsets(ti + 1, half * 2, oa, ea);
+        zfetch(za, xa, oa, ea, 0);
+        process(v, 16, zb, xb, ob);
+      }
     }
     double* gst = P.stats ? P.stats : (EPI ? P.bstats : nullptr);
     if (gst && nok) {
