@@ -60,9 +60,9 @@ struct Misc {
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldg((const float4*)p); }
 
 // LW: loader warps (8 or 16).  LD2: loaders read two tensors (dY and Z) and apply the BN-backward
-// affine.  EPI: the epilogue adds the skip gradient / applies the ReLU mask / accumulates the
+// affine.  EPI (0 plain, 1 mask, 2 mask + added tensor): the epilogue adds the skip gradient / applies the ReLU mask / accumulates the
 // BN-backward sums.
-template <int LW, bool LD2, bool EPI>
+template <int LW, bool LD2, int EPI>
 __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const __grid_constant__ IgemmParams P,
                                                                         const __grid_constant__ TcLayout Lo) {
   constexpr int NT = 32 * (4 + LW + EW);
@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
     const unsigned Mu = (unsigned)M, Lq = (unsigned)P.Lq;
     const float bias = (P.bias && nok) ? __ldg(P.bias + n) : 0.f;
     float mp0 = 1.f, mp2 = 0.f;
-    const bool use_mask = EPI && P.use_mask, has_extra = EPI && P.extra != nullptr;
+    const bool use_mask = EPI && P.use_mask, has_extra = EPI == 2 && P.extra != nullptr;
     if (use_mask && P.mp0 && nok) { mp0 = __ldg(P.mp0 + n); mp2 = __ldg(P.mp2 + n); }
     const bool do_stats = P.stats != nullptr, do_bstats = EPI && P.bstats != nullptr;
     const float bmean = (do_bstats && nok) ? __ldg(P.bmean + n) : 0.f;
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
         }
       }
     };
-    auto zfetch = [&](float (&z)[16], float (&x)[EPI ? 16 : 1], unsigned ooff, unsigned eoff, int src0) {
+    auto zfetch = [&](float (&z)[16], float (&x)[EPI == 2 ? 16 : 1], unsigned ooff, unsigned eoff, int src0) {
       if (EPI && use_mask) {
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
@@ -337,23 +337,23 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
           z[r] = (nok && off != 0xffffffffu) ? __ldg(zbase + off) : 0.f;
         }
       }
-      if (EPI && has_extra) {
+      if (EPI == 2 && has_extra) {
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
           const unsigned off = __shfl_sync(0xffffffffu, ooff, src0 + r);
           const unsigned eo = __shfl_sync(0xffffffffu, eoff, src0 + r);
-          x[EPI ? r : 0] = (nok && off != 0xffffffffu) ? __ldg(xbase + eo) : 0.f;
+          x[EPI == 2 ? r : 0] = (nok && off != 0xffffffffu) ? __ldg(xbase + eo) : 0.f;
         }
       }
     };
-    auto process = [&](const uint32_t (&v)[16], int src0, const float (&z)[16], const float (&x)[EPI ? 16 : 1], unsigned ooff) {
+    auto process = [&](const uint32_t (&v)[16], int src0, const float (&z)[16], const float (&x)[EPI == 2 ? 16 : 1], unsigned ooff) {
 #pragma unroll
       for (int r = 0; r < 16; ++r) {
         const unsigned off = __shfl_sync(0xffffffffu, ooff, src0 + r);
         const bool ok = nok && off != 0xffffffffu;
         float o = __uint_as_float(v[r]) + bias;
         if (EPI) {
-          if (has_extra) o += x[EPI ? r : 0];
+          if (EPI == 2 && has_extra) o += x[r];
           if (use_mask) o = (fmaf(z[r], mp0, mp2) > 0.f) ? o : 0.f;
         }
         if (ok) {
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
       }
     };
 
-    float za[16], zb[16], xa[EPI ? 16 : 1], xb[EPI ? 16 : 1];
+    float za[16], zb[16], xa[EPI == 2 ? 16 : 1], xb[EPI == 2 ? 16 : 1];
     unsigned oa, ea, ob, eb;
     row_offsets(0, half * 2, oa, ea);
     zfetch(za, xa, oa, ea, m64 ? src64 : 0);
@@ -498,28 +498,32 @@ bool plan(const IgemmParams& p, TcLayout& L, dim3& grid, size_t& smem_bytes) {
   return smem_bytes <= SMEM_MAX;
 }
 
-int g_loader_warps = 8;
+int g_loader_warps = 0;      // 0: 16 loader warps for plain epilogues (forward), 8 when the epilogue needs the registers
 
-template <int LW>
-int launch_one(const IgemmParams& p, const TcLayout& L, dim3 grid, size_t smem, cudaStream_t st) {
-  const bool epi = p.use_mask || p.extra != nullptr || p.bstats != nullptr;
-  bool ld2 = false;
-  for (int s = 0; s < p.nseg; ++s) ld2 |= (p.seg[s].src2 != nullptr);
+template <int LW, bool LD2, int EPI>
+int launch_inst(const IgemmParams& p, const TcLayout& L, dim3 grid, size_t smem, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
-    TRU_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<LW, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
-    TRU_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<LW, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
-    TRU_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<LW, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
-    TRU_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<LW, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+    TRU_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<LW, LD2, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
     attr_done = true;
   }
-  constexpr int NT = 32 * (4 + LW + EW);
-  if (ld2 && epi) tc_igemm_kernel<LW, true, true><<<grid, NT, smem, st>>>(p, L);
-  else if (ld2) tc_igemm_kernel<LW, true, false><<<grid, NT, smem, st>>>(p, L);
-  else if (epi) tc_igemm_kernel<LW, false, true><<<grid, NT, smem, st>>>(p, L);
-  else tc_igemm_kernel<LW, false, false><<<grid, NT, smem, st>>>(p, L);
+  tc_igemm_kernel<LW, LD2, EPI><<<grid, 32 * (4 + LW + EW), smem, st>>>(p, L);
   TRU_LAUNCH_CHECK();
   return TRU_OK;
+}
+
+// 16 loader warps unless the epilogue also prefetches an added tensor (its registers only fit the 8-warp layout)
+int launch_one(const IgemmParams& p, const TcLayout& L, dim3 grid, size_t smem, cudaStream_t st) {
+  const int epi = p.extra != nullptr ? 2 : ((p.use_mask || p.bstats != nullptr) ? 1 : 0);
+  bool ld2 = false;
+  for (int s = 0; s < p.nseg; ++s) ld2 |= (p.seg[s].src2 != nullptr);
+  const int lw = g_loader_warps ? g_loader_warps : (epi == 2 ? 8 : 16);
+  if (lw == 8 || epi == 2) {
+    if (ld2) return epi == 0 ? launch_inst<8, true, 0>(p, L, grid, smem, st) : epi == 1 ? launch_inst<8, true, 1>(p, L, grid, smem, st) : launch_inst<8, true, 2>(p, L, grid, smem, st);
+    return epi == 0 ? launch_inst<8, false, 0>(p, L, grid, smem, st) : epi == 1 ? launch_inst<8, false, 1>(p, L, grid, smem, st) : launch_inst<8, false, 2>(p, L, grid, smem, st);
+  }
+  if (ld2) return epi == 0 ? launch_inst<16, true, 0>(p, L, grid, smem, st) : launch_inst<16, true, 1>(p, L, grid, smem, st);
+  return epi == 0 ? launch_inst<16, false, 0>(p, L, grid, smem, st) : launch_inst<16, false, 1>(p, L, grid, smem, st);
 }
 
 int launch_planned(const IgemmParams& p, cudaStream_t st) {
@@ -527,7 +531,7 @@ int launch_planned(const IgemmParams& p, cudaStream_t st) {
   dim3 grid;
   size_t smem = 0;
   if (!plan(p, L, grid, smem)) return 1;
-  return g_loader_warps == 8 ? launch_one<8>(p, L, grid, smem, st) : launch_one<16>(p, L, grid, smem, st);
+  return launch_one(p, L, grid, smem, st);
 }
 
 // k-blocks [k0, k1) of p as a launch of their own
@@ -552,7 +556,7 @@ IgemmParams slice_kblocks(const IgemmParams& p, int k0, int k1) {
 
 }  // namespace
 
-void set_tc_loader_warps(int n) { g_loader_warps = (n == 8) ? 8 : 16; }
+void set_tc_loader_warps(int n) { g_loader_warps = (n == 8 || n == 16) ? n : 0; }
 
 bool igemm_tc_eligible(const IgemmParams& p) {
   if (!shape_ok(p)) return false;
