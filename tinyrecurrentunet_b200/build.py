@@ -12,6 +12,8 @@ OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(PKG, "libtru_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+if os.environ.get("TRU_MBAR_TIMEOUT"):       # debug build: mbarrier waits print and trap instead of hanging
+    NVCC_FLAGS.append("-DTRU_MBAR_TIMEOUT")
 
 
 def _nvcc():

@@ -40,7 +40,9 @@ bool igemm_tc_eligible(const IgemmParams& p);
 int launch_igemm_tc(const IgemmParams& p, cudaStream_t st);    // 0 launched, 1 not eligible, <0 error
 int launch_igemm_simt(const IgemmParams& p, cudaStream_t st);
 void set_tc_enabled(bool on);
-void set_tc_loader_warps(int n);   // 8 or 16 (tuning aid)
+void set_tc_loader_warps(int n);
+int read_mbar_debug(unsigned* out, int n);   // debug builds (-DTRU_MBAR_TIMEOUT): stuck mbarrier waits of the GEMM kernel
+void set_tc_debug_flags(int f);  // ablation switches (tuning aid)   // 8 or 16 (tuning aid)
 bool tc_enabled();
 
 struct WgradJob {

@@ -5,12 +5,16 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace tru {
 namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+#ifdef TRU_MBAR_TIMEOUT
+__device__ unsigned g_mbar_dbg[1028];       // [0] count, then (block, thread, tag, parity) records; one copy per translation unit
+#endif
 // ---- mbarrier ------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -18,15 +22,25 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
   const uint32_t addr = smem_u32(bar);
   uint32_t ok;
+#ifdef TRU_MBAR_TIMEOUT
+  long long spins = 0;
+#endif
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+#ifdef TRU_MBAR_TIMEOUT
+    if (!ok && ++spins > (1ll << 22)) {      // deadlock detector (debug builds only)
+      const unsigned slot = atomicAdd(&g_mbar_dbg[0], 1u);
+      if (slot < 255) { g_mbar_dbg[4 * slot + 4] = blockIdx.x; g_mbar_dbg[4 * slot + 5] = threadIdx.x; g_mbar_dbg[4 * slot + 6] = (unsigned)tag; g_mbar_dbg[4 * slot + 7] = parity; }
+      break;   // give up waiting: results are garbage but the kernel ends and the log can be read
+    }
+#endif
   } while (!ok);
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }

@@ -28,6 +28,7 @@
 // The dropped lo*lo term is <= 2^-21 relative per product.
 #include <algorithm>
 #include <string.h>
+#include <type_traits>
 #include "net_kernels.cuh"
 #include "tc_common.cuh"
 
@@ -45,6 +46,8 @@ constexpr int COEF_FLOATS = 96;                           // p0[32] p2[32] p1[32
 struct TcLayout {
   int MW;                       // MMA M = weight rows (output channels) per CTA: 64 or 128
   int nkb, nstage, ncoef;
+  unsigned lq_magic;            // ceil(2^32 / Lq) (0: Lq == 1) for the loaders' row decode
+  int dbg;                      // ablation switches for bottleneck hunting (tru_debug_set_flags): 1 no MMA, 2 no global loads, 4 no smem stores, 8 no epilogue stores
   uint32_t a_off, coef_off, misc_off;                      // W tiles at offset 0
   int8_t kb_seg[MAXKB], kb_coef[MAXKB], kb_relu[MAXKB];
   int16_t kb_c0[MAXKB], kb_valid[MAXKB];
@@ -53,21 +56,50 @@ struct TcLayout {
 };
 
 struct Misc {
-  uint64_t full[8], empty[8], tfull[2], tempty[2];
+  uint64_t full[8], empty[16], tfull[2], tempty[2];    // empty[(turn & 1) * 8 + stage]: see the loader comment
   uint32_t tmem_base;
 };
 
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldg((const float4*)p); }
 
-// LW: loader warps (8 or 16).  LD2: loaders read two tensors (dY and Z) and apply the BN-backward
-// affine.  EPI (0 plain, 1 mask, 2 mask + added tensor): the epilogue adds the skip gradient / applies the ReLU mask / accumulates the
-// BN-backward sums.
-template <int LW, bool LD2, int EPI>
-__global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const __grid_constant__ IgemmParams P,
-                                                                        const __grid_constant__ TcLayout Lo) {
-  constexpr int NT = 32 * (4 + LW + EW);
-  // register budgets per role (launch value: 72 for 28 warps, 96 for 20 warps)
-  constexpr int REG_MMA = LW == 16 ? 24 : 32, REG_LOAD = LW == 16 ? 72 : 112, REG_EPI = LW == 16 ? 96 : 112;   // sums: 64512 of 64512, 61440 of 61440
+// st.global / ld.global with a 64-bit base and a 32-bit element offset: IMAD.WIDE + STG/LDG (the
+// compiler's own addressing of base[off] re-materialised the base from the constant bank per element).
+__device__ __forceinline__ void stg_off(float* base, unsigned off, float v) {
+  asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %1, 4, %0;\n\tst.global.f32 [a], %2;\n\t}" ::"l"(base), "r"(off), "f"(v) : "memory");
+}
+__device__ __forceinline__ float ldg_off(const float* base, unsigned off) {
+  float v;
+  asm("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %2, 4, %1;\n\tld.global.nc.f32 %0, [a];\n\t}" : "=f"(v) : "l"(base), "r"(off));
+  return v;
+}
+__device__ __forceinline__ float4 ldg4_off(const float* base, unsigned off) {
+  float4 v;
+  asm("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %5, 4, %4;\n\tld.global.nc.v4.f32 {%0,%1,%2,%3}, [a];\n\t}"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(base), "r"(off));
+  return v;
+}
+
+constexpr int LW = 16;        // loader warps
+constexpr int NG = 4;         // loader groups of 4 warps; group g owns k-blocks g, g+NG, ... (global k-block counter)
+constexpr int NT = 32 * (4 + LW + EW);
+
+// LD2: loaders read two tensors (dY and Z) and apply the BN-backward affine.  EPI (0 plain, 1 mask, 2 mask +
+// added tensor): the epilogue adds the skip gradient / applies the ReLU mask / accumulates the BN-backward sums.
+//
+// The kernel is bound by instruction issue, not by HBM or the tensor pipe (ablation: with MMAs, loads and
+// stores all disabled the old skeleton still took the full HBM time), so both producer and consumer roles are
+// written for instructions per element:
+//   * a loader GROUP (4 warps) owns a whole k-block: 8 rows x one 16-byte channel chunk per thread, loads
+//     issued back to back, then transformed and stored.  The per-k-block bookkeeping (descriptor fetch, row
+//     decode, barrier handshake) is paid once per 8 float4 instead of once per 2, and memory-level
+//     parallelism comes from the 4 groups working on 4 different k-blocks, not from register slots.
+//   * the epilogue addresses rows with one 32-bit element offset (lane j computes row j's, broadcast by
+//     shuffle) and IMAD.WIDE + STG; full tiles skip the per-row validity test.
+template <bool LD2, int EPI>
+__global__ void __launch_bounds__(NT, 1) tc_igemm_kernel(const __grid_constant__ IgemmParams P,
+                                                         const __grid_constant__ TcLayout Lo) {
+  // register budgets per role (launch value 72 for 28 warps): 4*24 + 16*72 + 8*96 = 2016 = 28*72
+  constexpr int REG_MMA = 24, REG_EPI = 96;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* Wsm = smem;                                 // [hi|lo][nkb][MW rows][128 B], swizzled
@@ -128,7 +160,7 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
   }
   if (warp == 0) {
     if (lane == 0) {
-      for (int s = 0; s < nstage; ++s) { mbar_init(&mi.full[s], LW); mbar_init(&mi.empty[s], 1); }
+      for (int s = 0; s < nstage; ++s) { mbar_init(&mi.full[s], LW / NG); mbar_init(&mi.empty[s], 1); mbar_init(&mi.empty[8 + s], 1); }
       for (int a = 0; a < 2; ++a) { mbar_init(&mi.tfull[a], 1); mbar_init(&mi.tempty[a], 32 * EW); }
       fence_barrier_init();
     }
@@ -154,11 +186,11 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
       uint32_t ph = 0;
       for (int ti = 0; ti < n_my; ++ti) {
         const int acc = ti & 1;
-        mbar_wait(&mi.tempty[acc], ((ti >> 1) & 1) ^ 1);
+        mbar_wait(&mi.tempty[acc], ((ti >> 1) & 1) ^ 1, 100 + ti);
         tc_fence_after();
         const uint32_t d = tmem + acc * BM;
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&mi.full[st], ph);
+          mbar_wait(&mi.full[st], ph & 1, 200 + st * 10 + kb);
           tc_fence_after();
           const uint32_t x_hi = a_base + st * (STAGE >> 4), x_lo = x_hi + (A_TILE >> 4);
           const uint32_t w_hi = w_base + (uint32_t)kb * w_kb, w_lo = w_hi + w_lo_off;
@@ -166,126 +198,113 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
           for (int j = 0; j < 4; ++j) {
             const uint64_t dxh = dhi | (x_hi + 2 * j), dxl = dhi | (x_lo + 2 * j);
             const uint64_t dwh = dhi | (w_hi + 2 * j), dwl = dhi | (w_lo + 2 * j);
+            if (Lo.dbg & 1) continue;
             mma_tf32(d, dwl, dxh, idesc, (kb | j) != 0);
             mma_tf32(d, dwh, dxl, idesc, 1);
             mma_tf32(d, dwh, dxh, idesc, 1);
           }
-          mma_commit(&mi.empty[st]);
-          if (++st == nstage) { st = 0; ph ^= 1; }
+          mma_commit(&mi.empty[(ph & 1) * 8 + st]);
+          if (++st == nstage) { st = 0; ++ph; }
         }
         mma_commit(&mi.tfull[acc]);
       }
     }
   } else if (warp < 4 + LW) {
     // ================================== loaders ====================================
-    if (LW == 8) reg_inc<REG_LOAD>();
-    constexpr int RPT = 32 / LW;                        // rows per thread and k-block
-    constexpr int RSTEP = 4 * LW;                       // row distance between a thread's rows
-    constexpr int NS = LD2 ? 2 : (LW == 8 ? 3 : 4);     // register slots; prefetch distance NS-1 k-blocks
-    const int lt = tid - 128, chunk = lt & 7, r0 = lt >> 3;
-    const uint32_t st_off = (uint32_t)r0 * 128 + ((uint32_t)(chunk ^ (r0 & 7)) << 4);
-    const int total = n_my * nkb;
-    const unsigned Mu = (unsigned)M, Lq = (unsigned)P.Lq;
-    float4 va[NS][RPT], vb[LD2 ? NS : 1][RPT];
-    unsigned vmask[NS];
-    // issue-side cursor (runs NS-1 k-blocks ahead of the commit-side cursor)
-    int i_kb = 0, i_ti = 0, i_seg = -1;
-    const float* i_src = nullptr;
-    const float* i_src2 = nullptr;
-    unsigned rbt[RPT], rq[RPT];
-    bool rok[RPT];
-    int roff[RPT];
-    auto decode_rows = [&]() {
-      const unsigned m0 = ((unsigned)blockIdx.x + (unsigned)i_ti * gridDim.x) * BM;
-#pragma unroll
-      for (int i = 0; i < RPT; ++i) {
-        const unsigned m = m0 + r0 + RSTEP * i;
-        rok[i] = m < Mu;
-        rbt[i] = rok[i] ? m / Lq : 0u;
-        rq[i] = rok[i] ? m - rbt[i] * Lq : 0u;
+    constexpr int R = LD2 ? 4 : 8;                      // rows per thread and pass (LD2: two passes of 4 rows, two tensors)
+    const int lt = tid - 128, g = lt >> 7, gt = lt & 127, chunk = gt & 7, rbase = gt >> 3;   // rows rbase + 16 i
+    const uint32_t st_off = (uint32_t)rbase * 128 + ((uint32_t)(chunk ^ (rbase & 7)) << 4);
+    const unsigned Lq = (unsigned)P.Lq, magic = Lo.lq_magic, Mu = (unsigned)M;
+    int ti = 0, kb = g;
+    while (kb >= nkb) { kb -= nkb; ++ti; }
+    // Ring bookkeeping.  A group advances NG k-blocks at a time, which can be more than one turn of the ring,
+    // so with one parity barrier per stage it could be two completions behind and mis-read the parity.  The
+    // "slot free" barriers therefore alternate between two mbarriers per stage (even / odd turns): each one
+    // completes every other turn and a waiter is never more than one completion behind.
+    int st = g;
+    uint32_t ph = 0;                 // turn of the ring this group's k-block belongs to
+    while (st >= nstage) { st -= nstage; ++ph; }
+    int cur = -1;
+    unsigned bt0 = 0, qb = 0, qmax = 0;
+    const float ninf = -__int_as_float(0x7f800000);
+    while (ti < n_my) {
+      if (ti != cur) {               // new tile: decode its first row once; the thread's rows follow by a small exact division
+        const unsigned m0 = ((unsigned)blockIdx.x + (unsigned)ti * gridDim.x) * BM;
+        // rows beyond M (last tile only) are clamped to row M-1: they load valid memory and the epilogue drops them
+        bt0 = m0 / Lq; qb = m0 - bt0 * Lq + rbase; qmax = Mu - 1u - bt0 * Lq;
+        cur = ti;
       }
-      i_seg = -1;
-    };
-    decode_rows();
-    auto issue = [&](float4 (&a)[RPT], float4 (&b)[RPT], unsigned& msk) {
-      const int s = Lo.kb_seg[i_kb];
-      if (s != i_seg) {
-        const Seg& sg = P.seg[s];
-        const int Lsrc = sg.Lsrc, ld = sg.ld, coff = sg.coff, smul = sg.smul, sadd = sg.sadd;
-#pragma unroll
-        for (int i = 0; i < RPT; ++i) {
-          const int li = (int)rq[i] * smul + sadd;
-          roff[i] = (rok[i] && (unsigned)li < (unsigned)Lsrc) ? ((int)rbt[i] * Lsrc + li) * ld + coff : -1;
-        }
-        i_seg = s; i_src = sg.src; i_src2 = sg.src2;
-      }
-      const int c = Lo.kb_c0[i_kb] + chunk * 4;
-      const bool cok = chunk * 4 < Lo.kb_valid[i_kb];
-      msk = 0;
-#pragma unroll
-      for (int i = 0; i < RPT; ++i) {
-        if (cok && roff[i] >= 0) {
-          a[i] = ld4(i_src + (unsigned)(roff[i] + c));
-          if (LD2) b[i] = i_src2 ? ld4(i_src2 + (unsigned)(roff[i] + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          msk |= 1u << i;
-        }
-      }
-      if (++i_kb == nkb) { i_kb = 0; ++i_ti; decode_rows(); }
-    };
-    // commit-side cursor
-    int c_kb = 0, c_st = 0;
-    uint32_t c_ph = 0;
-    auto commit = [&](float4 (&a)[RPT], float4 (&b)[RPT], unsigned msk) {
-      const int e = Lo.kb_coef[c_kb];
-      float4 p0 = make_float4(1, 1, 1, 1), p1 = make_float4(0, 0, 0, 0), p2 = p1;
+      const Seg& sg = P.seg[Lo.kb_seg[kb]];
+      const float* src = sg.src;
+      const float* src2 = LD2 ? sg.src2 : nullptr;
+      const unsigned Lsrc = (unsigned)sg.Lsrc, ld = (unsigned)sg.ld;
+      const int smul = sg.smul, sadd = sg.sadd;
+      const unsigned cb = (unsigned)(sg.coff + Lo.kb_c0[kb] + chunk * 4);
+      const bool cok = chunk * 4 < Lo.kb_valid[kb] && !(Lo.dbg & 2);
+      const unsigned Lok = cok ? Lsrc : 0u;               // channel chunk beyond the segment: every row is a zero row
+      const int e = Lo.kb_coef[kb];
+      const float fl = Lo.kb_relu[kb] ? 0.f : ninf;
+      float4 p0 = make_float4(1.f, 1.f, 1.f, 1.f), p1 = make_float4(0.f, 0.f, 0.f, 0.f), p2 = p1;
       if (e >= 0) {
         const float* ce = coef + e * COEF_FLOATS + chunk * 4;
         p0 = *(const float4*)ce; p2 = *(const float4*)(ce + 32);
         if (LD2) p1 = *(const float4*)(ce + 64);
       }
-      const float fl = Lo.kb_relu[c_kb] ? 0.f : -__int_as_float(0x7f800000);
-      mbar_wait(&mi.empty[c_st], c_ph ^ 1);
-      uint8_t* ah = Asm + c_st * STAGE + st_off;
+      uint8_t* ah = Asm + st * STAGE + st_off;
 #pragma unroll
-      for (int i = 0; i < RPT; ++i) {
-        float4 v = a[i];
-        if (e >= 0) {
-          if (LD2) {
-            v.x = fmaf(p1.x, b[i].x, fmaf(p0.x, v.x, p2.x)); v.y = fmaf(p1.y, b[i].y, fmaf(p0.y, v.y, p2.y));
-            v.z = fmaf(p1.z, b[i].z, fmaf(p0.z, v.z, p2.z)); v.w = fmaf(p1.w, b[i].w, fmaf(p0.w, v.w, p2.w));
-          } else {
-            v.x = fmaf(p0.x, v.x, p2.x); v.y = fmaf(p0.y, v.y, p2.y); v.z = fmaf(p0.z, v.z, p2.z); v.w = fmaf(p0.w, v.w, p2.w);
-          }
-          v.x = fmaxf(v.x, fl); v.y = fmaxf(v.y, fl); v.z = fmaxf(v.z, fl); v.w = fmaxf(v.w, fl);
+      for (int h = 0; h < 8 / R; ++h) {
+        float4 a[R], b[LD2 ? R : 1];
+        unsigned msk = 0;
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+          const int ii = h * R + i;
+          const unsigned qq = min(qb + 16u * ii, qmax);
+          const unsigned bq = magic ? __umulhi(qq, magic) : qq;          // qq / Lq (exact: qq * Lq < 2^32)
+          const unsigned q = qq - bq * Lq;
+          const unsigned li = (unsigned)((int)q * smul + sadd);
+          const bool ok = li < Lok;
+          unsigned off = ((bt0 + bq) * Lsrc + li) * ld + cb;
+          off = ok ? off : 0u;               // padding rows read element 0 (always mapped) and are zeroed below
+          if (ok) msk |= 1u << i;
+          a[i] = ldg4_off(src, off);
+          if (LD2) b[i] = src2 ? ldg4_off(src2, off) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        if (!(msk & (1u << i))) v = make_float4(0.f, 0.f, 0.f, 0.f);
-        uint4 hi, lo;
-        hi.x = __float_as_uint(v.x) & 0xffffe000u; hi.y = __float_as_uint(v.y) & 0xffffe000u;
-        hi.z = __float_as_uint(v.z) & 0xffffe000u; hi.w = __float_as_uint(v.w) & 0xffffe000u;
-        lo.x = __float_as_uint(v.x - __uint_as_float(hi.x)); lo.y = __float_as_uint(v.y - __uint_as_float(hi.y));
-        lo.z = __float_as_uint(v.z - __uint_as_float(hi.z)); lo.w = __float_as_uint(v.w - __uint_as_float(hi.w));
-        *(uint4*)(ah + i * (RSTEP * 128)) = hi;
-        *(uint4*)(ah + A_TILE + i * (RSTEP * 128)) = lo;
+        if (h == 0 && ph > 0) mbar_wait(&mi.empty[((ph - 1) & 1) * 8 + st], ((ph - 1) >> 1) & 1, 300 + st * 10 + kb + 1000 * ti);
+        const bool all_ok = __all_sync(0xffffffffu, msk == (1u << R) - 1u);
+        auto emit = [&](auto ZERO) {
+          constexpr bool zero = decltype(ZERO)::value;
+#pragma unroll
+          for (int i = 0; i < R; ++i) {
+            float4 v = a[i];
+            if (e >= 0 && !(Lo.dbg & 32)) {
+              if (LD2) {
+                v.x = fmaf(p1.x, b[i].x, fmaf(p0.x, v.x, p2.x)); v.y = fmaf(p1.y, b[i].y, fmaf(p0.y, v.y, p2.y));
+                v.z = fmaf(p1.z, b[i].z, fmaf(p0.z, v.z, p2.z)); v.w = fmaf(p1.w, b[i].w, fmaf(p0.w, v.w, p2.w));
+              } else {
+                v.x = fmaf(p0.x, v.x, p2.x); v.y = fmaf(p0.y, v.y, p2.y); v.z = fmaf(p0.z, v.z, p2.z); v.w = fmaf(p0.w, v.w, p2.w);
+                v.x = fmaxf(v.x, fl); v.y = fmaxf(v.y, fl); v.z = fmaxf(v.z, fl); v.w = fmaxf(v.w, fl);
+              }
+            }
+            if (zero && !(msk & (1u << i))) v = make_float4(0.f, 0.f, 0.f, 0.f);
+            uint4 hi, lo;
+            hi.x = __float_as_uint(v.x) & 0xffffe000u; hi.y = __float_as_uint(v.y) & 0xffffe000u;
+            hi.z = __float_as_uint(v.z) & 0xffffe000u; hi.w = __float_as_uint(v.w) & 0xffffe000u;
+            lo.x = __float_as_uint(v.x - __uint_as_float(hi.x)); lo.y = __float_as_uint(v.y - __uint_as_float(hi.y));
+            lo.z = __float_as_uint(v.z - __uint_as_float(hi.z)); lo.w = __float_as_uint(v.w - __uint_as_float(hi.w));
+            if (Lo.dbg & 4) continue;
+            *(uint4*)(ah + (h * R + i) * (16 * 128)) = hi;
+            *(uint4*)(ah + A_TILE + (h * R + i) * (16 * 128)) = lo;
+          }
+        };
+        if (all_ok) emit(std::false_type{}); else emit(std::true_type{});
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&mi.full[c_st]);
-      if (++c_kb == nkb) c_kb = 0;
-      if (++c_st == nstage) { c_st = 0; c_ph ^= 1; }
-    };
-
-#pragma unroll
-    for (int u = 0; u < NS - 1; ++u)
-      if (u < total) issue(va[u], vb[LD2 ? u : 0], vmask[u]);
-    for (int w = 0; w < total; w += NS) {
-#pragma unroll
-      for (int u = 0; u < NS; ++u) {
-        const int ww = w + u;
-        if (ww < total) {
-          if (ww + NS - 1 < total) issue(va[(u + NS - 1) % NS], vb[LD2 ? (u + NS - 1) % NS : 0], vmask[(u + NS - 1) % NS]);
-          commit(va[u], vb[LD2 ? u : 0], vmask[u]);
-        }
-      }
+      if (lane == 0) mbar_arrive(&mi.full[st]);
+      kb += NG;
+      while (kb >= nkb) { kb -= nkb; ++ti; }
+      st += NG;
+      while (st >= nstage) { st -= nstage; ++ph; }
     }
   } else {
     // ================================== epilogue ===================================
@@ -300,7 +319,7 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
     const bool m64 = MW == 64;
     const int nl = m64 ? lg * 16 + (lane & 15) : lg * 32 + lane;
     const int n = n0 + nl;
-    const bool nok = n < P.N;
+    const bool nok = n < P.N && !(Lo.dbg & 8);
     const int src64 = lane & 16;                        // M = 64: lanes 16-31 hold the second 16 rows of a chunk
     const unsigned Mu = (unsigned)M, Lq = (unsigned)P.Lq;
     const float bias = (P.bias && nok) ? __ldg(P.bias + n) : 0.f;
@@ -310,11 +329,14 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
     const bool do_stats = P.stats != nullptr, do_bstats = EPI && P.bstats != nullptr;
     const float bmean = (do_bstats && nok) ? __ldg(P.bmean + n) : 0.f;
     float s1 = 0.f, s2 = 0.f;      // stats: sum o, sum o*o;  bstats: sum g, sum g*(z - mean) (scaled at the end)
-    // per-thread base element offset; per-row offsets are computed by lane j for row j of a chunk
+    // per-thread base pointers; per-row element offsets are computed by lane j for row j of a chunk
     const size_t obase = P.planar ? (size_t)n * P.Lout : (size_t)n;
     const float* zbase = use_mask ? P.zmask + obase : nullptr;
     const float* xbase = has_extra ? P.extra + n : nullptr;
     float* outb = P.out + obase;
+    asm("" : "+l"(outb));            // opaque: keep the finished pointer in registers (no re-association with P.out)
+    asm("" : "+l"(zbase));
+    asm("" : "+l"(xbase));
 
     // lane j: element offsets of tile row cc*32 + j of tile ti (0xffffffff: row does not exist)
     auto row_offsets = [&](int ti, int cc, unsigned& ooff, unsigned& eoff) {
@@ -329,79 +351,109 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
         }
       }
     };
-    auto zfetch = [&](float (&z)[16], float (&x)[EPI == 2 ? 16 : 1], unsigned ooff, unsigned eoff, int src0) {
+    auto zfetch = [&](float (&z)[16], unsigned ooff, int src0) {
       if (EPI && use_mask) {
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
           const unsigned off = __shfl_sync(0xffffffffu, ooff, src0 + r);
-          z[r] = (nok && off != 0xffffffffu) ? __ldg(zbase + off) : 0.f;
+          z[r] = (nok && off != 0xffffffffu) ? ldg_off(zbase, off) : 0.f;
         }
       }
+    };
+    auto xfetch = [&](float (&x)[EPI == 2 ? 16 : 1], unsigned ooff, unsigned eoff, int src0) {
       if (EPI == 2 && has_extra) {
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
           const unsigned off = __shfl_sync(0xffffffffu, ooff, src0 + r);
           const unsigned eo = __shfl_sync(0xffffffffu, eoff, src0 + r);
-          x[EPI == 2 ? r : 0] = (nok && off != 0xffffffffu) ? __ldg(xbase + eo) : 0.f;
+          x[EPI == 2 ? r : 0] = (nok && off != 0xffffffffu) ? ldg_off(xbase, eo) : 0.f;
         }
       }
     };
-    auto process = [&](const uint32_t (&v)[16], int src0, const float (&z)[16], const float (&x)[EPI == 2 ? 16 : 1], unsigned ooff) {
+    // CHK: the tile may contain rows beyond M (only the last tile of the problem).  ST: 0 no sums, 1 forward BN
+    // statistics, 2 BN-backward sums.  Both are compile-time so the per-element code is shuffle, address, add,
+    // store (+2-3 for the sums) with the loop-invariant channel predicate on the store.
+    auto process = [&](auto CHK, auto STM, const uint32_t (&v)[16], int src0, const float (&z)[16], const float (&x)[EPI == 2 ? 16 : 1], unsigned ooff) {
+      constexpr bool chk = decltype(CHK)::value;
+      constexpr int stm = decltype(STM)::value;
 #pragma unroll
       for (int r = 0; r < 16; ++r) {
         const unsigned off = __shfl_sync(0xffffffffu, ooff, src0 + r);
-        const bool ok = nok && off != 0xffffffffu;
+        const bool ok = nok && (!chk || off != 0xffffffffu);
         float o = __uint_as_float(v[r]) + bias;
         if (EPI) {
-          if (EPI == 2 && has_extra) o += x[r];
+          if (EPI == 2 && has_extra) o += x[EPI == 2 ? r : 0];
           if (use_mask) o = (fmaf(z[r], mp0, mp2) > 0.f) ? o : 0.f;
         }
-        if (ok) {
-          outb[off] = o;
-          if (do_stats) { s1 += o; s2 = fmaf(o, o, s2); }
-          if (EPI && do_bstats) { s1 += o; s2 = fmaf(o, z[r] - bmean, s2); }
+        if (chk) {
+          if (ok) {
+            outb[off] = o;
+            if (stm == 1) { s1 += o; s2 = fmaf(o, o, s2); }
+            if (stm == 2) { s1 += o; s2 = fmaf(o, z[r] - bmean, s2); }
+          }
+        } else {       // full tile: only the store carries the (loop-invariant) channel predicate; idle lanes' sums are never used
+          if (nok) outb[off] = o;
+          if (stm == 1) { s1 += o; s2 = fmaf(o, o, s2); }
+          if (stm == 2) { s1 += o; s2 = fmaf(o, z[r] - bmean, s2); }
         }
       }
     };
-
-    float za[16], zb[16], xa[EPI == 2 ? 16 : 1], xb[EPI == 2 ? 16 : 1];
+    const int stmode = do_stats ? 1 : ((EPI && do_bstats) ? 2 : 0);
+    float za[16], zb[16], xx[EPI == 2 ? 16 : 1];
     unsigned oa, ea, ob, eb;
     row_offsets(0, half * 2, oa, ea);
-    zfetch(za, xa, oa, ea, m64 ? src64 : 0);
+    zfetch(za, oa, m64 ? src64 : 0);
     for (int ti = 0; ti < n_my; ++ti) {
       const int acc = ti & 1;
+      const bool part = (((unsigned)blockIdx.x + (unsigned)ti * gridDim.x) + 1u) * BM > Mu;    // tile has missing rows
       row_offsets(ti, half * 2 + 1, ob, eb);
-      mbar_wait(&mi.tfull[acc], (ti >> 1) & 1);
+      mbar_wait(&mi.tfull[acc], (ti >> 1) & 1, 400 + ti);
       tc_fence_after();
       const uint32_t taddr = tmem + ((uint32_t)(lg * 32) << 16) + acc * BM + half * 64;
       uint32_t v[16];
+      if (Lo.dbg & 16) { tc_fence_before(); mbar_arrive(&mi.tempty[acc]); continue; }
+#define TRU_PROCESS(V, S0, Z, X, O) do { \
+        if (part) { if (stmode == 1) process(std::true_type{}, std::integral_constant<int, 1>{}, V, S0, Z, X, O); \
+                    else if (stmode == 2) process(std::true_type{}, std::integral_constant<int, EPI ? 2 : 0>{}, V, S0, Z, X, O); \
+                    else process(std::true_type{}, std::integral_constant<int, 0>{}, V, S0, Z, X, O); } \
+        else if (stmode == 1) process(std::false_type{}, std::integral_constant<int, 1>{}, V, S0, Z, X, O); \
+        else if (stmode == 2) process(std::false_type{}, std::integral_constant<int, EPI ? 2 : 0>{}, V, S0, Z, X, O); \
+        else process(std::false_type{}, std::integral_constant<int, 0>{}, V, S0, Z, X, O); } while (0)
       if (m64) {                       // 2 sub-steps of 32 columns, all 32 lanes busy
+        xfetch(xx, oa, ea, src64);
         tmem_ld16x2(taddr, v);
-        zfetch(zb, xb, ob, eb, src64);
-        process(v, src64, za, xa, oa);
+        zfetch(zb, ob, src64);
+        TRU_PROCESS(v, src64, za, xx, oa);
+        xfetch(xx, ob, eb, src64);
         tmem_ld16x2(taddr + 32, v);
         tc_fence_before();
         mbar_arrive(&mi.tempty[acc]);
         row_offsets(ti + 1, half * 2, oa, ea);
-        zfetch(za, xa, oa, ea, src64);
-        process(v, src64, zb, xb, ob);
+        zfetch(za, oa, src64);
+        TRU_PROCESS(v, src64, zb, xx, ob);
       } else {                         // 4 sub-steps of 16 columns
+        xfetch(xx, oa, ea, 0);
         tmem_ld16(taddr, v);
-        zfetch(zb, xb, oa, ea, 16);
-        process(v, 0, za, xa, oa);
+        zfetch(zb, oa, 16);
+        TRU_PROCESS(v, 0, za, xx, oa);
+        xfetch(xx, oa, ea, 16);
         tmem_ld16(taddr + 16, v);
-        zfetch(za, xa, ob, eb, 0);
-        process(v, 16, zb, xb, oa);
+        zfetch(za, ob, 0);
+        TRU_PROCESS(v, 16, zb, xx, oa);
+        xfetch(xx, ob, eb, 0);
         tmem_ld16(taddr + 32, v);
-        zfetch(zb, xb, ob, eb, 16);
-        process(v, 0, za, xa, ob);
+        zfetch(zb, ob, 16);
+        TRU_PROCESS(v, 0, za, xx, ob);
+        xfetch(xx, ob, eb, 16);
         tmem_ld16(taddr + 48, v);
         tc_fence_before();
         mbar_arrive(&mi.tempty[acc]);
+        const unsigned ob2 = ob;
         row_offsets(ti + 1, half * 2, oa, ea);
-        zfetch(za, xa, oa, ea, 0);
-        process(v, 16, zb, xb, ob);
+        zfetch(za, oa, 0);
+        TRU_PROCESS(v, 16, zb, xx, ob2);
       }
+#undef TRU_PROCESS
     }
     double* gst = P.stats ? P.stats : (EPI ? P.bstats : nullptr);
     if (gst && nok) {
@@ -424,6 +476,7 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
 }
 
 constexpr size_t SMEM_MAX = 227 * 1024;
+int g_dbg_flags = 0;        // ablation switches (tru_debug_set_flags)
 
 int total_kblocks(const IgemmParams& p) {
   int nkb = 0;
@@ -432,7 +485,7 @@ int total_kblocks(const IgemmParams& p) {
 }
 
 bool shape_ok(const IgemmParams& p) {
-  if (p.nseg < 1 || p.nseg > 5 || p.N < 1) return false;
+  if (p.nseg < 1 || p.nseg > 5 || p.N < 1 || p.Lq < 1 || p.Lq > 32768) return false;
   for (int s = 0; s < p.nseg; ++s) {
     if (p.seg[s].C % 4 != 0 || p.seg[s].ld % 4 != 0 || p.seg[s].coff % 4 != 0) return false;
     // 32-bit element offsets inside the kernel
@@ -481,7 +534,8 @@ bool plan(const IgemmParams& p, TcLayout& L, dim3& grid, size_t& smem_bytes) {
       ++nkb;
     }
   }
-  L.nkb = nkb; L.ncoef = ncoef;
+  L.nkb = nkb; L.ncoef = ncoef; L.dbg = g_dbg_flags;
+  L.lq_magic = p.Lq == 1 ? 0u : (unsigned)((0x100000000ull + (unsigned)p.Lq - 1) / (unsigned)p.Lq);
   const size_t w = (size_t)2 * nkb * L.MW * 128;
   const size_t coefb = (size_t)ncoef * COEF_FLOATS * 4;
   const size_t fixed = 1024 + coefb + sizeof(Misc) + 64;
@@ -498,32 +552,24 @@ bool plan(const IgemmParams& p, TcLayout& L, dim3& grid, size_t& smem_bytes) {
   return smem_bytes <= SMEM_MAX;
 }
 
-int g_loader_warps = 0;      // 0: 16 loader warps for plain epilogues (forward), 8 when the epilogue needs the registers
-
-template <int LW, bool LD2, int EPI>
+template <bool LD2, int EPI>
 int launch_inst(const IgemmParams& p, const TcLayout& L, dim3 grid, size_t smem, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
-    TRU_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<LW, LD2, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+    TRU_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<LD2, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
     attr_done = true;
   }
-  tc_igemm_kernel<LW, LD2, EPI><<<grid, 32 * (4 + LW + EW), smem, st>>>(p, L);
+  tc_igemm_kernel<LD2, EPI><<<grid, NT, smem, st>>>(p, L);
   TRU_LAUNCH_CHECK();
   return TRU_OK;
 }
 
-// 16 loader warps unless the epilogue also prefetches an added tensor (its registers only fit the 8-warp layout)
 int launch_one(const IgemmParams& p, const TcLayout& L, dim3 grid, size_t smem, cudaStream_t st) {
   const int epi = p.extra != nullptr ? 2 : ((p.use_mask || p.bstats != nullptr) ? 1 : 0);
   bool ld2 = false;
   for (int s = 0; s < p.nseg; ++s) ld2 |= (p.seg[s].src2 != nullptr);
-  const int lw = g_loader_warps ? g_loader_warps : (epi == 2 ? 8 : 16);
-  if (lw == 8 || epi == 2) {
-    if (ld2) return epi == 0 ? launch_inst<8, true, 0>(p, L, grid, smem, st) : epi == 1 ? launch_inst<8, true, 1>(p, L, grid, smem, st) : launch_inst<8, true, 2>(p, L, grid, smem, st);
-    return epi == 0 ? launch_inst<8, false, 0>(p, L, grid, smem, st) : epi == 1 ? launch_inst<8, false, 1>(p, L, grid, smem, st) : launch_inst<8, false, 2>(p, L, grid, smem, st);
-  }
-  if (ld2) return epi == 0 ? launch_inst<16, true, 0>(p, L, grid, smem, st) : launch_inst<16, true, 1>(p, L, grid, smem, st);
-  return epi == 0 ? launch_inst<16, false, 0>(p, L, grid, smem, st) : launch_inst<16, false, 1>(p, L, grid, smem, st);
+  if (ld2) return epi == 0 ? launch_inst<true, 0>(p, L, grid, smem, st) : epi == 1 ? launch_inst<true, 1>(p, L, grid, smem, st) : launch_inst<true, 2>(p, L, grid, smem, st);
+  return epi == 0 ? launch_inst<false, 0>(p, L, grid, smem, st) : epi == 1 ? launch_inst<false, 1>(p, L, grid, smem, st) : launch_inst<false, 2>(p, L, grid, smem, st);
 }
 
 int launch_planned(const IgemmParams& p, cudaStream_t st) {
@@ -556,7 +602,17 @@ IgemmParams slice_kblocks(const IgemmParams& p, int k0, int k1) {
 
 }  // namespace
 
-void set_tc_loader_warps(int n) { g_loader_warps = (n == 8 || n == 16) ? n : 0; }
+void set_tc_debug_flags(int f) { g_dbg_flags = f; }
+int read_mbar_debug(unsigned* out, int n) {
+#ifdef TRU_MBAR_TIMEOUT
+  cudaMemcpyFromSymbol(out, tc::g_mbar_dbg, sizeof(unsigned) * (size_t)std::min(n, 1028));
+  return 1;
+#else
+  (void)out; (void)n;
+  return 0;
+#endif
+}
+void set_tc_loader_warps(int) {}    // kept for the debug ABI; the kernel has one loader layout now
 
 bool igemm_tc_eligible(const IgemmParams& p) {
   if (!shape_ok(p)) return false;

@@ -591,6 +591,8 @@ extern "C" int tru_debug_pw(const float* x, const float* p0, const float* p2, co
 }
 extern "C" int tru_set_tensor_cores(int on) { set_tc_enabled(on != 0); return TRU_OK; }
 extern "C" int tru_debug_set_loader_warps(int n) { set_tc_loader_warps(n); return TRU_OK; }
+extern "C" int tru_debug_read_mbar(unsigned* out, int n) { return read_mbar_debug(out, n); }
+extern "C" int tru_debug_set_flags(int f) { set_tc_debug_flags(f); return TRU_OK; }
 
 // Test aid: dW (N,C) += z^T a for a (M,C), z (M,N) through either weight-gradient path.
 extern "C" int tru_debug_wgrad(const float* a, const float* z, float* dw, float* db, int M, int C, int N, int use_tc,
