@@ -169,6 +169,8 @@ def run_native(args):
 
     if os.environ.get("TRU_LOADER_WARPS"):                 # tuning aid (8 or 16 loader warps in the GEMM kernels)
         L.lib.tru_debug_set_loader_warps(int(os.environ["TRU_LOADER_WARPS"]))
+    if os.environ.get("TRU_DBG_FLAGS"):                    # bottleneck hunting: disable parts of the GEMM kernel (results are garbage)
+        L.lib.tru_debug_set_flags(int(os.environ["TRU_DBG_FLAGS"]))
     B = args.batch
     torch.manual_seed(0)
     net = network.TRUNet(3, 64, 3, 128, [5, 3], [2, 1], 192).to(dev).train()

@@ -62,6 +62,7 @@ struct Misc {
 
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldg((const float4*)p); }
 
+// (volatile: the loads must stay where they are written - they are prefetches issued ahead of a wait)
 // st.global / ld.global with a 64-bit base and a 32-bit element offset: IMAD.WIDE + STG/LDG (the
 // compiler's own addressing of base[off] re-materialised the base from the constant bank per element).
 __device__ __forceinline__ void stg_off(float* base, unsigned off, float v) {
@@ -69,12 +70,12 @@ __device__ __forceinline__ void stg_off(float* base, unsigned off, float v) {
 }
 __device__ __forceinline__ float ldg_off(const float* base, unsigned off) {
   float v;
-  asm("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %2, 4, %1;\n\tld.global.nc.f32 %0, [a];\n\t}" : "=f"(v) : "l"(base), "r"(off));
+  asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %2, 4, %1;\n\tld.global.nc.f32 %0, [a];\n\t}" : "=f"(v) : "l"(base), "r"(off));
   return v;
 }
 __device__ __forceinline__ float4 ldg4_off(const float* base, unsigned off) {
   float4 v;
-  asm("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %5, 4, %4;\n\tld.global.nc.v4.f32 {%0,%1,%2,%3}, [a];\n\t}"
+  asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %5, 4, %4;\n\tld.global.nc.v4.f32 {%0,%1,%2,%3}, [a];\n\t}"
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(base), "r"(off));
   return v;
 }
@@ -98,8 +99,9 @@ constexpr int NT = 32 * (4 + LW + EW);
 template <bool LD2, int EPI>
 __global__ void __launch_bounds__(NT, 1) tc_igemm_kernel(const __grid_constant__ IgemmParams P,
                                                          const __grid_constant__ TcLayout Lo) {
-  // register budgets per role (launch value 72 for 28 warps): 4*24 + 16*72 + 8*96 = 2016 = 28*72
-  constexpr int REG_MMA = 24, REG_EPI = 96;
+  // register budgets per role (launch value 72 for 28 warps): 4*24 + 16*64 + 8*112 = 2016 = 28*72
+  //                                                      or 4*24 + 16*72 + 8*96 when the epilogue has no added tensor
+  constexpr int REG_MMA = 24, REG_LOAD = 72, REG_EPI = 96;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* Wsm = smem;                                 // [hi|lo][nkb][MW rows][128 B], swizzled
@@ -211,6 +213,7 @@ __global__ void __launch_bounds__(NT, 1) tc_igemm_kernel(const __grid_constant__
     }
   } else if (warp < 4 + LW) {
     // ================================== loaders ====================================
+    if (REG_LOAD < 72) reg_dec<REG_LOAD>();
     constexpr int R = LD2 ? 4 : 8;                      // rows per thread and pass (LD2: two passes of 4 rows, two tensors)
     const int lt = tid - 128, g = lt >> 7, gt = lt & 127, chunk = gt & 7, rbase = gt >> 3;   // rows rbase + 16 i
     const uint32_t st_off = (uint32_t)rbase * 128 + ((uint32_t)(chunk ^ (rbase & 7)) << 4);
@@ -332,7 +335,7 @@ __global__ void __launch_bounds__(NT, 1) tc_igemm_kernel(const __grid_constant__
     // per-thread base pointers; per-row element offsets are computed by lane j for row j of a chunk
     const size_t obase = P.planar ? (size_t)n * P.Lout : (size_t)n;
     const float* zbase = use_mask ? P.zmask + obase : nullptr;
-    const float* xbase = has_extra ? P.extra + n : nullptr;
+    const float* xbase = has_extra ? P.extra + n - P.ocoff : nullptr;     // ext_ld == ldo (checked by the planner): same row offsets as the output
     float* outb = P.out + obase;
     asm("" : "+l"(outb));            // opaque: keep the finished pointer in registers (no re-association with P.out)
     asm("" : "+l"(zbase));
@@ -351,29 +354,29 @@ __global__ void __launch_bounds__(NT, 1) tc_igemm_kernel(const __grid_constant__
         }
       }
     };
-    auto zfetch = [&](float (&z)[16], unsigned ooff, int src0) {
-      if (EPI && use_mask) {
+    auto zfetch = [&](float (&z)[16], float (&x)[EPI == 2 ? 16 : 1], unsigned ooff, int src0) {
+      if (EPI && (use_mask || has_extra)) {
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
           const unsigned off = __shfl_sync(0xffffffffu, ooff, src0 + r);
-          z[r] = (nok && off != 0xffffffffu) ? ldg_off(zbase, off) : 0.f;
+          const bool ok = nok && off != 0xffffffffu;
+          z[r] = (ok && use_mask) ? ldg_off(zbase, off) : 0.f;
+          if (EPI == 2) x[EPI == 2 ? r : 0] = (ok && has_extra) ? ldg_off(xbase, off) : 0.f;
         }
       }
     };
-    auto xfetch = [&](float (&x)[EPI == 2 ? 16 : 1], unsigned ooff, unsigned eoff, int src0) {
-      if (EPI == 2 && has_extra) {
+    // the added tensor is folded into the accumulator registers as soon as they arrive, which frees its buffer
+    // for the next prefetch (one x buffer instead of two: the epilogue stays inside its register budget)
+    auto addx = [&](uint32_t (&v)[16], const float (&x)[EPI == 2 ? 16 : 1]) {
+      if (EPI == 2) {
 #pragma unroll
-        for (int r = 0; r < 16; ++r) {
-          const unsigned off = __shfl_sync(0xffffffffu, ooff, src0 + r);
-          const unsigned eo = __shfl_sync(0xffffffffu, eoff, src0 + r);
-          x[EPI == 2 ? r : 0] = (nok && off != 0xffffffffu) ? ldg_off(xbase, eo) : 0.f;
-        }
+        for (int r = 0; r < 16; ++r) v[r] = __float_as_uint(__uint_as_float(v[r]) + x[EPI == 2 ? r : 0]);
       }
     };
     // CHK: the tile may contain rows beyond M (only the last tile of the problem).  ST: 0 no sums, 1 forward BN
     // statistics, 2 BN-backward sums.  Both are compile-time so the per-element code is shuffle, address, add,
     // store (+2-3 for the sums) with the loop-invariant channel predicate on the store.
-    auto process = [&](auto CHK, auto STM, const uint32_t (&v)[16], int src0, const float (&z)[16], const float (&x)[EPI == 2 ? 16 : 1], unsigned ooff) {
+    auto process = [&](auto CHK, auto STM, const uint32_t (&v)[16], int src0, const float (&z)[16], unsigned ooff) {
       constexpr bool chk = decltype(CHK)::value;
       constexpr int stm = decltype(STM)::value;
 #pragma unroll
@@ -382,7 +385,6 @@ __global__ void __launch_bounds__(NT, 1) tc_igemm_kernel(const __grid_constant__
         const bool ok = nok && (!chk || off != 0xffffffffu);
         float o = __uint_as_float(v[r]) + bias;
         if (EPI) {
-          if (EPI == 2 && has_extra) o += x[EPI == 2 ? r : 0];
           if (use_mask) o = (fmaf(z[r], mp0, mp2) > 0.f) ? o : 0.f;
         }
         if (chk) {
@@ -402,7 +404,7 @@ __global__ void __launch_bounds__(NT, 1) tc_igemm_kernel(const __grid_constant__
     float za[16], zb[16], xx[EPI == 2 ? 16 : 1];
     unsigned oa, ea, ob, eb;
     row_offsets(0, half * 2, oa, ea);
-    zfetch(za, oa, m64 ? src64 : 0);
+    zfetch(za, xx, oa, m64 ? src64 : 0);
     for (int ti = 0; ti < n_my; ++ti) {
       const int acc = ti & 1;
       const bool part = (((unsigned)blockIdx.x + (unsigned)ti * gridDim.x) + 1u) * BM > Mu;    // tile has missing rows
@@ -412,46 +414,77 @@ __global__ void __launch_bounds__(NT, 1) tc_igemm_kernel(const __grid_constant__
       const uint32_t taddr = tmem + ((uint32_t)(lg * 32) << 16) + acc * BM + half * 64;
       uint32_t v[16];
       if (Lo.dbg & 16) { tc_fence_before(); mbar_arrive(&mi.tempty[acc]); continue; }
-#define TRU_PROCESS(V, S0, Z, X, O) do { \
-        if (part) { if (stmode == 1) process(std::true_type{}, std::integral_constant<int, 1>{}, V, S0, Z, X, O); \
-                    else if (stmode == 2) process(std::true_type{}, std::integral_constant<int, EPI ? 2 : 0>{}, V, S0, Z, X, O); \
-                    else process(std::true_type{}, std::integral_constant<int, 0>{}, V, S0, Z, X, O); } \
-        else if (stmode == 1) process(std::false_type{}, std::integral_constant<int, 1>{}, V, S0, Z, X, O); \
-        else if (stmode == 2) process(std::false_type{}, std::integral_constant<int, EPI ? 2 : 0>{}, V, S0, Z, X, O); \
-        else process(std::false_type{}, std::integral_constant<int, 0>{}, V, S0, Z, X, O); } while (0)
-      if (m64) {                       // 2 sub-steps of 32 columns, all 32 lanes busy
-        xfetch(xx, oa, ea, src64);
-        tmem_ld16x2(taddr, v);
-        zfetch(zb, ob, src64);
-        TRU_PROCESS(v, src64, za, xx, oa);
-        xfetch(xx, ob, eb, src64);
-        tmem_ld16x2(taddr + 32, v);
+#define TRU_PROCESS(V, S0, Z, O) do { \
+        if (part) { if (stmode == 1) process(std::true_type{}, std::integral_constant<int, 1>{}, V, S0, Z, O); \
+                    else if (stmode == 2) process(std::true_type{}, std::integral_constant<int, EPI ? 2 : 0>{}, V, S0, Z, O); \
+                    else process(std::true_type{}, std::integral_constant<int, 0>{}, V, S0, Z, O); } \
+        else if (stmode == 1) process(std::false_type{}, std::integral_constant<int, 1>{}, V, S0, Z, O); \
+        else if (stmode == 2) process(std::false_type{}, std::integral_constant<int, EPI ? 2 : 0>{}, V, S0, Z, O); \
+        else process(std::false_type{}, std::integral_constant<int, 0>{}, V, S0, Z, O); } while (0)
+      if (EPI != 2) {
+        // TMEM loads are software-pipelined: the load of sub-chunk s+1 is in flight while s is processed (a TMEM load
+        // that competes with the MMAs of the next tile takes ~1.5k cycles - the profile showed the epilogue, and
+        // behind it the whole ring, waiting on it four times per tile)
+        uint32_t w[16];
+        if (m64) {
+          tmem_ld16x2_issue(taddr, v); tmem_ld_wait(v);
+          tmem_ld16x2_issue(taddr + 32, w);
+          zfetch(zb, xx, ob, src64);
+          TRU_PROCESS(v, src64, za, oa);
+          tmem_ld_wait(w);
+          tc_fence_before();
+          mbar_arrive(&mi.tempty[acc]);
+          row_offsets(ti + 1, half * 2, oa, ea);
+          zfetch(za, xx, oa, src64);
+          TRU_PROCESS(w, src64, zb, ob);
+        } else {
+          tmem_ld16_issue(taddr, v); tmem_ld_wait(v);
+          tmem_ld16_issue(taddr + 16, w);
+          zfetch(zb, xx, oa, 16);
+          TRU_PROCESS(v, 0, za, oa);
+          tmem_ld_wait(w);
+          tmem_ld16_issue(taddr + 32, v);
+          zfetch(za, xx, ob, 0);
+          TRU_PROCESS(w, 16, zb, oa);
+          tmem_ld_wait(v);
+          tmem_ld16_issue(taddr + 48, w);
+          zfetch(zb, xx, ob, 16);
+          TRU_PROCESS(v, 0, za, ob);
+          tmem_ld_wait(w);
+          tc_fence_before();
+          mbar_arrive(&mi.tempty[acc]);
+          const unsigned ob2 = ob;
+          row_offsets(ti + 1, half * 2, oa, ea);
+          zfetch(za, xx, oa, 0);
+          TRU_PROCESS(w, 16, zb, ob2);
+        }
+      } else if (m64) {                // 2 sub-steps of 32 columns, all 32 lanes busy
+        tmem_ld16x2(taddr, v); addx(v, xx);
+        zfetch(zb, xx, ob, src64);
+        TRU_PROCESS(v, src64, za, oa);
+        tmem_ld16x2(taddr + 32, v); addx(v, xx);
         tc_fence_before();
         mbar_arrive(&mi.tempty[acc]);
         row_offsets(ti + 1, half * 2, oa, ea);
-        zfetch(za, oa, src64);
-        TRU_PROCESS(v, src64, zb, xx, ob);
+        zfetch(za, xx, oa, src64);
+        TRU_PROCESS(v, src64, zb, ob);
       } else {                         // 4 sub-steps of 16 columns
-        xfetch(xx, oa, ea, 0);
-        tmem_ld16(taddr, v);
-        zfetch(zb, oa, 16);
-        TRU_PROCESS(v, 0, za, xx, oa);
-        xfetch(xx, oa, ea, 16);
-        tmem_ld16(taddr + 16, v);
-        zfetch(za, ob, 0);
-        TRU_PROCESS(v, 16, zb, xx, oa);
-        xfetch(xx, ob, eb, 0);
-        tmem_ld16(taddr + 32, v);
-        zfetch(zb, ob, 16);
-        TRU_PROCESS(v, 0, za, xx, ob);
-        xfetch(xx, ob, eb, 16);
-        tmem_ld16(taddr + 48, v);
+        tmem_ld16(taddr, v); addx(v, xx);
+        zfetch(zb, xx, oa, 16);
+        TRU_PROCESS(v, 0, za, oa);
+        tmem_ld16(taddr + 16, v); addx(v, xx);
+        zfetch(za, xx, ob, 0);
+        TRU_PROCESS(v, 16, zb, oa);
+        tmem_ld16(taddr + 32, v); addx(v, xx);
+        zfetch(zb, xx, ob, 16);
+        TRU_PROCESS(v, 0, za, ob);
+        tmem_ld16(taddr + 48, v); addx(v, xx);
         tc_fence_before();
         mbar_arrive(&mi.tempty[acc]);
         const unsigned ob2 = ob;
         row_offsets(ti + 1, half * 2, oa, ea);
-        zfetch(za, oa, 0);
-        TRU_PROCESS(v, 16, zb, xx, ob2);
+        zfetch(za, xx, oa, 0);
+        TRU_PROCESS(v, 16, zb, ob2);
       }
 #undef TRU_PROCESS
     }
@@ -493,7 +526,7 @@ bool shape_ok(const IgemmParams& p) {
   }
   if ((double)p.BT * p.Lout * std::max(p.ldo, 1) >= 4294967296.0 || (double)p.BT * p.Lq + BM >= 4294967296.0) return false;
   if (p.planar && (double)p.BT * p.N * p.Lout >= 4294967296.0) return false;
-  if (p.extra && (double)p.BT * p.Lout * p.ext_ld >= 4294967296.0) return false;
+  if (p.extra && (p.ext_ld != p.ldo || p.planar)) return false;     // the added tensor shares the output's row offsets
   return true;
 }
 

@@ -589,6 +589,26 @@ extern "C" int tru_debug_pw(const float* x, const float* p0, const float* p2, co
   }
   return launch_igemm_simt(p, (cudaStream_t)stream);
 }
+// Test / profiling aid: the backward data-gradient variant of the GEMM kernel on plain operands.
+// dx (M,N) = mask(zmask) * ((q0*dy + q1*z + q2) (M,K) @ w (K,N) [+ extra]), BN-backward sums into bstats (2N doubles).
+extern "C" int tru_debug_pw_bwd(const float* dy, const float* z, const float* q0, const float* q1, const float* q2,
+                                const float* w, float* dx, const float* zmask, const float* mp0, const float* mp2,
+                                const float* bmean, const float* binv, double* bstats, const float* extra,
+                                int M, int K, int N, void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  IgemmParams p{};
+  Seg& sg = p.seg[0];
+  sg.src = dy; sg.src2 = z; sg.p0 = q0; sg.p1 = q1; sg.p2 = q2; sg.W = w;
+  sg.Lsrc = 1; sg.ld = K; sg.coff = 0; sg.C = K; sg.smul = 1; sg.sadd = 0; sg.relu = 0; sg.wbase = 0; sg.wsc = N; sg.wsn = 1;
+  p.nseg = 1; p.BT = M; p.Lq = 1; p.N = N;
+  p.out = dx; p.Lout = 1; p.ldo = N; p.omul = 1;
+  p.extra = extra; p.ext_ld = N;
+  if (zmask) { p.use_mask = 1; p.zmask = zmask; p.mp0 = mp0; p.mp2 = mp2; }
+  if (bstats) { p.bstats = bstats; p.bmean = bmean; p.binv = binv; }
+  rc = launch_igemm_tc(p, (cudaStream_t)stream);
+  return rc == 1 ? set_error(TRU_ERR_ARG, "debug_pw_bwd: shape not eligible for the tensor-core path") : rc;
+}
 extern "C" int tru_set_tensor_cores(int on) { set_tc_enabled(on != 0); return TRU_OK; }
 extern "C" int tru_debug_set_loader_warps(int n) { set_tc_loader_warps(n); return TRU_OK; }
 extern "C" int tru_debug_read_mbar(unsigned* out, int n) { return read_mbar_debug(out, n); }
