@@ -206,23 +206,53 @@ __global__ void __launch_bounds__(FNT) fgru_bwd_kernel(const __grid_constant__ G
 }
 
 // =============================== TGRU ========================================
-constexpr int TH = 128, TL = 16, TNT = 384;
+// One CTA carries SC sequences through all T steps.  The recurrence is a latency chain (T strictly sequential
+// steps of a 384 x 128 mat-vec per sequence), so the kernel is organised for issue rate per step: 768 threads,
+// thread (j, kh) keeps HALF a row of W_hh (64 floats) in registers, so each scheduler has 6 warps of
+// independent FFMA chains (4 sequences x 64 deep) instead of 3 warps of 128-deep ones; the two half sums meet
+// in shared memory, where the gate phase reads them.
+constexpr int TH = 128, TL = 16, TNT = 768, TROWS = 384, TKH = 64;
+
+// Per-step operands (input gates / saved gates) are staged through shared memory with cp.async one step ahead:
+// register prefetches were spilled by the compiler, which turned every step into a synchronous wait for HBM.
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int SC>
 __global__ void __launch_bounds__(TNT, 1) tgru_fwd_kernel(const __grid_constant__ GruParams p, int B, int T) {
   constexpr int NI = (SC * TH + TNT - 1) / TNT;        // (s,u) items per thread
+  constexpr int NCH = SC * 96;                         // 16-byte chunks of one step's input gates (384 floats per sequence)
   __shared__ __align__(16) float hs[SC][TH];
-  __shared__ __align__(16) float hid[SC][3 * TH];
-  const int tid = threadIdx.x;
-  float w[TH];
+  __shared__ __align__(16) float hid[2][SC][3 * TH];
+  __shared__ __align__(16) float gin[2][SC][3 * TH];
+  const int tid = threadIdx.x, j = tid % TROWS, kh = tid / TROWS;     // kh is warp-uniform (384 = 12 warps)
+  float w[TKH];
 #pragma unroll
-  for (int k4 = 0; k4 < TH / 4; ++k4) {
-    const float4 v = ld4(p.whh[0] + (long)tid * TH + k4 * 4);
+  for (int k4 = 0; k4 < TKH / 4; ++k4) {
+    const float4 v = ld4(p.whh[0] + (long)j * TH + kh * TKH + k4 * 4);
     w[k4 * 4] = v.x; w[k4 * 4 + 1] = v.y; w[k4 * 4 + 2] = v.z; w[k4 * 4 + 3] = v.w;
   }
-  const float bj = __ldg(p.bhh[0] + tid);
+  const float bj = kh == 0 ? __ldg(p.bhh[0] + j) : 0.f;
   const int nseq = B * TL;
   const int sbase = blockIdx.x * SC;
+  // copy plan: chunk c = tid + i*TNT -> sequence c / 96, 16-byte chunk c % 96 of its 384-float gate row
+  auto stage = [&](int t, int buf) {
+#pragma unroll
+    for (int i = 0; i < (NCH + TNT - 1) / TNT; ++i) {
+      const int c = tid + i * TNT;
+      if (c < NCH) {
+        const int s = c / 96, q = c % 96, sidx = sbase + s;
+        if (sidx < nseq) {
+          const long row = ((long)(sidx / TL) * T + t) * TL + sidx % TL;
+          cp_async16(&gin[buf][s][q * 4], p.G + row * (3 * TH) + q * 4);
+        }
+      }
+    }
+    cp_async_commit();
+  };
   int is[NI], iu[NI]; long ibase[NI]; bool iok[NI]; float hprev[NI];
 #pragma unroll
   for (int r = 0; r < NI; ++r) {
@@ -235,49 +265,36 @@ __global__ void __launch_bounds__(TNT, 1) tgru_fwd_kernel(const __grid_constant_
     hprev[r] = (iok[r] && p.h0) ? __ldg(p.h0 + (long)sidx * TH + iu[r]) : 0.f;
     if (it < SC * TH) hs[is[r]][iu[r]] = hprev[r];
   }
-  float gi[NI][3];
-#pragma unroll
-  for (int r = 0; r < NI; ++r)
-#pragma unroll
-    for (int g = 0; g < 3; ++g) gi[r][g] = iok[r] ? __ldg(p.G + ibase[r] * (3 * TH) + g * TH + iu[r]) : 0.f;
+  stage(0, 0);
   __syncthreads();
 
   for (int t = 0; t < T; ++t) {
-    float acc[SC];
+    if (t + 1 < T) stage(t + 1, (t + 1) & 1); else cp_async_commit();     // always one group per step (uniform wait below)
+    float acc[SC];             // (packed FFMA2 was slower here: measured 1.85 vs 1.35 ms; it does pay in the backward kernel)
 #pragma unroll
     for (int s = 0; s < SC; ++s) acc[s] = bj;
 #pragma unroll
-    for (int k4 = 0; k4 < TH / 4; ++k4) {
+    for (int k4 = 0; k4 < TKH / 4; ++k4) {
 #pragma unroll
       for (int s = 0; s < SC; ++s) {
-        const float4 h = *(const float4*)&hs[s][k4 * 4];
+        const float4 h = *(const float4*)&hs[s][kh * TKH + k4 * 4];
         acc[s] = fmaf(w[k4 * 4], h.x, acc[s]); acc[s] = fmaf(w[k4 * 4 + 1], h.y, acc[s]);
         acc[s] = fmaf(w[k4 * 4 + 2], h.z, acc[s]); acc[s] = fmaf(w[k4 * 4 + 3], h.w, acc[s]);
       }
     }
 #pragma unroll
-    for (int s = 0; s < SC; ++s) hid[s][tid] = acc[s];
+    for (int s = 0; s < SC; ++s) hid[kh][s][j] = acc[s];
+    cp_async_wait<1>();                                 // this step's gates (staged one step ago) have landed
     __syncthreads();
-    float gcur[NI][3];
-#pragma unroll
-    for (int r = 0; r < NI; ++r)
-#pragma unroll
-      for (int g = 0; g < 3; ++g) gcur[r][g] = gi[r][g];
-    if (t + 1 < T) {                                    // prefetch next step's input gates
-#pragma unroll
-      for (int r = 0; r < NI; ++r)
-#pragma unroll
-        for (int g = 0; g < 3; ++g)
-          gi[r][g] = iok[r] ? __ldg(p.G + (ibase[r] + (long)(t + 1) * TL) * (3 * TH) + g * TH + iu[r]) : 0.f;
-    }
 #pragma unroll
     for (int r = 0; r < NI; ++r) {
       if (tid + r * TNT < SC * TH) {
         const int s = is[r], u = iu[r];
-        const float hn = hid[s][2 * TH + u];
-        const float rr = sigmoidf_(gcur[r][0] + hid[s][u]);
-        const float zz = sigmoidf_(gcur[r][1] + hid[s][TH + u]);
-        const float nn = tanhf(gcur[r][2] + rr * hn);
+        const float* g = gin[t & 1][s];
+        const float hn = hid[0][s][2 * TH + u] + hid[1][s][2 * TH + u];
+        const float rr = sigmoidf_(g[u] + (hid[0][s][u] + hid[1][s][u]));
+        const float zz = sigmoidf_(g[TH + u] + (hid[0][s][TH + u] + hid[1][s][TH + u]));
+        const float nn = tanhf(g[2 * TH + u] + rr * hn);
         const float hnew = (1.0f - zz) * nn + zz * hprev[r];
         hprev[r] = hnew;
         hs[s][u] = hnew;
@@ -303,14 +320,34 @@ __global__ void __launch_bounds__(TNT, 1) tgru_fwd_kernel(const __grid_constant_
 template <int SC>
 __global__ void __launch_bounds__(TNT, 1) tgru_bwd_kernel(const __grid_constant__ GruParams p, int B, int T) {
   constexpr int NI = (SC * TH + TNT - 1) / TNT;
+  constexpr int NCH = SC * 192;                        // 16-byte chunks per step: dH (32) + cache r,z,n,hn (128) + h_prev (32) per sequence
   __shared__ __align__(16) float dgs[SC][3 * TH];
-  __shared__ float part[3][SC][TH];
-  const int tid = threadIdx.x, k = tid & (TH - 1), prt = tid >> 7;
-  float w[TH];                                          // w[jj] = W_hh[prt*128 + jj][k]
+  __shared__ float part[6][SC][TH];
+  __shared__ __align__(16) float sv[2][SC][6 * TH];     // staged: dh | r | z | n | hn | h_prev
+  const int tid = threadIdx.x, k = tid & (TH - 1), ph = tid >> 7, prt = ph % 3, half = ph / 3;   // ph: 0..5, warp-uniform
+  float w[TKH];                                         // w[jj] = W_hh[prt*128 + half*64 + jj][k]
 #pragma unroll
-  for (int jj = 0; jj < TH; ++jj) w[jj] = __ldg(p.whh[0] + (long)(prt * TH + jj) * TH + k);
+  for (int jj = 0; jj < TKH; ++jj) w[jj] = __ldg(p.whh[0] + (long)(prt * TH + half * TKH + jj) * TH + k);
   const int nseq = B * TL;
   const int sbase = blockIdx.x * SC;
+  auto stage = [&](int t, int buf) {
+#pragma unroll
+    for (int i = 0; i < (NCH + TNT - 1) / TNT; ++i) {
+      const int c = tid + i * TNT;
+      if (c < NCH) {
+        const int s = c / 192, q = c % 192, sidx = sbase + s;
+        if (sidx < nseq) {
+          const long row = ((long)(sidx / TL) * T + t) * TL + sidx % TL;
+          if (q < 32) cp_async16(&sv[buf][s][q * 4], p.dH + row * TH + q * 4);
+          else if (q < 160) cp_async16(&sv[buf][s][TH + (q - 32) * 4], p.cache + row * (4 * TH) + (q - 32) * 4);
+          else if (t > 0) cp_async16(&sv[buf][s][5 * TH + (q - 160) * 4], p.H + (row - TL) * TH + (q - 160) * 4);
+          else if (p.h0) cp_async16(&sv[buf][s][5 * TH + (q - 160) * 4], p.h0 + (long)sidx * TH + (q - 160) * 4);
+          else *(float4*)&sv[buf][s][5 * TH + (q - 160) * 4] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    }
+    cp_async_commit();
+  };
   int is[NI], iu[NI]; long ibase[NI]; bool iok[NI]; float carry[NI];
 #pragma unroll
   for (int r = 0; r < NI; ++r) {
@@ -322,38 +359,27 @@ __global__ void __launch_bounds__(TNT, 1) tgru_bwd_kernel(const __grid_constant_
     ibase[r] = ((long)b * T) * TL + l;
     carry[r] = 0.f;
   }
-  // software pipeline: values of step t are loaded one step ahead
-  float v_dh[NI], v_r[NI], v_z[NI], v_n[NI], v_hn[NI], v_hp[NI];
-  auto fetch = [&](int t) {
-#pragma unroll
-    for (int r = 0; r < NI; ++r) {
-      if (iok[r]) {
-        const long row = ibase[r] + (long)t * TL;
-        v_dh[r] = __ldg(p.dH + row * TH + iu[r]);
-        const float* c = p.cache + row * (4 * TH) + iu[r];
-        v_r[r] = __ldg(c); v_z[r] = __ldg(c + TH); v_n[r] = __ldg(c + 2 * TH); v_hn[r] = __ldg(c + 3 * TH);
-        v_hp[r] = t > 0 ? __ldg(p.H + (row - TL) * TH + iu[r])
-                        : (p.h0 ? __ldg(p.h0 + (long)(sbase + is[r]) * TH + iu[r]) : 0.f);
-      } else {
-        v_dh[r] = v_r[r] = v_z[r] = v_n[r] = v_hn[r] = v_hp[r] = 0.f;
-      }
-    }
-  };
-  fetch(T - 1);
+  stage(T - 1, (T - 1) & 1);
 
   for (int t = T - 1; t >= 0; --t) {
+    if (t > 0) stage(t - 1, (t - 1) & 1); else cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();                                     // step t's operands visible; also orders the previous step's part[] reads
     float dd[NI];
 #pragma unroll
     for (int r = 0; r < NI; ++r) {
       dd[r] = 0.f;
       if (tid + r * TNT < SC * TH) {
         const int s = is[r], u = iu[r];
-        const float dh = v_dh[r] + carry[r];
-        const float dn = dh * (1.0f - v_z[r]) * (1.0f - v_n[r] * v_n[r]);
-        const float dr = dn * v_hn[r] * v_r[r] * (1.0f - v_r[r]);
-        const float dz = dh * (v_hp[r] - v_n[r]) * v_z[r] * (1.0f - v_z[r]);
-        const float dhn = dn * v_r[r];
-        dd[r] = dh * v_z[r];
+        const float* v = sv[t & 1][s];
+        float v_dh = 0.f, v_r = 0.f, v_z = 0.f, v_n = 0.f, v_hn = 0.f, v_hp = 0.f;
+        if (iok[r]) { v_dh = v[u]; v_r = v[TH + u]; v_z = v[2 * TH + u]; v_n = v[3 * TH + u]; v_hn = v[4 * TH + u]; v_hp = v[5 * TH + u]; }
+        const float dh = v_dh + carry[r];
+        const float dn = dh * (1.0f - v_z) * (1.0f - v_n * v_n);
+        const float dr = dn * v_hn * v_r * (1.0f - v_r);
+        const float dz = dh * (v_hp - v_n) * v_z * (1.0f - v_z);
+        const float dhn = dn * v_r;
+        dd[r] = dh * v_z;
         dgs[s][u] = dr; dgs[s][TH + u] = dz; dgs[s][2 * TH + u] = dhn;
         if (iok[r]) {
           const long row = ibase[r] + (long)t * TL;
@@ -365,26 +391,27 @@ __global__ void __launch_bounds__(TNT, 1) tgru_bwd_kernel(const __grid_constant_
       }
     }
     __syncthreads();
-    if (t > 0) fetch(t - 1);
-    float acc[SC];
+    float2 acc[SC];
 #pragma unroll
-    for (int s = 0; s < SC; ++s) acc[s] = 0.f;
+    for (int s = 0; s < SC; ++s) acc[s] = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int j4 = 0; j4 < TH / 4; ++j4) {
+    for (int j4 = 0; j4 < TKH / 4; ++j4) {
 #pragma unroll
       for (int s = 0; s < SC; ++s) {
-        const float4 g = *(const float4*)&dgs[s][prt * TH + j4 * 4];
-        acc[s] = fmaf(w[j4 * 4], g.x, acc[s]); acc[s] = fmaf(w[j4 * 4 + 1], g.y, acc[s]);
-        acc[s] = fmaf(w[j4 * 4 + 2], g.z, acc[s]); acc[s] = fmaf(w[j4 * 4 + 3], g.w, acc[s]);
+        const float4 g = *(const float4*)&dgs[s][prt * TH + half * TKH + j4 * 4];
+        acc[s] = __ffma2_rn(make_float2(w[j4 * 4], w[j4 * 4 + 1]), make_float2(g.x, g.y), acc[s]);
+        acc[s] = __ffma2_rn(make_float2(w[j4 * 4 + 2], w[j4 * 4 + 3]), make_float2(g.z, g.w), acc[s]);
       }
     }
 #pragma unroll
-    for (int s = 0; s < SC; ++s) part[prt][s][k] = acc[s];
+    for (int s = 0; s < SC; ++s) part[ph][s][k] = acc[s].x + acc[s].y;
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < NI; ++r)
-      if (tid + r * TNT < SC * TH)
-        carry[r] = dd[r] + part[0][is[r]][iu[r]] + part[1][is[r]][iu[r]] + part[2][is[r]][iu[r]];
+      if (tid + r * TNT < SC * TH) {
+        const int s = is[r], u = iu[r];
+        carry[r] = dd[r] + ((part[0][s][u] + part[1][s][u]) + (part[2][s][u] + part[3][s][u])) + (part[4][s][u] + part[5][s][u]);
+      }
   }
 }
 
@@ -413,8 +440,7 @@ int launch_fgru_bwd(const GruParams& p, cudaStream_t st) {
 int launch_tgru_fwd(const GruParams& p, int B, int T, cudaStream_t st) {
   const int nseq = B * TL;
   ProfScope prof("tgru_fwd", 4.0 * nseq * T * (384 + 128 + 512), 2.0 * nseq * T * TH * 3 * TH, st);
-  if (nseq <= 4 * sm_count()) tgru_fwd_kernel<4><<<(nseq + 3) / 4, TNT, 0, st>>>(p, B, T);
-  else tgru_fwd_kernel<8><<<(nseq + 7) / 8, TNT, 0, st>>>(p, B, T);
+  tgru_fwd_kernel<4><<<(nseq + 3) / 4, TNT, 0, st>>>(p, B, T);
   TRU_LAUNCH_CHECK();
   return TRU_OK;
 }
@@ -422,8 +448,7 @@ int launch_tgru_fwd(const GruParams& p, int B, int T, cudaStream_t st) {
 int launch_tgru_bwd(const GruParams& p, int B, int T, cudaStream_t st) {
   const int nseq = B * TL;
   ProfScope prof("tgru_bwd", 4.0 * nseq * T * (128 + 512 + 128 + 768), 2.0 * nseq * T * TH * 3 * TH, st);
-  if (nseq <= 4 * sm_count()) tgru_bwd_kernel<4><<<(nseq + 3) / 4, TNT, 0, st>>>(p, B, T);
-  else tgru_bwd_kernel<8><<<(nseq + 7) / 8, TNT, 0, st>>>(p, B, T);
+  tgru_bwd_kernel<4><<<(nseq + 3) / 4, TNT, 0, st>>>(p, B, T);
   TRU_LAUNCH_CHECK();
   return TRU_OK;
 }
