@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=2, help="clips per CPU step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-inference", action="store_true", help="skip the streaming / offline inference RTF measurements")
+    ap.add_argument("--streams", type=int, default=4096, help="concurrent streams of the streaming measurement (configs[3])")
     return ap.parse_args()
 
 
@@ -143,6 +145,63 @@ def measured_peaks():
         d = json.load(open(p))
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def measured_traffic(kernel):
+    """DRAM bytes per launch of the dominant kernel family from the committed ncu pass (profiles/*_traffic.json)."""
+    import glob
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")), reverse=True):
+        try:
+            d = json.load(open(f))
+            if kernel in d:
+                return d[kernel]["dram_bytes_per_launch"], os.path.basename(f)
+        except Exception:
+            pass
+    return None, None
+
+
+def measure_inference(args, dev, state_dict):
+    """BASELINE.json metric, second half: inference real-time factor.  configs[3]: S concurrent streams, one frame per
+    stream and step (front end step -> TRU-Net step with carried TGRU state -> mask + iSTFT step);  configs[4]: offline
+    batch denoising of 10-s clips (front end -> TRU-Net -> mask + iSTFT).  RTF = seconds of audio per second."""
+    import torch
+    from tinyrecurrentunet_b200 import network, util
+    net = network.TRUNet().to(dev)
+    net.load_state_dict(state_dict)
+    net.eval()
+
+    def timed(fn, n, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    out = {}
+    S = args.streams
+    g = torch.Generator(device="cpu").manual_seed(7)
+    frames = (0.1 * torch.randn(S, 512, generator=g)).to(dev)
+    sd = util.StreamingDenoiser(net, S, device=dev)
+    ms = timed(lambda: sd.step(frames), 30)
+    out["stream"] = {"streams": S, "ms_per_step": round(ms, 4), "audio_ms_per_step": 8.0,
+                     "rtf": round(S * 0.008 / (ms / 1000.0), 1),
+                     "workload": "configs[3]: %d concurrent streams, 1 frame (hop 128 @16 kHz) per stream and step, "
+                                 "PCEN / TGRU / overlap-add state carried" % S}
+    del sd
+    Bo, No = 16, 160000
+    audio = (0.1 * torch.randn(Bo, No, generator=g)).to(dev)
+    with torch.no_grad():
+        ms = timed(lambda: util.denoise(net, audio)[0], 3, warm=1)
+    out["offline"] = {"clips": Bo, "clip_seconds": 10.0, "ms_per_batch": round(ms, 3),
+                      "rtf": round(Bo * 10.0 / (ms / 1000.0), 1),
+                      "workload": "configs[4] shard: %d x 10-s clips per call on one GPU (clips are independent: replicas, "
+                                  "no collective)" % Bo}
+    return out
 
 
 # ------------------------------------------------------------------ native arm
@@ -262,11 +321,16 @@ def run_native(args):
     ach = t["bytes"] / (t["ms"] / 1000.0) / 1e9
     roofline = {"kernel": tname, "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": round(t["bytes"] / t["launches"], 0),
                 "launches_per_step": t["launches"] / args.steps,
                 "avg_launch_ms": round(t["ms"] / t["launches"], 4),
                 "share_of_kernel_time": round(t["ms"] / total_kernel_ms, 4),
                 "tflops_fp32": round(t["flops"] / (t["ms"] / 1000.0) / 1e12, 2),
                 "ms_per_step_profiled": round(ms_p / args.steps, 3)}
+    traffic, tsrc = measured_traffic(tname)
+    if traffic is not None:
+        roofline["traffic"] = traffic
+        roofline["traffic_source"] = "ncu dram__bytes_read.sum + dram__bytes_write.sum, mean per launch (profiles/%s)" % tsrc
     kernels = {k: {"ms_per_step": round(v["ms"] / args.steps, 4), "launches_per_step": v["launches"] / args.steps,
                    "GBps": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1),
                    "TFLOPs": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 2)}
@@ -279,6 +343,15 @@ def run_native(args):
         cpu = {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "%d clips/step x 3 steps of the same training step (oracle, torch CPU)" % args.cpu_batch}
 
+    # ---- (5) inference real-time factors (rank 0, N = 1 only) ----------------------------
+    inference = None
+    if rank == 0 and world == 1 and not args.no_inference:
+        state = {k: v.detach().clone() for k, v in net.state_dict().items()}
+        opt = None
+        net = None
+        torch.cuda.empty_cache()
+        inference = measure_inference(args, dev, state)
+
     if rank == 0:
         line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
@@ -289,7 +362,7 @@ def run_native(args):
                            "clips_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world,
                            "l2": "no explicit flush: one step streams >10 GB of activations through the 126 MB L2"},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-                "cpu_baseline": cpu, "kernels": kernels}
+                "cpu_baseline": cpu, "inference": inference, "kernels": kernels}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

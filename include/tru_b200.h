@@ -92,6 +92,13 @@ typedef struct {
 
 int tru_backend_fwd(const TruBackendDesc* d, const float* net_out, float* audio,
                     void* stream);
+/* Streaming step (stream.py:83-109 intent): one network-output frame per stream,
+ * net_out (S,C,257) with S = d->batch; ola_state (S,384) in/out = overlap-add sums still waiting for
+ * later frames (zero-initialised by the caller); audio (S,128) = output block frame_index-2 of every
+ * stream (zeros while frame_index < 2: two hops of look-ahead, identical to the offline centre=True
+ * iSTFT).  add_frame = 0 flushes: no new frame, emits the block from the frames already seen. */
+int tru_backend_step(const TruBackendDesc* d, const float* net_out, float* ola_state, float* audio,
+                     int frame_index, int add_frame, void* stream);
 /* grad_audio (B, 128 (T'-1)) -> grad_net_out (B,T',C,257) (fully written). */
 int tru_backend_bwd(const TruBackendDesc* d, const float* net_out,
                     const float* grad_audio, float* grad_net_out, void* stream);

@@ -259,6 +259,29 @@ def test_eval_batched_equals_single_and_streaming():
         assert rel(hl, h_ref[0]) <= OUT_TOL and rel(h, h_ref[0]) <= OUT_TOL
 
 
+def test_streaming_denoiser_equals_offline_denoise():
+    """Config 4 (BASELINE.json): frame-by-frame inference with carried PCEN / TGRU / overlap-add state reproduces the
+    offline path sample for sample, including the two hops of look-ahead and the flush of the last block."""
+    from tinyrecurrentunet_b200 import util
+    _, net = make_pair(5)
+    net.eval()
+    S, T = 5, 21
+    _, noisy = O.synthetic_batch(S, n=128 * (T - 1))
+    x = noisy.cuda()
+    with torch.no_grad():
+        offline, _ = util.denoise(net, x)                       # (S, 128 (T-1))
+    xp = torch.nn.functional.pad(x.unsqueeze(1), (256, 256), mode="reflect").squeeze(1)
+    sd = util.StreamingDenoiser(net, S)
+    blocks = []
+    for t in range(T):
+        blocks.append(sd.step(xp[:, 128 * t:128 * t + 512].contiguous()))
+    blocks.append(sd.flush())
+    assert torch.count_nonzero(blocks[0]) == 0 and torch.count_nonzero(blocks[1]) == 0      # look-ahead
+    streamed = torch.cat(blocks[2:], dim=1)
+    assert streamed.shape == offline.shape
+    assert rel(streamed, offline) <= OUT_TOL
+
+
 def test_loss_fn_end_to_end_matches_oracle():
     """audio -> features -> net -> mask+iSTFT -> loss, both sides end to end.
 

@@ -59,6 +59,7 @@ _sig("tru_frontend_fwd", C.c_int, [C.POINTER(TruFrontendDesc), c_float_p, c_floa
                                   C.c_void_p, C.c_size_t, c_stream])
 _sig("tru_frontend_step", C.c_int, [C.POINTER(TruFrontendDesc), c_float_p, c_float_p, c_float_p, c_stream])
 _sig("tru_backend_fwd", C.c_int, [C.POINTER(TruBackendDesc), c_float_p, c_float_p, c_stream])
+_sig("tru_backend_step", C.c_int, [C.POINTER(TruBackendDesc), c_float_p, c_float_p, c_float_p, C.c_int, C.c_int, c_stream])
 _sig("tru_backend_bwd", C.c_int, [C.POINTER(TruBackendDesc), c_float_p, c_float_p, c_float_p, c_stream])
 _sig("tru_loss_fwd", C.c_int, [C.POINTER(TruLossDesc), c_float_p, c_float_p, C.POINTER(C.c_void_p),
                               C.c_void_p, c_float_p, c_stream])
@@ -78,7 +79,7 @@ _sig("tru_profile_enable", C.c_int, [C.c_int])
 _sig("tru_profile_report", C.c_int, [C.c_char_p, C.c_size_t])
 
 EXPORTS = ["tru_launch_count", "tru_profile_enable", "tru_profile_report", "tru_abi_version", "tru_last_error", "tru_init", "tru_frontend_workspace_bytes",
-           "tru_frontend_fwd", "tru_frontend_step", "tru_backend_fwd", "tru_backend_bwd",
+           "tru_frontend_fwd", "tru_frontend_step", "tru_backend_fwd", "tru_backend_bwd", "tru_backend_step",
            "tru_loss_fwd", "tru_loss_bwd", "tru_trunet_workspace_bytes", "tru_trunet_forward",
            "tru_trunet_backward", "tru_trunet_buffer_offset"]
 

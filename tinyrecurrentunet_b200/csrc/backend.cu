@@ -205,8 +205,61 @@ __global__ void __launch_bounds__(NT) backend_bwd_kernel(BackParams p) {
   }
 }
 
+// Streaming step: one new network-output frame per stream.  ola (S,384) holds the overlap-add sums of
+// the three hops that still wait for later frames; adding frame t completes output block t-2 (two hops of
+// look-ahead, exactly the offline centre=True framing).  8 streams per CTA, two streams per complex transform.
+__global__ void __launch_bounds__(NT) backend_step_kernel(BackParams p, float* __restrict__ ola, int frame_index, int add_frame) {
+  __shared__ __align__(16) float fre[4 * FPAD];
+  __shared__ __align__(16) float fim[4 * FPAD];
+  __shared__ float2 tw[NFFT];
+  const int tid = threadIdx.x, g = tid >> 6, l = tid & 63;
+  for (int k = tid; k < NFFT; k += NT) tw[k] = p.tw[k * (2048 / NFFT)];
+  float* re = fre + g * FPAD;
+  float* im = fim + g * FPAD;
+  const int sa = blockIdx.x * 8 + g * 2, sb = sa + 1;
+  const bool va = sa < p.B, vb = sb < p.B;
+  __syncthreads();
+  if (add_frame) {
+    for (int k = l; k <= NFFT / 2; k += 64) {
+      float ar = 0.f, ai = 0.f, br = 0.f, bi = 0.f;
+      if (va) bin_spectrum(p, p.net + (size_t)sa * p.C * NB, k, ar, ai);
+      if (vb) bin_spectrum(p, p.net + (size_t)sb * p.C * NB, k, br, bi);
+      if (k == 0 || k == NFFT / 2) {
+        re[TRU_FFT_IDX(k)] = ar; im[TRU_FFT_IDX(k)] = br;
+      } else {
+        re[TRU_FFT_IDX(k)] = ar - bi; im[TRU_FFT_IDX(k)] = ai + br;
+        re[TRU_FFT_IDX(NFFT - k)] = ar + bi; im[TRU_FFT_IDX(NFFT - k)] = br - ai;
+      }
+    }
+    fft_smem<NFFT, 1>(re, im, tw, l);
+  }
+  // frames contributing to block q = frame_index - 2 are q-1 .. q+2 = frame_index-3 .. frame_index (those that exist)
+  const int newest = add_frame ? frame_index : frame_index - 1;
+  const int cnt = newest - max(frame_index - 3, 0) + 1;
+  const float invn = 1.0f / NFFT, invc = (frame_index >= 2 && cnt > 0) ? 1.0f / (float)cnt : 0.0f;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int sidx = h == 0 ? sa : sb;
+    if (h == 0 ? !va : !vb) continue;
+    float* o = ola + (size_t)sidx * 384;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = l + 64 * j;
+      const float x = add_frame ? (h == 0 ? re[TRU_FFT_IDX(n)] : im[TRU_FFT_IDX(n)]) * invn : 0.0f;
+      v[j] = x + (n < 384 ? o[n] : 0.0f);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = l + 64 * j;
+      if (n < HOP) p.audio[(size_t)sidx * HOP + n] = v[j] * invc;
+      else o[n - HOP] = v[j];
+    }
+  }
+}
+
 int fill(const TruBackendDesc* d, BackParams& p) {
-  TRU_REQUIRE(d && d->batch > 0 && d->n_frames >= 2, TRU_ERR_ARG, "backend: need batch > 0 and >= 2 frames");
+  TRU_REQUIRE(d && d->batch > 0, TRU_ERR_ARG, "backend: need batch > 0");
   TRU_REQUIRE(d->n_channels >= 3 && d->n_channels <= 16, TRU_ERR_ARG, "backend: n_channels out of range");
   const int C = d->n_channels;
   TRU_REQUIRE(d->ch_mag >= 0 && d->ch_mag < C && d->ch_sin >= 0 && d->ch_sin < C && d->ch_cos >= 0 && d->ch_cos < C,
@@ -228,11 +281,26 @@ constexpr size_t BWD_SMEM = (size_t)(8 * FPAD) * 4 + NFFT * 8;
 
 using namespace tru;
 
+extern "C" int tru_backend_step(const TruBackendDesc* d, const float* net_out, float* ola_state, float* audio,
+                                int frame_index, int add_frame, void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  BackParams p{};
+  if ((rc = fill(d, p))) return rc;
+  TRU_REQUIRE(ola_state && audio && (net_out || !add_frame) && frame_index >= 0, TRU_ERR_ARG, "backend_step: null pointer / negative frame index");
+  p.net = net_out; p.audio = audio;
+  ProfScope prof("backend_step", 4.0 * p.B * ((double)p.C * NB + 2.0 * 384 + HOP), 0.5 * p.B * 5.0 * NFFT * 9, (cudaStream_t)stream);
+  backend_step_kernel<<<(p.B + 7) / 8, NT, 0, (cudaStream_t)stream>>>(p, ola_state, frame_index, add_frame);
+  TRU_LAUNCH_CHECK();
+  return TRU_OK;
+}
+
 extern "C" int tru_backend_fwd(const TruBackendDesc* d, const float* net_out, float* audio, void* stream) {
   int rc = ensure_init();
   if (rc) return rc;
   BackParams p{};
   if ((rc = fill(d, p))) return rc;
+  TRU_REQUIRE(d->n_frames >= 2, TRU_ERR_ARG, "backend: need >= 2 frames");
   TRU_REQUIRE(net_out && audio, TRU_ERR_ARG, "backend_fwd: null pointer");
   p.net = net_out; p.audio = audio;
   p.nchunks = (p.T - 1 + JC - 1) / JC;
@@ -250,6 +318,7 @@ extern "C" int tru_backend_bwd(const TruBackendDesc* d, const float* net_out, co
   if (rc) return rc;
   BackParams p{};
   if ((rc = fill(d, p))) return rc;
+  TRU_REQUIRE(d->n_frames >= 2, TRU_ERR_ARG, "backend: need >= 2 frames");
   TRU_REQUIRE(net_out && grad_audio && grad_net_out, TRU_ERR_ARG, "backend_bwd: null pointer");
   p.net = net_out; p.gaudio = grad_audio; p.gnet = grad_net_out;
   p.nchunks = (p.T + TCB - 1) / TCB;

@@ -85,6 +85,25 @@ def mask_istft(net_out, beta=0.5):
     return _MaskISTFT.apply(net_out, (0, 2, 3, 6, 7), True, float(beta))
 
 
+def mask_istft_step(net_out_frame, ola_state, frame_index, beta=0.5, flush=False):
+    """Streaming back end (D11): net_out_frame (S,8,257) (None when flushing), ola_state (S,384) updated in place
+    -> (S,128) = output block ``frame_index - 2`` of every stream (zeros while frame_index < 2)."""
+    L.require_cuda(net_out_frame, ola_state)
+    if not ola_state.is_contiguous() or ola_state.dtype != torch.float32 or ola_state.shape[-1] != 384:
+        raise L.TruError("ola_state must be a contiguous float32 (S,384) tensor (updated in place)")
+    S = ola_state.shape[0]
+    x = None
+    if not flush:
+        x = _f32c(net_out_frame)
+        if x.shape != (S, 8, NBINS):
+            raise L.TruError("net_out_frame must be (S,8,257) with S = ola_state.shape[0]")
+    d = L.TruBackendDesc(S, 1, 8, 0, 2, 3, 6, 7, 1, float(beta))
+    audio = torch.empty((S, HOP), device=ola_state.device, dtype=torch.float32)
+    L.check(L.lib.tru_backend_step(C.byref(d), L.ptr(x), L.ptr(ola_state), L.ptr(audio), int(frame_index),
+                                   0 if flush else 1, L.stream_ptr()), "tru_backend_step")
+    return audio
+
+
 def features_to_audio(feats3):
     """(B,T',3,257) [logmag, sin, cos] -> audio: ProcessAudio.backward, dataset.py:275-298."""
     return _MaskISTFT.apply(feats3, (0, 1, 2, 0, 0), False, 0.0)

@@ -20,6 +20,36 @@ def denoise(net, noisy_audio, beta=0.5):
     return ops.mask_istft(out, beta), out
 
 
+class StreamingDenoiser:
+    """Stateful frame-by-frame inference for S concurrent streams (rt.py:20-27 / stream.py:83-109 intent):
+    carries the PCEN smoother (S,257), the TGRU hidden state (S*16,128) and the overlap-add tail (S,384).
+    ``step(frames)`` takes the next 512-sample analysis frame of every stream (hop 128, the reference's centre /
+    reflect framing) and returns the 128 output samples that became final (block t-2; zeros for the first two
+    steps); ``flush()`` returns the last block after the final frame.  Output equals the offline ``denoise``."""
+
+    def __init__(self, net, n_streams, beta=0.5, device="cuda"):
+        if net.training:
+            raise ValueError("StreamingDenoiser needs net.eval()")
+        self.net, self.beta, self.t = net, beta, 0
+        self.pcen = torch.zeros(n_streams, 257, device=device)
+        self.h = torch.zeros(n_streams * 16, 128, device=device)
+        self.ola = torch.zeros(n_streams, 384, device=device)
+
+    @torch.no_grad()
+    def step(self, frames):
+        feats = ops.frontend_step(frames, self.pcen)
+        out, self.h = self.net.step(feats, self.h)
+        audio = ops.mask_istft_step(out, self.ola, self.t, self.beta)
+        self.t += 1
+        return audio
+
+    @torch.no_grad()
+    def flush(self):
+        audio = ops.mask_istft_step(None, self.ola, self.t, self.beta, flush=True)
+        self.t += 1
+        return audio
+
+
 def loss_fn(net, X, ell_p=1, ell_p_lambda=1, stft_lambda=1, mrstftloss=None, **kwargs):
     """util.py:186-251.  X = (clean_audio, noisy_audio); shapes (1,1,N)/(1,N) as the
     reference's loader yields them, or batched (B,N).  Returns
