@@ -90,6 +90,15 @@ int launch_bn_bwd_finalize(const BnBwdParams& p, cudaStream_t st);
 int launch_enc0_fwd(const float* x, const float* w, const float* b, float* out, int BT, cudaStream_t st);
 int launch_enc0_wgrad(const float* x, const float* dy, float* dw, float* db, int BT, cudaStream_t st);
 
+// ---- small-channel transposed conv (LastTrCNN: 8 -> 8, k5 s2), convt_small.cu ------------
+bool convt_small_eligible(int Cin, int Cout, int k, int s, int L, int Lout);
+int launch_convt_small_fwd(const float* z, const float* p0, const float* p2, const float* W, const float* bias, float* out,
+                           int BT, int L, int Lout, int planar, cudaStream_t st);
+int launch_convt_small_bwd_data(const float* dy, const float* W, float* dx, const float* zmask, const float* mp0, const float* mp2,
+                                const float* bmean, const float* binv, double* bstats, int BT, int L, int Lout, cudaStream_t st);
+int launch_convt_small_wgrad(const float* z, const float* p0, const float* p2, const float* dy, float* dW, float* db,
+                             int BT, int L, int Lout, cudaStream_t st);
+
 // ---- depthwise conv (network.py:33-40), C = 128 ----------------------------------
 struct DwParams {
   const float* src; const float* src2; const float* p0; const float* p1; const float* p2;  // loader (fwd or bwd)

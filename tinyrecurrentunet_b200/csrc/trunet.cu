@@ -150,6 +150,8 @@ int pw_fwd(Ctx& c, const Act& x1, int padL, const Act* skip, const float* W, con
 int convt_fwd(Ctx& c, const Act& x, const float* W, const float* bias, int Cout, int k, int s, int Lout, float* out,
               double* stats, int planar) {
   const int pad = s / 2;
+  if (!stats && convt_small_eligible(x.C, Cout, k, s, x.L, Lout))
+    return launch_convt_small_fwd(x.z, x.p0, x.p2, W, bias, out, (int)c.BT, x.L, Lout, planar, c.st);
   for (int par = 0; par < s; ++par) {
     IgemmParams p{};
     p.nseg = 0;
@@ -321,6 +323,12 @@ int pw_bwd(Ctx& c, const Grad& g, const Act& x1, int padL, const Act* skip, int 
 int convt_bwd(Ctx& c, const Grad& g, const Act& x, int ct_param, int k, int s, float* dX) {
   const float* W = c.prm[ct_param];
   const int Cout = g.C, Cin = x.C, pad = s / 2;
+  if (!g.q0 && convt_small_eligible(Cin, Cout, k, s, x.L, g.L)) {
+    TRY(launch_convt_small_wgrad(x.z, x.p0, x.p2, g.dy, c.grd[ct_param], c.grd[ct_param + 1], (int)c.BT, x.L, g.L, c.st));
+    const bool st = x.bn >= 0;
+    return launch_convt_small_bwd_data(g.dy, W, dX, x.z, x.p0, x.p2, st ? c.bn[x.bn].mean : nullptr, st ? c.bn[x.bn].inv : nullptr,
+                                       st ? c.bn[x.bn].bstats : nullptr, (int)c.BT, x.L, g.L, c.st);
+  }
   {
     WgStream ws{};
     ws.nsrc = 1;
