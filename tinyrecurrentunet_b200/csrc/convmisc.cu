@@ -44,6 +44,7 @@ __global__ void bn_bwd_finalize_kernel(BnBwdParams p) {
   p.dgamma[c] += (float)s2;
   p.dbeta[c] += (float)s1;
   if (p.db_acc) p.db_out[c] += (float)p.db_acc[c];
+  if (p.conv_db) p.conv_db[c] += (float)(g * inv * inv * s2 * (mean - p.fstats[c] / p.count));
 }
 
 // ---- encoder stem: Conv1d(4->64, k5, s2, p1) + ReLU; planar (BT,4,257) in, CL (BT,128,64) out ----

@@ -83,6 +83,10 @@ struct BnBwdParams {
   const float* gamma; const float* mean; const float* invstd;
   float* q0; float* q1; float* q2; float* dgamma; float* dbeta;
   const double* db_acc; float* db_out;      // optional: fp64 bias-gradient sums to add to a bias gradient
+  // optional: gradient of the bias of the conv in front of this BN = sum dz = q0 sum dY + q1 sum Z + q2 count, which
+  // cancels to g inv^2 s2 (mean - sum Z / count): the true value is zero, what is left is the rounding of the stored
+  // fp32 mean (PyTorch's autograd holds rounding noise of the same size there); no pass over the data needed
+  const double* fstats; float* conv_db;
 };
 int launch_bn_bwd_finalize(const BnBwdParams& p, cudaStream_t st);
 

@@ -121,9 +121,10 @@ int bn_fin(Ctx& c, int idx, int C, long rows, const float* gamma, const float* b
   p.p0 = c.bn[idx].p0; p.p2 = c.bn[idx].p2; p.mean = c.bn[idx].mean; p.invstd = c.bn[idx].inv;
   return launch_bn_finalize(p, c.st);
 }
-int bn_bfin(Ctx& c, int idx, int C, long rows, int pgamma, int pbias_acc = -1) {
+int bn_bfin(Ctx& c, int idx, int C, long rows, int pgamma, int pbias_acc = -1, int pconv_bias = -1) {
   BnBwdParams p{};
   if (pbias_acc >= 0) { p.db_acc = c.bn[idx].bstats + 256; p.db_out = c.grd[pbias_acc]; }
+  if (pconv_bias >= 0) { p.fstats = c.bn[idx].stats; p.conv_db = c.grd[pconv_bias]; }
   p.bstats = c.bn[idx].bstats; p.count = (double)rows; p.C = C;
   p.gamma = c.prm[pgamma]; p.mean = c.bn[idx].mean; p.invstd = c.bn[idx].inv;
   p.q0 = c.bn[idx].q0; p.q1 = c.bn[idx].q1; p.q2 = c.bn[idx].q2;
@@ -351,13 +352,15 @@ int convt_bwd(Ctx& c, const Grad& g, const Act& x, int ct_param, int k, int s, f
     w.njobs = k; w.BT = (int)c.BT; w.Lq = x.L;
     TRY(launch_wgrad(w, c.st));
     }
+    if (!g.q0) {      // bias gradient = column sums of dz; behind a BN it comes out of bn_bwd_finalize instead (conv_db)
     WgradParams b{};
     WgradJob& J = b.job[0];
     J.a_src = nullptr; J.C = 4; J.a_ld = 4;
-    J.z_src = g.dy; J.z_src2 = g.q0 ? g.z : nullptr; J.z_p0 = g.q0; J.z_p1 = g.q1; J.z_p2 = g.q2;
+    J.z_src = g.dy; J.z_src2 = nullptr;
     J.z_L = g.L; J.z_ld = Cout; J.z_mul = 1; J.z_add = 0; J.N = Cout; J.dW = nullptr; J.db = c.grd[ct_param + 1];
     b.njobs = 1; b.BT = (int)c.BT; b.Lq = g.L;
     TRY(launch_wgrad(b, c.st));
+    }
   }
   IgemmParams p{};
   for (int j = 0; j < k; ++j) p.seg[j] = bwd_seg(g, 0, Cout, Cout, W, j, k, Cout * k, s, j - pad);
@@ -380,7 +383,7 @@ int backward(Ctx& c, const float* x, const float* gout) {
     Act pw = c.act(P.ZDp[d], Lp, Co, b1);
     Grad gt = d == 5 ? Grad{c.F(P.dOUT), nullptr, nullptr, nullptr, nullptr, 257, 8}
                      : c.grad(P.dZDt[d], P.ZDt[d], DEC_LT[d], Co, BN_DEC(d, 1));
-    if (d < 5) TRY(bn_bfin(c, BN_DEC(d, 1), Co, BT * DEC_LT[d], P_DEC(d, 6)));
+    if (d < 5) TRY(bn_bfin(c, BN_DEC(d, 1), Co, BT * DEC_LT[d], P_DEC(d, 6), -1, P_DEC(d, 5)));
     TRY(convt_bwd(c, gt, pw, P_DEC(d, 4), DEC_K[d], DEC_S[d], c.F(P.dZDp[d])));
     TRY(bn_bfin(c, b1, Co, BT * Lp, P_DEC(d, 2)));
     Grad gp = c.grad(P.dZDp[d], P.ZDp[d], Lp, Co, b1);
