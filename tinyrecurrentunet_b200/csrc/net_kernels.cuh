@@ -63,6 +63,7 @@ int launch_wgrad_simt(const WgradParams& p, cudaStream_t st);
 struct WgStream {
   int nsrc; const float* a_src[2]; const float* a_p0[2]; const float* a_p2[2];     // a = relu(p0*src + p2) (p0 null: src)
   int a_L[2], a_ld[2], a_add[2], a_C[2], wbase[2];                                  // source row l = q + a_add
+  int a_coff[2], z_coff;                                                             // first channel inside a wider row (ld > C: per-row copies)
   const float* z_src; const float* z_src2; const float* z_p0; const float* z_p1; const float* z_p2;   // dz = p0*src + p1*src2 + p2
   int z_L, z_ld, N, ntap, zs, zpad;
   float* dW; int wsc, wsn, wtap; float* db;

@@ -39,12 +39,12 @@ constexpr int MAXRAW = 8;
 
 struct WgK {
   int nsrc; const float* a_src[2]; const float* a_p0[2]; const float* a_p2[2];
-  int a_L[2], a_ld[2], a_add[2], a_C[2], a_c0[2], Ca;
+  int a_L[2], a_ld[2], a_add[2], a_C[2], a_c0[2], a_coff[2], Ca;
   const float* z_src; const float* z_src2; const float* z_p0; const float* z_p1; const float* z_p2;
-  int z_L, z_ld, N, ntap, zs, zpad, NZ;
+  int z_L, z_ld, z_coff, N, ntap, zs, zpad, NZ;
   int p_is_z, PWt, QWt, Mmma, Pvalid, Qvalid, tmem_cols;
   uint32_t op_stage, p_tile, q_tile, raw_off, raw_stage, raw_a[2], raw_dy, raw_z, coef_off, misc_off;
-  int nraw;
+  int nraw, strided;            // strided: bit o set if operand o (0/1 A sources, 2 dY, 3 Z) is a channel slice of wider rows
   float* dW; int wbase[2], wsc, wsn, wtap; float* db;
   int BT, Lq; unsigned units_total, units_per_cta;
 };
@@ -158,45 +158,62 @@ __global__ void __launch_bounds__(NT, 1) tc_wgrad_stream_kernel(const __grid_con
     }
   } else if (warp == 1) {
     // ================================ producer (TMA bulk copies) =====================
-    // Rows of a unit that exist are one contiguous run in their frame and (ld == channels) in memory,
-    // so each operand needs ONE bulk copy per unit: lane 0/1 = activation sources, lane 2 = dY, lane 3 = Z.
+    // Rows of a unit that exist are one contiguous run in their frame.  Dense operands (ld == channels) need ONE bulk
+    // copy per unit (lane 0/1 = activation sources, lane 2 = dY, lane 3 = Z); an operand that is a channel slice of wider
+    // rows (GRU gate / hidden-state slices) is copied row by row, the rows spread over the 32 lanes.
     const unsigned Lq = (unsigned)K.Lq;
+    struct Run { int lo, hi, ld; const float* src; uint32_t dst, rowb; };
+    // operand o of the unit starting at (bt, q0): 0/1 activation sources, 2 dY, 3 Z
+    auto plan = [&](int o, unsigned bt, unsigned q0) {
+      Run r{0, 0, 0, nullptr, 0u, 0u};
+      if (o < K.nsrc) {
+        const int l0 = (int)q0 + K.a_add[o];
+        r.lo = max(0, -l0); r.hi = min(UR, K.a_L[o] - l0);
+        r.rowb = (uint32_t)K.a_C[o] * 4u; r.ld = K.a_ld[o];
+        r.src = K.a_src[o] + ((size_t)bt * K.a_L[o] + (l0 + r.lo)) * r.ld + K.a_coff[o];
+        r.dst = K.raw_a[o] + (uint32_t)r.lo * r.rowb;
+      } else if (o == 2 || (o == 3 && K.z_src2)) {
+        const int r0 = K.zs * (int)q0 - K.zpad;
+        r.lo = max(0, -r0); r.hi = min(K.NZ, K.z_L - r0);
+        r.rowb = (uint32_t)K.N * 4u; r.ld = K.z_ld;
+        r.src = (o == 2 ? K.z_src : K.z_src2) + ((size_t)bt * K.z_L + (r0 + r.lo)) * r.ld + K.z_coff;
+        r.dst = (o == 2 ? K.raw_dy : K.raw_z) + (uint32_t)r.lo * r.rowb;
+      }
+      return r;
+    };
     int rs = 0;
     uint32_t ph = 0;
     for (unsigned u = 0; u < nun; ++u) {
       const unsigned m0 = (u0 + u) * UR, bt = m0 / Lq, q0 = m0 - bt * Lq;
-      int lo = 0, hi = 0;                       // valid run [lo, hi) of this lane's operand, in raw-stage rows
-      const float* src = nullptr;
-      uint32_t dst = 0, rowb = 0;
-      if (lane < K.nsrc) {
-        const int l0 = (int)q0 + K.a_add[lane];
-        lo = max(0, -l0); hi = min(UR, K.a_L[lane] - l0);
-        rowb = (uint32_t)K.a_C[lane] * 4u;
-        src = K.a_src[lane] + ((size_t)bt * K.a_L[lane] + (l0 + lo)) * K.a_C[lane];
-        dst = K.raw_a[lane] + (uint32_t)lo * rowb;
-      } else if (lane == 2 || (lane == 3 && K.z_src2)) {
-        const int r0 = K.zs * (int)q0 - K.zpad;
-        lo = max(0, -r0); hi = min(K.NZ, K.z_L - r0);
-        rowb = (uint32_t)K.N * 4u;
-        src = (lane == 2 ? K.z_src : K.z_src2) + ((size_t)bt * K.z_L + (r0 + lo)) * K.N;
-        dst = (lane == 2 ? K.raw_dy : K.raw_z) + (uint32_t)lo * rowb;
-      }
-      const bool has = hi > lo;
-      uint32_t bytes = has ? (uint32_t)(hi - lo) * rowb : 0u;
-      const uint32_t mybytes = bytes;
+      const Run r = plan(lane, bt, q0);              // lane o < 4 plans operand o (lanes >= 4: empty run)
+      const bool has = lane < 4 && r.hi > r.lo;
+      const uint32_t mybytes = has ? (uint32_t)(r.hi - r.lo) * r.rowb : 0u;
+      uint32_t bytes = mybytes;
       bytes += __shfl_xor_sync(0xffffffffu, bytes, 1);
       bytes += __shfl_xor_sync(0xffffffffu, bytes, 2);
-      const unsigned long long run = has ? (((hi >= 64 ? ~0ull : (1ull << hi) - 1ull)) & ~((1ull << lo) - 1ull)) : 0ull;
+      const unsigned long long run = has ? (((r.hi >= 64 ? ~0ull : (1ull << r.hi) - 1ull)) & ~((1ull << r.lo) - 1ull)) : 0ull;
       const unsigned long long r0m = __shfl_sync(0xffffffffu, run, 0), r1m = __shfl_sync(0xffffffffu, run, 1), r2m = __shfl_sync(0xffffffffu, run, 2);
       mbar_wait(&mi.raw_empty[rs], ph ^ 1);
       uint8_t* st = raws + (size_t)rs * K.raw_stage;
-      if (lane == 0) {
+      if (lane == 0) {              // flags and the expected byte count are posted before the first copy can land
         mi.flags[rs].amask[0] = (uint32_t)r0m; mi.flags[rs].amask[1] = (uint32_t)r1m;
         mi.flags[rs].zmask[0] = (uint32_t)r2m; mi.flags[rs].zmask[1] = (uint32_t)(r2m >> 32);
         mbar_arrive_expect_tx(&mi.raw_full[rs], bytes);
       }
       __syncwarp();
-      if (has) bulk_g2s(st + dst, src, mybytes, &mi.raw_full[rs]);
+      if (has && !((K.strided >> lane) & 1)) bulk_g2s(st + r.dst, r.src, mybytes, &mi.raw_full[rs]);     // dense rows: one copy
+      if (K.strided) {              // channel slices of wider rows: one copy per row, rows spread over the lanes
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          if (!((K.strided >> o) & 1)) continue;
+          const int n = __shfl_sync(0xffffffffu, has ? r.hi - r.lo : 0, o);
+          const unsigned long long sp = __shfl_sync(0xffffffffu, (unsigned long long)r.src, o);
+          const uint32_t dst = __shfl_sync(0xffffffffu, r.dst, o), rowb = __shfl_sync(0xffffffffu, r.rowb, o);
+          const int ld = __shfl_sync(0xffffffffu, r.ld, o);
+          for (int i = lane; i < n; i += 32)
+            bulk_g2s(st + dst + (uint32_t)i * rowb, (const float*)sp + (size_t)i * ld, rowb, &mi.raw_full[rs]);
+        }
+      }
       if (++rs == nraw) { rs = 0; ph ^= 1; }
     }
   }
@@ -257,7 +274,9 @@ __global__ void __launch_bounds__(NT, 1) tc_wgrad_stream_kernel(const __grid_con
       rp0 = *(const float4*)(coef + ca); rp2 = *(const float4*)(coef + K.Ca + ca); rfl = *(const float4*)(coef + 2 * K.Ca + ca);
       rq0 = *(const float4*)(zc + cz); rq1 = *(const float4*)(zc + K.N + cz); rq2 = *(const float4*)(zc + 2 * K.N + cz);
     }
-    float bs[4] = {0.f, 0.f, 0.f, 0.f};
+    float bs[IZ][4];
+#pragma unroll
+    for (int k = 0; k < IZ; ++k) bs[k][0] = bs[k][1] = bs[k][2] = bs[k][3] = 0.f;
     int rs = 0;
     uint32_t ph = 0;
     for (unsigned u = 0; u < nun; ++u) {
@@ -305,7 +324,7 @@ __global__ void __launch_bounds__(NT, 1) tc_wgrad_stream_kernel(const __grid_con
             const float4 q2 = CREG ? rq2 : *(const float4*)(zc + 2 * K.N + c);
             v.x = fmaf(q1.x, xz[k].x, fmaf(q0.x, xy[k].x, q2.x)); v.y = fmaf(q1.y, xz[k].y, fmaf(q0.y, xy[k].y, q2.y));
             v.z = fmaf(q1.z, xz[k].z, fmaf(q0.z, xy[k].z, q2.z)); v.w = fmaf(q1.w, xz[k].w, fmaf(q0.w, xy[k].w, q2.w));
-            if (k == 0) { bs[0] += v.x; bs[1] += v.y; bs[2] += v.z; bs[3] += v.w; }
+            bs[k][0] += v.x; bs[k][1] += v.y; bs[k][2] += v.z; bs[k][3] += v.w;
           }
           uint4 hi, lo;
           hi.x = __float_as_uint(v.x) & 0xffffe000u; hi.y = __float_as_uint(v.y) & 0xffffe000u;
@@ -322,10 +341,15 @@ __global__ void __launch_bounds__(NT, 1) tc_wgrad_stream_kernel(const __grid_con
       if (lane == 0) { mbar_arrive(&mi.op_full[os]); mbar_arrive(&mi.raw_empty[rs]); }
       if (++rs == nraw) { rs = 0; ph ^= 1; }
     }
-    if (K.db && z_raw[0] != NONE) {                      // (eligibility: one dz item per thread, one tap)
-      const int c = z_cb[0] & 0xffff;
+    if (K.db) {                                          // (eligibility: one tap, so every dz row is seen exactly once)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) atomicAdd(K.db + c + e, bs[e]);
+      for (int k = 0; k < IZ; ++k) {
+        if (z_raw[k] != NONE) {
+          const int c = z_cb[k] & 0xffff;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) atomicAdd(K.db + c + e, bs[k][e]);
+        }
+      }
     }
     // ---- epilogue: warps 4-7 add the accumulator to dW -----------------------------------
     if (warp <= 7 && nun > 0) {
@@ -380,37 +404,39 @@ int launch_variant(const WgK& K, int grid, size_t smem, cudaStream_t st) {
 // returns TRU_OK if launched, 1 if the job does not fit this kernel (caller uses the per-job kernels)
 int launch_wgrad_stream(const WgStream& w, cudaStream_t st) {
   WgK K{};
-  if (w.nsrc < 1 || w.nsrc > 2 || w.ntap < 1 || w.ntap > 5 || w.Lq % UR != 0 || w.N % 4 != 0 || w.N > 128) return 1;
+  if (w.nsrc < 1 || w.nsrc > 2 || w.ntap < 1 || w.ntap > 5 || w.Lq % UR != 0 || w.N % 4 != 0 || w.N > (w.ntap == 1 ? 384 : 128)) return 1;
   if (w.nsrc == 2 && w.ntap > 1) return 1;
   int Ca = 0;
   for (int s = 0; s < w.nsrc; ++s) {
-    if (w.a_C[s] % 4 != 0 || (w.nsrc == 2 && w.a_C[s] % 32 != 0) || w.a_ld[s] % 4 != 0 || !aligned16(w.a_src[s])) return 1;
+    if (w.a_C[s] % 4 != 0 || (w.nsrc == 2 && w.a_C[s] % 32 != 0) || w.a_ld[s] % 4 != 0 || w.a_coff[s] % 4 != 0 || !aligned16(w.a_src[s])) return 1;
     K.a_src[s] = w.a_src[s]; K.a_p0[s] = w.a_p0[s]; K.a_p2[s] = w.a_p2[s];
-    K.a_L[s] = w.a_L[s]; K.a_ld[s] = w.a_ld[s]; K.a_add[s] = w.a_add[s]; K.a_C[s] = w.a_C[s]; K.a_c0[s] = Ca;
+    K.a_L[s] = w.a_L[s]; K.a_ld[s] = w.a_ld[s]; K.a_add[s] = w.a_add[s]; K.a_C[s] = w.a_C[s]; K.a_c0[s] = Ca; K.a_coff[s] = w.a_coff[s];
     K.wbase[s] = w.wbase[s];
     Ca += w.a_C[s];
   }
-  if (w.z_ld % 4 != 0 || !aligned16(w.z_src) || (w.z_src2 && !aligned16(w.z_src2))) return 1;
+  if (w.z_ld % 4 != 0 || w.z_coff % 4 != 0 || !aligned16(w.z_src) || (w.z_src2 && !aligned16(w.z_src2))) return 1;
   K.nsrc = w.nsrc; K.Ca = Ca;
   K.z_src = w.z_src; K.z_src2 = w.z_p0 ? w.z_src2 : nullptr; K.z_p0 = w.z_p0; K.z_p1 = w.z_p1; K.z_p2 = w.z_p2;
-  K.z_L = w.z_L; K.z_ld = w.z_ld; K.N = w.N; K.ntap = w.ntap; K.zs = w.zs; K.zpad = w.zpad;
+  K.z_L = w.z_L; K.z_ld = w.z_ld; K.z_coff = w.z_coff; K.N = w.N;
+  K.strided = (w.z_ld != w.N ? (4 | (K.z_src2 ? 8 : 0)) : 0);
+  for (int s = 0; s < w.nsrc; ++s) if (w.a_ld[s] != w.a_C[s]) K.strided |= 1 << s; K.ntap = w.ntap; K.zs = w.zs; K.zpad = w.zpad;
   K.NZ = (UR - 1) * w.zs + w.ntap;
   if (K.NZ > 64) return 1;
   const int Zcols = w.ntap * w.N;
-  K.p_is_z = (w.ntap == 1 && (Ca > 128 || w.N > Ca)) ? 1 : 0;
+  K.p_is_z = (w.ntap == 1 && w.N <= 128 && (Ca > 128 || w.N > Ca)) ? 1 : 0;
   const int Pc = K.p_is_z ? w.N : Ca, Qc = K.p_is_z ? Ca : Zcols;
   if (Pc > 128 || Qc > 384) return 1;
   K.Mmma = Pc <= 64 ? 64 : 128; K.PWt = K.Mmma; K.QWt = (Qc + 31) / 32 * 32; K.Pvalid = Pc; K.Qvalid = Qc;
   K.tmem_cols = K.QWt <= 32 ? 32 : K.QWt <= 64 ? 64 : K.QWt <= 128 ? 128 : K.QWt <= 256 ? 256 : 512;
   const int nA = UR * ((Ca + 31) / 32) * 8, nZ = ((K.NZ + 3) & ~3) * ((w.N + 31) / 32) * 8;
   const int ia = (nA + NTR - 1) / NTR, iz = (nZ + NTR - 1) / NTR, nt = w.ntap == 1 ? 1 : (w.ntap <= 3 ? 3 : 5);
-  if (ia > 2 || iz > 2) return 1;
-  if (w.db && (w.ntap != 1 || nZ > NTR)) return 1;
+  if (ia > 2 || iz > 3) return 1;
+  if (w.db && w.ntap != 1) return 1;
   K.db = w.db;
   K.p_tile = (uint32_t)UR * K.PWt * 4; K.q_tile = (uint32_t)UR * K.QWt * 4;
   K.op_stage = (uint32_t)align_up(2 * K.p_tile + 2 * K.q_tile, 1024);
-  if (w.z_ld != w.N) return 1;                          // rows must be contiguous in memory (one bulk copy per run)
-  for (int s = 0; s < w.nsrc; ++s) if (w.a_ld[s] != w.a_C[s]) return 1;
+  if (w.z_ld < w.N + w.z_coff) return 1;
+  for (int s = 0; s < w.nsrc; ++s) if (w.a_ld[s] < w.a_C[s] + w.a_coff[s]) return 1;
   K.raw_a[0] = 0; K.raw_a[1] = (uint32_t)UR * K.a_C[0] * 4;
   K.raw_dy = (uint32_t)align_up((size_t)UR * Ca * 4, 128);
   K.raw_z = K.raw_dy + (uint32_t)align_up((size_t)K.NZ * w.N * 4, 128);
@@ -450,6 +476,7 @@ int launch_wgrad_stream(const WgStream& w, cudaStream_t st) {
     case 211: return launch_variant<2, 1, 1>(K, grid, smem, st);
     case 121: return launch_variant<1, 2, 1>(K, grid, smem, st);
     case 221: return launch_variant<2, 2, 1>(K, grid, smem, st);
+    case 131: return launch_variant<1, 3, 1>(K, grid, smem, st);
     default: break;
   }
   return set_error(TRU_ERR_ARG, "wgrad_stream: no kernel variant for slots (%d,%d) taps %d", ia, iz, w.ntap);

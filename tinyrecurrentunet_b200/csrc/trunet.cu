@@ -254,6 +254,19 @@ void set_mask(IgemmParams& p, Ctx& c, const Act& a, bool stats) {
   if (stats && a.bn >= 0) { p.bstats = c.bn[a.bn].bstats; p.bmean = c.bn[a.bn].mean; p.binv = c.bn[a.bn].inv; }
 }
 
+// GRU weight / bias gradient dW (N,C) += dz^T a, db += column sums of dz, on the streaming weight-gradient kernel: a and dz
+// may be channel slices of wider rows (gate / direction slices) and a may be shifted by a_add rows inside its frame (h_{t-1}).
+// Returns 1 if the shape does not fit the kernel.
+int gru_wgrad(Ctx& c, const Act& a, int a_L, int a_ld, int a_coff, int a_add, int C, const float* dz, int z_L, int z_ld, int z_coff,
+              int N, float* dW, float* db, int BT, int Lq) {
+  WgStream w{};
+  w.nsrc = 1; w.a_src[0] = a.z; w.a_p0[0] = a.p0; w.a_p2[0] = a.p2; w.a_L[0] = a_L; w.a_ld[0] = a_ld; w.a_coff[0] = a_coff;
+  w.a_add[0] = a_add; w.a_C[0] = C; w.wbase[0] = 0;
+  w.z_src = dz; w.z_L = z_L; w.z_ld = z_ld; w.z_coff = z_coff; w.N = N; w.ntap = 1; w.zs = 1; w.zpad = 0;
+  w.dW = dW; w.wsc = 1; w.wsn = C; w.wtap = 0; w.db = db; w.BT = BT; w.Lq = Lq;
+  return launch_wgrad_stream(w, c.st);
+}
+
 // pointwise conv backward: weight grads (+bias), data grads to x1 (masked, BN sums) and to skip (raw)
 int pw_bwd(Ctx& c, const Grad& g, const Act& x1, int padL, const Act* skip, int pw_param, float* dX1, bool mask_x1,
            const float* extra, float* dSkip) {
@@ -410,26 +423,37 @@ int backward(Ctx& c, const float* x, const float* gout) {
     g.dH = c.F(P.dHT); g.dGi = c.F(P.dGTi); g.dGh = c.F(P.dGTh);
     TRY(launch_tgru_bwd(g, c.B, c.T, c.st));
     Act fo = c.act(P.ZFp, 16, 64, BN_FGRU);
+    const int TL16 = c.T * 16;            // a clip is one "frame" of T*16 rows: h_{t-1} of row r is row r - 16
+    Act hprev = c.act(P.HT, 16, 128, -1);
+    int r1 = gru_wgrad(c, fo, TL16, 64, 0, 0, 64, c.F(P.dGTi), TL16, 384, 0, 384, c.grd[P_TGRU], c.grd[P_TGRU + 2], c.B, TL16);
+    if (r1 < 0) return r1;
+    int r2 = gru_wgrad(c, hprev, TL16, 128, 0, -16, 128, c.F(P.dGTh), TL16, 384, 0, 384, c.grd[P_TGRU + 1], c.grd[P_TGRU + 3], c.B, TL16);
+    if (r2 < 0) return r2;
+    if (r1 == 1 || r2 == 1) {
     WgradParams w{};
-    {   // W_ih, b_ih
-      WgradJob& J = w.job[0];
+    w.njobs = 0;
+    if (r1 == 1) {   // W_ih, b_ih
+      WgradJob& J = w.job[w.njobs++];
       J.a_src = fo.z; J.a_p0 = fo.p0; J.a_p2 = fo.p2; J.a_relu = 1; J.a_L = c.T * 16; J.a_ld = 64; J.a_mul = 1; J.C = 64;
       J.z_src = c.F(P.dGTi); J.z_L = c.T * 16; J.z_ld = 384; J.z_mul = 1; J.N = 384;
       J.dW = c.grd[P_TGRU]; J.wsc = 1; J.wsn = 64; J.db = c.grd[P_TGRU + 2];
     }
+    if (r2 == 1) {
     {   // W_hh: h_{t-1} rows are 16 rows up inside a clip
-      WgradJob& J = w.job[1];
+      WgradJob& J = w.job[w.njobs++];
       J.a_src = c.F(P.HT); J.a_L = c.T * 16; J.a_ld = 128; J.a_mul = 1; J.a_add = -16; J.C = 128;
       J.z_src = c.F(P.dGTh); J.z_L = c.T * 16; J.z_ld = 384; J.z_mul = 1; J.N = 384;
       J.dW = c.grd[P_TGRU + 1]; J.wsc = 1; J.wsn = 128;
     }
     {   // b_hh
-      WgradJob& J = w.job[2];
+      WgradJob& J = w.job[w.njobs++];
       J.C = 4; J.a_ld = 4;
       J.z_src = c.F(P.dGTh); J.z_L = c.T * 16; J.z_ld = 384; J.z_mul = 1; J.N = 384; J.db = c.grd[P_TGRU + 3];
     }
-    w.njobs = 3; w.BT = c.B; w.Lq = c.T * 16;
+    }
+    w.BT = c.B; w.Lq = c.T * 16;
     TRY(launch_wgrad(w, c.st));
+    }
     IgemmParams p{};
     Grad gi{c.F(P.dGTi), nullptr, nullptr, nullptr, nullptr, 16, 384};
     p.seg[0] = bwd_seg(gi, 0, 384, 384, c.prm[P_TGRU], 0, 64, 1, 1, 0);
@@ -448,6 +472,23 @@ int backward(Ctx& c, const float* x, const float* gout) {
     g.whh[0] = c.prm[P_FGRU + 1]; g.whh[1] = c.prm[P_FGRU + 5]; g.H = c.F(P.HF); g.cache = c.F(P.CF);
     g.nseq = (int)BT; g.steps = 16; g.dH = c.F(P.dHF); g.dGi = c.F(P.dGFi); g.dGh = c.F(P.dGFh);
     TRY(launch_fgru_bwd(g, c.st));
+    bool streamed = true;
+    Act hfa = c.act(P.HF, 16, 128, -1);
+    for (int dir = 0; dir < 2 && streamed; ++dir) {
+      // W_ih, b_ih: gates of this direction are channels 192 dir .. of the 384-wide dGFi rows
+      int r1 = gru_wgrad(c, e5, 16, 128, 0, 0, 128, c.F(P.dGFi), 16, 384, 192 * dir, 192, c.grd[P_FGRU + 4 * dir], c.grd[P_FGRU + 4 * dir + 2],
+                         (int)BT, 16);
+      if (r1 < 0) return r1;
+      // W_hh, b_hh: h_prev is the neighbouring frequency position, channels 64 dir .. of the 128-wide HF rows
+      int r2 = r1 ? 1 : gru_wgrad(c, hfa, 16, 128, 64 * dir, dir ? 1 : -1, 64, c.F(P.dGFh), 16, 384, 192 * dir, 192, c.grd[P_FGRU + 4 * dir + 1],
+                                  c.grd[P_FGRU + 4 * dir + 3], (int)BT, 16);
+      if (r2 < 0) return r2;
+      if (r1 == 1 || r2 == 1) {
+        if (dir != 0 || r1 == 0) return set_error(TRU_ERR_ARG, "FGRU weight gradient: streaming kernel took only part of the jobs");
+        streamed = false;
+      }
+    }
+    if (!streamed) {
     WgradParams w{};
     for (int dir = 0; dir < 2; ++dir) {
       WgradJob& Ji = w.job[dir];          // W_ih, b_ih
@@ -465,6 +506,7 @@ int backward(Ctx& c, const float* x, const float* gout) {
     }
     w.njobs = 6; w.BT = (int)BT; w.Lq = 16;
     TRY(launch_wgrad(w, c.st));
+    }
     IgemmParams p{};
     Grad gi{c.F(P.dGFi), nullptr, nullptr, nullptr, nullptr, 16, 384};
     p.seg[0] = bwd_seg(gi, 0, 192, 384, c.prm[P_FGRU], 0, 128, 1, 1, 0);
