@@ -67,6 +67,7 @@ struct WgStream {
   const float* z_src; const float* z_src2; const float* z_p0; const float* z_p1; const float* z_p2;   // dz = p0*src + p1*src2 + p2
   int z_L, z_ld, N, ntap, zs, zpad;
   float* dW; int wsc, wsn, wtap; float* db;
+  int n_split; float* dW2; float* db2;      // optional: dz columns n >= n_split belong to a second weight / bias tensor (FGRU directions)
   int BT, Lq;
 };
 int launch_wgrad_stream(const WgStream& w, cudaStream_t st);     // 0 launched, 1 not eligible

@@ -46,6 +46,7 @@ struct WgK {
   uint32_t op_stage, p_tile, q_tile, raw_off, raw_stage, raw_a[2], raw_dy, raw_z, coef_off, misc_off;
   int nraw, strided;            // strided: bit o set if operand o (0/1 A sources, 2 dY, 3 Z) is a channel slice of wider rows
   float* dW; int wbase[2], wsc, wsn, wtap; float* db;
+  int n_split; float* dW2; float* db2;
   int BT, Lq; unsigned units_total, units_per_cta;
 };
 
@@ -347,7 +348,10 @@ __global__ void __launch_bounds__(NT, 1) tc_wgrad_stream_kernel(const __grid_con
         if (z_raw[k] != NONE) {
           const int c = z_cb[k] & 0xffff;
 #pragma unroll
-          for (int e = 0; e < 4; ++e) atomicAdd(K.db + c + e, bs[k][e]);
+          for (int e = 0; e < 4; ++e) {
+            float* dst = (K.n_split > 0 && c + e >= K.n_split) ? K.db2 + (c + e - K.n_split) : K.db + c + e;
+            atomicAdd(dst, bs[k][e]);
+          }
         }
       }
     }
@@ -369,7 +373,10 @@ __global__ void __launch_bounds__(NT, 1) tc_wgrad_stream_kernel(const __grid_con
               const int acol = K.p_is_z ? q : p, zcol = K.p_is_z ? p : q;
               const int s = (K.nsrc == 2 && acol >= K.a_c0[1]) ? 1 : 0, c = acol - K.a_c0[s];
               const int tap = zcol / K.N, n = zcol - tap * K.N;
-              atomicAdd(K.dW + K.wbase[s] + (long)tap * K.wtap + (long)c * K.wsc + (long)n * K.wsn, __uint_as_float(v[j]));
+              if (K.n_split > 0 && n >= K.n_split)
+                atomicAdd(K.dW2 + K.wbase[s] + (long)c * K.wsc + (long)(n - K.n_split) * K.wsn, __uint_as_float(v[j]));
+              else
+                atomicAdd(K.dW + K.wbase[s] + (long)tap * K.wtap + (long)c * K.wsc + (long)n * K.wsn, __uint_as_float(v[j]));
             }
           }
         }
@@ -450,6 +457,8 @@ int launch_wgrad_stream(const WgStream& w, cudaStream_t st) {
   K.misc_off = K.coef_off + (uint32_t)coefb;
   const size_t smem = 1024 + K.misc_off + miscb;
   K.dW = w.dW; K.wsc = w.wsc; K.wsn = w.wsn; K.wtap = w.wtap;
+  K.n_split = (w.dW2 && w.ntap == 1) ? w.n_split : 0; K.dW2 = w.dW2; K.db2 = w.db2;
+  if (w.dW2 && (w.ntap != 1 || w.n_split % 4 != 0 || (w.db && !w.db2))) return 1;
   K.BT = w.BT; K.Lq = w.Lq;
   const long M = (long)w.BT * w.Lq;
   if ((double)w.BT * w.z_L * w.z_ld >= 1.8e19) return 1;

@@ -474,11 +474,19 @@ int backward(Ctx& c, const float* x, const float* gout) {
     TRY(launch_fgru_bwd(g, c.st));
     bool streamed = true;
     Act hfa = c.act(P.HF, 16, 128, -1);
+    {   // W_ih, b_ih of both directions in one pass: dGFi rows are [gates fwd (192) | gates bwd (192)], the input is shared
+      WgStream w{};
+      w.nsrc = 1; w.a_src[0] = e5.z; w.a_p0[0] = e5.p0; w.a_p2[0] = e5.p2; w.a_L[0] = 16; w.a_ld[0] = 128; w.a_C[0] = 128;
+      w.z_src = c.F(P.dGFi); w.z_L = 16; w.z_ld = 384; w.N = 384; w.ntap = 1; w.zs = 1;
+      w.dW = c.grd[P_FGRU]; w.wsc = 1; w.wsn = 128; w.db = c.grd[P_FGRU + 2];
+      w.n_split = 192; w.dW2 = c.grd[P_FGRU + 4]; w.db2 = c.grd[P_FGRU + 6];
+      w.BT = (int)BT; w.Lq = 16;
+      const int r0 = launch_wgrad_stream(w, c.st);
+      if (r0 < 0) return r0;
+      if (r0 == 1) streamed = false;
+    }
     for (int dir = 0; dir < 2 && streamed; ++dir) {
-      // W_ih, b_ih: gates of this direction are channels 192 dir .. of the 384-wide dGFi rows
-      int r1 = gru_wgrad(c, e5, 16, 128, 0, 0, 128, c.F(P.dGFi), 16, 384, 192 * dir, 192, c.grd[P_FGRU + 4 * dir], c.grd[P_FGRU + 4 * dir + 2],
-                         (int)BT, 16);
-      if (r1 < 0) return r1;
+      int r1 = 0;
       // W_hh, b_hh: h_prev is the neighbouring frequency position, channels 64 dir .. of the 128-wide HF rows
       int r2 = r1 ? 1 : gru_wgrad(c, hfa, 16, 128, 64 * dir, dir ? 1 : -1, 64, c.F(P.dGFh), 16, 384, 192 * dir, 192, c.grd[P_FGRU + 4 * dir + 1],
                                   c.grd[P_FGRU + 4 * dir + 3], (int)BT, 16);
