@@ -80,6 +80,12 @@ __device__ __forceinline__ float4 ldg4_off(const float* base, unsigned off) {
   return v;
 }
 
+#ifndef TRU_EPI2_PIPE
+#define TRU_EPI2_PIPE 1
+#endif
+#ifndef TRU_EPI2_REGS
+#define TRU_EPI2_REGS 1
+#endif
 constexpr int LW = 16;        // loader warps
 constexpr int NG = 4;         // loader groups of 4 warps; group g owns k-blocks g, g+NG, ... (global k-block counter)
 constexpr int NT = 32 * (4 + LW + EW);
@@ -101,7 +107,7 @@ __global__ void __launch_bounds__(NT, 1) tc_igemm_kernel(const __grid_constant__
                                                          const __grid_constant__ TcLayout Lo) {
   // register budgets per role (launch value 72 for 28 warps): 4*24 + 16*64 + 8*112 = 2016 = 28*72
   //                                                      or 4*24 + 16*72 + 8*96 when the epilogue has no added tensor
-  constexpr int REG_MMA = 24, REG_LOAD = 72, REG_EPI = 96;
+  constexpr int REG_MMA = 24, REG_LOAD = (EPI == 2 && TRU_EPI2_REGS) ? 64 : 72, REG_EPI = (EPI == 2 && TRU_EPI2_REGS) ? 112 : 96;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* Wsm = smem;                                 // [hi|lo][nkb][MW rows][128 B], swizzled
@@ -421,36 +427,36 @@ __global__ void __launch_bounds__(NT, 1) tc_igemm_kernel(const __grid_constant__
         else if (stmode == 1) process(std::false_type{}, std::integral_constant<int, 1>{}, V, S0, Z, O); \
         else if (stmode == 2) process(std::false_type{}, std::integral_constant<int, EPI ? 2 : 0>{}, V, S0, Z, O); \
         else process(std::false_type{}, std::integral_constant<int, 0>{}, V, S0, Z, O); } while (0)
-      if (EPI != 2) {
+      if (EPI != 2 || TRU_EPI2_PIPE) {
         // TMEM loads are software-pipelined: the load of sub-chunk s+1 is in flight while s is processed (a TMEM load
         // that competes with the MMAs of the next tile takes ~1.5k cycles - the profile showed the epilogue, and
         // behind it the whole ring, waiting on it four times per tile)
         uint32_t w[16];
         if (m64) {
-          tmem_ld16x2_issue(taddr, v); tmem_ld_wait(v);
+          tmem_ld16x2_issue(taddr, v); tmem_ld_wait(v); addx(v, xx);
           tmem_ld16x2_issue(taddr + 32, w);
           zfetch(zb, xx, ob, src64);
           TRU_PROCESS(v, src64, za, oa);
-          tmem_ld_wait(w);
+          tmem_ld_wait(w); addx(w, xx);
           tc_fence_before();
           mbar_arrive(&mi.tempty[acc]);
           row_offsets(ti + 1, half * 2, oa, ea);
           zfetch(za, xx, oa, src64);
           TRU_PROCESS(w, src64, zb, ob);
         } else {
-          tmem_ld16_issue(taddr, v); tmem_ld_wait(v);
+          tmem_ld16_issue(taddr, v); tmem_ld_wait(v); addx(v, xx);
           tmem_ld16_issue(taddr + 16, w);
           zfetch(zb, xx, oa, 16);
           TRU_PROCESS(v, 0, za, oa);
-          tmem_ld_wait(w);
+          tmem_ld_wait(w); addx(w, xx);
           tmem_ld16_issue(taddr + 32, v);
           zfetch(za, xx, ob, 0);
           TRU_PROCESS(w, 16, zb, oa);
-          tmem_ld_wait(v);
+          tmem_ld_wait(v); addx(v, xx);
           tmem_ld16_issue(taddr + 48, w);
           zfetch(zb, xx, ob, 16);
           TRU_PROCESS(v, 0, za, ob);
-          tmem_ld_wait(w);
+          tmem_ld_wait(w); addx(w, xx);
           tc_fence_before();
           mbar_arrive(&mi.tempty[acc]);
           const unsigned ob2 = ob;
