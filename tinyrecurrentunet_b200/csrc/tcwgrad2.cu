@@ -157,8 +157,14 @@ __global__ void __launch_bounds__(NT, 1) tc_wgrad_stream_kernel(const __grid_con
       }
       mma_commit(&mi.done);
     }
-  } else if (warp == 1) {
-    // ================================ producer (TMA bulk copies) =====================
+  } else {
+    // ================================ producers (TMA bulk copies) ====================
+    // Three warps take turns (unit u belongs to warp 1 + u % 3): one warp's serial per-unit chain (plan, shuffles, flags,
+    // expect_tx, copies) was as long as the unit's HBM time, so the ring could not be kept full.
+    // (a producer that advances NPW units at a time must not run two ring turns ahead of the consumers, or it mis-reads
+    // the parity of raw_empty: NPW <= nraw)
+    const int NPW = min(3, nraw);
+    const int pw = warp - 1;
     // Rows of a unit that exist are one contiguous run in their frame.  Dense operands (ld == channels) need ONE bulk
     // copy per unit (lane 0/1 = activation sources, lane 2 = dY, lane 3 = Z); an operand that is a channel slice of wider
     // rows (GRU gate / hidden-state slices) is copied row by row, the rows spread over the 32 lanes.
@@ -182,9 +188,10 @@ __global__ void __launch_bounds__(NT, 1) tc_wgrad_stream_kernel(const __grid_con
       }
       return r;
     };
-    int rs = 0;
+    int rs = pw;
     uint32_t ph = 0;
-    for (unsigned u = 0; u < nun; ++u) {
+    while (rs >= nraw) { rs -= nraw; ph ^= 1; }
+    for (unsigned u = pw; pw < NPW && u < nun; u += NPW) {
       const unsigned m0 = (u0 + u) * UR, bt = m0 / Lq, q0 = m0 - bt * Lq;
       const Run r = plan(lane, bt, q0);              // lane o < 4 plans operand o (lanes >= 4: empty run)
       const bool has = lane < 4 && r.hi > r.lo;
@@ -215,7 +222,8 @@ __global__ void __launch_bounds__(NT, 1) tc_wgrad_stream_kernel(const __grid_con
             bulk_g2s(st + dst + (uint32_t)i * rowb, (const float*)sp + (size_t)i * ld, rowb, &mi.raw_full[rs]);
         }
       }
-      if (++rs == nraw) { rs = 0; ph ^= 1; }
+      rs += NPW;
+      while (rs >= nraw) { rs -= nraw; ph ^= 1; }
     }
   }
   } else {
