@@ -193,7 +193,7 @@ def measure_inference(args, dev, state_dict):
                      "workload": "configs[3]: %d concurrent streams, 1 frame (hop 128 @16 kHz) per stream and step, "
                                  "PCEN / TGRU / overlap-add state carried" % S}
     del sd
-    Bo, No = 16, 160000
+    Bo, No = 32, 160000
     audio = (0.1 * torch.randn(Bo, No, generator=g)).to(dev)
     with torch.no_grad():
         ms = timed(lambda: util.denoise(net, audio)[0], 3, warm=1)

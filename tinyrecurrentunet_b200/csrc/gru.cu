@@ -415,7 +415,44 @@ __global__ void __launch_bounds__(TNT, 1) tgru_bwd_kernel(const __grid_constant_
   }
 }
 
+// Single-step TGRU (streaming inference, T = 1): the hidden projection G_h = h W_hh^T + b_hh is one dense GEMM over all
+// sequences (done by the caller on the tensor-core kernel) instead of nseq / 4 CTAs each pulling the 192 KB W_hh
+// through L2; this kernel is the gate arithmetic.  Thread = (sequence, 4 hidden units).
+__global__ void __launch_bounds__(256) tgru_step_gates_kernel(const float* __restrict__ Gi, const float* __restrict__ Gh,
+                                                              const float* __restrict__ bhh, const float* __restrict__ h0,
+                                                              float* __restrict__ H, float* __restrict__ hlast, long nseq) {
+  const long idx = (long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= nseq * (TH / 4)) return;
+  const long s = idx / (TH / 4);
+  const int u = (int)(idx % (TH / 4)) * 4;
+  const float* gi = Gi + s * (3 * TH) + u;
+  const float4 ir = ld4(gi), iz = ld4(gi + TH), in = ld4(gi + 2 * TH);
+  float4 hr, hz, hn, hp = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (Gh) {
+    const float* gh = Gh + s * (3 * TH) + u;
+    hr = ld4(gh); hz = ld4(gh + TH); hn = ld4(gh + 2 * TH);
+    hp = ld4(h0 + s * TH + u);
+  } else {
+    hr = ld4(bhh + u); hz = ld4(bhh + TH + u); hn = ld4(bhh + 2 * TH + u);
+  }
+  float4 o;
+#define TRU_GATE(c) { const float rr = sigmoidf_(ir.c + hr.c), zz = sigmoidf_(iz.c + hz.c), nn = tanhf(in.c + rr * hn.c); \
+                      o.c = (1.0f - zz) * nn + zz * hp.c; }
+  TRU_GATE(x) TRU_GATE(y) TRU_GATE(z) TRU_GATE(w)
+#undef TRU_GATE
+  *(float4*)(H + s * TH + u) = o;
+  if (hlast) *(float4*)(hlast + s * TH + u) = o;
+}
+
 }  // namespace
+
+int launch_tgru_step_gates(const float* Gi, const float* Gh, const float* bhh, const float* h0, float* H, float* hlast, long nseq,
+                           cudaStream_t st) {
+  ProfScope prof("tgru_step_gates", 4.0 * nseq * (384.0 * (Gh ? 2 : 1) + 128.0 * (Gh ? 3 : 2)), 0.0, st);
+  tgru_step_gates_kernel<<<(unsigned)((nseq * (TH / 4) + 255) / 256), 256, 0, st>>>(Gi, Gh, bhh, h0, H, hlast, nseq);
+  TRU_LAUNCH_CHECK();
+  return TRU_OK;
+}
 
 int launch_fgru_fwd(const GruParams& p, cudaStream_t st) {
   const size_t smem = (size_t)(FH * F_WT_LD + FSEQ * F_H_LD) * 4;

@@ -144,5 +144,8 @@ int launch_fgru_fwd(const GruParams& p, cudaStream_t st);   // nseq = B*T, steps
 int launch_fgru_bwd(const GruParams& p, cudaStream_t st);
 int launch_tgru_fwd(const GruParams& p, int B, int T, cudaStream_t st);   // sequences (b,l), l<16, Hd = 128
 int launch_tgru_bwd(const GruParams& p, int B, int T, cudaStream_t st);
+// T = 1 (streaming): gate arithmetic on precomputed projections; Gh null = zero initial state (uses b_hh directly)
+int launch_tgru_step_gates(const float* Gi, const float* Gh, const float* bhh, const float* h0, float* H, float* hlast, long nseq,
+                           cudaStream_t st);
 
 }  // namespace tru

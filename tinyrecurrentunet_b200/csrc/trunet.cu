@@ -199,7 +199,7 @@ int forward(Ctx& c, const float* x, const float* h0, float* out, float* hlast) {
     GruParams g{};
     g.G = c.F(P.GF); g.whh[0] = c.prm[P_FGRU + 1]; g.whh[1] = c.prm[P_FGRU + 5];
     g.bhh[0] = c.prm[P_FGRU + 3]; g.bhh[1] = c.prm[P_FGRU + 7];
-    g.H = c.F(P.HF); g.cache = c.F(P.CF); g.nseq = (int)BT; g.steps = 16;
+    g.H = c.F(P.HF); g.cache = c.d->training ? c.F(P.CF) : nullptr; g.nseq = (int)BT; g.steps = 16;
     TRY(launch_fgru_fwd(g, c.st));
   }
   Act hf = c.act(P.HF, 16, 128, -1);
@@ -208,10 +208,19 @@ int forward(Ctx& c, const float* x, const float* h0, float* out, float* hlast) {
   Act fo = c.act(P.ZFp, 16, 64, BN_FGRU);
   // TGRU (network.py:150, wiring D4): sequences (b, l) over t
   TRY(pw_fwd(c, fo, 0, nullptr, c.prm[P_TGRU], c.prm[P_TGRU + 2], 384, 16, c.F(P.GT), 384, 0, nullptr));
-  {
+  if (c.T == 1 && !c.d->training) {
+    // streaming step: hidden projection of all sequences as one GEMM (scratch: the gate-cache region, unused in inference)
+    const float* Gh = nullptr;
+    if (h0) {
+      Act hp{h0, 16, 128, nullptr, nullptr, -1};
+      TRY(pw_fwd(c, hp, 0, nullptr, c.prm[P_TGRU + 1], c.prm[P_TGRU + 3], 384, 16, c.F(P.CT), 384, 0, nullptr));
+      Gh = c.F(P.CT);
+    }
+    TRY(launch_tgru_step_gates(c.F(P.GT), Gh, c.prm[P_TGRU + 3], h0, c.F(P.HT), hlast, (long)c.B * 16, c.st));
+  } else {
     GruParams g{};
     g.G = c.F(P.GT); g.whh[0] = c.prm[P_TGRU + 1]; g.bhh[0] = c.prm[P_TGRU + 3];
-    g.H = c.F(P.HT); g.cache = c.F(P.CT); g.h0 = h0; g.hlast = hlast; g.nseq = c.B * 16; g.steps = c.T;
+    g.H = c.F(P.HT); g.cache = c.d->training ? c.F(P.CT) : nullptr; g.h0 = h0; g.hlast = hlast; g.nseq = c.B * 16; g.steps = c.T;
     TRY(launch_tgru_fwd(g, c.B, c.T, c.st));
   }
   Act ht = c.act(P.HT, 16, 128, -1);
