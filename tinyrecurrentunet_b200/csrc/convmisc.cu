@@ -32,6 +32,16 @@ __global__ void bn_finalize_kernel(BnFwdParams p) {
   p.invstd[c] = (float)inv;
 }
 
+__global__ void bn_finalize_eval_all_kernel(const __grid_constant__ BnEvalAll p) {
+  const int l = blockIdx.y, c = threadIdx.x;
+  if (c >= p.C[l]) return;
+  const double mean = p.rmean[l][c], inv = 1.0 / sqrt((double)p.rvar[l][c] + (double)p.eps), g = p.gamma[l][c];
+  p.p0[l][c] = (float)(g * inv);
+  p.p2[l][c] = (float)((double)p.beta[l][c] - mean * g * inv);
+  p.mean[l][c] = (float)mean;
+  p.inv[l][c] = (float)inv;
+}
+
 // dZ = q0*dY + q1*Z + q2 with  q0 = g*inv, q1 = -g*inv^2*s2/M, q2 = g*inv*(mean*inv*s2 - s1)/M
 __global__ void bn_bwd_finalize_kernel(BnBwdParams p) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -391,6 +401,12 @@ int dw_grid(long rows) { return (int)std::min<long>((rows + DW_ROWS - 1) / DW_RO
 int launch_bn_finalize(const BnFwdParams& p, cudaStream_t st) {
   ProfScope prof("bn_finalize", 0, 0, st);
   bn_finalize_kernel<<<(p.C + 127) / 128, 128, 0, st>>>(p);
+  TRU_LAUNCH_CHECK();
+  return TRU_OK;
+}
+int launch_bn_finalize_eval_all(const BnEvalAll& p, cudaStream_t st) {
+  ProfScope prof("bn_finalize_eval_all", 0, 0, st);
+  bn_finalize_eval_all_kernel<<<dim3(1, TRU_NET_NBN), 128, 0, st>>>(p);
   TRU_LAUNCH_CHECK();
   return TRU_OK;
 }

@@ -80,6 +80,10 @@ struct BnFwdParams {
   float* p0; float* p2; float* mean; float* invstd;
 };
 int launch_bn_finalize(const BnFwdParams& p, cudaStream_t st);
+// inference: the coefficients of all BN layers depend only on parameters and running statistics -> one launch for all of them
+struct BnEvalAll { const float* gamma[TRU_NET_NBN]; const float* beta[TRU_NET_NBN]; const float* rmean[TRU_NET_NBN]; const float* rvar[TRU_NET_NBN];
+                   float* p0[TRU_NET_NBN]; float* p2[TRU_NET_NBN]; float* mean[TRU_NET_NBN]; float* inv[TRU_NET_NBN]; int C[TRU_NET_NBN]; float eps; };
+int launch_bn_finalize_eval_all(const BnEvalAll& p, cudaStream_t st);
 struct BnBwdParams {
   const double* bstats; double count; int C;
   const float* gamma; const float* mean; const float* invstd;

@@ -76,7 +76,7 @@ struct Ctx {
   float* F(size_t off) const { return (float*)(ws + off); }
   void slots() {
     for (int i = 0; i < NBN; ++i) {
-      bn[i].stats = (double*)(ws + plan.stats) + i * 256;
+      bn[i].stats = (d && !d->training) ? nullptr : (double*)(ws + plan.stats) + i * 256;    // inference: no batch statistics
       bn[i].bstats = (double*)(ws + plan.bstats) + i * 384;
       float* s = (float*)(ws + plan.small) + (size_t)i * 7 * 128;
       bn[i].p0 = s; bn[i].p2 = s + 128; bn[i].mean = s + 256; bn[i].inv = s + 384;
@@ -112,7 +112,21 @@ Seg bwd_seg(const Grad& g, int coff, int C, int ld, const float* W, int wbase, i
   return s;
 }
 
+// inference: all 23 BN layers in one launch at the start of the forward (nothing depends on batch statistics)
+int bn_fin_eval_all(Ctx& c) {
+  BnEvalAll p{};
+  auto set = [&](int idx, int pg, int C) {
+    p.gamma[idx] = c.prm[pg]; p.beta[idx] = c.prm[pg + 1]; p.rmean[idx] = c.rmean[idx]; p.rvar[idx] = c.rvar[idx];
+    p.p0[idx] = c.bn[idx].p0; p.p2[idx] = c.bn[idx].p2; p.mean[idx] = c.bn[idx].mean; p.inv[idx] = c.bn[idx].inv; p.C[idx] = C;
+  };
+  for (int i = 1; i <= 5; ++i) { set(BN_ENC(i, 0), P_ENC(i, 2), 128); set(BN_ENC(i, 1), P_ENC(i, 6), 128); }
+  for (int d = 0; d <= 5; ++d) { set(BN_DEC(d, 0), P_DEC(d, 2), DEC_COUT[d]); if (d < 5) set(BN_DEC(d, 1), P_DEC(d, 6), 64); }
+  set(BN_FGRU, P_FGRU + 10, 64); set(BN_TGRU, P_TGRU + 6, 64);
+  p.eps = (float)c.d->bn_eps;
+  return launch_bn_finalize_eval_all(p, c.st);
+}
 int bn_fin(Ctx& c, int idx, int C, long rows, const float* gamma, const float* beta) {
+  if (!c.d->training) return TRU_OK;        // done by bn_fin_eval_all
   BnFwdParams p{};
   p.stats = c.bn[idx].stats; p.count = (double)rows; p.C = C; p.training = c.d->training;
   p.gamma = gamma; p.beta = beta; p.running_mean = c.rmean[idx]; p.running_var = c.rvar[idx];
@@ -174,7 +188,8 @@ int convt_fwd(Ctx& c, const Act& x, const float* W, const float* bias, int Cout,
 int forward(Ctx& c, const float* x, const float* h0, float* out, float* hlast) {
   const Plan& P = c.plan;
   const long BT = c.BT;
-  TRU_CUDA(cudaMemsetAsync(c.ws + P.stats, 0, NBN * 256 * 8, c.st));
+  if (c.d->training) TRU_CUDA(cudaMemsetAsync(c.ws + P.stats, 0, NBN * 256 * 8, c.st));
+  else TRY(bn_fin_eval_all(c));
   // encoder stem
   TRY(launch_enc0_fwd(x, c.prm[0], c.prm[1], c.F(P.A0), (int)BT, c.st));
   Act cur = c.act(P.A0, 128, 64, -1);
