@@ -220,8 +220,19 @@ def run_native(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", init_method="env://", world_size=world, rank=rank,
-                                device_id=dev)
+        # NCCL prints its version banner on stdout when the communicator is created; the contract is ONE JSON line on
+        # stdout, so stdout points at stderr until the communicator exists
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", init_method="env://", world_size=world, rank=rank, device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     from oracle import tru_oracle as O                      # synthetic data generator + cpu_baseline only
     from tinyrecurrentunet_b200 import _lib as L, network, stft_loss, util
     from tinyrecurrentunet_b200 import distributed as tdist
