@@ -60,24 +60,41 @@ __global__ void bn_bwd_finalize_kernel(BnBwdParams p) {
 // ---- encoder stem: Conv1d(4->64, k5, s2, p1) + ReLU; planar (BT,4,257) in, CL (BT,128,64) out ----
 constexpr int E_F = 257, E_LO = 128, E_CO = 64, E_CI = 4, E_K = 5;
 
+// Thread = 4 output channels x 8 output positions; its 80 weights live in registers, the input frame (4 x 257 floats)
+// in shared memory, the next frame is prefetched into registers while the current one is computed.
+constexpr int E_XN = E_CI * (E_F + 3);               // padded frame in shared memory
+constexpr int E_XI = (E_XN + 255) / 256;             // prefetch registers per thread
 __global__ void __launch_bounds__(256) enc0_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                        const float* __restrict__ b, float* __restrict__ out, int BT) {
   __shared__ float xs[E_CI][E_F + 3];        // xs[ci][1 + f], zeros at both ends
-  __shared__ __align__(16) float ws[E_CI * E_K][E_CO];
   const int tid = threadIdx.x;
-  for (int i = tid; i < E_CO * E_CI * E_K; i += 256) {
-    const int co = i / (E_CI * E_K), r = i % (E_CI * E_K);
-    ws[r][co] = w[i];
-  }
   const int c4 = (tid & 15) * 4, l0 = tid >> 4;
+  float wr[E_CI * E_K][4];
+#pragma unroll
+  for (int r = 0; r < E_CI * E_K; ++r)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) wr[r][e] = __ldg(w + (c4 + e) * (E_CI * E_K) + r);
   const float4 bias = ld4(b + c4);
-  for (int bt = blockIdx.x; bt < BT; bt += gridDim.x) {
-    __syncthreads();
-    for (int i = tid; i < E_CI * (E_F + 3); i += 256) {
+  float pre[E_XI];
+  auto fetch = [&](int bt) {
+#pragma unroll
+    for (int k = 0; k < E_XI; ++k) {
+      const int i = tid + k * 256;
       const int ci = i / (E_F + 3), f = i % (E_F + 3) - 1;
-      xs[ci][f + 1] = (f >= 0 && f < E_F) ? __ldg(x + ((size_t)bt * E_CI + ci) * E_F + f) : 0.f;
+      pre[k] = (i < E_XN && f >= 0 && f < E_F) ? __ldg(x + ((size_t)bt * E_CI + ci) * E_F + f) : 0.f;
+    }
+  };
+  int bt = blockIdx.x;
+  if (bt < BT) fetch(bt);
+  for (; bt < BT; bt += gridDim.x) {
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < E_XI; ++k) {
+      const int i = tid + k * 256;
+      if (i < E_XN) (&xs[0][0])[i] = pre[k];
     }
     __syncthreads();
+    if (bt + (int)gridDim.x < BT) fetch(bt + gridDim.x);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int lo = l0 + 16 * i;
@@ -87,8 +104,8 @@ __global__ void __launch_bounds__(256) enc0_fwd_kernel(const float* __restrict__
 #pragma unroll
         for (int j = 0; j < E_K; ++j) {
           const float xv = xs[ci][2 * lo + j];                 // input index 2*lo - 1 + j
-          const float4 wv = *(const float4*)&ws[ci * E_K + j][c4];
-          a.x = fmaf(xv, wv.x, a.x); a.y = fmaf(xv, wv.y, a.y); a.z = fmaf(xv, wv.z, a.z); a.w = fmaf(xv, wv.w, a.w);
+          const int r = ci * E_K + j;
+          a.x = fmaf(xv, wr[r][0], a.x); a.y = fmaf(xv, wr[r][1], a.y); a.z = fmaf(xv, wr[r][2], a.z); a.w = fmaf(xv, wr[r][3], a.w);
         }
       a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
       *(float4*)(out + ((size_t)bt * E_LO + lo) * E_CO + c4) = a;
@@ -97,32 +114,80 @@ __global__ void __launch_bounds__(256) enc0_fwd_kernel(const float* __restrict__
 }
 
 // dW[co][ci][j] = sum dy[bt][lo][co] * x[bt][ci][2lo-1+j]; db[co] = sum dy.  dy is already ReLU-masked.
+// Thread = 4 output channels x one group of 8 output positions, 80 accumulators in registers: one 16-byte load of dy
+// feeds 80 FMAs and every input value (a broadcast load) feeds 4; the 16 position groups meet in shared memory at the end.
 __global__ void __launch_bounds__(256) enc0_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                          float* __restrict__ dw, float* __restrict__ db, int BT) {
   __shared__ float xs[E_CI][E_F + 3];
-  __shared__ float dys[E_LO][E_CO + 1];
+  __shared__ float red[16][E_CO];                  // per position group, one output at a time
   const int tid = threadIdx.x;
-  const int co = tid & 63, rg = tid >> 6;          // each thread: channel co, taps r = rg*5 .. rg*5+4 (ci = rg)
-  float acc[E_K] = {0.f, 0.f, 0.f, 0.f, 0.f};
-  float bacc = 0.f;
-  for (int bt = blockIdx.x; bt < BT; bt += gridDim.x) {
-    __syncthreads();
-    for (int i = tid; i < E_CI * (E_F + 3); i += 256) {
-      const int ci = i / (E_F + 3), f = i % (E_F + 3) - 1;
-      xs[ci][f + 1] = (f >= 0 && f < E_F) ? __ldg(x + ((size_t)bt * E_CI + ci) * E_F + f) : 0.f;
-    }
-    for (int i = tid; i < E_LO * E_CO; i += 256) dys[i / E_CO][i % E_CO] = __ldg(dy + (size_t)bt * E_LO * E_CO + i);
-    __syncthreads();
-    for (int lo = 0; lo < E_LO; ++lo) {
-      const float g = dys[lo][co];
+  const int c4 = (tid & 15) * 4, lg = tid >> 4;    // channels c4..c4+3, positions lg*8 .. lg*8+7
+  float acc[E_CI * E_K][4];
+  float bacc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int j = 0; j < E_K; ++j) acc[j] = fmaf(g, xs[rg][2 * lo + j], acc[j]);
-      if (rg == 0) bacc += g;
+  for (int r = 0; r < E_CI * E_K; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
+  float pre[E_XI];
+  auto fetch = [&](int bt) {
+#pragma unroll
+    for (int k = 0; k < E_XI; ++k) {
+      const int i = tid + k * 256;
+      const int ci = i / (E_F + 3), f = i % (E_F + 3) - 1;
+      pre[k] = (i < E_XN && f >= 0 && f < E_F) ? __ldg(x + ((size_t)bt * E_CI + ci) * E_F + f) : 0.f;
+    }
+  };
+  float4 g[8], gn[8];
+  auto fetch_dy = [&](int bt) {
+    const float* dyf = dy + (size_t)bt * E_LO * E_CO + c4;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) gn[i] = ld4(dyf + (size_t)(lg * 8 + i) * E_CO);
+  };
+  int bt = blockIdx.x;
+  if (bt < BT) { fetch(bt); fetch_dy(bt); }
+  for (; bt < BT; bt += gridDim.x) {
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < E_XI; ++k) {
+      const int i = tid + k * 256;
+      if (i < E_XN) (&xs[0][0])[i] = pre[k];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = gn[i];
+    __syncthreads();
+    if (bt + (int)gridDim.x < BT) { fetch(bt + gridDim.x); fetch_dy(bt + gridDim.x); }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int lo = lg * 8 + i;
+      bacc[0] += g[i].x; bacc[1] += g[i].y; bacc[2] += g[i].z; bacc[3] += g[i].w;
+#pragma unroll
+      for (int ci = 0; ci < E_CI; ++ci)
+#pragma unroll
+        for (int j = 0; j < E_K; ++j) {
+          const float xv = xs[ci][2 * lo + j];
+          const int r = ci * E_K + j;
+          acc[r][0] = fmaf(g[i].x, xv, acc[r][0]); acc[r][1] = fmaf(g[i].y, xv, acc[r][1]);
+          acc[r][2] = fmaf(g[i].z, xv, acc[r][2]); acc[r][3] = fmaf(g[i].w, xv, acc[r][3]);
+        }
     }
   }
+  // reduce the 16 position groups: one (ci, j) at a time through shared memory, then one atomic per output and CTA
+  for (int r = 0; r <= E_CI * E_K; ++r) {
+    __syncthreads();
 #pragma unroll
-  for (int j = 0; j < E_K; ++j) atomicAdd(dw + (co * E_CI + rg) * E_K + j, acc[j]);
-  if (rg == 0) atomicAdd(db + co, bacc);
+    for (int e = 0; e < 4; ++e) {
+      float v = bacc[e];
+#pragma unroll
+      for (int q = 0; q < E_CI * E_K; ++q) if (q == r) v = acc[q][e];
+      red[lg][c4 + e] = v;
+    }
+    __syncthreads();
+    if (tid < E_CO) {
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) s += red[q][tid];
+      if (r < E_CI * E_K) atomicAdd(dw + tid * (E_CI * E_K) + r, s);
+      else atomicAdd(db + tid, s);
+    }
+  }
 }
 
 // ---- depthwise conv, C = 128: thread = (row lane, 4 channels) ----------------------
