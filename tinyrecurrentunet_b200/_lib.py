@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_PKG, "libtru_b200.so")
 if not os.path.exists(LIB_PATH):
     raise ImportError(
         "tinyrecurrentunet_b200: %s not found. Build it with "
-        "`python -m tinyrecurrentunet_b200.build` (needs nvcc, targets sm_100a). "
+        "`python tinyrecurrentunet_b200/build.py` (needs nvcc, targets sm_100a). "
         "There is no CPU/PyTorch fallback for this path." % LIB_PATH)
 
 lib = C.CDLL(LIB_PATH)
