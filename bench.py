@@ -301,10 +301,13 @@ def run_native(args):
     # ---- (2) end to end: pinned host buffers in, loss read back, every step ----------
     e2e = None
     if not args.no_e2e:
+        pre = util.CudaPrefetcher(dev)      # H2D of the next batch on a side stream while the current step runs
+
         def e2e_step():
-            c = clean_h.to(dev, non_blocking=True)
-            n = noisy_h.to(dev, non_blocking=True)
-            return step(c, n).item()
+            bufs = pre.next(clean_h, noisy_h)          # every step: pinned host buffers -> device (this step's inputs)
+            loss = step(bufs[0], bufs[1])
+            pre.release(bufs)
+            return loss.item()                         # every step: loss read back
         e2e_step()
         ms_e = timed(args.steps, e2e_step)
         e2e = {"value": round(world * B * args.steps / (ms_e / 1000.0), 2), "unit": UNIT,

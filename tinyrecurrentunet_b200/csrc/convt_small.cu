@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(NTH) convt8_bwd_data_kernel(const float* __res
                                                               float* __restrict__ dx, const float* __restrict__ zmask,
                                                               const float* __restrict__ mp0, const float* __restrict__ mp2,
                                                               const float* __restrict__ bmean, const float* __restrict__ binv,
-                                                              double* __restrict__ bstats, int BT, int L, int Lout) {
+                                                              double* __restrict__ bstats, int BT, int L, int Lout, int dy_planar) {
   __shared__ __align__(16) float w[KK][CC][CC];      // [j][co][ci]
   __shared__ float s0[CC], s2[CC], sm[CC];
   __shared__ float red[NTH / 32][2 * CC];
@@ -105,8 +105,14 @@ __global__ void __launch_bounds__(NTH) convt8_bwd_data_kernel(const float* __res
     for (int j = 0; j < KK; ++j) {
       const int lo = ST * l - PAD + j;
       if (lo >= 0 && lo < Lout) {
-        const float4 u = __ldg((const float4*)(df + (size_t)lo * CC)), v = __ldg((const float4*)(df + (size_t)lo * CC) + 1);
-        const float d[CC] = {u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w};
+        float d[CC];
+        if (dy_planar) {                               // the network-output gradient as autograd hands it over: (B,T,8,257)
+#pragma unroll
+          for (int co = 0; co < CC; ++co) d[co] = __ldg(df + (size_t)co * Lout + lo);
+        } else {
+          const float4 u = __ldg((const float4*)(df + (size_t)lo * CC)), v = __ldg((const float4*)(df + (size_t)lo * CC) + 1);
+          d[0] = u.x; d[1] = u.y; d[2] = u.z; d[3] = u.w; d[4] = v.x; d[5] = v.y; d[6] = v.z; d[7] = v.w;
+        }
 #pragma unroll
         for (int co = 0; co < CC; ++co) {
           const float4 w0 = *(const float4*)&w[j][co][0], w1 = *(const float4*)&w[j][co][4];
@@ -149,12 +155,12 @@ constexpr int WG_NT = 352;
 __global__ void __launch_bounds__(WG_NT) convt8_wgrad_kernel(const float* __restrict__ z, const float* __restrict__ p0,
                                                              const float* __restrict__ p2, const float* __restrict__ dy,
                                                              float* __restrict__ dW, float* __restrict__ db,
-                                                             int BT, int L, int Lout) {
+                                                             int BT, int L, int Lout, int dy_planar) {
   extern __shared__ __align__(16) float sm_w[];
   float* as = sm_w;                    // [L][8] activations (BN + ReLU applied)
   float* ds = as + L * CC;             // [Lout][8]
   const int tid = threadIdx.x;
-  const int nA4 = L * CC / 4, nD4 = Lout * CC / 4, n4 = nA4 + nD4;
+  const int nA4 = L * CC / 4, nD4 = (Lout * CC + 3) / 4, n4 = nA4 + nD4;
   constexpr int MAXI = 3;              // float4 items per thread and frame (planner: n4 <= MAXI * WG_NT)
   float4 pre[MAXI];
   float ap0[4] = {1.f, 1.f, 1.f, 1.f}, ap2[4] = {0.f, 0.f, 0.f, 0.f};
@@ -163,7 +169,16 @@ __global__ void __launch_bounds__(WG_NT) convt8_wgrad_kernel(const float* __rest
     for (int i = 0; i < MAXI; ++i) {
       const int it = tid + i * WG_NT;
       if (it < nA4) pre[i] = __ldg((const float4*)(z + (size_t)bt * L * CC) + it);
-      else if (it < n4) pre[i] = __ldg((const float4*)(dy + (size_t)bt * Lout * CC) + (it - nA4));
+      else if (it < n4) {
+        const int e = (it - nA4) * 4;                  // planar: 4 consecutive positions of one channel; else 4 channels of one row
+        if (dy_planar) {
+          const float* g = dy + (size_t)bt * Lout * CC;
+          pre[i].x = __ldg(g + e); pre[i].y = e + 1 < Lout * CC ? __ldg(g + e + 1) : 0.f;
+          pre[i].z = e + 2 < Lout * CC ? __ldg(g + e + 2) : 0.f; pre[i].w = e + 3 < Lout * CC ? __ldg(g + e + 3) : 0.f;
+        } else {
+          pre[i] = __ldg((const float4*)(dy + (size_t)bt * Lout * CC) + (it - nA4));
+        }
+      }
     }
   };
   // role
@@ -186,7 +201,14 @@ __global__ void __launch_bounds__(WG_NT) convt8_wgrad_kernel(const float* __rest
         }
         ((float4*)as)[it] = v;
       } else if (it < n4) {
-        ((float4*)ds)[it - nA4] = pre[i];
+        if (dy_planar) {                               // element e of the planar frame = (channel e / Lout, position e % Lout)
+          const int e = (it - nA4) * 4;
+          const float v4[4] = {pre[i].x, pre[i].y, pre[i].z, pre[i].w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) if (e + q < Lout * CC) ds[((e + q) % Lout) * CC + (e + q) / Lout] = v4[q];
+        } else {
+          ((float4*)ds)[it - nA4] = pre[i];
+        }
       }
     }
     __syncthreads();
@@ -234,20 +256,21 @@ int launch_convt_small_fwd(const float* z, const float* p0, const float* p2, con
 }
 
 int launch_convt_small_bwd_data(const float* dy, const float* W, float* dx, const float* zmask, const float* mp0, const float* mp2,
-                                const float* bmean, const float* binv, double* bstats, int BT, int L, int Lout, cudaStream_t st) {
+                                const float* bmean, const float* binv, double* bstats, int BT, int L, int Lout, int dy_planar,
+                                cudaStream_t st) {
   const long blocks = ((long)BT * L + NTH - 1) / NTH;
   ProfScope prof("convt8_bwd_data", 4.0 * BT * CC * ((double)Lout + 2.0 * L), 2.0 * BT * L * CC * CC * KK, st);
-  convt8_bwd_data_kernel<<<(unsigned)blocks, NTH, 0, st>>>(dy, W, dx, zmask, mp0, mp2, bmean, binv, bstats, BT, L, Lout);
+  convt8_bwd_data_kernel<<<(unsigned)blocks, NTH, 0, st>>>(dy, W, dx, zmask, mp0, mp2, bmean, binv, bstats, BT, L, Lout, dy_planar);
   TRU_LAUNCH_CHECK();
   return TRU_OK;
 }
 
 int launch_convt_small_wgrad(const float* z, const float* p0, const float* p2, const float* dy, float* dW, float* db,
-                             int BT, int L, int Lout, cudaStream_t st) {
+                             int BT, int L, int Lout, int dy_planar, cudaStream_t st) {
   const size_t smem = (size_t)(L + Lout) * CC * 4;
   const int grid = std::min(BT, 4 * sm_count());
   ProfScope prof("convt8_wgrad", 4.0 * BT * CC * ((double)L + Lout), 2.0 * BT * L * CC * CC * KK, st);
-  convt8_wgrad_kernel<<<grid, WG_NT, smem, st>>>(z, p0, p2, dy, dW, db, BT, L, Lout);
+  convt8_wgrad_kernel<<<grid, WG_NT, smem, st>>>(z, p0, p2, dy, dW, db, BT, L, Lout, dy_planar);
   TRU_LAUNCH_CHECK();
   return TRU_OK;
 }

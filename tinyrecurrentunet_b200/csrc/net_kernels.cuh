@@ -105,9 +105,10 @@ bool convt_small_eligible(int Cin, int Cout, int k, int s, int L, int Lout);
 int launch_convt_small_fwd(const float* z, const float* p0, const float* p2, const float* W, const float* bias, float* out,
                            int BT, int L, int Lout, int planar, cudaStream_t st);
 int launch_convt_small_bwd_data(const float* dy, const float* W, float* dx, const float* zmask, const float* mp0, const float* mp2,
-                                const float* bmean, const float* binv, double* bstats, int BT, int L, int Lout, cudaStream_t st);
+                                const float* bmean, const float* binv, double* bstats, int BT, int L, int Lout, int dy_planar,
+                                cudaStream_t st);   // dy_planar: dy is (BT, 8, Lout) as autograd hands the output gradient over
 int launch_convt_small_wgrad(const float* z, const float* p0, const float* p2, const float* dy, float* dW, float* db,
-                             int BT, int L, int Lout, cudaStream_t st);
+                             int BT, int L, int Lout, int dy_planar, cudaStream_t st);
 
 // ---- depthwise conv (network.py:33-40), C = 128 ----------------------------------
 struct DwParams {

@@ -358,14 +358,15 @@ int pw_bwd(Ctx& c, const Grad& g, const Act& x1, int padL, const Act* skip, int 
 }
 
 // transposed conv backward: g = grad of the convT output (Lout rows, Cout ch), x = its input activation
-int convt_bwd(Ctx& c, const Grad& g, const Act& x, int ct_param, int k, int s, float* dX) {
+int convt_bwd(Ctx& c, const Grad& g, const Act& x, int ct_param, int k, int s, float* dX, const float* planar_dy = nullptr) {
   const float* W = c.prm[ct_param];
   const int Cout = g.C, Cin = x.C, pad = s / 2;
   if (!g.q0 && convt_small_eligible(Cin, Cout, k, s, x.L, g.L)) {
-    TRY(launch_convt_small_wgrad(x.z, x.p0, x.p2, g.dy, c.grd[ct_param], c.grd[ct_param + 1], (int)c.BT, x.L, g.L, c.st));
+    const float* dy = planar_dy ? planar_dy : g.dy;
+    TRY(launch_convt_small_wgrad(x.z, x.p0, x.p2, dy, c.grd[ct_param], c.grd[ct_param + 1], (int)c.BT, x.L, g.L, planar_dy != nullptr, c.st));
     const bool st = x.bn >= 0;
-    return launch_convt_small_bwd_data(g.dy, W, dX, x.z, x.p0, x.p2, st ? c.bn[x.bn].mean : nullptr, st ? c.bn[x.bn].inv : nullptr,
-                                       st ? c.bn[x.bn].bstats : nullptr, (int)c.BT, x.L, g.L, c.st);
+    return launch_convt_small_bwd_data(dy, W, dX, x.z, x.p0, x.p2, st ? c.bn[x.bn].mean : nullptr, st ? c.bn[x.bn].inv : nullptr,
+                                       st ? c.bn[x.bn].bstats : nullptr, (int)c.BT, x.L, g.L, planar_dy != nullptr, c.st);
   }
   {
     WgStream ws{};
@@ -411,7 +412,8 @@ int backward(Ctx& c, const float* x, const float* gout) {
   const Plan& P = c.plan;
   const long BT = c.BT;
   TRU_CUDA(cudaMemsetAsync(c.ws + P.bstats, 0, NBN * 384 * 8, c.st));
-  TRY(launch_planar_to_cl(gout, c.F(P.dOUT), (int)BT, 8, 257, c.st));
+  const bool small5 = convt_small_eligible(8, 8, DEC_K[5], DEC_S[5], DEC_LP[5], DEC_LT[5]);   // the last block reads the planar gradient directly
+  if (!small5) TRY(launch_planar_to_cl(gout, c.F(P.dOUT), (int)BT, 8, 257, c.st));
 
   // ---- decoder, last block first ----
   for (int d = 5; d >= 0; --d) {
@@ -421,7 +423,7 @@ int backward(Ctx& c, const float* x, const float* gout) {
     Grad gt = d == 5 ? Grad{c.F(P.dOUT), nullptr, nullptr, nullptr, nullptr, 257, 8}
                      : c.grad(P.dZDt[d], P.ZDt[d], DEC_LT[d], Co, BN_DEC(d, 1));
     if (d < 5) TRY(bn_bfin(c, BN_DEC(d, 1), Co, BT * DEC_LT[d], P_DEC(d, 6), -1, P_DEC(d, 5)));
-    TRY(convt_bwd(c, gt, pw, P_DEC(d, 4), DEC_K[d], DEC_S[d], c.F(P.dZDp[d])));
+    TRY(convt_bwd(c, gt, pw, P_DEC(d, 4), DEC_K[d], DEC_S[d], c.F(P.dZDp[d]), (d == 5 && small5) ? gout : nullptr));
     TRY(bn_bfin(c, b1, Co, BT * Lp, P_DEC(d, 2)));
     Grad gp = c.grad(P.dZDp[d], P.ZDp[d], Lp, Co, b1);
     if (d >= 1) {

@@ -20,6 +20,49 @@ def denoise(net, noisy_audio, beta=0.5):
     return ops.mask_istft(out, beta), out
 
 
+class CudaPrefetcher:
+    """Double-buffered host -> device staging of (clean, noisy) batches on a side stream, so the copy of batch i+1 overlaps
+    the training step of batch i (train.py:124-125 copies synchronously).  ``next(clean_host, noisy_host)`` returns device
+    tensors holding the batch passed in the PREVIOUS call (the first call copies and returns its own batch) and starts
+    the copy of the new one; host tensors must be pinned for the copy to be asynchronous."""
+
+    def __init__(self, device="cuda"):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.bufs = [None, None]
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.free = [torch.cuda.Event(), torch.cuda.Event()]
+        self.k = 0
+        self.primed = False
+
+    def _issue(self, k, clean_h, noisy_h):
+        if self.bufs[k] is None or self.bufs[k][0].shape != clean_h.shape:
+            self.bufs[k] = (torch.empty(clean_h.shape, device=self.device, dtype=clean_h.dtype),
+                            torch.empty(noisy_h.shape, device=self.device, dtype=noisy_h.dtype))
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(self.free[k])          # the step that last read this buffer has finished
+            self.bufs[k][0].copy_(clean_h, non_blocking=True)
+            self.bufs[k][1].copy_(noisy_h, non_blocking=True)
+            self.ready[k].record(self.stream)
+
+    def next(self, clean_h, noisy_h):
+        cur = torch.cuda.current_stream(self.device)
+        if not self.primed:
+            self.free[0].record(cur); self.free[1].record(cur)
+            self._issue(self.k, clean_h, noisy_h)
+            self.primed = True
+        k = self.k
+        self._issue(k ^ 1, clean_h, noisy_h)              # next batch goes into the other buffer while this one is used
+        cur.wait_event(self.ready[k])
+        self.k = k ^ 1
+        return self.bufs[k]
+
+    def release(self, k_bufs):
+        """Call after the step that consumed ``k_bufs`` has been enqueued (marks the buffer reusable)."""
+        k = 0 if k_bufs is self.bufs[0] else 1
+        self.free[k].record(torch.cuda.current_stream(self.device))
+
+
 class StreamingDenoiser:
     """Stateful frame-by-frame inference for S concurrent streams (rt.py:20-27 / stream.py:83-109 intent):
     carries the PCEN smoother (S,257), the TGRU hidden state (S*16,128) and the overlap-add tail (S,384).
