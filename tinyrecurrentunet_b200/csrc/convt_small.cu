@@ -204,8 +204,9 @@ __global__ void __launch_bounds__(WG_NT) convt8_wgrad_kernel(const float* __rest
         if (dy_planar) {                               // element e of the planar frame = (channel e / Lout, position e % Lout)
           const int e = (it - nA4) * 4;
           const float v4[4] = {pre[i].x, pre[i].y, pre[i].z, pre[i].w};
+          constexpr int LO = 257;                      // (planner: the planar path is only taken for Lout == 257; constant divisor)
 #pragma unroll
-          for (int q = 0; q < 4; ++q) if (e + q < Lout * CC) ds[((e + q) % Lout) * CC + (e + q) / Lout] = v4[q];
+          for (int q = 0; q < 4; ++q) if (e + q < LO * CC) ds[((e + q) % LO) * CC + (e + q) / LO] = v4[q];
         } else {
           ((float4*)ds)[it - nA4] = pre[i];
         }
@@ -241,7 +242,7 @@ __global__ void __launch_bounds__(WG_NT) convt8_wgrad_kernel(const float* __rest
 }  // namespace
 
 bool convt_small_eligible(int Cin, int Cout, int k, int s, int L, int Lout) {
-  return Cin == CC && Cout == CC && k == KK && s == ST && L % 4 == 0 && Lout == (L - 1) * ST - 2 * PAD + KK &&
+  return Cin == CC && Cout == CC && k == KK && s == ST && L == 128 && Lout == 257 && Lout == (L - 1) * ST - 2 * PAD + KK &&
          (L * CC / 4 + Lout * CC / 4) <= 3 * WG_NT;
 }
 
