@@ -60,11 +60,12 @@ __global__ void __launch_bounds__(FNT) fgru_fwd_kernel(const __grid_constant__ G
 #pragma unroll
       for (int q = 0; q < 3; ++q) gi[s][q] = ok ? ld4(g + q * FH) : make_float4(0, 0, 0, 0);
     }
-    float acc[4][3][4];
+    // packed FFMA2 (sm_100): two hidden units per instruction, h broadcast into both halves
+    float2 acc2[4][3][2];
 #pragma unroll
     for (int s = 0; s < 4; ++s)
 #pragma unroll
-      for (int g = 0; g < 3; ++g) { acc[s][g][0] = bh[g].x; acc[s][g][1] = bh[g].y; acc[s][g][2] = bh[g].z; acc[s][g][3] = bh[g].w; }
+      for (int g = 0; g < 3; ++g) { acc2[s][g][0] = make_float2(bh[g].x, bh[g].y); acc2[s][g][1] = make_float2(bh[g].z, bh[g].w); }
 #pragma unroll 4
     for (int k4 = 0; k4 < FH / 4; ++k4) {
       float4 hv[4];
@@ -72,18 +73,29 @@ __global__ void __launch_bounds__(FNT) fgru_fwd_kernel(const __grid_constant__ G
       for (int s = 0; s < 4; ++s) hv[s] = *(const float4*)(hs + (ts * 4 + s) * F_H_LD + k4 * 4);
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
+        float2 hh[4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          const float h = kk == 0 ? hv[s].x : kk == 1 ? hv[s].y : kk == 2 ? hv[s].z : hv[s].w;
+          hh[s] = make_float2(h, h);
+        }
 #pragma unroll
         for (int g = 0; g < 3; ++g) {
           const float4 w = *(const float4*)(WT + (k4 * 4 + kk) * F_WT_LD + g * FH + tu * 4);
+          const float2 w01 = make_float2(w.x, w.y), w23 = make_float2(w.z, w.w);
 #pragma unroll
           for (int s = 0; s < 4; ++s) {
-            const float h = kk == 0 ? hv[s].x : kk == 1 ? hv[s].y : kk == 2 ? hv[s].z : hv[s].w;
-            acc[s][g][0] = fmaf(h, w.x, acc[s][g][0]); acc[s][g][1] = fmaf(h, w.y, acc[s][g][1]);
-            acc[s][g][2] = fmaf(h, w.z, acc[s][g][2]); acc[s][g][3] = fmaf(h, w.w, acc[s][g][3]);
+            acc2[s][g][0] = __ffma2_rn(hh[s], w01, acc2[s][g][0]);
+            acc2[s][g][1] = __ffma2_rn(hh[s], w23, acc2[s][g][1]);
           }
         }
       }
     }
+    float acc[4][3][4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+#pragma unroll
+      for (int g = 0; g < 3; ++g) { acc[s][g][0] = acc2[s][g][0].x; acc[s][g][1] = acc2[s][g][0].y; acc[s][g][2] = acc2[s][g][1].x; acc[s][g][3] = acc2[s][g][1].y; }
     __syncthreads();                      // everyone has read hs
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
