@@ -282,6 +282,22 @@ def test_streaming_denoiser_equals_offline_denoise():
     assert rel(streamed, offline) <= OUT_TOL
 
 
+def test_cuda_prefetcher_delivers_batches_in_order():
+    """util.CudaPrefetcher (used by bench.py's end-to-end timing): call i returns the batch passed in call i-1 (the first
+    call its own batch), copied on a side stream; a consumer on the current stream always sees complete data."""
+    from tinyrecurrentunet_b200 import util
+    pre = util.CudaPrefetcher("cuda")
+    hosts = [(torch.full((4, 1000), float(i)).pin_memory(), torch.full((4, 1000), float(-i)).pin_memory()) for i in range(6)]
+    seen = []
+    for i, (c, n) in enumerate(hosts):
+        bufs = pre.next(c, n)
+        seen.append((bufs[0].sum().item() / 4000.0, bufs[1].sum().item() / 4000.0))      # consumer work on the current stream
+        pre.release(bufs)
+    assert seen[0] == (0.0, 0.0)
+    for i in range(1, 6):
+        assert seen[i] == (float(i - 1), float(-(i - 1))), (i, seen[i])
+
+
 def test_loss_fn_end_to_end_matches_oracle():
     """audio -> features -> net -> mask+iSTFT -> loss, both sides end to end.
 
