@@ -188,11 +188,9 @@ __global__ void __launch_bounds__(FNT) fgru_bwd_kernel(const __grid_constant__ G
       *(float4*)(d) = dr; *(float4*)(d + FH) = dz; *(float4*)(d + 2 * FH) = dhn;
     }
     __syncthreads();
-    float acc[4][4];
+    float2 acc2[4][2];                    // packed FFMA2: two hidden units per instruction
 #pragma unroll
-    for (int s = 0; s < 4; ++s)
-#pragma unroll
-      for (int u = 0; u < 4; ++u) acc[s][u] = 0.f;
+    for (int s = 0; s < 4; ++s) acc2[s][0] = acc2[s][1] = make_float2(0.f, 0.f);
 #pragma unroll 4
     for (int j4 = 0; j4 < 3 * FH / 4; ++j4) {
       float4 gv[4];
@@ -201,18 +199,21 @@ __global__ void __launch_bounds__(FNT) fgru_bwd_kernel(const __grid_constant__ G
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
         const float4 w = *(const float4*)(W + (j4 * 4 + jj) * F_W_LD + tu * 4);
+        const float2 w01 = make_float2(w.x, w.y), w23 = make_float2(w.z, w.w);
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
           const float g = jj == 0 ? gv[s].x : jj == 1 ? gv[s].y : jj == 2 ? gv[s].z : gv[s].w;
-          acc[s][0] = fmaf(g, w.x, acc[s][0]); acc[s][1] = fmaf(g, w.y, acc[s][1]);
-          acc[s][2] = fmaf(g, w.z, acc[s][2]); acc[s][3] = fmaf(g, w.w, acc[s][3]);
+          const float2 gg = make_float2(g, g);
+          acc2[s][0] = __ffma2_rn(gg, w01, acc2[s][0]);
+          acc2[s][1] = __ffma2_rn(gg, w23, acc2[s][1]);
         }
       }
     }
 #pragma unroll
-    for (int s = 0; s < 4; ++s)
-#pragma unroll
-      for (int u = 0; u < 4; ++u) carry[s][u] = dd[s][u] + acc[s][u];
+    for (int s = 0; s < 4; ++s) {
+      carry[s][0] = dd[s][0] + acc2[s][0].x; carry[s][1] = dd[s][1] + acc2[s][0].y;
+      carry[s][2] = dd[s][2] + acc2[s][1].x; carry[s][3] = dd[s][3] + acc2[s][1].y;
+    }
     __syncthreads();
   }
 }
