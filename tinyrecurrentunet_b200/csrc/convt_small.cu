@@ -225,17 +225,23 @@ __global__ void __launch_bounds__(WG_NT) convt8_wgrad_kernel(const float* __rest
           acc[0] = fmaf(a, d.x, acc[0]); acc[1] = fmaf(a, d.y, acc[1]); acc[2] = fmaf(a, d.z, acc[2]); acc[3] = fmaf(a, d.w, acc[3]);
         }
       }
-    } else if (tid < 320 + CC && db) {
-      const int co = tid - 320;
-      for (int lo = 0; lo < Lout; ++lo) bsum += ds[lo * CC + co];
+    } else if (db) {                       // warp 10: lane = (quarter of the rows, channel); 4 independent partial sums each
+      const int co = (tid - 320) & 7, qt = (tid - 320) >> 3;
+      float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+      int lo = qt;
+      for (; lo + 12 < Lout; lo += 16) {
+        b0 += ds[lo * CC + co]; b1 += ds[(lo + 4) * CC + co]; b2 += ds[(lo + 8) * CC + co]; b3 += ds[(lo + 12) * CC + co];
+      }
+      for (; lo < Lout; lo += 4) b0 += ds[lo * CC + co];
+      bsum += (b0 + b1) + (b2 + b3);
     }
   }
   (void)ap0; (void)ap2;
   if (tid < 320) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) atomicAdd(dW + (ci * CC + cq * 4 + e) * KK + j, acc[e]);
-  } else if (tid < 320 + CC && db) {
-    atomicAdd(db + (tid - 320), bsum);
+  } else if (db) {
+    atomicAdd(db + ((tid - 320) & 7), bsum);
   }
 }
 
