@@ -103,3 +103,39 @@ def test_cpu_helpers_match_oracle():
     torch.testing.assert_close(phm.PhaseAwareMask(0.5)(a, b), O.phase_aware_mask(a, b, 0.5))
     with pytest.raises(NotImplementedError):
         dataset.ProcessAudio(n_fft=1024)
+
+
+def test_checkpoint_round_trip_in_the_reference_format(tmp_path):
+    """train.py:155-162 / :70-95: a checkpoint {iter, model_state_dict, optimizer_state_dict, training_time_seconds} written by
+    the reference layer list (the oracle's TRUNet is network.py:9-150 verbatim) loads into the drop-in module and back, key for
+    key, and util.find_max_epoch-style resume (largest <iter>.pkl) picks the right file."""
+    import torch
+    from oracle import tru_oracle as O
+    from tinyrecurrentunet_b200 import network
+    torch.manual_seed(3)
+    ref = O.randomize_bn(O.TRUNet())
+    opt = torch.optim.AdamW(ref.parameters(), lr=4e-4)
+    ckdir = tmp_path / "checkpoint"
+    ckdir.mkdir()
+    for it in (5000, 10000):
+        torch.save({"iter": it, "model_state_dict": ref.state_dict(), "optimizer_state_dict": opt.state_dict(),
+                    "training_time_seconds": 12.5}, str(ckdir / ("%d.pkl" % it)))
+    newest = max(int(f.name[:-4]) for f in ckdir.iterdir() if f.name.endswith(".pkl"))
+    assert newest == 10000
+    ck = torch.load(str(ckdir / ("%d.pkl" % newest)), map_location="cpu")
+    net = network.TRUNet(3, 64, 3, 128, [5, 3], [2, 1], 192)
+    missing = net.load_state_dict(ck["model_state_dict"], strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    sd = net.state_dict()
+    assert list(sd.keys()) == list(ref.state_dict().keys())
+    for k, v in ref.state_dict().items():
+        assert torch.equal(sd[k], v), k
+    # and back: a checkpoint written from the drop-in module restores the reference model and its optimizer state
+    opt2 = torch.optim.AdamW(net.parameters(), lr=4e-4)
+    opt2.load_state_dict(ck["optimizer_state_dict"])
+    torch.save({"iter": 15000, "model_state_dict": net.state_dict(), "optimizer_state_dict": opt2.state_dict(),
+                "training_time_seconds": 20.0}, str(ckdir / "15000.pkl"))
+    back = O.TRUNet()
+    back.load_state_dict(torch.load(str(ckdir / "15000.pkl"), map_location="cpu")["model_state_dict"], strict=True)
+    for (k, a), (_, b) in zip(back.state_dict().items(), ref.state_dict().items()):
+        assert torch.equal(a, b), k
