@@ -80,14 +80,17 @@ __device__ __forceinline__ float4 ldg4_off(const float* base, unsigned off) {
   return v;
 }
 
+#ifndef TRU_CACHE_ROWS
+#define TRU_CACHE_ROWS 1
+#endif
 #ifndef TRU_EPI2_PIPE
 #define TRU_EPI2_PIPE 1
 #endif
 #ifndef TRU_EPI2_REGS
 #define TRU_EPI2_REGS 1
 #endif
-constexpr int LW = 16;        // loader warps
-constexpr int NG = 4;         // loader groups of 4 warps; group g owns k-blocks g, g+NG, ... (global k-block counter)
+constexpr int LW = 12;        // loader warps
+constexpr int NG = 3;         // loader groups of 4 warps; group g owns k-blocks g, g+NG, ... (global k-block counter)
 constexpr int NT = 32 * (4 + LW + EW);
 
 // LD2: loaders read two tensors (dY and Z) and apply the BN-backward affine.  EPI (0 plain, 1 mask, 2 mask +
@@ -96,10 +99,11 @@ constexpr int NT = 32 * (4 + LW + EW);
 // The kernel is bound by instruction issue, not by HBM or the tensor pipe (ablation: with MMAs, loads and
 // stores all disabled the old skeleton still took the full HBM time), so both producer and consumer roles are
 // written for instructions per element:
-//   * a loader GROUP (4 warps) owns a whole k-block: 8 rows x one 16-byte channel chunk per thread, loads
+//   * 12 loader warps as 3 groups (16 warps at 72 registers spilled as soon as anything was added; 12 at 88 registers
+//     hold the per-tile row decode and are slightly faster); a loader GROUP (4 warps) owns a whole k-block: 8 rows x one 16-byte channel chunk per thread, loads
 //     issued back to back, then transformed and stored.  The per-k-block bookkeeping (descriptor fetch, row
 //     decode, barrier handshake) is paid once per 8 float4 instead of once per 2, and memory-level
-//     parallelism comes from the 4 groups working on 4 different k-blocks, not from register slots.
+//     parallelism comes from the groups working on different k-blocks, not from register slots.
 //   * the epilogue addresses rows with one 32-bit element offset (lane j computes row j's, broadcast by
 //     shuffle) and IMAD.WIDE + STG; full tiles skip the per-row validity test.
 template <bool LD2, int EPI>
@@ -107,7 +111,8 @@ __global__ void __launch_bounds__(NT, 1) tc_igemm_kernel(const __grid_constant__
                                                          const __grid_constant__ TcLayout Lo) {
   // register budgets per role (launch value 72 for 28 warps): 4*24 + 16*64 + 8*112 = 2016 = 28*72
   //                                                      or 4*24 + 16*72 + 8*96 when the epilogue has no added tensor
-  constexpr int REG_MMA = 24, REG_LOAD = (EPI == 2 && TRU_EPI2_REGS) ? 64 : 72, REG_EPI = (EPI == 2 && TRU_EPI2_REGS) ? 112 : 96;
+  // 24 warps x 80 launch registers = 1920: 4*24 + 12*88 + 8*96 = 1920   (EPI 2: 4*24 + 12*80 + 8*104 = 1888)
+  constexpr int REG_MMA = 24, REG_LOAD = (EPI == 2 && TRU_EPI2_REGS) ? 80 : 88, REG_EPI = (EPI == 2 && TRU_EPI2_REGS) ? 104 : 96;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* Wsm = smem;                                 // [hi|lo][nkb][MW rows][128 B], swizzled
@@ -219,7 +224,7 @@ __global__ void __launch_bounds__(NT, 1) tc_igemm_kernel(const __grid_constant__
     }
   } else if (warp < 4 + LW) {
     // ================================== loaders ====================================
-    if (REG_LOAD < 72) reg_dec<REG_LOAD>();
+    if (REG_LOAD > 80) reg_inc<REG_LOAD>();
     constexpr int R = LD2 ? 4 : 8;                      // rows per thread and pass (LD2: two passes of 4 rows, two tensors)
     const int lt = tid - 128, g = lt >> 7, gt = lt & 127, chunk = gt & 7, rbase = gt >> 3;   // rows rbase + 16 i
     const uint32_t st_off = (uint32_t)rbase * 128 + ((uint32_t)(chunk ^ (rbase & 7)) << 4);
@@ -235,6 +240,8 @@ __global__ void __launch_bounds__(NT, 1) tc_igemm_kernel(const __grid_constant__
     while (st >= nstage) { st -= nstage; ++ph; }
     int cur = -1;
     unsigned bt0 = 0, qb = 0, qmax = 0;
+    constexpr bool CACHE_ROWS = TRU_CACHE_ROWS != 0;
+    unsigned rbt[CACHE_ROWS ? 8 : 1], rqq[CACHE_ROWS ? 8 : 1];
     const float ninf = -__int_as_float(0x7f800000);
     while (ti < n_my) {
       if (ti != cur) {               // new tile: decode its first row once; the thread's rows follow by a small exact division
@@ -242,6 +249,14 @@ __global__ void __launch_bounds__(NT, 1) tc_igemm_kernel(const __grid_constant__
         // rows beyond M (last tile only) are clamped to row M-1: they load valid memory and the epilogue drops them
         bt0 = m0 / Lq; qb = m0 - bt0 * Lq + rbase; qmax = Mu - 1u - bt0 * Lq;
         cur = ti;
+        if (CACHE_ROWS) {            // the (frame, position) of the thread's 8 rows is the same for every k-block of the tile
+#pragma unroll
+          for (int ii = 0; ii < 8; ++ii) {
+            const unsigned qq = min(qb + 16u * ii, qmax);
+            const unsigned bq = magic ? __umulhi(qq, magic) : qq;
+            rbt[ii] = bt0 + bq; rqq[ii] = qq - bq * Lq;
+          }
+        }
       }
       const Seg& sg = P.seg[Lo.kb_seg[kb]];
       const float* src = sg.src;
@@ -267,12 +282,16 @@ __global__ void __launch_bounds__(NT, 1) tc_igemm_kernel(const __grid_constant__
 #pragma unroll
         for (int i = 0; i < R; ++i) {
           const int ii = h * R + i;
-          const unsigned qq = min(qb + 16u * ii, qmax);
-          const unsigned bq = magic ? __umulhi(qq, magic) : qq;          // qq / Lq (exact: qq * Lq < 2^32)
-          const unsigned q = qq - bq * Lq;
+          unsigned bt, q;
+          if (CACHE_ROWS) { bt = rbt[ii]; q = rqq[ii]; }
+          else {
+            const unsigned qq = min(qb + 16u * ii, qmax);
+            const unsigned bq = magic ? __umulhi(qq, magic) : qq;        // qq / Lq (exact: qq * Lq < 2^32)
+            bt = bt0 + bq; q = qq - bq * Lq;
+          }
           const unsigned li = (unsigned)((int)q * smul + sadd);
           const bool ok = li < Lok;
-          unsigned off = ((bt0 + bq) * Lsrc + li) * ld + cb;
+          unsigned off = (bt * Lsrc + li) * ld + cb;
           off = ok ? off : 0u;               // padding rows read element 0 (always mapped) and are zeroed below
           if (ok) msk |= 1u << i;
           a[i] = ldg4_off(src, off);
