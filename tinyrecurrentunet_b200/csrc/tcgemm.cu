@@ -111,8 +111,8 @@ __global__ void __launch_bounds__(NT, 1) tc_igemm_kernel(const __grid_constant__
                                                          const __grid_constant__ TcLayout Lo) {
   // register budgets per role (launch value 72 for 28 warps): 4*24 + 16*64 + 8*112 = 2016 = 28*72
   //                                                      or 4*24 + 16*72 + 8*96 when the epilogue has no added tensor
-  // 24 warps x 80 launch registers = 1920: 4*24 + 12*88 + 8*96 = 1920   (EPI 2: 4*24 + 12*80 + 8*104 = 1888)
-  constexpr int REG_MMA = 24, REG_LOAD = (EPI == 2 && TRU_EPI2_REGS) ? 80 : 88, REG_EPI = (EPI == 2 && TRU_EPI2_REGS) ? 104 : 96;
+  // 24 warps x 80 launch registers = 1920: 4*24 + 12*88 + 8*96 = 1920   (EPI 2: 4*24 + 12*72 + 8*112 = 1856)
+  constexpr int REG_MMA = 24, REG_LOAD = (EPI == 2 && TRU_EPI2_REGS) ? 72 : 88, REG_EPI = (EPI == 2 && TRU_EPI2_REGS) ? 112 : 96;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* Wsm = smem;                                 // [hi|lo][nkb][MW rows][128 B], swizzled
@@ -225,6 +225,7 @@ __global__ void __launch_bounds__(NT, 1) tc_igemm_kernel(const __grid_constant__
   } else if (warp < 4 + LW) {
     // ================================== loaders ====================================
     if (REG_LOAD > 80) reg_inc<REG_LOAD>();
+    if (REG_LOAD < 80) reg_dec<REG_LOAD>();
     constexpr int R = LD2 ? 4 : 8;                      // rows per thread and pass (LD2: two passes of 4 rows, two tensors)
     const int lt = tid - 128, g = lt >> 7, gt = lt & 127, chunk = gt & 7, rbase = gt >> 3;   // rows rbase + 16 i
     const uint32_t st_off = (uint32_t)rbase * 128 + ((uint32_t)(chunk ^ (rbase & 7)) << 4);
