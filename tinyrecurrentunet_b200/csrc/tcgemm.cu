@@ -89,8 +89,11 @@ __device__ __forceinline__ float4 ldg4_off(const float* base, unsigned off) {
 #ifndef TRU_EPI2_REGS
 #define TRU_EPI2_REGS 1
 #endif
-constexpr int LW = 12;        // loader warps
-constexpr int NG = 3;         // loader groups of 4 warps; group g owns k-blocks g, g+NG, ... (global k-block counter)
+#ifndef TRU_LW
+#define TRU_LW 12
+#endif
+constexpr int LW = TRU_LW;    // loader warps
+constexpr int NG = LW / 4;     // loader groups of 4 warps; group g owns k-blocks g, g+NG, ... (global k-block counter)
 constexpr int NT = 32 * (4 + LW + EW);
 
 // LD2: loaders read two tensors (dY and Z) and apply the BN-backward affine.  EPI (0 plain, 1 mask, 2 mask +
@@ -111,8 +114,13 @@ __global__ void __launch_bounds__(NT, 1) tc_igemm_kernel(const __grid_constant__
                                                          const __grid_constant__ TcLayout Lo) {
   // register budgets per role (launch value 72 for 28 warps): 4*24 + 16*64 + 8*112 = 2016 = 28*72
   //                                                      or 4*24 + 16*72 + 8*96 when the epilogue has no added tensor
-  // 24 warps x 80 launch registers = 1920: 4*24 + 12*88 + 8*96 = 1920   (EPI 2: 4*24 + 12*72 + 8*112 = 1856)
-  constexpr int REG_MMA = 24, REG_LOAD = (EPI == 2 && TRU_EPI2_REGS) ? 72 : 88, REG_EPI = (EPI == 2 && TRU_EPI2_REGS) ? 112 : 96;
+  // register budgets per role; launch value = 65536 / threads rounded down to a multiple of 8:
+  //   LW = 12: 24 warps x 80 = 1920 >= 4*24 + 12*88 + 8*96      (EPI 2: 4*24 + 12*72 + 8*112 = 1856)
+  //   LW =  8: 20 warps x 96 = 1920 >= 4*24 +  8*104 + 8*120
+  constexpr int REG_LAUNCH = LW == 8 ? 96 : 80;
+  constexpr int REG_MMA = 24;
+  constexpr int REG_LOAD = LW == 8 ? 104 : ((EPI == 2 && TRU_EPI2_REGS) ? 72 : 88);
+  constexpr int REG_EPI = LW == 8 ? 120 : ((EPI == 2 && TRU_EPI2_REGS) ? 112 : 96);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* Wsm = smem;                                 // [hi|lo][nkb][MW rows][128 B], swizzled
@@ -224,8 +232,8 @@ __global__ void __launch_bounds__(NT, 1) tc_igemm_kernel(const __grid_constant__
     }
   } else if (warp < 4 + LW) {
     // ================================== loaders ====================================
-    if (REG_LOAD > 80) reg_inc<REG_LOAD>();
-    if (REG_LOAD < 80) reg_dec<REG_LOAD>();
+    if (REG_LOAD > REG_LAUNCH) reg_inc<REG_LOAD>();
+    if (REG_LOAD < REG_LAUNCH) reg_dec<REG_LOAD>();
     constexpr int R = LD2 ? 4 : 8;                      // rows per thread and pass (LD2: two passes of 4 rows, two tensors)
     const int lt = tid - 128, g = lt >> 7, gt = lt & 127, chunk = gt & 7, rbase = gt >> 3;   // rows rbase + 16 i
     const uint32_t st_off = (uint32_t)rbase * 128 + ((uint32_t)(chunk ^ (rbase & 7)) << 4);
