@@ -329,3 +329,43 @@ def test_loss_fn_end_to_end_matches_oracle():
         num += (p.grad.cpu().double() - gref[k].grad.double()).pow(2).sum().item()
         den += gref[k].grad.double().pow(2).sum().item()
     assert (num / den) ** 0.5 <= 2e-2, (num / den) ** 0.5
+
+
+@pytest.mark.parametrize("B,N,ref_shapes", [(1, 128 * 13 + 77, True), (3, 128 * 9 + 5, False), (1, 1153, True)])
+def test_loss_fn_ragged_and_reference_call_shapes(B, N, ref_shapes):
+    """Edge cases of the path: a clip length that is not a multiple of the hop (the tail beyond 128*(N//128) samples is not
+    reconstructed by the iSTFT: util.py / dataset.py:293-296), the shortest clip the 2048-point loss STFT allows (reflect padding
+    needs more than 1024 reconstructed samples), and the reference's
+    own call shapes - clean (1,N), noisy (1,1,N) as its loader yields them (dataset.py:388-390)."""
+    from tinyrecurrentunet_b200 import stft_loss, util
+    ref, net = make_pair(6)
+    ref.train()
+    net.train()
+    clean, noisy = O.synthetic_batch(B, n=N, first=9)
+    loss_ref, d_ref, _ = O.loss_fn(ref, clean, noisy)
+    mr = stft_loss.MultiResolutionSTFTLoss(fft_sizes=[512, 1024, 2048], hop_sizes=[50, 120, 240],
+                                           win_lengths=[240, 600, 1200], sc_lambda=0.5, mag_lambda=0.5).cuda()
+    c, n = clean.cuda(), noisy.cuda()
+    if ref_shapes:
+        c, n = c.view(1, N), n.view(1, 1, N)
+    loss, d = util.loss_fn(net, (c, n), ell_p=1, ell_p_lambda=1, stft_lambda=1, mrstftloss=mr)
+    assert rel(loss, loss_ref) <= OUT_TOL
+    for k in ("l1", "stft_sc", "stft_mag"):
+        assert rel(d[k], d_ref[k]) <= OUT_TOL, k
+    loss.backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
+
+
+def test_too_short_clip_fails_loudly_like_the_reference():
+    """torch.stft's reflect padding rejects a signal that is not longer than n_fft/2 (the oracle raises RuntimeError for a
+    896-sample clip at the 2048-point resolution); the CUDA path must refuse it too instead of reading out of bounds."""
+    from tinyrecurrentunet_b200 import _lib as L, stft_loss, util
+    _, net = make_pair(6)
+    net.train()
+    clean, noisy = O.synthetic_batch(2, n=896, first=1)
+    mr = stft_loss.MultiResolutionSTFTLoss(fft_sizes=[512, 1024, 2048], hop_sizes=[50, 120, 240],
+                                           win_lengths=[240, 600, 1200], sc_lambda=0.5, mag_lambda=0.5).cuda()
+    with pytest.raises(L.TruError):
+        util.loss_fn(net, (clean.cuda(), noisy.cuda()), ell_p=1, ell_p_lambda=1, stft_lambda=1, mrstftloss=mr)
+    with pytest.raises(RuntimeError):
+        O.loss_fn(O.TRUNet().train(), clean, noisy)
