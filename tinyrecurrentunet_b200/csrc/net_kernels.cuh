@@ -67,6 +67,7 @@ struct WgStream {
   const float* z_src; const float* z_src2; const float* z_p0; const float* z_p1; const float* z_p2;   // dz = p0*src + p1*src2 + p2
   int z_L, z_ld, N, ntap, zs, zpad;
   float* dW; int wsc, wsn, wtap; float* db;
+  float* scratch; size_t scratch_floats;    // optional: per-CTA partial results (>= SMs x 128 x 384 floats) -> ordered 2-stage reduction instead of atomics
   int n_split; float* dW2; float* db2;      // optional: dz columns n >= n_split belong to a second weight / bias tensor (FGRU directions)
   int BT, Lq;
 };

@@ -47,6 +47,7 @@ struct WgK {
   int nraw, strided;            // strided: bit o set if operand o (0/1 A sources, 2 dY, 3 Z) is a channel slice of wider rows
   float* dW; int wbase[2], wsc, wsn, wtap; float* db;
   int n_split; float* dW2; float* db2;
+  float* scratch;                // per-CTA partial accumulators [CTA][Mmma][QWt] (null: atomics straight into dW)
   int BT, Lq; unsigned units_total, units_per_cta;
 };
 
@@ -77,6 +78,39 @@ __device__ __forceinline__ void split_store(uint8_t* hi_ptr, uint32_t lo_delta, 
   lo.z = __float_as_uint(v.z - __uint_as_float(hi.z)); lo.w = __float_as_uint(v.w - __uint_as_float(hi.w));
   *(uint4*)hi_ptr = hi;
   *(uint4*)(hi_ptr + lo_delta) = lo;
+}
+
+// destination of accumulator element (p, q)
+__device__ __forceinline__ float* wgrad_dst(const WgK& K, int p, int q) {
+  const int acol = K.p_is_z ? q : p, zcol = K.p_is_z ? p : q;
+  const int s = (K.nsrc == 2 && acol >= K.a_c0[1]) ? 1 : 0, c = acol - K.a_c0[s];
+  const int tap = zcol / K.N, n = zcol - tap * K.N;
+  if (K.n_split > 0 && n >= K.n_split) return K.dW2 + K.wbase[s] + (long)c * K.wsc + (long)(n - K.n_split) * K.wsn;
+  return K.dW + K.wbase[s] + (long)tap * K.wtap + (long)c * K.wsc + (long)n * K.wsn;
+}
+
+// second stage of the weight-gradient reduction: dW[p][q] += sum over CTAs of scratch[cta][p][q] (fixed order: deterministic).
+// Block = one accumulator row p x 32 columns; 8 warps each sum every 8th partial (short load chains), then meet in shared memory.
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const __grid_constant__ WgK K, int nctas) {
+  __shared__ float red[8][32];
+  const int nqb = K.QWt >> 5;
+  const int p = blockIdx.x / nqb, q = (blockIdx.x - p * nqb) * 32 + (threadIdx.x & 31), cg = threadIdx.x >> 5;
+  const float* src = K.scratch + (size_t)p * K.QWt + q;
+  const size_t stride = (size_t)K.Mmma * K.QWt;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int c = cg;
+  for (; c + 24 < nctas; c += 32) {
+    s0 += src[(size_t)c * stride]; s1 += src[(size_t)(c + 8) * stride]; s2 += src[(size_t)(c + 16) * stride]; s3 += src[(size_t)(c + 24) * stride];
+  }
+  for (; c < nctas; c += 8) s0 += src[(size_t)c * stride];
+  red[cg][threadIdx.x & 31] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (cg == 0 && p < K.Pvalid && q < K.Qvalid) {
+    float s = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) s += red[g][threadIdx.x];
+    *wgrad_dst(K, p, q) += s;
+  }
 }
 
 // IA / IZ: per-thread item slots (activation / dz float4s per unit), NTAP: taps (compile-time so that unused
@@ -373,19 +407,20 @@ __global__ void __launch_bounds__(NT, 1) tc_wgrad_stream_kernel(const __grid_con
       for (int cb = 0; cb < NBq; ++cb) {
         uint32_t v[32];
         tmem_ld32(tmem + ((uint32_t)(lg * 32) << 16) + cb * 32, v);
-        if (pok) {
+        if (K.scratch) {
+          // 2-stage reduction: the L2 atomic units were the tail of every launch (P x Q atomics per CTA, all CTAs on the same
+          // addresses: ~0.65 ms per training step); partials go to scratch with plain 16-byte stores, wgrad_reduce_kernel adds them up
+          if (K.Mmma == 128 || lane < 16) {
+            float4* dst = (float4*)(K.scratch + ((size_t)blockIdx.x * K.Mmma + p) * K.QWt + cb * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          }
+        } else if (pok) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int q = cb * 32 + j;
-            if (q < K.Qvalid) {
-              const int acol = K.p_is_z ? q : p, zcol = K.p_is_z ? p : q;
-              const int s = (K.nsrc == 2 && acol >= K.a_c0[1]) ? 1 : 0, c = acol - K.a_c0[s];
-              const int tap = zcol / K.N, n = zcol - tap * K.N;
-              if (K.n_split > 0 && n >= K.n_split)
-                atomicAdd(K.dW2 + K.wbase[s] + (long)c * K.wsc + (long)(n - K.n_split) * K.wsn, __uint_as_float(v[j]));
-              else
-                atomicAdd(K.dW + K.wbase[s] + (long)tap * K.wtap + (long)c * K.wsc + (long)n * K.wsn, __uint_as_float(v[j]));
-            }
+            if (q < K.Qvalid) atomicAdd(wgrad_dst(K, p, q), __uint_as_float(v[j]));
           }
         }
       }
@@ -483,20 +518,29 @@ int launch_wgrad_stream(const WgStream& w, cudaStream_t st) {
     nm = it->second;
   }
   ProfScope prof(nm, 4.0 * M * (Ca + (double)w.N * w.zs * (K.z_src2 ? 2 : 1)), 2.0 * M * Ca * (double)w.N * w.ntap, st);
+  K.scratch = (w.scratch && w.scratch_floats >= (size_t)grid * K.Mmma * K.QWt) ? w.scratch : nullptr;
   const int key = ia * 100 + iz * 10 + nt;
+  int rc;
   switch (key) {
-    case 111: return launch_variant<1, 1, 1>(K, grid, smem, st);
-    case 113: return launch_variant<1, 1, 3>(K, grid, smem, st);
-    case 115: return launch_variant<1, 1, 5>(K, grid, smem, st);
-    case 123: return launch_variant<1, 2, 3>(K, grid, smem, st);
-    case 125: return launch_variant<1, 2, 5>(K, grid, smem, st);
-    case 211: return launch_variant<2, 1, 1>(K, grid, smem, st);
-    case 121: return launch_variant<1, 2, 1>(K, grid, smem, st);
-    case 221: return launch_variant<2, 2, 1>(K, grid, smem, st);
-    case 131: return launch_variant<1, 3, 1>(K, grid, smem, st);
-    default: break;
+    case 111: rc = launch_variant<1, 1, 1>(K, grid, smem, st); break;
+    case 113: rc = launch_variant<1, 1, 3>(K, grid, smem, st); break;
+    case 115: rc = launch_variant<1, 1, 5>(K, grid, smem, st); break;
+    case 123: rc = launch_variant<1, 2, 3>(K, grid, smem, st); break;
+    case 125: rc = launch_variant<1, 2, 5>(K, grid, smem, st); break;
+    case 211: rc = launch_variant<2, 1, 1>(K, grid, smem, st); break;
+    case 121: rc = launch_variant<1, 2, 1>(K, grid, smem, st); break;
+    case 221: rc = launch_variant<2, 2, 1>(K, grid, smem, st); break;
+    case 131: rc = launch_variant<1, 3, 1>(K, grid, smem, st); break;
+    default: return set_error(TRU_ERR_ARG, "wgrad_stream: no kernel variant for slots (%d,%d) taps %d", ia, iz, w.ntap);
   }
-  return set_error(TRU_ERR_ARG, "wgrad_stream: no kernel variant for slots (%d,%d) taps %d", ia, iz, w.ntap);
+  if (rc) return rc;
+  if (K.scratch) {
+    // CTAs past the last unit (units_per_cta is rounded up) have no partial result
+    const int nact = (int)((K.units_total + K.units_per_cta - 1) / K.units_per_cta);
+    wgrad_reduce_kernel<<<K.Mmma * (K.QWt >> 5), 256, 0, st>>>(K, nact);
+    TRU_LAUNCH_CHECK();
+  }
+  return TRU_OK;
 }
 
 }  // namespace tru

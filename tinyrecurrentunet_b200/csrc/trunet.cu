@@ -35,6 +35,8 @@ constexpr int BN_FGRU = 21, BN_TGRU = 22;
 
 struct BnSlot { double* stats; double* bstats; float *p0, *p2, *mean, *inv, *q0, *q1, *q2; };
 
+constexpr size_t WG_SCRATCH_FLOATS = (size_t)160 * 128 * 384;     // up to 160 CTAs x (128 x 384) accumulator
+
 struct Plan {
   size_t total = 0;
   size_t take(size_t bytes) { size_t o = total; total += align_up(bytes, 256); return o; }
@@ -42,7 +44,7 @@ struct Plan {
   size_t A0, Zp[6], Zd[6], GF, HF, CF, ZFp, GT, HT, CT, ZTp, ZDp[6], ZDt[5];
   size_t stats, bstats, small;
   // backward
-  size_t dA0, dZp[6], dZd[6], dGFi, dGFh, dHF, dZFp, dGTi, dGTh, dHT, dZTp, dZDp[6], dZDt[5], dOUT, dSkip[5];
+  size_t dA0, dZp[6], dZd[6], dGFi, dGFh, dHF, dZFp, dGTi, dGTh, dHT, dZTp, dZDp[6], dZDt[5], dOUT, dSkip[5], wgScratch;
   void build(long BT, bool bwd) {
     auto f = [&](long per_frame) { return take((size_t)BT * per_frame * 4); };
     A0 = f(128 * 64);
@@ -60,6 +62,7 @@ struct Plan {
     for (int d = 0; d <= 5; ++d) { dZDp[d] = f((long)DEC_LP[d] * DEC_COUT[d]); if (d < 5) dZDt[d] = f((long)DEC_LT[d] * 64); }
     dOUT = f(257 * 8);
     dSkip[0] = f(128 * 64); dSkip[1] = f(128 * 128); dSkip[2] = f(64 * 128); dSkip[3] = f(64 * 128); dSkip[4] = f(32 * 128);
+    wgScratch = take(WG_SCRATCH_FLOATS * 4);      // per-CTA partial weight gradients (2-stage reduction)
   }
 };
 
@@ -284,6 +287,7 @@ void set_mask(IgemmParams& p, Ctx& c, const Act& a, bool stats) {
 int gru_wgrad(Ctx& c, const Act& a, int a_L, int a_ld, int a_coff, int a_add, int C, const float* dz, int z_L, int z_ld, int z_coff,
               int N, float* dW, float* db, int BT, int Lq) {
   WgStream w{};
+  w.scratch = c.F(c.plan.wgScratch); w.scratch_floats = WG_SCRATCH_FLOATS;
   w.nsrc = 1; w.a_src[0] = a.z; w.a_p0[0] = a.p0; w.a_p2[0] = a.p2; w.a_L[0] = a_L; w.a_ld[0] = a_ld; w.a_coff[0] = a_coff;
   w.a_add[0] = a_add; w.a_C[0] = C; w.wbase[0] = 0;
   w.z_src = dz; w.z_L = z_L; w.z_ld = z_ld; w.z_coff = z_coff; w.N = N; w.ntap = 1; w.zs = 1; w.zpad = 0;
@@ -299,6 +303,7 @@ int pw_bwd(Ctx& c, const Grad& g, const Act& x1, int padL, const Act* skip, int 
   int streamed = 1;
   {
     WgStream w{};
+    w.scratch = c.F(c.plan.wgScratch); w.scratch_floats = WG_SCRATCH_FLOATS;
     w.nsrc = skip ? 2 : 1;
     w.a_src[0] = x1.z; w.a_p0[0] = x1.p0; w.a_p2[0] = x1.p2; w.a_L[0] = x1.L; w.a_ld[0] = x1.C; w.a_add[0] = -padL; w.a_C[0] = x1.C; w.wbase[0] = 0;
     if (skip) {
@@ -370,6 +375,7 @@ int convt_bwd(Ctx& c, const Grad& g, const Act& x, int ct_param, int k, int s, f
   }
   {
     WgStream ws{};
+    ws.scratch = c.F(c.plan.wgScratch); ws.scratch_floats = WG_SCRATCH_FLOATS;
     ws.nsrc = 1;
     ws.a_src[0] = x.z; ws.a_p0[0] = x.p0; ws.a_p2[0] = x.p2; ws.a_L[0] = x.L; ws.a_ld[0] = Cin; ws.a_add[0] = 0; ws.a_C[0] = Cin; ws.wbase[0] = 0;
     ws.z_src = g.dy; ws.z_src2 = g.q0 ? g.z : nullptr; ws.z_p0 = g.q0; ws.z_p1 = g.q1; ws.z_p2 = g.q2;
@@ -502,6 +508,7 @@ int backward(Ctx& c, const float* x, const float* gout) {
     Act hfa = c.act(P.HF, 16, 128, -1);
     {   // W_ih, b_ih of both directions in one pass: dGFi rows are [gates fwd (192) | gates bwd (192)], the input is shared
       WgStream w{};
+      w.scratch = c.F(c.plan.wgScratch); w.scratch_floats = WG_SCRATCH_FLOATS;
       w.nsrc = 1; w.a_src[0] = e5.z; w.a_p0[0] = e5.p0; w.a_p2[0] = e5.p2; w.a_L[0] = 16; w.a_ld[0] = 128; w.a_C[0] = 128;
       w.z_src = c.F(P.dGFi); w.z_L = 16; w.z_ld = 384; w.N = 384; w.ntap = 1; w.zs = 1;
       w.dW = c.grd[P_FGRU]; w.wsc = 1; w.wsn = 128; w.db = c.grd[P_FGRU + 2];
