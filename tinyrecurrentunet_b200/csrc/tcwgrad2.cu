@@ -537,6 +537,7 @@ int launch_wgrad_stream(const WgStream& w, cudaStream_t st) {
   if (K.scratch) {
     // CTAs past the last unit (units_per_cta is rounded up) have no partial result
     const int nact = (int)((K.units_total + K.units_per_cta - 1) / K.units_per_cta);
+    count_launch();
     wgrad_reduce_kernel<<<K.Mmma * (K.QWt >> 5), 256, 0, st>>>(K, nact);
     TRU_LAUNCH_CHECK();
   }
