@@ -137,15 +137,16 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
     for (uint32_t i = tid; i < wwords / 4; i += NT) ((uint4*)Wsm)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
     const uint32_t lo_off = (uint32_t)nkb * MW * 128;
+    constexpr int WU = 8;          // weight loads in flight per thread (the prologue is on the critical path of every launch)
     int kbb = 0;
     for (int s = 0; s < P.nseg; ++s) {
       const Seg& sg = P.seg[s];
       const int tot = sg.C * MW;
-      for (int i0 = tid; i0 < tot; i0 += NT * 4) {
-        float v[4];
-        int cc[4], nn[4];
+      for (int i0 = tid; i0 < tot; i0 += NT * WU) {
+        float v[WU];
+        int cc[WU], nn[WU];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < WU; ++u) {
           const int i = i0 + u * NT;
           int c = 0, n = MW;
           if (i < tot) { if (sg.wsc == 1) { c = i % sg.C; n = i / sg.C; } else { n = i % MW; c = i / MW; } }
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
           v[u] = (n < MW && n0 + n < P.N) ? __ldg(sg.W + sg.wbase + (long)c * sg.wsc + (long)(n0 + n) * sg.wsn) : 0.f;
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < WU; ++u) {
           if (nn[u] < MW) {
             const int c = cc[u], n = nn[u];
             const int kb = kbb + (c >> 5), kk = c & 31;
