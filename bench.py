@@ -26,6 +26,8 @@ sys.path.insert(0, ROOT)
 METRIC = "train_4s_clips_per_sec"
 UNIT = "clips/s"
 CLIP_SAMPLES = 64000           # 4 s at 16 kHz
+WORKLOAD = ("tiny.json training step (BASELINE.json configs[1]): %d clean/noisy 4-s 16 kHz pairs per GPU, front end + TRU-Net + "
+            "mask/iSTFT + L1/MRSTFT loss, fwd+bwd, flat-bucket NCCL all-reduce (N>1), AdamW")
 STFT_CFG = dict(fft_sizes=[512, 1024, 2048], hop_sizes=[50, 120, 240], win_lengths=[240, 600, 1200],
                 sc_lambda=0.5, mag_lambda=0.5)          # config/tiny.json:30-37
 
@@ -82,8 +84,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": round(1000.0 * args.cpu_batch / v, 2),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "tiny.json training step, 4-s 16 kHz clips (BASELINE.json configs[1])",
-                       "clips_per_step": args.cpu_batch, "device": "host CPU"},
+            "config": {"workload": WORKLOAD % args.batch, "clips_per_gpu": args.batch, "global_batch": args.batch * args.gpus,
+                       "parallelism": "dp%d" % args.gpus, "device": "host CPU (rank 0 only)",
+                       "sample_clips_per_step": args.cpu_batch},
             "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": round(v, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -370,9 +373,7 @@ def run_native(args):
         line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "tiny.json training step (BASELINE.json configs[1]): %d clean/noisy 4-s 16 kHz "
-                                       "pairs per GPU, front end + TRU-Net + mask/iSTFT + L1/MRSTFT loss, fwd+bwd, "
-                                       "flat-bucket NCCL all-reduce (N>1), AdamW" % B,
+                "config": {"workload": WORKLOAD % B,
                            "clips_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world,
                            "l2": "no explicit flush: one step streams >10 GB of activations through the 126 MB L2"},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
