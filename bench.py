@@ -27,7 +27,7 @@ METRIC = "train_4s_clips_per_sec"
 UNIT = "clips/s"
 CLIP_SAMPLES = 64000           # 4 s at 16 kHz
 WORKLOAD = ("tiny.json training step (BASELINE.json configs[1]): %d clean/noisy 4-s 16 kHz pairs per GPU, front end + TRU-Net + "
-            "mask/iSTFT + L1/MRSTFT loss, fwd+bwd, flat-bucket NCCL all-reduce (N>1), AdamW")
+            "mask/iSTFT + L1/MRSTFT loss, fwd+bwd, flat-bucket NCCL all-reduce (N>1), grad norm + LR schedule + AdamW")
 STFT_CFG = dict(fft_sizes=[512, 1024, 2048], hop_sizes=[50, 120, 240], win_lengths=[240, 600, 1200],
                 sc_lambda=0.5, mag_lambda=0.5)          # config/tiny.json:30-37
 
@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="clips per GPU")
     ap.add_argument("--cpu-batch", type=int, default=2, help="clips per CPU step (bounded sample)")
+    ap.add_argument("--optimizer", default="flat", choices=["flat", "torch"],
+                    help="flat: optim.FlatAdamW (grad norm + AdamW in one C call); torch: stock fused AdamW (A/B aid)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-inference", action="store_true", help="skip the streaming / offline inference RTF measurements")
@@ -65,6 +67,7 @@ def cpu_training_clips_per_sec(batch, steps, warmup):
         opt.zero_grad(set_to_none=True)
         loss, _, _ = O.loss_fn(net, clean, noisy)
         loss.backward()
+        torch.nn.utils.clip_grad_norm_(net.parameters(), 1e9)      # train.py:138
         opt.step()
         dt = time.perf_counter() - t0
         if it >= warmup:
@@ -237,7 +240,7 @@ def run_native(args):
             os.dup2(saved, 1)
             os.close(saved)
     from oracle import tru_oracle as O                      # synthetic data generator + cpu_baseline only
-    from tinyrecurrentunet_b200 import _lib as L, network, stft_loss, util
+    from tinyrecurrentunet_b200 import _lib as L, network, optim, stft_loss, util
     from tinyrecurrentunet_b200 import distributed as tdist
 
     if os.environ.get("TRU_LOADER_WARPS"):                 # tuning aid (8 or 16 loader warps in the GEMM kernels)
@@ -250,7 +253,12 @@ def run_native(args):
     mr = stft_loss.MultiResolutionSTFTLoss(**STFT_CFG).to(dev)
     if world > 1:
         tdist.apply_gradient_allreduce(net)
-    opt = torch.optim.AdamW(net.parameters(), lr=4e-4, fused=True)       # train.py:68
+    if args.optimizer == "flat":                          # train.py:68 + :138-140 as one C call (two launches)
+        opt = optim.FlatAdamW(net.parameters(), lr=4e-4, max_grad_norm=1e9)
+    else:                                                 # A/B aid: stock torch (fused multi-tensor AdamW, no norm)
+        opt = torch.optim.AdamW(net.parameters(), lr=4e-4, fused=True)
+    sched = util.LinearWarmupCosineDecay(opt, lr_max=4e-4, n_iter=25_000_000, iteration=0, divider=25,
+                                         warmup_proportion=0.05)          # train.py:98-104 (tiny.json: 25M iterations)
 
     # synthetic clips: a pool of distinct clips, rank-dependent, tiled to the batch
     pool = min(B, 8)
@@ -265,7 +273,8 @@ def run_native(args):
         opt.zero_grad(set_to_none=True)
         loss, _ = util.loss_fn(net, (clean, noisy), ell_p=1, ell_p_lambda=1, stft_lambda=1, mrstftloss=mr)
         loss.backward()                  # N>1: the all-reduce fires from the engine callback
-        opt.step()
+        sched.step()                     # train.py:139 (host float, no sync)
+        opt.step()                       # train.py:138 + :140
         return loss
 
     def sync_all():
@@ -375,6 +384,7 @@ def run_native(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD % B,
                            "clips_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world,
+                           "optimizer": "FlatAdamW (tru_flat_adamw_step)" if args.optimizer == "flat" else "torch.optim.AdamW(fused)",
                            "l2": "no explicit flush: one step streams >10 GB of activations through the 126 MB L2"},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
                 "cpu_baseline": cpu, "inference": inference, "kernels": kernels}

@@ -168,6 +168,32 @@ int tru_trunet_backward(const TruNetDesc* d, const float* const* params,
 /* Test aid: byte offset of a named saved buffer inside the workspace (-1 if unknown). */
 long long tru_trunet_buffer_offset(const TruNetDesc* d, const char* name, int index);
 
+/* ------------------------------------------------------------------ *
+ * Optimizer step on flat buffers: train.py:138
+ * (nn.utils.clip_grad_norm_(params, 1e9): the L2 norm of all gradients, and
+ * the in-place scaling by min(1, max/(norm+1e-6)) when it exceeds max) fused
+ * with train.py:140 (torch.optim.AdamW.step, decoupled weight decay, no
+ * amsgrad).  params / grads / exp_avg / exp_avg_sq are flat fp32 buffers of n
+ * elements in one common layout (n a multiple of 4; padding elements stay 0).
+ * lr is the value util.py:81-156 (LinearWarmupCosineDecay) set for this step;
+ * step is the 1-based update count.  grad_norm_out (device float, may be
+ * null) receives the pre-clip norm.  Two launches, no host synchronisation.
+ * ------------------------------------------------------------------ */
+typedef struct {
+  long long n;          /* elements per flat buffer, multiple of 4 */
+  long long step;       /* t >= 1 */
+  double lr, beta1, beta2, eps, weight_decay;   /* train.py:68: lr 4e-4; torch defaults .9 .999 1e-8 1e-2 */
+  double max_grad_norm; /* <= 0: report the norm only */
+} TruAdamWDesc;
+
+size_t tru_flat_adamw_workspace_bytes(const TruAdamWDesc* d);
+int tru_flat_adamw_step(const TruAdamWDesc* d, float* params, float* grads,
+                        float* exp_avg, float* exp_avg_sq, float* grad_norm_out,
+                        void* workspace, size_t workspace_bytes, void* stream);
+/* The norm alone (what train.py:138 returns): grads (n floats) -> norm_out. */
+int tru_flat_grad_norm(long long n, const float* grads, float* norm_out,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,8 +12,11 @@ What is pinned:
                so its first 120 lines are exec'd as they lie on disk; nothing is
                copied into this repo)
   phm.py       formula :34-44, executed with the two misspelt names aliased (X7)
+  util.py      LinearWarmupCosineDecay, lines 81-156 (the file has a SyntaxError
+               further down, X8; this slice is exec'd as it lies on disk)
 Everything is small (a few hundred kB in total) and committed.
 """
+import json
 import os
 import sys
 import types
@@ -140,6 +143,25 @@ def main():
                         mix_re=mix.real.numpy(), mix_im=mix.imag.numpy(),
                         est_re=est.real.numpy(), est_im=est.imag.numpy(),
                         out=env["estimated"].numpy())
+    # ---- learning-rate schedule (util.py:81-156) ---------------------------
+    # util.py does not parse as a whole (X8); the schedule's own lines do, so that slice is executed as it lies on disk.
+    usrc = open(os.path.join(REF, "util.py")).read()
+    sl = usrc[usrc.index("def anneal_linear"):usrc.index("def std_normal")]
+    uns = {}
+    exec(compile("from math import cos, pi\n" + sl, "reference/util.py[81:156]", "exec"), uns)
+    cases = []
+    for lr_max, n_iter, it0, warm, steps in ((4e-4, 1000, 0, 0.05, 2100), (4e-4, 1000, 30, 0.05, 1200),
+                                             (4e-4, 1000, 500, 0.05, 700), (1e-3, 77, 0, 0.3, 200), (2e-4, 40, 39, 0.3, 90)):
+        opt = types.SimpleNamespace(param_groups=[{"lr": None}])
+        sch = uns["LinearWarmupCosineDecay"](opt, lr_max=lr_max, n_iter=n_iter, iteration=it0, divider=25,
+                                             warmup_proportion=warm)
+        lrs = [sch.step() for _ in range(steps)]
+        assert opt.param_groups[0]["lr"] == lrs[-1]
+        cases.append(dict(lr_max=lr_max, n_iter=n_iter, iteration=it0, warmup_proportion=warm,
+                          lr_hex=[float(v).hex() for v in lrs]))
+    with open(os.path.join(OUT, "lr_schedule_ref.json"), "w") as fh:
+        json.dump(cases, fh)
+
     print("golden fixtures written to", os.path.normpath(OUT))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

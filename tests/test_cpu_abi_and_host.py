@@ -139,3 +139,41 @@ def test_checkpoint_round_trip_in_the_reference_format(tmp_path):
     back.load_state_dict(torch.load(str(ckdir / "15000.pkl"), map_location="cpu")["model_state_dict"], strict=True)
     for (k, a), (_, b) in zip(back.state_dict().items(), ref.state_dict().items()):
         assert torch.equal(a, b), k
+
+
+def test_lr_schedule_matches_reference_golden(golden_dir):
+    """util.LinearWarmupCosineDecay vs the reference's own class (util.py:109-156, executed by oracle/make_golden.py):
+    every learning rate bit-identical, including resumed starts and the wrap-around after n_iter steps."""
+    import json
+    import types
+    from tinyrecurrentunet_b200 import util
+    cases = json.load(open(os.path.join(golden_dir, "lr_schedule_ref.json")))
+    assert len(cases) >= 5
+    for c in cases:
+        opt = types.SimpleNamespace(param_groups=[{"lr": None}, {"lr": None}])
+        sch = util.LinearWarmupCosineDecay(opt, lr_max=c["lr_max"], n_iter=c["n_iter"], iteration=c["iteration"],
+                                           divider=25, warmup_proportion=c["warmup_proportion"])
+        for i, want in enumerate(c["lr_hex"]):
+            got = sch.step()
+            assert got == float.fromhex(want), (c["n_iter"], c["iteration"], i, got, float.fromhex(want))
+            assert opt.param_groups[0]["lr"] == got and opt.param_groups[1]["lr"] == got
+
+
+def test_flat_adamw_keeps_the_adamw_interface_and_has_no_cpu_path():
+    """optim.FlatAdamW is a torch.optim.AdamW (same defaults / param_groups keys, so train.py:68 and the checkpoint
+    code work unchanged); stepping CPU parameters must fail loudly, not fall back."""
+    from tinyrecurrentunet_b200 import _lib, optim
+    p = torch.nn.Parameter(torch.randn(5, 3))
+    opt = optim.FlatAdamW([p], lr=4e-4)
+    ref = torch.optim.AdamW([torch.nn.Parameter(torch.randn(5, 3))], lr=4e-4)
+    assert isinstance(opt, torch.optim.AdamW)
+    assert set(opt.param_groups[0]) == set(ref.param_groups[0])
+    for k in ("lr", "betas", "eps", "weight_decay"):
+        assert opt.param_groups[0][k] == ref.param_groups[0][k]
+    p.grad = torch.randn(5, 3)
+    with pytest.raises(_lib.TruError):
+        opt.step()
+    with pytest.raises(_lib.TruError):
+        optim.FlatAdamW([{"params": [p]}, {"params": [torch.nn.Parameter(torch.zeros(2))]}])
+    with pytest.raises(_lib.TruError):
+        optim.FlatAdamW([p], amsgrad=True)

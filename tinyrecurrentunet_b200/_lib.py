@@ -39,6 +39,11 @@ class TruLossDesc(C.Structure):
                 ("sc_lambda", C.c_double), ("mag_lambda", C.c_double)]
 
 
+class TruAdamWDesc(C.Structure):
+    _fields_ = [("n", C.c_longlong), ("step", C.c_longlong), ("lr", C.c_double), ("beta1", C.c_double),
+                ("beta2", C.c_double), ("eps", C.c_double), ("weight_decay", C.c_double), ("max_grad_norm", C.c_double)]
+
+
 class TruNetDesc(C.Structure):
     _fields_ = [("batch", C.c_int), ("n_frames", C.c_int), ("training", C.c_int),
                 ("bn_eps", C.c_double), ("bn_momentum", C.c_double)]
@@ -77,11 +82,16 @@ _sig("tru_trunet_buffer_offset", C.c_longlong, [C.POINTER(TruNetDesc), C.c_char_
 _sig("tru_launch_count", C.c_longlong, [])
 _sig("tru_profile_enable", C.c_int, [C.c_int])
 _sig("tru_profile_report", C.c_int, [C.c_char_p, C.c_size_t])
+_sig("tru_flat_adamw_workspace_bytes", C.c_size_t, [C.POINTER(TruAdamWDesc)])
+_sig("tru_flat_adamw_step", C.c_int, [C.POINTER(TruAdamWDesc), c_float_p, c_float_p, c_float_p, c_float_p, c_float_p,
+                                     C.c_void_p, C.c_size_t, c_stream])
+_sig("tru_flat_grad_norm", C.c_int, [C.c_longlong, c_float_p, c_float_p, C.c_void_p, C.c_size_t, c_stream])
 
 EXPORTS = ["tru_launch_count", "tru_profile_enable", "tru_profile_report", "tru_abi_version", "tru_last_error", "tru_init", "tru_frontend_workspace_bytes",
            "tru_frontend_fwd", "tru_frontend_step", "tru_backend_fwd", "tru_backend_bwd", "tru_backend_step",
            "tru_loss_fwd", "tru_loss_bwd", "tru_trunet_workspace_bytes", "tru_trunet_forward",
-           "tru_trunet_backward", "tru_trunet_buffer_offset"]
+           "tru_trunet_backward", "tru_trunet_buffer_offset", "tru_flat_adamw_workspace_bytes", "tru_flat_adamw_step",
+           "tru_flat_grad_norm"]
 
 
 class TruError(RuntimeError):

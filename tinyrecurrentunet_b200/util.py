@@ -1,7 +1,9 @@
 """Objective glue: drop-in for the hot-path part of the reference's util.py
-(loss_fn :186-251, sampling :178-183), repaired per SURVEY D5-D9 (the reference
+(loss_fn :186-251, sampling :178-183, LinearWarmupCosineDecay :109-156), repaired per SURVEY D5-D9 (the reference
 file does not parse: X8).  Four fused CUDA stages: front end -> TRU-Net ->
 mask + iSTFT -> L1 + multi-resolution STFT loss."""
+import math
+
 import torch
 
 from . import ops
@@ -91,6 +93,49 @@ class StreamingDenoiser:
         audio = ops.mask_istft_step(None, self.ola, self.t, self.beta, flush=True)
         self.t += 1
         return audio
+
+
+def _ramp_linear(a, b, x):
+    return a + x * (b - a)
+
+
+def _ramp_cosine(a, b, x):
+    c = math.cos(math.pi * x) + 1
+    return b + (a - b) / 2 * c
+
+
+class LinearWarmupCosineDecay:
+    """util.py:109-156 (train.py:98-104 builds it, :139 steps it before every optimizer step): a warm-up leg from
+    ``lr_max / divider`` to ``lr_max`` over the first ``int(n_iter * warmup_proportion)`` steps, then a decay leg down
+    to ``lr_max / divider / 1e4``; after both legs the schedule starts over.  ``iteration`` resumes mid-schedule.
+    ``step()`` writes the new rate into every ``optimizer.param_groups[i]["lr"]`` (a host float: FlatAdamW passes it
+    to the kernel by value, nothing synchronises) and returns it."""
+
+    def __init__(self, optimizer, lr_max, n_iter, iteration=0, divider=25, warmup_proportion=0.3,
+                 phase=("linear", "cosine")):
+        self.optimizer = optimizer
+        ramps = {"linear": _ramp_linear, "cosine": _ramp_cosine}
+        n_warm = int(n_iter * warmup_proportion)
+        lr_min = lr_max / divider
+        # one (start, end, length, ramp) tuple per leg and the number of steps already taken on it
+        self._legs = [(lr_min, lr_max, n_warm, ramps[phase[0]]),
+                      (lr_max, lr_min / 1e4, n_iter - n_warm, ramps[phase[1]])]
+        self._taken = [iteration, max(0, iteration - n_warm)]
+        self.phase = 0 if iteration < n_warm else 1
+
+    def step(self):
+        k = self.phase
+        start, end, length, ramp = self._legs[k]
+        self._taken[k] += 1
+        lr = ramp(start, end, self._taken[k] / length)
+        for group in self.optimizer.param_groups:
+            group["lr"] = lr
+        if self._taken[k] >= length:
+            self.phase += 1
+            if self.phase == len(self._legs):
+                self._taken = [0] * len(self._legs)
+                self.phase = 0
+        return lr
 
 
 def loss_fn(net, X, ell_p=1, ell_p_lambda=1, stft_lambda=1, mrstftloss=None, **kwargs):
