@@ -194,6 +194,29 @@ int tru_flat_adamw_step(const TruAdamWDesc* d, float* params, float* grads,
 int tru_flat_grad_norm(long long n, const float* grads, float* norm_out,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------ *
+ * Batch assembly on the device: dataset.py:79-126
+ * (DataAugment.__call__: F.gain, F.lowpass_biquad, F.highpass_biquad of
+ * torchaudio, each biquad output clamped to [-1,1]) for B noise clips at
+ * once, and dataset.py:367-379 (random crop of the clean clip,
+ * noisy = clean + augmented noise).
+ * coef (B, TRU_AUGMENT_NCOEF) per clip: {10^(gain_db/20),
+ *   low-pass  {b0,b1,b2,a1,a2}/a0 and the 2x2 matrix A^TRU_AUGMENT_CHUNK (row major),
+ *   high-pass the same 9}, A = [[-a1,-a2],[1,0]]: the zero-input response of
+ *   the recurrence over one chunk, which the kernel uses to stitch chunks that
+ *   it filters in parallel (tinyrecurrentunet_b200/dataset.py builds the rows).
+ * ------------------------------------------------------------------ */
+#define TRU_AUGMENT_CHUNK 63
+#define TRU_AUGMENT_NCOEF 19
+int tru_augment_fwd(int batch, int n_samples, const float* noise, const float* coef,
+                    float* out, void* stream);
+/* clean (B,n_clean), aug_noise (B,n_noise), clean_start / noise_start (B) device ints (null = 0):
+ * clean_out[b,i] = clean[b, clean_start[b]+i], noisy_out[b,i] = clean_out[b,i] +
+ * aug_noise[b, (noise_start[b]+i) mod n_noise], i < n_out <= n_clean. */
+int tru_mix_crop(int batch, int n_clean, int n_noise, int n_out, const float* clean,
+                 const float* aug_noise, const int* clean_start, const int* noise_start,
+                 float* clean_out, float* noisy_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

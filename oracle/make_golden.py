@@ -12,6 +12,7 @@ What is pinned:
                so its first 120 lines are exec'd as they lie on disk; nothing is
                copied into this repo)
   phm.py       formula :34-44, executed with the two misspelt names aliased (X7)
+  dataset.py   DataAugment (gain + low/high-pass biquads of torchaudio) with seeded draws
   util.py      LinearWarmupCosineDecay, lines 81-156 (the file has a SyntaxError
                further down, X8; this slice is exec'd as it lies on disk)
 Everything is small (a few hundred kB in total) and committed.
@@ -161,6 +162,24 @@ def main():
                           lr_hex=[float(v).hex() for v in lrs]))
     with open(os.path.join(OUT, "lr_schedule_ref.json"), "w") as fh:
         json.dump(cases, fh)
+
+    # ---- augmentation (dataset.py:79-126) ---------------------------------
+    import random
+    aug = ref_dataset.DataAugment()
+    g = torch.Generator().manual_seed(99)
+    na = 3 * 16128 + 777                                  # a few kernel tiles plus a ragged tail
+    tt = torch.arange(na) / 16000.0
+    noise = (0.6 * torch.randn(1, na, generator=g) * (0.3 + 0.7 * torch.sin(2 * np.pi * 1.5 * tt) ** 2)).float()
+    noise[:, 5000:5400] *= 8.0                            # loud burst: the per-biquad clamp to [-1, 1] is active
+    rec = {"noise": noise.numpy()}
+    for k in range(4):
+        random.seed(100 + k)
+        out = aug(noise.clone())
+        random.seed(100 + k)                              # replay the three draws (order: low-pass, high-pass, gain)
+        lp = random.choice(aug.lp_freqs); hp = random.choice(aug.hp_freqs); gain = random.choice(aug.gains)
+        rec["out%d" % k] = out.numpy()
+        rec["par%d" % k] = np.array([float(gain), float(lp), float(hp)], dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "augment_ref.npz"), **rec)
 
     print("golden fixtures written to", os.path.normpath(OUT))
     for f in sorted(os.listdir(OUT)):

@@ -18,6 +18,9 @@ Parity pinning (see tests/test_oracle_vs_reference.py, oracle/make_golden.py):
   * layer classes / parameter counts / state-dict keys: pinned against
     network.py:9-120 (executed with the 4 textual repairs) and docs/net.jpg.
   * gradient all-reduce: pinned against distributed.py (gloo, 2 processes).
+  * augmentation (gain + two biquads) and the LR schedule: pinned against the
+    reference's dataset.DataAugment / util.LinearWarmupCosineDecay executed
+    with seeded ``random`` (tests/golden/augment_ref.npz, lr_schedule_ref.json).
   * model wiring (D4), output channel meaning (D5), mask wiring (D7) and the
     streaming step (D11) have NO runnable reference: **parity unpinned** for
     those; the oracle defines them.
@@ -379,3 +382,30 @@ def loss_fn(net, clean, noisy, stft_lambda=1.0, cfg=STFT_CFG, beta=0.5):
     loss = l1 + (sc + mg) * stft_lambda
     return loss, {"l1": l1.detach(), "stft_sc": sc.detach() * stft_lambda,
                   "stft_mag": mg.detach() * stft_lambda}, den
+
+
+# ---------------------------------------------------------------------------
+# Batch assembly
+# ---------------------------------------------------------------------------
+def augment(noise, gain_db, lp_cutoff, hp_cutoff, sr=48000, q=0.7):
+    """dataset.py:121-125: F.gain -> F.lowpass_biquad -> F.highpass_biquad, the calls of torchaudio.functional (the
+    reference's third-party dependency for this step; unpinned in requirements.txt, 2.11.0 here) in the reference's
+    order.  noise (..., N) CPU float32."""
+    import torchaudio.functional as AF
+    x = AF.gain(noise, gain_db=gain_db)
+    x = AF.lowpass_biquad(x, sr, lp_cutoff, Q=q)
+    return AF.highpass_biquad(x, sr, hp_cutoff, Q=q)
+
+
+def assemble_batch(clean, noise, params, clean_start, noise_start, crop_length):
+    """dataset.py:352-386 for a list of rows: augment the whole noise row (:360), crop the clean row (:367-373), add
+    (:375).  Noise shorter / longer than the crop is read from noise_start and wraps (with equal lengths and start 0 this
+    is the reference's ``clean_audio + noise_audio``)."""
+    cs, ns = [], []
+    for b in range(clean.shape[0]):
+        a = augment(noise[b:b + 1], *params[b])[0]
+        c = clean[b, clean_start[b]:clean_start[b] + crop_length]
+        idx = (noise_start[b] + torch.arange(crop_length)) % a.shape[0]
+        cs.append(c)
+        ns.append(c + a[idx])
+    return torch.stack(cs), torch.stack(ns)

@@ -132,3 +132,25 @@ def test_loss_fn_runs_and_is_differentiable():
     loss.backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
     assert set(d) == {"l1", "stft_sc", "stft_mag"}
+
+
+def test_augment_oracle_and_parameter_draws_match_reference(golden_dir):
+    """oracle.augment (torchaudio calls in the order of dataset.py:121-125) against the reference's DataAugment output,
+    and the drop-in DataAugment's seeded draws + coefficient rows (host logic only, no GPU) against the same run."""
+    import random
+    from tinyrecurrentunet_b200 import dataset
+    g = np.load(os.path.join(golden_dir, "augment_ref.npz"))
+    noise = torch.from_numpy(g["noise"])
+    aug = dataset.DataAugment()
+    for k in range(4):
+        random.seed(100 + k)
+        gain, lp, hp = aug.sample_params()
+        assert (float(gain), float(lp), float(hp)) == tuple(g["par%d" % k])
+        out = O.augment(noise, gain, lp, hp)
+        assert (out - torch.from_numpy(g["out%d" % k])).abs().max().item() <= 1e-7
+        row = aug.coefficients([(gain, lp, hp)])
+        assert row.shape == (1, 19) and torch.isfinite(row).all()
+        # the chunk matrix is the 63rd power of the recurrence's companion matrix
+        a1, a2 = row[0, 4].double().item(), row[0, 5].double().item()
+        A = np.array([[-a1, -a2], [1.0, 0.0]])
+        assert np.allclose(np.linalg.matrix_power(A, 63).reshape(-1), row[0, 6:10].double().numpy(), rtol=1e-5, atol=1e-12)

@@ -85,13 +85,18 @@ _sig("tru_profile_report", C.c_int, [C.c_char_p, C.c_size_t])
 _sig("tru_flat_adamw_workspace_bytes", C.c_size_t, [C.POINTER(TruAdamWDesc)])
 _sig("tru_flat_adamw_step", C.c_int, [C.POINTER(TruAdamWDesc), c_float_p, c_float_p, c_float_p, c_float_p, c_float_p,
                                      C.c_void_p, C.c_size_t, c_stream])
+_sig("tru_augment_fwd", C.c_int, [C.c_int, C.c_int, c_float_p, c_float_p, c_float_p, c_stream])
+_sig("tru_mix_crop", C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_float_p, c_float_p, C.c_void_p, C.c_void_p, c_float_p,
+                              c_float_p, c_stream])
 _sig("tru_flat_grad_norm", C.c_int, [C.c_longlong, c_float_p, c_float_p, C.c_void_p, C.c_size_t, c_stream])
 
 EXPORTS = ["tru_launch_count", "tru_profile_enable", "tru_profile_report", "tru_abi_version", "tru_last_error", "tru_init", "tru_frontend_workspace_bytes",
            "tru_frontend_fwd", "tru_frontend_step", "tru_backend_fwd", "tru_backend_bwd", "tru_backend_step",
            "tru_loss_fwd", "tru_loss_bwd", "tru_trunet_workspace_bytes", "tru_trunet_forward",
            "tru_trunet_backward", "tru_trunet_buffer_offset", "tru_flat_adamw_workspace_bytes", "tru_flat_adamw_step",
-           "tru_flat_grad_norm"]
+           "tru_flat_grad_norm", "tru_augment_fwd", "tru_mix_crop"]
+AUGMENT_CHUNK = 63        # TRU_AUGMENT_CHUNK
+AUGMENT_NCOEF = 19        # TRU_AUGMENT_NCOEF
 
 
 class TruError(RuntimeError):

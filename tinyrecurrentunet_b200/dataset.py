@@ -1,11 +1,18 @@
 """Feature front end / back end: drop-in for the hot-path part of the reference's
 dataset.py (ProcessAudio :130-298, pcenfunc :56-76).  forward/backward run the
 fused CUDA kernels (csrc/frontend.cu, csrc/backend.cu); the small elementwise
-helpers keep the reference's names for API compatibility.  The wav-file dataset
-and augmentation classes (dataset.py:79-126,301-412) are out of scope."""
+helpers keep the reference's names for API compatibility.  DataAugment
+(dataset.py:79-126) and the crop + mix of CleanNoisyPairDataset.__getitem__
+(dataset.py:367-379) run batched on the device (csrc/augment.cu);
+reading wav files stays with the caller."""
+import math
+import random
+
+import numpy as np
 import torch
 import torch.nn as nn
 
+from . import _lib as L
 from . import ops
 
 
@@ -112,3 +119,105 @@ class ProcessAudio(nn.Module):
         if f.shape[2] == 4:
             f = f[:, :, [0, 2, 3]]
         return ops.features_to_audio(f.contiguous())
+
+
+def _biquad_row(kind, sample_rate, cutoff_freq, Q, chunk):
+    """Coefficient row of one biquad for tru_augment_fwd: torchaudio.functional.lowpass_biquad / highpass_biquad design
+    (the SoX formulas, evaluated in float32 tensors exactly as torchaudio evaluates them, then divided by a0 as its
+    lfilter does) followed by the chunk matrix A^chunk, A = [[-a1, -a2], [1, 0]], evaluated in float64."""
+    f32 = torch.float32
+    cutoff_freq = torch.as_tensor(cutoff_freq, dtype=f32)
+    Q = torch.as_tensor(Q, dtype=f32)
+    w0 = 2 * math.pi * cutoff_freq / sample_rate
+    cw = torch.cos(w0)
+    alpha = torch.sin(w0) / 2 / Q
+    if kind == "lowpass":
+        b0 = (1 - cw) / 2
+        b1 = 1 - cw
+    elif kind == "highpass":
+        b0 = (1 + cw) / 2
+        b1 = -1 - cw
+    else:
+        raise ValueError(kind)
+    a0 = 1 + alpha
+    b = torch.stack([b0, b1, b0]) / a0
+    a = torch.stack([-2 * cw, 1 - alpha]) / a0
+    A = np.array([[-float(a[0]), -float(a[1])], [1.0, 0.0]], dtype=np.float64)
+    M = np.linalg.matrix_power(A, chunk)
+    return [float(v) for v in b] + [float(v) for v in a] + [float(v) for v in M.reshape(-1)]
+
+
+class DataAugment:
+    """dataset.py:79-126.  Same parameter grids and the same ``random.choice`` draws (low-pass, high-pass, gain - in
+    that order) as the reference, so a seeded run picks the same augmentation; the filtering itself is one CUDA kernel
+    for the whole batch.  ``aug(x)`` takes a CUDA tensor (N,), (1,N) or (B,N) and draws one parameter set per row;
+    ``aug(x, params)`` uses the given list of (gain_db, lp_cutoff, hp_cutoff) instead."""
+
+    def __init__(self):
+        self.min_gain, self.max_gain = -12.0, -5.0
+        self.lp_min, self.lp_max = 7000, 10000
+        self.hp_min, self.hp_max = 800, 1200
+        self.sr = 48000                                            # dataset.py:110 (fixed, whatever the data rate is)
+        self.Q = 0.7
+        self.gains = torch.arange(self.min_gain, self.max_gain, 0.033)
+        self.lp_freqs = torch.arange(self.lp_min, self.lp_max, 100)
+        self.hp_freqs = torch.arange(self.hp_min, self.hp_max, 50)
+
+    def sample_params(self):
+        lp_cutoff = random.choice(self.lp_freqs)
+        hp_cutoff = random.choice(self.hp_freqs)
+        gain = random.choice(self.gains)
+        return gain, lp_cutoff, hp_cutoff
+
+    def coefficients(self, params):
+        """(B, 19) float32 host tensor of kernel coefficient rows for a list of (gain_db, lp_cutoff, hp_cutoff)."""
+        rows = []
+        for gain_db, lp_cutoff, hp_cutoff in params:
+            if float(gain_db) == 0:                                                      # F.gain
+                ratio = 1.0
+            elif torch.is_tensor(gain_db):          # the reference draws a 0-d float32 tensor: tensor arithmetic
+                ratio = float(10 ** (gain_db / 20))
+            else:                                   # a Python number: torchaudio evaluates it in double
+                ratio = 10 ** (gain_db / 20)
+            rows.append([ratio] + _biquad_row("lowpass", self.sr, lp_cutoff, self.Q, L.AUGMENT_CHUNK)
+                        + _biquad_row("highpass", self.sr, hp_cutoff, self.Q, L.AUGMENT_CHUNK))
+        return torch.tensor(rows, dtype=torch.float32)
+
+    def __call__(self, x, params=None):
+        L.require_cuda(x)
+        if x.dtype != torch.float32 or x.dim() not in (1, 2):
+            raise L.TruError("DataAugment expects a float32 CUDA tensor (N,), (1,N) or (B,N)")
+        rows = x.reshape(-1, x.shape[-1]).contiguous()
+        if params is None:
+            params = [self.sample_params() for _ in range(rows.shape[0])]
+        if len(params) != rows.shape[0]:
+            raise L.TruError("DataAugment: %d parameter sets for %d rows" % (len(params), rows.shape[0]))
+        coef = self.coefficients(params).to(x.device, non_blocking=True)
+        return ops.augment(rows, coef).view(x.shape)
+
+
+def assemble_batch(clean, noise, crop_length, aug=None, params=None, clean_start=None, noise_start=None):
+    """The training pair of dataset.py:352-386 for a whole batch on the device: noise rows augmented over their full
+    length (:360), clean rows cropped to ``crop_length`` samples at a random start (:367-373, ``np.random.randint`` like
+    the reference), noisy = clean crop + augmented noise (:375).  The reference adds the uncropped noise, which only
+    works when the noise file has exactly ``crop_length`` samples; that case is reproduced exactly, and other noise
+    lengths are read from ``noise_start`` (default 0) and wrap around.
+    clean (B,Nc), noise (B,Nn) float32 CUDA -> (clean (B,crop_length), noisy (B,crop_length))."""
+    L.require_cuda(clean, noise)
+    B, n_clean = clean.shape
+    if noise.shape[0] != B:
+        raise L.TruError("assemble_batch: %d clean rows, %d noise rows" % (B, noise.shape[0]))
+    if not 0 < crop_length <= n_clean:
+        raise L.TruError("assemble_batch: crop_length %d does not fit %d samples" % (crop_length, n_clean))
+    aug = aug or DataAugment()
+    aug_noise = aug(noise, params)
+    if clean_start is None:
+        clean_start = [int(np.random.randint(low=0, high=n_clean - crop_length + 1)) for _ in range(B)]
+    if noise_start is None:
+        noise_start = [0] * B
+    if len(clean_start) != B or len(noise_start) != B:
+        raise L.TruError("assemble_batch: need one start offset per row")
+    if min(clean_start) < 0 or max(clean_start) > n_clean - crop_length or min(noise_start) < 0:
+        raise L.TruError("assemble_batch: start offset out of range")
+    starts = torch.tensor([list(clean_start), list(noise_start)], dtype=torch.int32).to(clean.device, non_blocking=True)
+    return ops.mix_crop(clean.contiguous(), aug_noise, starts[0], starts[1], crop_length)

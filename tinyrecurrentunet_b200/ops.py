@@ -154,3 +154,29 @@ def mrstft_l1(x, y, windows, cfg):
     """Fused (l1, sc_loss, mag_loss) of prediction x vs target y, both (B,N)."""
     l1, sc, mag, _ = _MRSTFTL1.apply(x, y, tuple(windows), cfg)
     return l1, sc, mag
+
+
+def augment(noise, coef):
+    """dataset.py:79-126 for B rows: noise (B,N) float32 CUDA, coef (B,19) (dataset.DataAugment.coefficients) -> (B,N)."""
+    L.require_cuda(noise, coef)
+    noise, coef = noise.contiguous(), coef.contiguous()
+    if noise.dim() != 2 or coef.shape != (noise.shape[0], L.AUGMENT_NCOEF) or coef.dtype != torch.float32:
+        raise L.TruError("augment: noise (B,N) and coef (B,%d) float32 expected" % L.AUGMENT_NCOEF)
+    out = torch.empty_like(noise)
+    L.check(L.lib.tru_augment_fwd(noise.shape[0], noise.shape[1], L.ptr(noise), L.ptr(coef), L.ptr(out), L.stream_ptr()),
+            "tru_augment_fwd")
+    return out
+
+
+def mix_crop(clean, aug_noise, clean_start, noise_start, n_out):
+    """dataset.py:367-379: clean (B,Nc), aug_noise (B,Nn), int32 CUDA start offsets (B) -> (clean crop, noisy) (B,n_out)."""
+    L.require_cuda(clean, aug_noise, clean_start, noise_start)
+    if clean_start.dtype != torch.int32 or noise_start.dtype != torch.int32:
+        raise L.TruError("mix_crop: start offsets must be int32")
+    B = clean.shape[0]
+    clean_out = torch.empty((B, n_out), device=clean.device, dtype=torch.float32)
+    noisy_out = torch.empty_like(clean_out)
+    L.check(L.lib.tru_mix_crop(B, clean.shape[1], aug_noise.shape[1], n_out, L.ptr(clean), L.ptr(aug_noise),
+                               L.ptr(clean_start.contiguous()), L.ptr(noise_start.contiguous()), L.ptr(clean_out),
+                               L.ptr(noisy_out), L.stream_ptr()), "tru_mix_crop")
+    return clean_out, noisy_out
