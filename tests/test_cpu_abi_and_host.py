@@ -177,3 +177,32 @@ def test_flat_adamw_keeps_the_adamw_interface_and_has_no_cpu_path():
         optim.FlatAdamW([{"params": [p]}, {"params": [torch.nn.Parameter(torch.zeros(2))]}])
     with pytest.raises(_lib.TruError):
         optim.FlatAdamW([p], amsgrad=True)
+
+
+def test_checkpoint_helpers_follow_train_py(tmp_path):
+    """util.find_max_epoch (util.py:30-49) and save / load in the layout of train.py:155-161 / :70-95."""
+    from oracle import tru_oracle as O
+    from tinyrecurrentunet_b200 import network, util
+    d = tmp_path / "ck"
+    d.mkdir()
+    assert util.find_max_epoch(str(d)) == -1
+    for name in ("7.txt", "abc.pkl", ".pkl", "3000.pkl.bak", "-5.pkl"):
+        (d / name).write_text("")
+    assert util.find_max_epoch(str(d)) == -1
+    torch.manual_seed(4)
+    ref = O.randomize_bn(O.TRUNet())
+    opt = torch.optim.AdamW(ref.parameters(), lr=4e-4)
+    for it in (10, 200):
+        path = util.save_checkpoint(str(d), it, ref, opt, 33.9)
+        assert path.endswith("%d.pkl" % it)
+    assert util.find_max_epoch(str(d)) == 200
+    ck = torch.load(str(d / "200.pkl"), map_location="cpu")
+    assert set(ck) == {"iter", "model_state_dict", "optimizer_state_dict", "training_time_seconds"}
+    assert ck["iter"] == 200 and ck["training_time_seconds"] == 33
+    net = network.TRUNet()
+    it, secs = util.load_checkpoint(str(d), "max", net, torch.optim.AdamW(net.parameters(), lr=4e-4))
+    assert (it, secs) == (200, 33)
+    for k, v in ref.state_dict().items():
+        assert torch.equal(net.state_dict()[k], v), k
+    assert util.load_checkpoint(str(d), 11, net) == (-1, 0)
+    assert util.load_checkpoint(str(tmp_path), "max", net) == (-1, 0)

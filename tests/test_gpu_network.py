@@ -282,6 +282,34 @@ def test_streaming_denoiser_equals_offline_denoise():
     assert rel(streamed, offline) <= OUT_TOL
 
 
+def test_streaming_feed_loop_equals_offline_denoise():
+    """The real-time loop (stream.py:83-109 intent): raw audio fed one hop at a time through StreamingDenoiser.feed /
+    finish - which keeps the 512-sample window and does the reflect framing itself - gives the offline result, block for
+    block, with three hops of latency."""
+    from tinyrecurrentunet_b200 import util
+    _, net = make_pair(6)
+    net.eval()
+    S, nb = 3, 17
+    _, noisy = O.synthetic_batch(S, n=128 * nb, first=40)
+    x = noisy.cuda()
+    with torch.no_grad():
+        offline, _ = util.denoise(net, x)
+    sd = util.StreamingDenoiser(net, S)
+    blocks, per_hop = [], []
+    for k in range(nb):
+        got = sd.feed(x[:, 128 * k:128 * k + 128])
+        per_hop.append(len(got))
+        blocks += got
+    assert per_hop == [0, 0, 0] + [1] * (nb - 3)
+    blocks += sd.finish()
+    assert len(blocks) == nb
+    streamed = torch.cat(blocks, dim=1)
+    assert streamed.shape == offline.shape
+    assert rel(streamed, offline) <= OUT_TOL
+    with pytest.raises(ValueError):
+        util.StreamingDenoiser(net, S).finish()
+
+
 def test_cuda_prefetcher_delivers_batches_in_order():
     """util.CudaPrefetcher (used by bench.py's end-to-end timing): call i returns the batch passed in call i-1 (the first
     call its own batch), copied on a side stream; a consumer on the current stream always sees complete data."""

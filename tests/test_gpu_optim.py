@@ -154,3 +154,50 @@ def test_flat_adamw_c_abi_argument_checks():
     assert call(desc, p=bufs[0][1:]) == -4                                                  # misaligned
     assert b"flat_adamw" in L.lib.tru_last_error()
     torch.cuda.synchronize()
+
+
+def test_resume_from_checkpoint_continues_the_same_training(tmp_path):
+    """train.py:70-104: four training iterations, with a checkpoint (util.save_checkpoint) after the second.  A fresh set
+    of objects restored with util.load_checkpoint + LinearWarmupCosineDecay(iteration=n_iter) and fed the gradients of
+    iterations 3 and 4 must land on bit-identical parameters: model, BatchNorm buffers, both moments, the step count
+    and the learning-rate schedule all survive the round trip."""
+    from oracle import tru_oracle as O
+    from tinyrecurrentunet_b200 import network, optim, stft_loss, util
+    mr = stft_loss.MultiResolutionSTFTLoss(fft_sizes=[512, 1024, 2048], hop_sizes=[50, 120, 240],
+                                           win_lengths=[240, 600, 1200]).cuda()
+    sched = dict(lr_max=4e-4, n_iter=10, divider=25, warmup_proportion=0.3)
+    torch.manual_seed(5)
+    net = network.TRUNet().cuda().train()
+    opt = optim.FlatAdamW(net.parameters(), lr=4e-4, max_grad_norm=1e9)
+    sch = util.LinearWarmupCosineDecay(opt, iteration=0, **sched)
+    grads, lrs = [], []
+    for i in range(4):
+        clean, noisy = O.synthetic_batch(2, n=128 * 24, first=10 * i)
+        opt.zero_grad()
+        loss, _ = util.loss_fn(net, (clean.cuda(), noisy.cuda()), mrstftloss=mr)
+        loss.backward()
+        grads.append([p.grad.clone() for p in net.parameters()])
+        lrs.append(sch.step())
+        opt.step()
+        if i == 1:
+            util.save_checkpoint(str(tmp_path), i, net, opt, 5)
+            at_save = {k: v.clone() for k, v in net.state_dict().items()}
+
+    net_c = network.TRUNet().cuda().train()                # different random weights until the checkpoint is loaded
+    opt_c = optim.FlatAdamW(net_c.parameters(), lr=4e-4, max_grad_norm=1e9)
+    it, secs = util.load_checkpoint(str(tmp_path), "max", net_c, opt_c)
+    assert (it, secs) == (1, 5)
+    for k, v in net_c.state_dict().items():
+        assert torch.equal(v, at_save[k]), k
+    n_iter = it + 1                                        # train.py:98
+    sch_c = util.LinearWarmupCosineDecay(opt_c, iteration=n_iter, **sched)
+    for i in range(n_iter, 4):
+        for p, g in zip(net_c.parameters(), grads[i]):
+            p.grad = g.clone()
+        assert sch_c.step() == lrs[i]
+        opt_c.step()
+    for (name, p), q in zip(net.named_parameters(), net_c.parameters()):
+        assert torch.equal(p, q), name
+        assert torch.equal(opt.state[p]["exp_avg"], opt_c.state[q]["exp_avg"]), name
+        assert torch.equal(opt.state[p]["exp_avg_sq"], opt_c.state[q]["exp_avg_sq"]), name
+    assert float(opt_c.state[next(net_c.parameters())]["step"]) == 4.0

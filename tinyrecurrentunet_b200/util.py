@@ -1,8 +1,11 @@
 """Objective glue: drop-in for the hot-path part of the reference's util.py
-(loss_fn :186-251, sampling :178-183, LinearWarmupCosineDecay :109-156), repaired per SURVEY D5-D9 (the reference
+(loss_fn :186-251, sampling :178-183, LinearWarmupCosineDecay :109-156, find_max_epoch :30-49;
+checkpoint save / resume of train.py:70-95,155-161), repaired per SURVEY D5-D9 (the reference
 file does not parse: X8).  Four fused CUDA stages: front end -> TRU-Net ->
 mask + iSTFT -> L1 + multi-resolution STFT loss."""
 import math
+import os
+import re
 
 import torch
 
@@ -93,6 +96,84 @@ class StreamingDenoiser:
         audio = ops.mask_istft_step(None, self.ola, self.t, self.beta, flush=True)
         self.t += 1
         return audio
+
+    # -- the real-time loop of stream.py:83-109: raw audio in, hop by hop, through a 512-sample window per stream --
+    @torch.no_grad()
+    def feed(self, block):
+        """Next 128 input samples of every stream, (S,128) float32 CUDA.  Keeps the sliding analysis window (the
+        reference's ring buffer), builds the centre / reflect framing of the offline front end on the fly and returns
+        the list of 128-sample output blocks that became final (none for the first three hops: one hop to fill the
+        window's look-ahead plus the two hops of overlap-add look-ahead; one per hop afterwards)."""
+        if block.shape[-1] != 128:
+            raise ValueError("feed() takes one hop (128 samples) per stream")
+        if not hasattr(self, "win"):
+            self.win = torch.zeros(block.shape[0], 512, device=block.device)      # the last 512 samples received
+            self.nblk = 0
+        self.win = torch.cat((self.win[:, 128:], block), dim=1)
+        self.nblk += 1
+        k = self.nblk - 1                                    # index of the block just received
+        frames = []
+        if k == 2:                                           # samples 0..383 are in win[:, 128:]: frames 0 and 1 exist now
+            a = self.win[:, 128:]
+            frames.append(torch.cat((a[:, 1:257].flip(1), a[:, :256]), dim=1))   # reflect-padded start
+            frames.append(torch.cat((a[:, 1:129].flip(1), a), dim=1))
+        elif k > 2:
+            frames.append(self.win)                          # frame k-1 = samples 128(k-1)-256 .. 128(k-1)+255
+        out = []
+        for fr in frames:
+            y = self.step(fr.contiguous())
+            if self.t > 2:                                   # steps 0 and 1 emit the look-ahead zeros
+                out.append(y)
+        return out
+
+    @torch.no_grad()
+    def finish(self):
+        """End of the streams: the last two frames need the reflected tail, then the overlap-add is flushed.  Returns the
+        remaining output blocks; in total as many blocks come out as went in."""
+        if getattr(self, "nblk", 0) < 3:
+            raise ValueError("finish() needs at least three hops of audio (the reflect padding reads 257 samples)")
+        w = self.win                                         # samples N-512 .. N-1
+        tail = w[:, 255:511].flip(1)                         # samples N-2, N-3, ..., N-257: the reflection of the end
+        frames = [torch.cat((w[:, 128:], tail[:, :128]), dim=1), torch.cat((w[:, 256:], tail), dim=1)]
+        out = []
+        for fr in frames:
+            y = self.step(fr.contiguous())
+            if self.t > 2:
+                out.append(y)
+        out.append(self.flush())
+        return out
+
+
+def find_max_epoch(path):
+    """util.py:30-49: the largest <iter> among the files ``<iter>.pkl`` in ``path``; -1 if there is none."""
+    iters = [int(m.group(1)) for m in (re.fullmatch(r"([+-]?\d+)\.pkl", f) for f in os.listdir(path)) if m]
+    return max([-1] + iters)
+
+
+def save_checkpoint(ckpt_directory, n_iter, net, optimizer, training_time_seconds):
+    """train.py:155-161: ``<n_iter>.pkl`` = {iter, model_state_dict, optimizer_state_dict, training_time_seconds}, the
+    reference's on-disk format (a FlatAdamW state dict has torch.optim.AdamW's layout, so either side can load it)."""
+    name = os.path.join(ckpt_directory, "{}.pkl".format(n_iter))
+    torch.save({"iter": n_iter, "model_state_dict": net.state_dict(), "optimizer_state_dict": optimizer.state_dict(),
+                "training_time_seconds": int(training_time_seconds)}, name)
+    return name
+
+
+def load_checkpoint(ckpt_directory, ckpt_iter, net, optimizer=None):
+    """train.py:70-95: resume from ``<ckpt_iter>.pkl`` (``"max"`` = the newest).  Returns (ckpt_iter, seconds trained), or
+    (-1, 0) when there is no usable checkpoint - the reference then trains from initialisation."""
+    if ckpt_iter == "max":
+        ckpt_iter = find_max_epoch(ckpt_directory)
+    if ckpt_iter < 0:
+        return -1, 0
+    path = os.path.join(ckpt_directory, "{}.pkl".format(ckpt_iter))
+    if not os.path.exists(path):
+        return -1, 0
+    checkpoint = torch.load(path, map_location="cpu")
+    net.load_state_dict(checkpoint["model_state_dict"])
+    if optimizer is not None:
+        optimizer.load_state_dict(checkpoint["optimizer_state_dict"])
+    return ckpt_iter, checkpoint["training_time_seconds"]
 
 
 def _ramp_linear(a, b, x):
