@@ -9,6 +9,8 @@ __device__ __forceinline__ float4 ld4(const float* p) { return __ldg((const floa
 
 // ---- BatchNorm1d (training: biased batch variance, running_var unbiased; eps 1e-5) ----
 __global__ void bn_finalize_kernel(BnFwdParams p) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c == 0 && p.training && p.nbt) *p.nbt += 1;
   if (c >= p.C) return;
@@ -44,6 +46,8 @@ __global__ void bn_finalize_eval_all_kernel(const __grid_constant__ BnEvalAll p)
 
 // dZ = q0*dY + q1*Z + q2 with  q0 = g*inv, q1 = -g*inv^2*s2/M, q2 = g*inv*(mean*inv*s2 - s1)/M
 __global__ void bn_bwd_finalize_kernel(BnBwdParams p) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= p.C) return;
   const double s1 = p.bstats[c], s2 = p.bstats[p.C + c];
@@ -66,6 +70,7 @@ constexpr int E_XN = E_CI * (E_F + 3);               // padded frame in shared m
 constexpr int E_XI = (E_XN + 255) / 256;             // prefetch registers per thread
 __global__ void __launch_bounds__(256) enc0_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                        const float* __restrict__ b, float* __restrict__ out, int BT) {
+  pdl_trigger();                               // a PDL-launched successor (GEMM) may stage its weights while this runs
   __shared__ float xs[E_CI][E_F + 3];        // xs[ci][1 + f], zeros at both ends
   const int tid = threadIdx.x;
   const int c4 = (tid & 15) * 4, l0 = tid >> 4;
@@ -465,7 +470,7 @@ int dw_grid(long rows) { return (int)std::min<long>((rows + DW_ROWS - 1) / DW_RO
 
 int launch_bn_finalize(const BnFwdParams& p, cudaStream_t st) {
   ProfScope prof("bn_finalize", 0, 0, st);
-  bn_finalize_kernel<<<(p.C + 127) / 128, 128, 0, st>>>(p);
+  TRU_CUDA(launch_pdl(bn_finalize_kernel, dim3((p.C + 127) / 128), dim3(128), 0, st, p));
   TRU_LAUNCH_CHECK();
   return TRU_OK;
 }
@@ -477,7 +482,7 @@ int launch_bn_finalize_eval_all(const BnEvalAll& p, cudaStream_t st) {
 }
 int launch_bn_bwd_finalize(const BnBwdParams& p, cudaStream_t st) {
   ProfScope prof("bn_bwd_finalize", 0, 0, st);
-  bn_bwd_finalize_kernel<<<(p.C + 127) / 128, 128, 0, st>>>(p);
+  TRU_CUDA(launch_pdl(bn_bwd_finalize_kernel, dim3((p.C + 127) / 128), dim3(128), 0, st, p));
   TRU_LAUNCH_CHECK();
   return TRU_OK;
 }

@@ -63,6 +63,7 @@ struct DwK {
 // unit = (frame bt, RO output rows lo0..): stage holds the input rows [ra, rb) it needs
 template <int K, int S>
 __global__ void __launch_bounds__(NT, 1) dw_fwd_stream_kernel(const __grid_constant__ DwK Kp) {
+  pdl_trigger();
   const DwParams& p = Kp.p;
   extern __shared__ __align__(128) uint8_t smem[];
   DwMisc& mi = *(DwMisc*)(smem + Kp.misc_off);
@@ -74,6 +75,7 @@ __global__ void __launch_bounds__(NT, 1) dw_fwd_stream_kernel(const __grid_const
     for (int s = 0; s < nst; ++s) { mbar_init(&mi.full[s], 1); mbar_init(&mi.empty[s], CW); }
     fence_barrier_init();
   }
+  pdl_wait();                                            // barrier setup above overlaps the predecessor's tail
   __syncthreads();
   const unsigned n_my = Kp.units > blockIdx.x ? (Kp.units - 1 - blockIdx.x) / gridDim.x + 1 : 0;
   if (warp == 0) {
@@ -142,6 +144,7 @@ __global__ void __launch_bounds__(NT, 1) dw_fwd_stream_kernel(const __grid_const
 // unit = (frame bt, RU input rows li0..): stage holds Zp rows [li0, li0+RI) and the dY / Zd rows [la, lb] they touch.
 template <int K, int S>
 __global__ void __launch_bounds__(NT, 1) dw_bwd_stream_kernel(const __grid_constant__ DwK Kp) {
+  pdl_trigger();
   const DwParams& p = Kp.p;
   extern __shared__ __align__(128) uint8_t smem[];
   DwMisc& mi = *(DwMisc*)(smem + Kp.misc_off);
@@ -153,6 +156,7 @@ __global__ void __launch_bounds__(NT, 1) dw_bwd_stream_kernel(const __grid_const
     for (int s = 0; s < nst; ++s) { mbar_init(&mi.full[s], 1); mbar_init(&mi.empty[s], CW); }
     fence_barrier_init();
   }
+  pdl_wait();                                            // barrier setup above overlaps the predecessor's tail
   __syncthreads();
   const unsigned n_my = Kp.units > blockIdx.x ? (Kp.units - 1 - blockIdx.x) / gridDim.x + 1 : 0;
   auto lo_range = [&](int li0, int& la, int& lb) {
@@ -257,7 +261,7 @@ template <int K, int S>
 int launch_fwd_t(DwK& Kp, int grid, size_t smem, cudaStream_t st) {
   static bool attr = false;
   if (!attr) { TRU_CUDA(cudaFuncSetAttribute(dw_fwd_stream_kernel<K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX)); attr = true; }
-  dw_fwd_stream_kernel<K, S><<<grid, NT, smem, st>>>(Kp);
+  TRU_CUDA(launch_pdl(dw_fwd_stream_kernel<K, S>, dim3(grid), dim3(NT), smem, st, Kp));
   TRU_LAUNCH_CHECK();
   return TRU_OK;
 }
@@ -265,7 +269,7 @@ template <int K, int S>
 int launch_bwd_t(DwK& Kp, int grid, size_t smem, cudaStream_t st) {
   static bool attr = false;
   if (!attr) { TRU_CUDA(cudaFuncSetAttribute(dw_bwd_stream_kernel<K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX)); attr = true; }
-  dw_bwd_stream_kernel<K, S><<<grid, NT, smem, st>>>(Kp);
+  TRU_CUDA(launch_pdl(dw_bwd_stream_kernel<K, S>, dim3(grid), dim3(NT), smem, st, Kp));
   TRU_LAUNCH_CHECK();
   return TRU_OK;
 }

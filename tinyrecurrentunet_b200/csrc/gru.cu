@@ -28,6 +28,7 @@ constexpr int F_W_LD = FH + 4;           // backward: W[j][k]
 constexpr int F_G_LD = 3 * FH + 4;
 
 __global__ void __launch_bounds__(FNT) fgru_fwd_kernel(const __grid_constant__ GruParams p) {
+  pdl_trigger();                               // a PDL-launched successor (GEMM) may stage its weights while this runs
   extern __shared__ __align__(16) float smem[];
   float* WT = smem;                       // [64][196]
   float* hs = WT + FH * F_WT_LD;          // [64][68]
@@ -236,6 +237,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 
 template <int SC>
 __global__ void __launch_bounds__(TNT, 1) tgru_fwd_kernel(const __grid_constant__ GruParams p, int B, int T) {
+  pdl_trigger();                               // a PDL-launched successor (GEMM) may stage its weights while this runs
   constexpr int NI = (SC * TH + TNT - 1) / TNT;        // (s,u) items per thread
   constexpr int NCH = SC * 96;                         // 16-byte chunks of one step's input gates (384 floats per sequence)
   __shared__ __align__(16) float hs[SC][TH];
@@ -434,6 +436,7 @@ __global__ void __launch_bounds__(TNT, 1) tgru_bwd_kernel(const __grid_constant_
 __global__ void __launch_bounds__(256) tgru_step_gates_kernel(const float* __restrict__ Gi, const float* __restrict__ Gh,
                                                               const float* __restrict__ bhh, const float* __restrict__ h0,
                                                               float* __restrict__ H, float* __restrict__ hlast, long nseq) {
+  pdl_trigger();                               // a PDL-launched successor (GEMM) may stage its weights while this runs
   const long idx = (long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= nseq * (TH / 4)) return;
   const long s = idx / (TH / 4);

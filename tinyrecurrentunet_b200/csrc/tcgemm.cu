@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
   const int n_my = ((int)blockIdx.x < ntiles) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
   // ---- one-time setup: resident weight slice (hi/lo), affine coefficient table, barriers, TMEM ------
+  pdl_trigger();       // the weights are parameters: nothing in the step writes them, so staging them may overlap the predecessor's tail
   {
     const uint32_t wwords = (uint32_t)nkb * MW * 64;    // hi + lo, in 32-bit words
     for (uint32_t i = tid; i < wwords / 4; i += NT) ((uint4*)Wsm)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -167,6 +168,7 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
       }
       kbb += (sg.C + KBLK - 1) / KBLK;
     }
+    pdl_wait();        // everything below reads what earlier kernels of the step produced (BN coefficients first)
     for (int i = tid; i < Lo.ncoef * 32; i += NT) {
       const int e = i >> 5, j = i & 31;
       const Seg& sg = P.seg[Lo.coef_seg[e]];
@@ -624,7 +626,7 @@ int launch_inst(const IgemmParams& p, const TcLayout& L, dim3 grid, size_t smem,
     TRU_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<LW, LD2, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
     attr_done = true;
   }
-  tc_igemm_kernel<LW, LD2, EPI><<<grid, 32 * (4 + LW + EW), smem, st>>>(p, L);
+  TRU_CUDA(launch_pdl(tc_igemm_kernel<LW, LD2, EPI>, grid, dim3(32 * (4 + LW + EW)), smem, st, p, L));
   TRU_LAUNCH_CHECK();
   return TRU_OK;
 }

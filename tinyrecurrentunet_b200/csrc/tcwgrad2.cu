@@ -92,6 +92,8 @@ __device__ __forceinline__ float* wgrad_dst(const WgK& K, int p, int q) {
 // second stage of the weight-gradient reduction: dW[p][q] += sum over CTAs of scratch[cta][p][q] (fixed order: deterministic).
 // Block = one accumulator row p x 32 columns; 8 warps each sum every 8th partial (short load chains), then meet in shared memory.
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const __grid_constant__ WgK K, int nctas) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[8][32];
   const int nqb = K.QWt >> 5;
   const int p = blockIdx.x / nqb, q = (blockIdx.x - p * nqb) * 32 + (threadIdx.x & 31), cg = threadIdx.x >> 5;
@@ -129,6 +131,8 @@ __global__ void __launch_bounds__(NT, 1) tc_wgrad_stream_kernel(const __grid_con
   const int nraw = K.nraw;
 
   // ---- setup: coefficient tables, barriers, TMEM -----------------------------------------
+  pdl_trigger();
+  pdl_wait();                                            // the coefficient tables come from bn_finalize / bn_bwd_finalize
   for (int i = tid; i < K.Ca; i += NT) {
     const int s = (K.nsrc == 2 && i >= K.a_c0[1]) ? 1 : 0, c = i - K.a_c0[s];
     const bool aff = K.a_p0[s] != nullptr;
@@ -444,7 +448,7 @@ int launch_variant(const WgK& K, int grid, size_t smem, cudaStream_t st) {
     TRU_CUDA(cudaFuncSetAttribute(tc_wgrad_stream_kernel<IA, IZ, NTAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
     attr = true;
   }
-  tc_wgrad_stream_kernel<IA, IZ, NTAP><<<grid, NT, smem, st>>>(K);
+  TRU_CUDA(launch_pdl(tc_wgrad_stream_kernel<IA, IZ, NTAP>, dim3(grid), dim3(NT), smem, st, K));
   TRU_LAUNCH_CHECK();
   return TRU_OK;
 }
@@ -538,7 +542,7 @@ int launch_wgrad_stream(const WgStream& w, cudaStream_t st) {
     // CTAs past the last unit (units_per_cta is rounded up) have no partial result
     const int nact = (int)((K.units_total + K.units_per_cta - 1) / K.units_per_cta);
     count_launch();
-    wgrad_reduce_kernel<<<K.Mmma * (K.QWt >> 5), 256, 0, st>>>(K, nact);
+    TRU_CUDA(launch_pdl(wgrad_reduce_kernel, dim3(K.Mmma * (K.QWt >> 5)), dim3(256), 0, st, K, nact));
     TRU_LAUNCH_CHECK();
   }
   return TRU_OK;

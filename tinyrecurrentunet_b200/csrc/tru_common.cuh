@@ -51,11 +51,32 @@ struct ProfScope {
   ~ProfScope() { if (on) prof_end(st); }
 };
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------
+// The long-running kernels call pdl_trigger() first thing (the next kernel of the stream may then be scheduled onto SMs as
+// they free up) and pdl_wait() before they touch anything an earlier kernel of the step produced; what runs before the
+// wait (staging the weight slice into shared memory, barrier setup) overlaps the tail of the predecessor.  Only kernels
+// that contain a pdl_wait() may be launched through launch_pdl().  Without the launch attribute the device instructions are
+// no-ops.  pdl_scope(true) is set by the inference entry points; TRU_PDL in the environment overrides (common.cu).
+bool pdl_enabled();
+void pdl_scope(bool inference);
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 #if defined(__CUDACC__)
 // ---- device helpers ---------------------------------------------------------
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -619,7 +619,10 @@ extern "C" int tru_trunet_forward(const TruNetDesc* d, const float* const* param
   Ctx c{};
   if ((rc = make_ctx(c, d, ws, ws_bytes, false, stream))) return rc;
   c.prm = params; c.rmean = bn_running_mean; c.rvar = bn_running_var; c.nbt = bn_num_batches;
-  return forward(c, x, h0, out, h_last);
+  pdl_scope(!d->training);
+  rc = forward(c, x, h0, out, h_last);
+  pdl_scope(false);
+  return rc;
 }
 
 extern "C" int tru_trunet_backward(const TruNetDesc* d, const float* const* params, const float* x,
