@@ -41,7 +41,11 @@ for k, v in d["kernels"].items():
 w("\nSum of kernel times %.2f ms vs %.2f ms per profiled step (launch gaps + torch optimizer/zero-grad kernels make up the rest).\n"
   % (tot, r["ms_per_step_profiled"]))
 if os.path.exists(launches_path):
-    rows = [x for x in csv.reader(open(launches_path)) if len(x) > 14 and x[0].isdigit()]
+    rows = [x for x in csv.reader(open(launches_path)) if len(x) > 14 and x[0].isdigit() and x[12] == "gpu__time_duration.sum"]
+    # the capture window spans about two steps: keep exactly one, from one front-end launch to the next
+    starts = [i for i, x in enumerate(rows) if "frontend_kernel" in x[4]]
+    if len(starts) >= 2:
+        rows = rows[starts[0]:starts[1]]
     agg = collections.OrderedDict()
     for x in rows:
         if x[12] != "gpu__time_duration.sum":
@@ -52,8 +56,8 @@ if os.path.exists(launches_path):
         a[1] += float(x[14].replace(",", "")) / (1e6 if x[13] in ("ns", "nsecond") else 1e3 if x[13] in ("us", "usecond") else 1.0)
     t = sum(a[1] for a in agg.values())
     w("## ncu launch list of the same command (`profiles/%s_ncu_launches.csv`)\n" % tag)
-    w("`ncu --metrics gpu__time_duration.sum --clock-control none -s <3 steps> -c <1 step> --csv python bench.py --steps 3 --warmup 3 "
-      "--no-cpu-baseline --no-e2e --no-inference` (one training step; cold-cache, serialised: compare SHARES with the table above, not absolutes).\n")
+    w("`ncu --metrics gpu__time_duration.sum --clock-control none -s <3 steps> -c <2 steps> --csv python bench.py --steps 3 --warmup 3 "
+      "--no-cpu-baseline --no-e2e --no-inference` (rows between two consecutive front-end launches = one training step; cold-cache, serialised: compare SHARES with the table above, not absolutes).\n")
     w("| kernel | launches | ms | share |")
     w("|---|---|---|---|")
     for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
