@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Write profiles/<tag>_summary.md from a bench.py JSON line, the ncu launch list of the same command and the
-ncu DRAM-traffic pass.  Usage: python tools/make_profile_summary.py r01 gpurun_out/bench.json gpurun_out/launches.csv"""
+ncu DRAM-traffic pass.  Usage: python tools/make_profile_summary.py r01 gpurun_out/bench.json gpurun_out/launches.csv [gpurun_out/traffic.csv]"""
 import collections
 import csv
 import json
@@ -10,6 +10,21 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag, bench_path, launches_path = sys.argv[1], sys.argv[2], sys.argv[3]
 d = json.load(open(bench_path))
+if len(sys.argv) > 4:        # ncu DRAM-traffic pass over the GEMM launches of one step -> profiles/<tag>_traffic.json (+ the csv)
+    rows = [x for x in csv.reader(open(sys.argv[4])) if len(x) > 14 and x[0].isdigit()]
+    rd = sum(float(x[14].replace(",", "")) for x in rows if x[12] == "dram__bytes_read.sum")
+    wr = sum(float(x[14].replace(",", "")) for x in rows if x[12] == "dram__bytes_write.sum")
+    ns = sum(float(x[14].replace(",", "")) for x in rows if x[12] == "gpu__time_duration.sum")
+    nk = len({x[0] for x in rows})                       # kernels of one step (a strided transposed conv is 2 kernels, 1 launch scope)
+    n = int(d["roofline"]["launches_per_step"])          # launch scopes of one step: what roofline.achieved is averaged over
+    t = {"igemm_tc": {"dram_bytes_per_launch": int((rd + wr) / n), "launches": n, "kernels": nk, "dram_read_bytes_step": rd,
+                      "dram_write_bytes_step": wr, "ncu_time_ms_step": ns / 1e6,
+                      "command": "tools/prof_bench.sh (ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum "
+                                 "--clock-control none -k regex:tc_igemm -s 162 -c 54)"}}
+    json.dump(t, open(os.path.join(ROOT, "profiles", "%s_traffic.json" % tag), "w"), indent=1)
+    open(os.path.join(ROOT, "profiles", "%s_ncu_igemm_traffic.csv" % tag), "w").write(open(sys.argv[4]).read())
+    d["roofline"]["traffic"] = t["igemm_tc"]["dram_bytes_per_launch"]
+    d["roofline"]["traffic_source"] = ("ncu dram__bytes_read.sum + dram__bytes_write.sum, mean per launch (profiles/%s_traffic.json)" % tag)
 peak = d["roofline"]["peak"]
 out = []
 w = out.append
@@ -65,4 +80,6 @@ if os.path.exists(launches_path):
     w("\ntotal %.2f ms over %d launches" % (t, sum(a[0] for a in agg.values())))
 open(os.path.join(ROOT, "profiles", "%s_summary.md" % tag), "w").write("\n".join(out) + "\n")
 json.dump(d, open(os.path.join(ROOT, "profiles", "%s_bench_n1.json" % tag), "w"))
+if os.path.exists(launches_path):
+    open(os.path.join(ROOT, "profiles", "%s_ncu_launches.csv" % tag), "w").write(open(launches_path).read())
 print("\n".join(out[:12]))
