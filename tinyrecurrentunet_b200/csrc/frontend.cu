@@ -111,12 +111,16 @@ __global__ void __launch_bounds__(NT) frontend_kernel(FrontParams p) {
   __syncthreads();
   if (tid == 0) st_release(p.flags + b * p.nchunks + c, 1);
 
+  // Wait for every predecessor's aggregate with one flag per thread (in parallel: a chain of c dependent acquire loads per
+  // thread cost ~1400 cycles per predecessor, 28 us per CTA on 10-s clips), then fold the aggregates with independent loads.
+  for (int cc = tid; cc < c; cc += NT)
+    while (ld_acquire(p.flags + b * p.nchunks + cc) == 0) { }
+  __syncthreads();
   for (int f = tid; f < NB; f += NT) {
     float M = p.state_in ? __ldg(p.state_in + (size_t)b * NB + f) : 0.0f;
-    for (int cc = 0; cc < c; ++cc) {
-      while (ld_acquire(p.flags + b * p.nchunks + cc) == 0) { }
-      M = p.decay_chunk * M + __ldcg(p.agg + ((size_t)b * p.nchunks + cc) * NB + f);
-    }
+    const float* pa = p.agg + (size_t)b * p.nchunks * NB + f;
+#pragma unroll 8
+    for (int cc = 0; cc < c; ++cc) M = p.decay_chunk * M + __ldcg(pa + (size_t)cc * NB);
     for (int t = 0; t < nfr; ++t) {
       const float xm = tile[t * FEAT + NB + f];
       M = p.oms * M + p.s * xm;                     // dataset.py:66-68
