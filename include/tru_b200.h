@@ -200,14 +200,14 @@ int tru_flat_grad_norm(long long n, const float* grads, float* norm_out,
  * torchaudio, each biquad output clamped to [-1,1]) for B noise clips at
  * once, and dataset.py:367-379 (random crop of the clean clip,
  * noisy = clean + augmented noise).
- * coef (B, TRU_AUGMENT_NCOEF) per clip: {10^(gain_db/20),
- *   low-pass  {b0,b1,b2,a1,a2}/a0 and the 2x2 matrix A^TRU_AUGMENT_CHUNK (row major),
- *   high-pass the same 9}, A = [[-a1,-a2],[1,0]]: the zero-input response of
- *   the recurrence over one chunk, which the kernel uses to stitch chunks that
- *   it filters in parallel (tinyrecurrentunet_b200/dataset.py builds the rows).
+ * coef (B, TRU_AUGMENT_NCOEF) per clip: {10^(gain_db/20), low-pass row, high-pass row}; a row is
+ *   {b0,b1,b2,a1,a2}/a0 followed by six 2x2 matrices (row major) A^(TRU_AUGMENT_CHUNK * p),
+ *   p = 1, 8, 16, 32, 64, 128, with A = [[-a1,-a2],[1,0]]: the zero-input response of the
+ *   recurrence over p chunks, which the kernel uses to stitch the chunks it filters in
+ *   parallel (tinyrecurrentunet_b200/dataset.py builds the rows, powers in float64).
  * ------------------------------------------------------------------ */
 #define TRU_AUGMENT_CHUNK 63
-#define TRU_AUGMENT_NCOEF 19
+#define TRU_AUGMENT_NCOEF 59
 int tru_augment_fwd(int batch, int n_samples, const float* noise, const float* coef,
                     float* out, void* stream);
 /* clean (B,n_clean), aug_noise (B,n_noise), clean_start / noise_start (B) device ints (null = 0):

@@ -149,8 +149,9 @@ def test_augment_oracle_and_parameter_draws_match_reference(golden_dir):
         out = O.augment(noise, gain, lp, hp)
         assert (out - torch.from_numpy(g["out%d" % k])).abs().max().item() <= 1e-7
         row = aug.coefficients([(gain, lp, hp)])
-        assert row.shape == (1, 19) and torch.isfinite(row).all()
+        assert row.shape == (1, 59) and torch.isfinite(row).all()
         # the chunk matrix is the 63rd power of the recurrence's companion matrix
         a1, a2 = row[0, 4].double().item(), row[0, 5].double().item()
         A = np.array([[-a1, -a2], [1.0, 0.0]])
         assert np.allclose(np.linalg.matrix_power(A, 63).reshape(-1), row[0, 6:10].double().numpy(), rtol=1e-5, atol=1e-12)
+        assert np.allclose(np.linalg.matrix_power(A, 63 * 8).reshape(-1), row[0, 10:14].double().numpy(), rtol=1e-5, atol=1e-12)

@@ -96,7 +96,7 @@ EXPORTS = ["tru_launch_count", "tru_profile_enable", "tru_profile_report", "tru_
            "tru_trunet_backward", "tru_trunet_buffer_offset", "tru_flat_adamw_workspace_bytes", "tru_flat_adamw_step",
            "tru_flat_grad_norm", "tru_augment_fwd", "tru_mix_crop"]
 AUGMENT_CHUNK = 63        # TRU_AUGMENT_CHUNK
-AUGMENT_NCOEF = 19        # TRU_AUGMENT_NCOEF
+AUGMENT_NCOEF = 59        # TRU_AUGMENT_NCOEF
 
 
 class TruError(RuntimeError):

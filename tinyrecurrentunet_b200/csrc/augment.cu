@@ -8,7 +8,8 @@
 // owns 63 consecutive samples (63 is odd: the 32 lanes of a warp hit 32 different banks) and the recurrence is split by
 // superposition, which is exact for a linear recurrence:
 //   pass A   every thread runs its chunk from a ZERO state and publishes the end state e_j;
-//   carry    s_{j+1} = A^63 s_j + e_j over the 256 chunks (A^63 comes from the host in the coefficient row);
+//   carry    s_{j+1} = A^63 s_j + e_j over the 256 chunks: warp 0, 8 chunks per lane + a 5-step scan across lanes with
+//            A^(63*8*2^k) (all powers come from the host, evaluated in fp64, in the coefficient row);
 //   pass B   every thread reruns its chunk from its true start state s_j and stores clamp(y).
 // The clamp is applied to the stored output only, the recurrence continues on the unclamped values (torchaudio clamps
 // after the whole filter has run).
@@ -24,11 +25,13 @@ constexpr int ANT = 256;                 // threads = chunks per tile
 constexpr int AK = TRU_AUGMENT_CHUNK;    // samples per chunk
 constexpr int ATS = ANT * AK;            // samples per tile (16,128 = 63 KB of shared memory)
 constexpr int ACO = TRU_AUGMENT_NCOEF;   // floats per coefficient row
+static_assert(ANT == 256 && ACO == 59, "the carry scan is written for 32 lanes x 8 chunks and 6 matrix powers per filter");
 static_assert(AK % 2 == 1 && AK >= 3, "an odd chunk keeps the strided shared-memory walk conflict-free");
 
 struct Biquad {
   float b0, b1, b2, a1, a2;              // already divided by a0 (in fp32, as torchaudio does)
   float m00, m01, m10, m11;              // A^AK, A = [[-a1, -a2], [1, 0]] acting on (y[n-1], y[n-2])
+  const float* pw;                       // the row's five further powers A^(AK * {8, 16, 32, 64, 128}), row major (read by the scan)
 };
 
 struct StageCarry {                      // lives in thread 0's registers across tiles
@@ -59,19 +62,43 @@ __device__ __forceinline__ void biquad_tile(float* tile, int nv, const Biquad& c
     es[j] = make_float2(y1, y2);
   }
   __syncthreads();
-  if (j == 0) {
-    float s1 = carry.y1, s2 = carry.y2;
-    const int nch = (nv + AK - 1) / AK;
-#pragma unroll 4
-    for (int q = 0; q < nch; ++q) {
-      ss[q] = make_float2(s1, s2);
-      const float2 e = es[q];
-      const float t1 = fmaf(c.m00, s1, fmaf(c.m01, s2, e.x));
-      const float t2 = fmaf(c.m10, s1, fmaf(c.m11, s2, e.y));
+  // carry over the 256 chunk ends by warp 0: lane L folds its 8 chunks (Horner), a 5-step scan across the lanes with the
+  // precomputed powers A^(63*8*2^k) composes them, then the lane replays its 8 chunks from its true start state.
+  if (j < 32) {
+    const float m00 = c.m00, m01 = c.m01, m10 = c.m10, m11 = c.m11;
+    const float in1 = __shfl_sync(0xffffffffu, carry.y1, 0), in2 = __shfl_sync(0xffffffffu, carry.y2, 0);
+    float2 e[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) e[i] = es[j * 8 + i];
+    float p1 = j == 0 ? in1 : 0.f, p2 = j == 0 ? in2 : 0.f;           // lane 0 starts from the tile's incoming state
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float t1 = fmaf(m00, p1, fmaf(m01, p2, e[i].x)), t2 = fmaf(m10, p1, fmaf(m11, p2, e[i].y));
+      p1 = t1; p2 = t2;
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {                                      // inclusive scan: P_L = A^(63*8*d) P_{L-d} + P_L
+      const int d = 1 << k;
+      const float q1 = __shfl_up_sync(0xffffffffu, p1, d), q2 = __shfl_up_sync(0xffffffffu, p2, d);
+      const float w0 = __ldg(c.pw + 4 * k), w1 = __ldg(c.pw + 4 * k + 1), w2 = __ldg(c.pw + 4 * k + 2), w3 = __ldg(c.pw + 4 * k + 3);
+      if (j >= d) {
+        const float t1 = fmaf(w0, q1, fmaf(w1, q2, p1)), t2 = fmaf(w2, q1, fmaf(w3, q2, p2));
+        p1 = t1; p2 = t2;
+      }
+    }
+    float s1 = __shfl_up_sync(0xffffffffu, p1, 1), s2 = __shfl_up_sync(0xffffffffu, p2, 1);   // state after the previous lane's chunks
+    if (j == 0) { s1 = in1; s2 = in2; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      ss[j * 8 + i] = make_float2(s1, s2);
+      const float t1 = fmaf(m00, s1, fmaf(m01, s2, e[i].x)), t2 = fmaf(m10, s1, fmaf(m11, s2, e[i].y));
       s1 = t1; s2 = t2;
     }
-    carry.y1 = s1; carry.y2 = s2;          // meaningful when the tile is full (otherwise it is the last tile)
-    carry.x1 = nx1; carry.x2 = nx2;
+    const float o1 = __shfl_sync(0xffffffffu, p1, 31), o2 = __shfl_sync(0xffffffffu, p2, 31);
+    if (j == 0) {
+      carry.y1 = o1; carry.y2 = o2;        // state after the tile's last chunk (meaningful when the tile is full)
+      carry.x1 = nx1; carry.x2 = nx2;
+    }
   }
   __syncthreads();
   // pass B: the same chunk from its true start state
@@ -93,10 +120,11 @@ __device__ __forceinline__ Biquad load_biquad(const float* p) {
   Biquad c;
   c.b0 = p[0]; c.b1 = p[1]; c.b2 = p[2]; c.a1 = p[3]; c.a2 = p[4];
   c.m00 = p[5]; c.m01 = p[6]; c.m10 = p[7]; c.m11 = p[8];
+  c.pw = p + 9;
   return c;
 }
 
-// noise (B, n) -> out (B, n); coef (B, ACO) = {gain ratio, low-pass row[9], high-pass row[9]}
+// noise (B, n) -> out (B, n); coef (B, ACO) = {gain ratio, low-pass row[29], high-pass row[29]}
 __global__ void __launch_bounds__(ANT) augment_kernel(const float* __restrict__ noise, const float* __restrict__ coef,
                                                       float* __restrict__ out, int n) {
   extern __shared__ float tile[];
@@ -106,7 +134,7 @@ __global__ void __launch_bounds__(ANT) augment_kernel(const float* __restrict__ 
   float* dst = out + (size_t)b * n;
   const float* cf = coef + (size_t)b * ACO;
   const float gain = cf[0];
-  const Biquad lp = load_biquad(cf + 1), hp = load_biquad(cf + 10);
+  const Biquad lp = load_biquad(cf + 1), hp = load_biquad(cf + 1 + (ACO - 1) / 2);
   StageCarry c1{0.f, 0.f, 0.f, 0.f}, c2{0.f, 0.f, 0.f, 0.f};
   for (int t0 = 0; t0 < n; t0 += ATS) {
     const int nv = min(ATS, n - t0);

@@ -124,7 +124,8 @@ class ProcessAudio(nn.Module):
 def _biquad_row(kind, sample_rate, cutoff_freq, Q, chunk):
     """Coefficient row of one biquad for tru_augment_fwd: torchaudio.functional.lowpass_biquad / highpass_biquad design
     (the SoX formulas, evaluated in float32 tensors exactly as torchaudio evaluates them, then divided by a0 as its
-    lfilter does) followed by the chunk matrix A^chunk, A = [[-a1, -a2], [1, 0]], evaluated in float64."""
+    lfilter does) followed by the chunk matrices A^(chunk * {1, 8, 16, 32, 64, 128}), A = [[-a1, -a2], [1, 0]], evaluated in
+    float64 (the kernel's carry scan composes chunk end states with them)."""
     f32 = torch.float32
     cutoff_freq = torch.as_tensor(cutoff_freq, dtype=f32)
     Q = torch.as_tensor(Q, dtype=f32)
@@ -143,8 +144,8 @@ def _biquad_row(kind, sample_rate, cutoff_freq, Q, chunk):
     b = torch.stack([b0, b1, b0]) / a0
     a = torch.stack([-2 * cw, 1 - alpha]) / a0
     A = np.array([[-float(a[0]), -float(a[1])], [1.0, 0.0]], dtype=np.float64)
-    M = np.linalg.matrix_power(A, chunk)
-    return [float(v) for v in b] + [float(v) for v in a] + [float(v) for v in M.reshape(-1)]
+    powers = [np.linalg.matrix_power(A, chunk * p) for p in (1, 8, 16, 32, 64, 128)]
+    return [float(v) for v in b] + [float(v) for v in a] + [float(v) for M in powers for v in M.reshape(-1)]
 
 
 class DataAugment:
@@ -170,7 +171,7 @@ class DataAugment:
         return gain, lp_cutoff, hp_cutoff
 
     def coefficients(self, params):
-        """(B, 19) float32 host tensor of kernel coefficient rows for a list of (gain_db, lp_cutoff, hp_cutoff)."""
+        """(B, 59) float32 host tensor of kernel coefficient rows for a list of (gain_db, lp_cutoff, hp_cutoff)."""
         rows = []
         for gain_db, lp_cutoff, hp_cutoff in params:
             if float(gain_db) == 0:                                                      # F.gain

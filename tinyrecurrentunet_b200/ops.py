@@ -157,7 +157,7 @@ def mrstft_l1(x, y, windows, cfg):
 
 
 def augment(noise, coef):
-    """dataset.py:79-126 for B rows: noise (B,N) float32 CUDA, coef (B,19) (dataset.DataAugment.coefficients) -> (B,N)."""
+    """dataset.py:79-126 for B rows: noise (B,N) float32 CUDA, coef (B,59) (dataset.DataAugment.coefficients) -> (B,N)."""
     L.require_cuda(noise, coef)
     noise, coef = noise.contiguous(), coef.contiguous()
     if noise.dim() != 2 or coef.shape != (noise.shape[0], L.AUGMENT_NCOEF) or coef.dtype != torch.float32:
