@@ -206,3 +206,32 @@ def test_checkpoint_helpers_follow_train_py(tmp_path):
         assert torch.equal(net.state_dict()[k], v), k
     assert util.load_checkpoint(str(d), 11, net) == (-1, 0)
     assert util.load_checkpoint(str(tmp_path), "max", net) == (-1, 0)
+
+
+def test_fold_batchnorm_export_keeps_the_eval_outputs():
+    """util.fold_batchnorm: same keys, BatchNorm entries become the identity, and the reference layer list (oracle TRUNet)
+    loaded with the folded weights reproduces the eval-mode output of the original (<= 1e-5 of the output scale)."""
+    from oracle import tru_oracle as O
+    from tinyrecurrentunet_b200 import util
+    torch.manual_seed(8)
+    ref = O.randomize_bn(O.TRUNet(), 8).eval()
+    x = O.frontend(O.synthetic_batch(1, n=128 * 12)[1])
+    with torch.no_grad():
+        y = ref(x)
+    sd = ref.state_dict()
+    folded = util.fold_batchnorm(sd)
+    assert list(folded.keys()) == list(sd.keys())
+    n_bn = 0
+    for k, v in folded.items():
+        if k.endswith("running_mean"):
+            n_bn += 1
+            assert torch.count_nonzero(v) == 0 and torch.count_nonzero(folded[k[:-12] + "bias"]) == 0
+            assert torch.all(folded[k[:-12] + "weight"] == 1)
+    assert n_bn == 23
+    ref2 = O.TRUNet()
+    ref2.load_state_dict(folded)
+    ref2.eval()
+    with torch.no_grad():
+        y2 = ref2(x)
+    assert ((y2 - y).abs().max() / y.abs().max()).item() <= 1e-5
+    assert not torch.equal(folded["encoder.1.DepthwiseSeparableConv1d.0.weight"], sd["encoder.1.DepthwiseSeparableConv1d.0.weight"])

@@ -310,6 +310,23 @@ def test_streaming_feed_loop_equals_offline_denoise():
         util.StreamingDenoiser(net, S).finish()
 
 
+def test_bn_folded_export_runs_on_the_cuda_path():
+    """util.fold_batchnorm (inference export): the folded weights loaded into the CUDA module give the eval-mode output of
+    the original weights, and of the oracle."""
+    from tinyrecurrentunet_b200 import network, util
+    ref, net = make_pair(9)
+    ref.eval(); net.eval()
+    x = feats_like(2, 9, 3)
+    with torch.no_grad():
+        y_ref = ref(x)
+        y = net(x.cuda())
+        net2 = network.TRUNet().cuda().eval()
+        net2.load_state_dict(util.fold_batchnorm(net.state_dict()))
+        y2 = net2(x.cuda())
+    assert rel(y, y_ref) <= OUT_TOL
+    assert rel(y2, y) <= 1e-5 and rel(y2, y_ref) <= OUT_TOL
+
+
 def test_cuda_prefetcher_delivers_batches_in_order():
     """util.CudaPrefetcher (used by bench.py's end-to-end timing): call i returns the batch passed in call i-1 (the first
     call its own batch), copied on a side stream; a consumer on the current stream always sees complete data."""

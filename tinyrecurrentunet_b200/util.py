@@ -176,6 +176,35 @@ def load_checkpoint(ckpt_directory, ckpt_iter, net, optimizer=None):
     return ckpt_iter, checkpoint["training_time_seconds"]
 
 
+def fold_batchnorm(state_dict, eps=1e-5):
+    """Inference export (the artefact onnx.py:15-30 / rt.py:13-18 want to load): a state dict with the SAME 177 keys in
+    which every eval-mode BatchNorm is folded into the convolution in front of it - ``w' = w * g / sqrt(var + eps)`` per
+    output channel, ``b' = (b - mean) * g / sqrt(var + eps) + beta`` - and the BatchNorm entries are set to the identity
+    (weight 1, bias 0, running_mean 0, running_var 1 - eps).  Loads into TRUNet (this package's or the reference's layer
+    list) and gives the eval-mode outputs of the original; the CUDA kernels gain nothing from it (they apply the
+    eval-mode affine while loading), it exists for exchange with other runtimes."""
+    out = type(state_dict)((k, v.clone()) for k, v in state_dict.items())
+    for key in state_dict:
+        if not key.endswith(".running_mean"):
+            continue
+        bn = key[:-len(".running_mean")]
+        parent, idx = bn.rsplit(".", 1)
+        conv = "%s.%d" % (parent, int(idx) - 1)
+        g, beta = state_dict[bn + ".weight"].double(), state_dict[bn + ".bias"].double()
+        mean, var = state_dict[bn + ".running_mean"].double(), state_dict[bn + ".running_var"].double()
+        scale = g / torch.sqrt(var + eps)
+        w = state_dict[conv + ".weight"].double()
+        transposed = parent.startswith("decoder.") and int(idx) - 1 == 3          # ConvTranspose1d: (C_in, C_out, k)
+        shape = (1, -1, 1) if transposed else (-1, 1, 1)
+        out[conv + ".weight"] = (w * scale.view(shape)).to(state_dict[conv + ".weight"].dtype)
+        out[conv + ".bias"] = ((state_dict[conv + ".bias"].double() - mean) * scale + beta).to(state_dict[conv + ".bias"].dtype)
+        out[bn + ".weight"] = torch.ones_like(state_dict[bn + ".weight"])
+        out[bn + ".bias"] = torch.zeros_like(state_dict[bn + ".bias"])
+        out[bn + ".running_mean"] = torch.zeros_like(state_dict[bn + ".running_mean"])
+        out[bn + ".running_var"] = torch.full_like(state_dict[bn + ".running_var"], 1.0 - eps)
+    return out
+
+
 def _ramp_linear(a, b, x):
     return a + x * (b - a)
 
