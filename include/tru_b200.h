@@ -217,6 +217,25 @@ int tru_mix_crop(int batch, int n_clean, int n_noise, int n_out, const float* cl
                  const float* aug_noise, const int* clean_start, const int* noise_start,
                  float* clean_out, float* noisy_out, void* stream);
 
+/* ------------------------------------------------------------------ *
+ * cos_loss.py:41-56 (CosSimLoss.forward): mean over the
+ * segments [bounds[i], bounds[i+1]) and the batch rows of 1 - cosine similarity
+ * (nn.CosineSimilarity: each norm clamped to eps) of x (prediction) and y
+ * (target), both (B, n_samples).  The reference only runs for one row and
+ * detaches the result; this one averages rows and has a backward w.r.t. x.
+ * stats (B, n_seg, 3) doubles = {x.y, |x|^2, |y|^2}, written by fwd, read by bwd.
+ * ------------------------------------------------------------------ */
+typedef struct {
+  int batch, n_samples, n_seg;   /* n_seg <= 8 */
+  int bounds[9];                 /* cos_loss.py:25 default g = [508,1016,2032,4062] -> {0,508,1016,2032,4062} */
+  double eps;                    /* 1e-5 */
+} TruCosSimDesc;
+int tru_cossim_fwd(const TruCosSimDesc* d, const float* x, const float* y, double* stats,
+                   float* loss, void* stream);
+/* grad_loss: device float (upstream gradient of the scalar); grad_x (B, n_samples) fully written. */
+int tru_cossim_bwd(const TruCosSimDesc* d, const float* x, const float* y, const double* stats,
+                   const float* grad_loss, float* grad_x, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,6 +13,7 @@ What is pinned:
                copied into this repo)
   phm.py       formula :34-44, executed with the two misspelt names aliased (X7)
   dataset.py   DataAugment (gain + low/high-pass biquads of torchaudio) with seeded draws
+  cos_loss.py  CosSimLoss on one row (imported unmodified)
   util.py      LinearWarmupCosineDecay, lines 81-156 (the file has a SyntaxError
                further down, X8; this slice is exec'd as it lies on disk)
 Everything is small (a few hundred kB in total) and committed.
@@ -180,6 +181,16 @@ def main():
         rec["out%d" % k] = out.numpy()
         rec["par%d" % k] = np.array([float(gain), float(lp), float(hp)], dtype=np.float64)
     np.savez_compressed(os.path.join(OUT, "augment_ref.npz"), **rec)
+
+    # ---- cosine-similarity loss (cos_loss.py, imported unmodified; it only runs for one row) ----
+    sys.path.insert(0, REF)
+    import cos_loss as ref_cos_loss         # noqa
+    sys.path.pop(0)
+    gc = torch.Generator().manual_seed(77)
+    cy = torch.randn(1, 4500, generator=gc) * 0.2
+    cx = cy + 0.1 * torch.randn(1, 4500, generator=gc)
+    cout = ref_cos_loss.CosSimLoss()(cx, cy)
+    np.savez_compressed(os.path.join(OUT, "cos_loss_ref.npz"), x=cx.numpy(), y=cy.numpy(), out=np.float64(float(cout)))
 
     print("golden fixtures written to", os.path.normpath(OUT))
     for f in sorted(os.listdir(OUT)):

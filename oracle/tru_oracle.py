@@ -409,3 +409,14 @@ def assemble_batch(clean, noise, params, clean_start, noise_start, crop_length):
         cs.append(c)
         ns.append(c + a[idx])
     return torch.stack(cs), torch.stack(ns)
+
+
+def cos_sim_loss(x, y, eps=1e-5, g=(508, 1016, 2032, 4062)):
+    """cos_loss.py:41-56: mean over the slices [g[i-1], g[i]) of 1 - nn.CosineSimilarity(dim=1, eps).  For one row this is the
+    reference's value exactly; rows are averaged and the graph is kept (the reference's torch.FloatTensor(list) can do
+    neither)."""
+    terms, lo = [], 0
+    for hi in g:
+        terms.append(1 - F.cosine_similarity(x[:, lo:hi], y[:, lo:hi], dim=1, eps=eps))
+        lo = hi
+    return torch.stack(terms).mean()

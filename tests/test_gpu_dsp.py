@@ -164,3 +164,33 @@ def test_errors_are_loud(T):
         T["ops"].frontend(torch.zeros(1, 64000))                 # CPU tensor: no CPU path
     with pytest.raises(Exception):
         T["ops"].frontend(torch.zeros(1, 200, device="cuda"))    # N <= 256: reflect pad impossible
+
+
+def test_cos_sim_loss_matches_reference_golden_and_oracle(golden_dir):
+    """cos_loss.CosSimLoss (tru_cossim_fwd / _bwd): the reference's value on its one-row golden, the oracle's value and
+    gradient on a batch (<= 1e-4 on the loss, <= 1e-3 on the gradient), zeros outside the slices, loud argument errors."""
+    import os
+    import numpy as np
+    from oracle import tru_oracle as O
+    from tinyrecurrentunet_b200 import _lib as L, cos_loss
+    g = np.load(os.path.join(golden_dir, "cos_loss_ref.npz"))
+    mod = cos_loss.CosSimLoss()
+    out = mod(torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["y"]).cuda())
+    assert abs(out.item() - float(g["out"])) <= 1e-5 * abs(float(g["out"]))
+    gen = torch.Generator().manual_seed(3)
+    y = torch.randn(5, 6000, generator=gen) * 0.3
+    x = (y + 0.2 * torch.randn(5, 6000, generator=gen)).requires_grad_(True)
+    x[0].data[:508] = 0                                   # a silent slice: the clamped-norm branch
+    ref = O.cos_sim_loss(x, y)
+    ref.backward()
+    xc = x.detach().cuda().requires_grad_(True)
+    out = mod(xc, y.cuda())
+    (out * 2.0).backward()
+    assert abs(out.item() - ref.item()) <= 1e-4 * abs(ref.item())
+    gx = xc.grad.cpu() / 2.0
+    assert ((gx - x.grad).abs().max() / x.grad.abs().max()).item() <= 1e-3
+    assert torch.count_nonzero(gx[:, 4062:]) == 0
+    with pytest.raises(L.TruError):
+        mod(xc[:, :4000], y.cuda()[:, :4000])             # shorter than the last slice
+    with pytest.raises(L.TruError):
+        mod(x.detach(), y)                                # CPU tensors: no fallback

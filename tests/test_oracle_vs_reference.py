@@ -155,3 +155,10 @@ def test_augment_oracle_and_parameter_draws_match_reference(golden_dir):
         A = np.array([[-a1, -a2], [1.0, 0.0]])
         assert np.allclose(np.linalg.matrix_power(A, 63).reshape(-1), row[0, 6:10].double().numpy(), rtol=1e-5, atol=1e-12)
         assert np.allclose(np.linalg.matrix_power(A, 63 * 8).reshape(-1), row[0, 10:14].double().numpy(), rtol=1e-5, atol=1e-12)
+
+
+def test_cos_sim_loss_oracle_matches_reference(golden_dir):
+    """oracle.cos_sim_loss against the reference's CosSimLoss (cos_loss.py:41-56) on the one-row input it can run."""
+    g = np.load(os.path.join(golden_dir, "cos_loss_ref.npz"))
+    out = O.cos_sim_loss(torch.from_numpy(g["x"]), torch.from_numpy(g["y"]))
+    assert abs(out.item() - float(g["out"])) <= 1e-6 * abs(float(g["out"]))

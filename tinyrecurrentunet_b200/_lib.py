@@ -44,6 +44,10 @@ class TruAdamWDesc(C.Structure):
                 ("beta2", C.c_double), ("eps", C.c_double), ("weight_decay", C.c_double), ("max_grad_norm", C.c_double)]
 
 
+class TruCosSimDesc(C.Structure):
+    _fields_ = [("batch", C.c_int), ("n_samples", C.c_int), ("n_seg", C.c_int), ("bounds", C.c_int * 9), ("eps", C.c_double)]
+
+
 class TruNetDesc(C.Structure):
     _fields_ = [("batch", C.c_int), ("n_frames", C.c_int), ("training", C.c_int),
                 ("bn_eps", C.c_double), ("bn_momentum", C.c_double)]
@@ -88,13 +92,16 @@ _sig("tru_flat_adamw_step", C.c_int, [C.POINTER(TruAdamWDesc), c_float_p, c_floa
 _sig("tru_augment_fwd", C.c_int, [C.c_int, C.c_int, c_float_p, c_float_p, c_float_p, c_stream])
 _sig("tru_mix_crop", C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_float_p, c_float_p, C.c_void_p, C.c_void_p, c_float_p,
                               c_float_p, c_stream])
+_sig("tru_cossim_fwd", C.c_int, [C.POINTER(TruCosSimDesc), c_float_p, c_float_p, C.c_void_p, c_float_p, c_stream])
+_sig("tru_cossim_bwd", C.c_int, [C.POINTER(TruCosSimDesc), c_float_p, c_float_p, C.c_void_p, c_float_p, c_float_p, c_stream])
 _sig("tru_flat_grad_norm", C.c_int, [C.c_longlong, c_float_p, c_float_p, C.c_void_p, C.c_size_t, c_stream])
 
 EXPORTS = ["tru_launch_count", "tru_profile_enable", "tru_profile_report", "tru_abi_version", "tru_last_error", "tru_init", "tru_frontend_workspace_bytes",
            "tru_frontend_fwd", "tru_frontend_step", "tru_backend_fwd", "tru_backend_bwd", "tru_backend_step",
            "tru_loss_fwd", "tru_loss_bwd", "tru_trunet_workspace_bytes", "tru_trunet_forward",
            "tru_trunet_backward", "tru_trunet_buffer_offset", "tru_flat_adamw_workspace_bytes", "tru_flat_adamw_step",
-           "tru_flat_grad_norm", "tru_augment_fwd", "tru_mix_crop"]
+           "tru_flat_grad_norm", "tru_augment_fwd", "tru_mix_crop", "tru_cossim_fwd",
+           "tru_cossim_bwd"]
 AUGMENT_CHUNK = 63        # TRU_AUGMENT_CHUNK
 AUGMENT_NCOEF = 59        # TRU_AUGMENT_NCOEF
 
