@@ -76,14 +76,16 @@ def test_module_tree_matches_reference_schema():
 
 
 def test_reference_api_names_exist():
-    from tinyrecurrentunet_b200 import dataset, distributed, network, phm, stft_loss, util
+    from tinyrecurrentunet_b200 import cos_loss, dataset, distributed, network, optim, phm, stft_loss, util
     for mod, names in ((network, ["StandardConv1d", "DepthwiseSeparableConv1d", "GRUBlock", "FirstTrCNN", "TrCNN",
                                   "LastTrCNN", "TRUNet"]),
                        (phm, ["PhaseAwareMask"]),
                        (stft_loss, ["stft", "SpectralConvergenceLoss", "LogSTFTMagnitudeLoss", "STFTLoss",
                                     "MultiResolutionSTFTLoss"]),
-                       (dataset, ["ProcessAudio", "pcenfunc", "unwrap", "diff"]),
-                       (util, ["loss_fn", "sampling"]),
+                       (dataset, ["ProcessAudio", "pcenfunc", "unwrap", "diff", "DataAugment"]),
+                       (util, ["loss_fn", "sampling", "find_max_epoch", "LinearWarmupCosineDecay"]),
+                       (cos_loss, ["CosSimLoss"]),
+                       (optim, ["FlatAdamW"]),
                        (distributed, ["init_distributed", "apply_gradient_allreduce", "reduce_tensor"])):
         for n in names:
             assert hasattr(mod, n), (mod.__name__, n)
