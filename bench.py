@@ -49,6 +49,26 @@ def parse():
     return ap.parse_args()
 
 
+# ------------------------------------------------------------------ synthetic workload
+def synthetic_batch(b, n, first=0):
+    """Deterministic (clean, noisy) clips of SURVEY section 8d: seeded Gaussian speech-band noise under a 3 Hz envelope plus three
+    tones, and white noise at -30 dB.  Kept here so that the native arm does not touch oracle/ (the tests use the oracle's own
+    copy of the same recipe)."""
+    import math
+    import torch
+    cleans, noisies = [], []
+    t = torch.arange(n, dtype=torch.float64)
+    env = 0.5 * (1.0 + torch.sin(2 * math.pi * 3 * t / n))
+    tones = sum(0.05 * torch.sin(2 * math.pi * f0 * t / 16000) for f0 in (220.0, 440.0, 1760.0))
+    for i in range(first, first + b):
+        g = torch.Generator().manual_seed(1000 + i)
+        clean = (0.1 * torch.randn(n, generator=g, dtype=torch.float32).double() * env + tones).float()
+        noise = 0.03 * torch.randn(n, generator=g, dtype=torch.float32).double()
+        cleans.append(clean)
+        noisies.append((clean.double() + noise).float())
+    return torch.stack(cleans), torch.stack(noisies)
+
+
 # ------------------------------------------------------------------ CPU arm (oracle)
 def cpu_training_clips_per_sec(batch, steps, warmup):
     """The reference algorithm (oracle restatement, SURVEY section 8c: the reference itself does
@@ -239,7 +259,6 @@ def run_native(args):
             sys.stdout.flush()
             os.dup2(saved, 1)
             os.close(saved)
-    from oracle import tru_oracle as O                      # synthetic data generator + cpu_baseline only
     from tinyrecurrentunet_b200 import _lib as L, network, optim, stft_loss, util
     from tinyrecurrentunet_b200 import distributed as tdist
 
@@ -262,7 +281,7 @@ def run_native(args):
 
     # synthetic clips: a pool of distinct clips, rank-dependent, tiled to the batch
     pool = min(B, 8)
-    clean_h, noisy_h = O.synthetic_batch(pool, n=CLIP_SAMPLES, first=rank * pool)
+    clean_h, noisy_h = synthetic_batch(pool, CLIP_SAMPLES, first=rank * pool)
     reps = (B + pool - 1) // pool
     clean_h = clean_h.repeat(reps, 1)[:B].contiguous().pin_memory()
     noisy_h = noisy_h.repeat(reps, 1)[:B].contiguous().pin_memory()
