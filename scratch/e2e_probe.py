@@ -6,7 +6,6 @@ import time
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import tru_oracle as O
 from tinyrecurrentunet_b200 import network, optim, stft_loss, util
 
 dev = torch.device("cuda")
@@ -16,7 +15,8 @@ net = network.TRUNet().to(dev).train()
 mr = stft_loss.MultiResolutionSTFTLoss(fft_sizes=[512, 1024, 2048], hop_sizes=[50, 120, 240], win_lengths=[240, 600, 1200]).to(dev)
 opt = optim.FlatAdamW(net.parameters(), lr=4e-4, max_grad_norm=1e9)
 sched = util.LinearWarmupCosineDecay(opt, lr_max=4e-4, n_iter=25_000_000, iteration=0, divider=25, warmup_proportion=0.05)
-clean_h, noisy_h = O.synthetic_batch(8, n=N)
+clean_h = torch.randn(8, N) * 0.1
+noisy_h = clean_h + 0.03 * torch.randn(8, N)
 clean_h = clean_h.repeat(4, 1).contiguous().pin_memory()
 noisy_h = noisy_h.repeat(4, 1).contiguous().pin_memory()
 clean_d, noisy_d = clean_h.to(dev), noisy_h.to(dev)
