@@ -1,14 +1,16 @@
 #!/usr/bin/env python
-"""bench.py - TRU-Net training-step throughput (BASELINE.json: "train 4-s clips/sec").
+"""bench.py - TRU-Net training-step throughput (BASELINE.json: "train 4-s clips/sec") plus the inference real-time factors.
 
-    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
-    python bench.py --impl reference --gpus N --steps K ...  # reference algorithm on host CPU
+    python bench.py --gpus N --steps K --warmup W             # this repo (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on the host CPU (oracle port)
+    python bench.py --impl torch-gpu  --steps K ...           # the reference algorithm on stock PyTorch on the same GPU
+                                                              # (cuDNN / cuBLAS / cuFFT): the bar the hand kernels must beat
 
 A "step" = one pass of the hot path over one batch of synthetic 16 kHz clips:
 front end -> TRU-Net -> mask + iSTFT -> L1 + multi-resolution STFT loss -> backward ->
-(N > 1: one NCCL all-reduce of the flat gradient bucket) -> AdamW step.
-Workload = BASELINE.json configs[1]: tiny.json, 32 clean/noisy 4-s pairs per GPU
-(weak scaling: global batch 32*N).  One JSON line is printed by rank 0.
+(N > 1: one NCCL all-reduce of the flat gradient bucket) -> grad norm + LR schedule + AdamW.
+Workload = BASELINE.json configs[1]: tiny.json, 32 distinct clean/noisy 4-s pairs per GPU (weak scaling: global batch 32*N;
+for N > 1 the strong-scaling point of configs[2], global batch 256, is timed as well).  One JSON line is printed by rank 0.
 """
 import argparse
 import json
@@ -17,7 +19,6 @@ import statistics
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -26,10 +27,14 @@ sys.path.insert(0, ROOT)
 METRIC = "train_4s_clips_per_sec"
 UNIT = "clips/s"
 CLIP_SAMPLES = 64000           # 4 s at 16 kHz
+LONG_SAMPLES = 160000          # 10 s at 16 kHz (configs[4])
 WORKLOAD = ("tiny.json training step (BASELINE.json configs[1]): %d clean/noisy 4-s 16 kHz pairs per GPU, front end + TRU-Net + "
             "mask/iSTFT + L1/MRSTFT loss, fwd+bwd, flat-bucket NCCL all-reduce (N>1), grad norm + LR schedule + AdamW")
 STFT_CFG = dict(fft_sizes=[512, 1024, 2048], hop_sizes=[50, 120, 240], win_lengths=[240, 600, 1200],
                 sc_lambda=0.5, mag_lambda=0.5)          # config/tiny.json:30-37
+# block-boundary bytes of the model per frame (forward), front end / back end bytes per clip
+MODEL_BYTES_PER_FRAME = 801328
+STEP_BYTES_B32 = 3 * MODEL_BYTES_PER_FRAME * 32 * 501      # 38.5 GB: "3 x forward" convention for fwd+bwd
 
 
 def parse():
@@ -37,16 +42,27 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--impl", default="native", choices=["native", "reference", "torch-gpu"])
     ap.add_argument("--batch", type=int, default=32, help="clips per GPU")
-    ap.add_argument("--cpu-batch", type=int, default=2, help="clips per CPU step (bounded sample)")
+    ap.add_argument("--cpu-seconds", type=float, default=150.0, help="time budget of the CPU arm (steps are cut to fit)")
     ap.add_argument("--optimizer", default="flat", choices=["flat", "torch"],
                     help="flat: optim.FlatAdamW (grad norm + AdamW in one C call); torch: stock fused AdamW (A/B aid)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-inference", action="store_true", help="skip the streaming / offline inference RTF measurements")
+    ap.add_argument("--no-inference", action="store_true", help="skip the streaming / offline inference measurements")
+    ap.add_argument("--no-stock-gpu", action="store_true", help="skip the stock-PyTorch-on-this-GPU baseline")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the global-batch-256 strong-scaling point")
     ap.add_argument("--streams", type=int, default=4096, help="concurrent streams of the streaming measurement (configs[3])")
+    ap.add_argument("--offline-clips", type=int, default=1250, help="10-s clips per GPU of the offline measurement (configs[4])")
     return ap.parse_args()
+
+
+def config_of(args, world):
+    """The workload description; identical for every --impl so the driver can pair the arms."""
+    B = args.batch
+    return {"workload": WORKLOAD % B, "clips_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world,
+            "clip_samples": CLIP_SAMPLES, "distinct_clips_per_gpu": B,
+            "l2": "no explicit flush: one step streams >10 GB of activations through the 126 MB L2"}
 
 
 # ------------------------------------------------------------------ synthetic workload
@@ -69,49 +85,151 @@ def synthetic_batch(b, n, first=0):
     return torch.stack(cleans), torch.stack(noisies)
 
 
-# ------------------------------------------------------------------ CPU arm (oracle)
-def cpu_training_clips_per_sec(batch, steps, warmup):
-    """The reference algorithm (oracle restatement, SURVEY section 8c: the reference itself does
-    not run) on the host cores with every thread torch can use.  Returns (clips/s, cores)."""
+# ------------------------------------------------------------------ baseline legs (the ONLY code here that touches oracle/)
+def oracle_training_step(device, batch, allow_tf32=False):
+    """The reference algorithm (oracle restatement, SURVEY section 8c: the reference itself does not run) as a training step
+    on `device` with stock PyTorch: train.py:118-140.  Returns (step, stage_step): callables running one step; stage_step
+    returns per-stage times."""
     import torch
     from oracle import tru_oracle as O
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     torch.manual_seed(0)
-    net = O.randomize_bn(O.TRUNet()).train()
+    net = O.randomize_bn(O.TRUNet()).to(device).train()
     opt = torch.optim.AdamW(net.parameters(), lr=4e-4)
-    clean, noisy = O.synthetic_batch(batch, n=CLIP_SAMPLES)
-    times = []
-    for it in range(warmup + steps):
-        t0 = time.perf_counter()
+    clean, noisy = synthetic_batch(batch, CLIP_SAMPLES)
+    clean, noisy = clean.to(device), noisy.to(device)
+    if device.type == "cuda":
+        torch.backends.cuda.matmul.allow_tf32 = allow_tf32
+        torch.backends.cudnn.allow_tf32 = allow_tf32
+
+    def step():
         opt.zero_grad(set_to_none=True)
         loss, _, _ = O.loss_fn(net, clean, noisy)
         loss.backward()
         torch.nn.utils.clip_grad_norm_(net.parameters(), 1e9)      # train.py:138
         opt.step()
+        return loss
+
+    def stage_step():
+        """One step with CUDA events between the stages (front end / network forward / mask+iSTFT+loss / backward / optimizer)."""
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        opt.zero_grad(set_to_none=True)
+        ev[0].record()
+        feats = O.frontend(noisy)
+        ev[1].record()
+        out = net(feats)
+        ev[2].record()
+        den = O.backend(out)
+        l1 = torch.abs(torch.nn.functional.l1_loss(den, clean))
+        sc, mg = O.mrstft_loss(den, clean)
+        loss = l1 + sc + mg
+        ev[3].record()
+        loss.backward()
+        ev[4].record()
+        torch.nn.utils.clip_grad_norm_(net.parameters(), 1e9)
+        opt.step()
+        ev[5].record()
+        torch.cuda.synchronize()
+        names = ["frontend", "net_fwd", "mask_istft_loss_fwd", "backward_all", "gradnorm_adamw"]
+        return {n: round(ev[i].elapsed_time(ev[i + 1]), 3) for i, n in enumerate(names)}
+    return step, stage_step
+
+
+def cpu_training_clips_per_sec(batch, steps, warmup, threads=None, budget_s=150.0):
+    """Oracle training step on the host cores.  Returns (clips/s, threads, timed steps)."""
+    import torch
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step, _ = oracle_training_step(torch.device("cpu"), batch)
+    t_begin = time.perf_counter()
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        step()
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
-    return batch * len(times) / sum(times), torch.get_num_threads()
+        # stop early when the next step would not fit the budget (at least one timed step)
+        if times and time.perf_counter() - t_begin + dt > budget_s:
+            break
+    return batch * len(times) / sum(times), torch.get_num_threads(), len(times)
+
+
+def cpu_forward_latency_ms(threads):
+    """configs[0]: features + network + mask + iSTFT of ONE 4-s clip on the CPU (oracle, eval mode)."""
+    import torch
+    from oracle import tru_oracle as O
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    net = O.randomize_bn(O.TRUNet()).eval()
+    _, noisy = synthetic_batch(1, CLIP_SAMPLES)
+    ts = []
+    with torch.no_grad():
+        for it in range(4):
+            t0 = time.perf_counter()
+            O.backend(net(O.frontend(noisy)))
+            ts.append(1000.0 * (time.perf_counter() - t0))
+    return round(statistics.median(ts[1:]), 2)
 
 
 def run_reference(args):
+    """--impl reference: rank 0 alone times the oracle on every host core, at the native arm's batch size and config."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 5))
-    warm = max(1, min(args.warmup, 2))
-    v, cores = cpu_training_clips_per_sec(args.cpu_batch, steps, warm)
-    sample = "%d clips/step x %d steps of the tiny.json training step (fwd+bwd+AdamW), torch CPU, %d threads" % (
-        args.cpu_batch, steps, cores)
+    warm = 1 if args.warmup >= 1 else 0
+    v, cores, steps = cpu_training_clips_per_sec(args.batch, max(1, args.steps), warm, budget_s=args.cpu_seconds)
+    sample = ("%d clips/step x %d timed steps (+%d warm-up) of the same tiny.json training step, oracle port of the reference on torch "
+              "CPU, %d threads; steps cut from %d to fit %.0f s" % (args.batch, steps, warm, cores, args.steps, args.cpu_seconds))
     line = {"impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT, "n_gpus": args.gpus,
-            "steps": steps, "warmup": warm, "ms_per_step": round(1000.0 * args.cpu_batch / v, 2),
+            "steps": steps, "warmup": warm, "ms_per_step": round(1000.0 * args.batch / v, 2),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD % args.batch, "clips_per_gpu": args.batch, "global_batch": args.batch * args.gpus,
-                       "parallelism": "dp%d" % args.gpus, "device": "host CPU (rank 0 only)",
-                       "sample_clips_per_step": args.cpu_batch},
+            "config": config_of(args, args.gpus),
             "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": round(v, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def stock_gpu_numbers(dev, batch, steps=3, warmup=2):
+    """The oracle with .cuda(): stock PyTorch (cuDNN convs / GRUs, cuBLAS, cuFFT, ATen elementwise + a Python PCEN loop) on this
+    GPU, same batch, fp32 with TF32 off and on.  The bar of SURVEY section 8(d) / BASELINE.md."""
+    import torch
+    out = {}
+    for tf32 in (False, True):
+        step, stage_step = oracle_training_step(dev, batch, allow_tf32=tf32)
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        key = "tf32" if tf32 else "fp32"
+        out[key] = {"clips_per_sec": round(batch / (ms / 1000.0), 2), "ms_per_step": round(ms, 3), "stages_ms": stage_step()}
+        del step, stage_step
+        torch.cuda.empty_cache()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = True
+    out["what"] = ("oracle restatement of the reference with .cuda(): torch %s, cuDNN convs and GRUs, cuFFT, Python PCEN loop; "
+                   "%d clips/step, %d timed steps" % (torch.__version__, batch, steps))
+    return out
+
+
+def run_torch_gpu(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    s = stock_gpu_numbers(dev, args.batch, steps=max(1, min(args.steps, 10)), warmup=max(1, min(args.warmup, 3)))
+    v = s["fp32"]["clips_per_sec"]
+    line = {"impl": "torch-gpu", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": 1, "steps": max(1, min(args.steps, 10)),
+            "warmup": max(1, min(args.warmup, 3)), "ms_per_step": s["fp32"]["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_of(args, 1),
+            "stock_gpu": s}
     print(json.dumps(line), flush=True)
 
 
@@ -186,47 +304,141 @@ def measured_traffic(kernel):
     return None, None
 
 
-def measure_inference(args, dev, state_dict):
-    """BASELINE.json metric, second half: inference real-time factor.  configs[3]: S concurrent streams, one frame per
-    stream and step (front end step -> TRU-Net step with carried TGRU state -> mask + iSTFT step);  configs[4]: offline
-    batch denoising of 10-s clips (front end -> TRU-Net -> mask + iSTFT).  RTF = seconds of audio per second."""
+def device_ms(fn, n, warm, sync):
+    """Average milliseconds of fn() over n calls, CUDA events on the current stream, after `warm` untimed calls."""
     import torch
-    from tinyrecurrentunet_b200 import network, util
+    for _ in range(warm):
+        fn()
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    sync()
+    return e0.elapsed_time(e1) / n
+
+
+def measure_inference(args, dev, state_dict, world, rank, dist):
+    """BASELINE.json metric, second half: inference real-time factor (seconds of audio per second).
+    configs[3]  S concurrent streams, one frame per stream and step (front-end step -> TRU-Net step with carried TGRU state ->
+                mask + iSTFT step); e2e: the step's frames come from pinned host memory and its audio goes back, every step.
+    configs[4]  offline batch denoising of 10-s clips, `--offline-clips` per GPU (1,250 = 10,000 / 8), host buffers in and out
+                (util.denoise_host_batches); clips are independent: replicas, no collective; aggregate = sum over ranks / max time.
+    configs[0]  ONE 4-s clip, host buffer in, host buffer out, synchronous: latency."""
+    import torch
+    from tinyrecurrentunet_b200 import _lib as L, network, util
+    peak, _ = measured_peaks()
     net = network.TRUNet().to(dev)
     net.load_state_dict(state_dict)
     net.eval()
-
-    def timed(fn, n, warm=3):
-        for _ in range(warm):
-            fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(n):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / n
-
+    sync = torch.cuda.synchronize
     out = {}
-    S = args.streams
-    g = torch.Generator(device="cpu").manual_seed(7)
-    frames = (0.1 * torch.randn(S, 512, generator=g)).to(dev)
-    sd = util.StreamingDenoiser(net, S, device=dev)
-    ms = timed(lambda: sd.step(frames), 30)
-    out["stream"] = {"streams": S, "ms_per_step": round(ms, 4), "audio_ms_per_step": 8.0,
-                     "rtf": round(S * 0.008 / (ms / 1000.0), 1),
-                     "workload": "configs[3]: %d concurrent streams, 1 frame (hop 128 @16 kHz) per stream and step, "
-                                 "PCEN / TGRU / overlap-add state carried" % S}
-    del sd
-    Bo, No = 32, 160000
-    audio = (0.1 * torch.randn(Bo, No, generator=g)).to(dev)
+    g = torch.Generator(device="cpu").manual_seed(7 + rank)
+    if rank == 0:
+        # ---- configs[3] ------------------------------------------------------------------------------------------
+        S = args.streams
+        frames_h = (0.1 * torch.randn(S, 512, generator=g)).pin_memory()
+        audio_h = torch.empty(S, 128).pin_memory()
+        frames_d = frames_h.to(dev)
+        sd = util.StreamingDenoiser(net, S, device=dev)
+        ms = device_ms(lambda: sd.step(frames_d), 30, 5, sync)
+
+        def e2e_stream():
+            audio_h.copy_(sd.step(frames_h.to(dev, non_blocking=True)), non_blocking=True)
+        ms_e = device_ms(e2e_stream, 30, 3, sync)
+        L.profile_enable(True)
+        for _ in range(5):
+            sd.step(frames_d)
+        prof = L.profile_report()
+        L.profile_enable(False)
+        fam = {}
+        for k, v in prof.items():
+            a = fam.setdefault(k.split(":")[0], [0.0, 0])
+            a[0] += v["ms"] / 5
+            a[1] += v["launches"] // 5
+        alg = MODEL_BYTES_PER_FRAME * S + 2 * (S * 16 * 128 * 4) + 2 * (S * 257 * 4) + S * 512 * 4 + S * 128 * 4 + 2 * S * 384 * 4
+        out["stream"] = {"streams": S, "ms_per_step": round(ms, 4), "audio_ms_per_step": 8.0,
+                         "rtf": round(S * 0.008 / (ms / 1000.0), 1),
+                         "e2e": {"ms_per_step": round(ms_e, 4), "rtf": round(S * 0.008 / (ms_e / 1000.0), 1),
+                                 "h2d_bytes_per_step": S * 512 * 4, "d2h_bytes_per_step": S * 128 * 4},
+                         "roofline": {"bound": "hbm", "algorithmic_bytes_per_step": alg, "achieved": round(alg / ms / 1e6, 1),
+                                      "peak": peak, "unit": "GB/s", "frac": round(alg / ms / 1e6 / peak, 4)},
+                         "kernels_ms": {k: [round(v[0], 4), v[1]] for k, v in sorted(fam.items(), key=lambda kv: -kv[1][0])},
+                         "workload": "configs[3]: %d concurrent streams, 1 frame (hop 128 @16 kHz) per stream and step, "
+                                     "PCEN / TGRU / overlap-add state carried" % S}
+        del sd
+        # ---- configs[0] ------------------------------------------------------------------------------------------
+        one_h = synthetic_batch(1, CLIP_SAMPLES)[1].pin_memory()
+        res_h = torch.empty(1, CLIP_SAMPLES).pin_memory()
+        lat = []
+        with torch.no_grad():
+            for it in range(25):
+                sync()
+                t0 = time.perf_counter()
+                res_h.copy_(util.denoise(net, one_h.to(dev, non_blocking=True))[0], non_blocking=True)
+                sync()
+                lat.append(1000.0 * (time.perf_counter() - t0))
+        sd1 = util.StreamingDenoiser(net, 1, device=dev)
+        fr1 = torch.zeros(1, 512, device=dev)
+        lat1 = []
+        for it in range(60):
+            sync()
+            t0 = time.perf_counter()
+            sd1.step(fr1)
+            sync()
+            lat1.append(1000.0 * (time.perf_counter() - t0))
+        out["latency"] = {"workload": "configs[0]: one 4-s clip, batch 1: features + network + mask + iSTFT, host buffer in and out, "
+                                      "synchronous (wall clock, median of 20)",
+                          "gpu_ms": round(statistics.median(lat[5:]), 3), "gpu_rtf": round(4000.0 / statistics.median(lat[5:]), 1),
+                          "gpu_single_frame_step_ms": round(statistics.median(lat1[10:]), 3),
+                          "single_frame_note": "rt.py:20-27: one stream, one frame per call, state carried; hop = 8 ms of audio"}
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            out["latency"]["cpu_ms"] = cpu_forward_latency_ms(cores)
+            out["latency"]["cpu_threads"] = cores
+            out["latency"]["cpu_1thread_ms"] = cpu_forward_latency_ms(1)
+    # ---- configs[4] (every rank) ---------------------------------------------------------------------------------
+    Bo = 25
+    nclips = max(Bo, args.offline_clips // Bo * Bo)
+    pool = [(0.1 * torch.randn(Bo, LONG_SAMPLES, generator=g)).pin_memory() for _ in range(2)]   # 50 distinct clips, cycled
+
+    def host_batches(n):
+        for i in range(n):
+            yield pool[i & 1]
+    for _ in util.denoise_host_batches(net, host_batches(2), dev):      # warm-up (allocations, pinned staging)
+        pass
+    if world > 1:
+        dist.barrier()
+    sync()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    checksum = 0.0
+    for host_audio in util.denoise_host_batches(net, host_batches(nclips // Bo), dev):
+        checksum += float(host_audio[0, 1000])                         # the consumer touches every result
+    e1.record()
+    sync()
+    ms_off = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms_off, op=dist.ReduceOp.MAX)
+    ms_off = ms_off.item()
     with torch.no_grad():
-        ms = timed(lambda: util.denoise(net, audio)[0], 3, warm=1)
-    out["offline"] = {"clips": Bo, "clip_seconds": 10.0, "ms_per_batch": round(ms, 3),
-                      "rtf": round(Bo * 10.0 / (ms / 1000.0), 1),
-                      "workload": "configs[4] shard: %d x 10-s clips per call on one GPU (clips are independent: replicas, "
-                                  "no collective)" % Bo}
+        dev_ms = device_ms(lambda: util.denoise(net, pool[0].to(dev))[0], 3, 1, sync)     # device-side time of one batch (incl. its H2D)
+    if rank == 0:
+        frames = 1 + LONG_SAMPLES // 128
+        alg = Bo * (MODEL_BYTES_PER_FRAME * frames + 4 * LONG_SAMPLES + 16 * 257 * frames + 8 * 257 * 4 * frames + 4 * LONG_SAMPLES)
+        out["offline"] = {"clips_per_gpu": nclips, "gpus": world, "clip_seconds": 10.0, "batch": Bo,
+                          "seconds": round(ms_off / 1000.0, 4),
+                          "rtf": round(world * nclips * 10.0 / (ms_off / 1000.0), 1),
+                          "rtf_per_gpu": round(nclips * 10.0 / (ms_off / 1000.0), 1),
+                          "h2d_bytes_per_batch": Bo * LONG_SAMPLES * 4, "d2h_bytes_per_batch": Bo * LONG_SAMPLES * 4,
+                          "ms_per_batch_device": round(dev_ms, 3),
+                          "roofline": {"bound": "hbm", "algorithmic_bytes_per_batch": alg, "achieved": round(alg / dev_ms / 1e6, 1),
+                                       "peak": peak, "unit": "GB/s", "frac": round(alg / dev_ms / 1e6 / peak, 4)},
+                          "workload": "configs[4]: %d x 10-s clips per GPU on %d GPU(s) in batches of %d, pinned host buffers in and "
+                                      "out every batch (util.denoise_host_batches), 50 distinct clips cycled; no collective"
+                                      % (nclips, world, Bo)}
     return out
 
 
@@ -262,8 +474,6 @@ def run_native(args):
     from tinyrecurrentunet_b200 import _lib as L, network, optim, stft_loss, util
     from tinyrecurrentunet_b200 import distributed as tdist
 
-    if os.environ.get("TRU_LOADER_WARPS"):                 # tuning aid (8 or 16 loader warps in the GEMM kernels)
-        L.lib.tru_debug_set_loader_warps(int(os.environ["TRU_LOADER_WARPS"]))
     if os.environ.get("TRU_DBG_FLAGS"):                    # bottleneck hunting: disable parts of the GEMM kernel (results are garbage)
         L.lib.tru_debug_set_flags(int(os.environ["TRU_DBG_FLAGS"]))
     B = args.batch
@@ -279,21 +489,19 @@ def run_native(args):
     sched = util.LinearWarmupCosineDecay(opt, lr_max=4e-4, n_iter=25_000_000, iteration=0, divider=25,
                                          warmup_proportion=0.05)          # train.py:98-104 (tiny.json: 25M iterations)
 
-    # synthetic clips: a pool of distinct clips, rank-dependent, tiled to the batch
-    pool = min(B, 8)
-    clean_h, noisy_h = synthetic_batch(pool, CLIP_SAMPLES, first=rank * pool)
-    reps = (B + pool - 1) // pool
-    clean_h = clean_h.repeat(reps, 1)[:B].contiguous().pin_memory()
-    noisy_h = noisy_h.repeat(reps, 1)[:B].contiguous().pin_memory()
-    clean_d = clean_h.to(dev)
-    noisy_d = noisy_h.to(dev)
+    # synthetic clips: B distinct clips per rank
+    clean_h, noisy_h = synthetic_batch(B, CLIP_SAMPLES, first=rank * B)
+    clean_h, noisy_h = clean_h.pin_memory(), noisy_h.pin_memory()
+    clean_d, noisy_d = clean_h.to(dev), noisy_h.to(dev)
 
     def step(clean, noisy):
         opt.zero_grad(set_to_none=True)
         loss, _ = util.loss_fn(net, (clean, noisy), ell_p=1, ell_p_lambda=1, stft_lambda=1, mrstftloss=mr)
-        loss.backward()                  # N>1: the all-reduce fires from the engine callback
-        sched.step()                     # train.py:139 (host float, no sync)
-        opt.step()                       # train.py:138 + :140
+        if world > 1:
+            tdist.attach_loss(net, loss)     # train.py:133's logging mean rides in the gradient bucket (net.reduced_loss)
+        loss.backward()                      # N>1: the all-reduce fires from the engine callback
+        sched.step()                         # train.py:139 (host float, no sync)
+        opt.step()                           # train.py:138 + :140
         return loss
 
     def sync_all():
@@ -315,8 +523,19 @@ def run_native(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
-    for _ in range(max(args.warmup, 3)):
+    dp_check = None
+    for it in range(max(args.warmup, 3)):
         step(clean_d, noisy_d)
+        if it == 0 and world > 1:
+            # after the all-reduce every rank must hold the same (mean) gradients, bit for bit, and the same mean loss
+            flat = net._tru_flat_grad
+            hi, lo = flat.clone(), flat.clone()
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            same = bool(torch.equal(hi, lo)) and bool(torch.isfinite(flat).all())
+            if not same:
+                raise RuntimeError("data-parallel check failed: gradients differ across ranks after the all-reduce")
+            dp_check = {"gradients_identical_across_ranks": True, "mean_loss_in_bucket_tail": float(net.reduced_loss.item())}
     sync_all()
 
     # ---- (1) device-resident throughput -------------------------------------------
@@ -332,15 +551,18 @@ def run_native(args):
     # ---- (2) end to end: pinned host buffers in, loss read back, every step ----------
     e2e = None
     if not args.no_e2e:
-        pre = util.CudaPrefetcher(dev)      # H2D of the next batch on a side stream while the current step runs
+        def host_batches(n):
+            for _ in range(n):
+                yield clean_h, noisy_h
 
-        def e2e_step():
-            bufs = pre.next(clean_h, noisy_h)          # every step: pinned host buffers -> device (this step's inputs)
-            loss = step(bufs[0], bufs[1])
-            pre.release(bufs)
-            return loss.item()                         # every step: loss read back
-        e2e_step()
-        ms_e = timed(args.steps, e2e_step)
+        def e2e_epoch():
+            # every step: this step's inputs travel pinned host -> device (one batch ahead, on a side stream) and the loss
+            # comes back to the host
+            for clean, noisy in util.CudaPrefetcher(host_batches(args.steps), dev):
+                step(clean, noisy).item()
+        for clean, noisy in util.CudaPrefetcher(host_batches(1), dev):
+            step(clean, noisy).item()
+        ms_e = timed(1, e2e_epoch)
         e2e = {"value": round(world * B * args.steps / (ms_e / 1000.0), 2), "unit": UNIT,
                "h2d_bytes_per_step": 2 * B * CLIP_SAMPLES * 4 * world, "d2h_bytes_per_step": 4 * world}
 
@@ -355,7 +577,7 @@ def run_native(args):
         for f in a:
             a[f] += v[f]
     if os.environ.get("TRU_BENCH_DETAIL") and rank == 0:
-        for k, v in sorted(prof_detail.items(), key=lambda kv: -kv[1]["ms"])[:60]:
+        for k, v in sorted(prof_detail.items(), key=lambda kv: -kv[1]["ms"])[:80]:
             print("# %-60s n=%5.1f %8.3f ms/step %7.1f GB/s %7.1f TF" % (
                 k, v["launches"] / args.steps, v["ms"] / args.steps, v["bytes"] / max(v["ms"], 1e-9) / 1e6,
                 v["flops"] / max(v["ms"], 1e-9) / 1e9), file=sys.stderr)
@@ -371,7 +593,11 @@ def run_native(args):
                 "avg_launch_ms": round(t["ms"] / t["launches"], 4),
                 "share_of_kernel_time": round(t["ms"] / total_kernel_ms, 4),
                 "tflops_fp32": round(t["flops"] / (t["ms"] / 1000.0) / 1e12, 2),
-                "ms_per_step_profiled": round(ms_p / args.steps, 3)}
+                "ms_per_step_profiled": round(ms_p / args.steps, 3),
+                # the whole step against SURVEY section 8(d)'s algorithmic bytes (3 x forward block-boundary traffic)
+                "whole_step": {"algorithmic_bytes": STEP_BYTES_B32 * B // 32, "achieved": round(STEP_BYTES_B32 * B / 32 / (ms / args.steps) / 1e6, 1),
+                               "frac": round(STEP_BYTES_B32 * B / 32 / (ms / args.steps) / 1e6 / peak, 4),
+                               "bytes_moved_by_kernels": round(sum(v["bytes"] for v in prof.values()) / args.steps, 0)}}
     traffic, tsrc = measured_traffic(tname)
     if traffic is not None:
         roofline["traffic"] = traffic
@@ -381,32 +607,57 @@ def run_native(args):
                    "TFLOPs": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 2)}
                for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
 
-    # ---- (4) CPU baseline on this box's host cores (rank 0, N = 1 only) ---------------
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores = cpu_training_clips_per_sec(args.cpu_batch, 3, 1)
-        cpu = {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "%d clips/step x 3 steps of the same training step (oracle, torch CPU)" % args.cpu_batch}
-
-    # ---- (5) inference real-time factors (rank 0, N = 1 only) ----------------------------
-    inference = None
-    if rank == 0 and world == 1 and not args.no_inference:
-        state = {k: v.detach().clone() for k, v in net.state_dict().items()}
-        opt = None
-        net = None
+    # ---- (4) strong-scaling point of configs[2]: global batch 256 over the N ranks ---------
+    strong = None
+    if world > 1 and not args.no_strong and 256 % world == 0:
+        per = 256 // world
+        try:
+            torch.cuda.empty_cache()
+            reps = (per + B - 1) // B
+            cs, ns = clean_d.repeat(reps, 1)[:per].contiguous(), noisy_d.repeat(reps, 1)[:per].contiguous()
+            step(cs, ns)
+            ms_s = timed(3, lambda: step(cs, ns))
+            strong = {"global_batch": 256, "clips_per_gpu": per, "steps": 3, "ms_per_step": round(ms_s / 3, 3),
+                      "value": round(256 * 3 / (ms_s / 1000.0), 2), "unit": UNIT,
+                      "note": "configs[2] as BASELINE.json states it (config/tiny.json:24 x 256): the %d distinct clips of this rank "
+                              "tiled to %d" % (B, per)}
+            del cs, ns
+        except Exception as e:          # e.g. out of memory at N = 2 on a smaller part: report, do not lose the main line
+            strong = {"global_batch": 256, "clips_per_gpu": per, "error": str(e)[:200]}
         torch.cuda.empty_cache()
-        inference = measure_inference(args, dev, state)
+
+    # ---- (5) baselines on this box (rank 0, N = 1 only): host CPU, stock PyTorch on this GPU ---------------
+    cpu = None
+    stock = None
+    state = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    opt = None
+    net = None
+    torch.cuda.empty_cache()
+    if rank == 0 and world == 1 and not args.no_stock_gpu:
+        stock = stock_gpu_numbers(dev, B)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cores, n = cpu_training_clips_per_sec(B, 1, 1, budget_s=60.0)
+        v1, _, _ = cpu_training_clips_per_sec(2, 1, 0, threads=1, budget_s=30.0)
+        torch.set_num_threads(os.cpu_count() or 1)
+        cpu = {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "%d clips/step x %d timed step (+1 warm-up) of the same training step (oracle port, torch CPU, %d threads)" % (B, n, cores),
+               "value_1thread": round(v1, 4), "sample_1thread": "2 clips x 1 step, 1 thread"}
+
+    # ---- (6) inference real-time factors ----------------------------------------------------------------------
+    inference = None
+    if not args.no_inference:
+        inference = measure_inference(args, dev, state, world, rank, dist)
 
     if rank == 0:
+        cfg = config_of(args, world)
         line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD % B,
-                           "clips_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world,
-                           "optimizer": "FlatAdamW (tru_flat_adamw_step)" if args.optimizer == "flat" else "torch.optim.AdamW(fused)",
-                           "l2": "no explicit flush: one step streams >10 GB of activations through the 126 MB L2"},
+                "config": cfg,
+                "optimizer": "FlatAdamW (tru_flat_adamw_step)" if args.optimizer == "flat" else "torch.optim.AdamW(fused)",
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-                "cpu_baseline": cpu, "inference": inference, "kernels": kernels}
+                "cpu_baseline": cpu, "stock_gpu": stock, "strong_scaling": strong, "dp_check": dp_check,
+                "inference": inference, "kernels": kernels}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -416,6 +667,8 @@ def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "torch-gpu":
+        run_torch_gpu(args)
     else:
         run_native(args)
 

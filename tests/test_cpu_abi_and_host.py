@@ -29,6 +29,16 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), "missing export: %s" % name
     lib.tru_abi_version.restype = ctypes.c_int
     assert lib.tru_abi_version() == 1
+    # the test / tuning entry points are declared too (include/tru_b200_debug.h), and nothing is exported undeclared
+    dbg = open(os.path.join(ROOT, "include", "tru_b200_debug.h")).read()
+    dbg = re.sub(r"/\*.*?\*/", "", dbg, flags=re.S)
+    declared_dbg = set(re.findall(r"\b(tru_[a-z0-9_]+)\s*\(", dbg))
+    for name in sorted(declared_dbg):
+        assert hasattr(lib, name), "missing export: %s" % name
+    import subprocess
+    syms = subprocess.run(["nm", "-D", "--defined-only", lib_path], capture_output=True, text=True).stdout
+    exported = {ln.split()[-1] for ln in syms.splitlines() if ln.split() and ln.split()[-1].startswith("tru_")}
+    assert exported == declared | declared_dbg, (exported ^ (declared | declared_dbg))
 
 
 def test_binding_table_matches_header():

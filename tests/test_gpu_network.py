@@ -327,20 +327,22 @@ def test_bn_folded_export_runs_on_the_cuda_path():
     assert rel(y2, y) <= 1e-5 and rel(y2, y_ref) <= OUT_TOL
 
 
-def test_cuda_prefetcher_delivers_batches_in_order():
-    """util.CudaPrefetcher (used by bench.py's end-to-end timing): call i returns the batch passed in call i-1 (the first
-    call its own batch), copied on a side stream; a consumer on the current stream always sees complete data."""
+def test_cuda_prefetcher_delivers_every_batch_once_in_order():
+    """util.CudaPrefetcher (used by bench.py's end-to-end timing): an iterator over host batches that yields every batch
+    exactly once, in order, copied on a side stream one batch ahead; a consumer on the current stream always sees complete
+    data, also when a batch has another shape (ragged last batch) and its buffer is re-allocated."""
     from tinyrecurrentunet_b200 import util
-    pre = util.CudaPrefetcher("cuda")
     hosts = [(torch.full((4, 1000), float(i)).pin_memory(), torch.full((4, 1000), float(-i)).pin_memory()) for i in range(6)]
+    hosts.append((torch.full((3, 700), 6.0).pin_memory(), torch.full((3, 700), -6.0).pin_memory()))     # ragged tail
     seen = []
-    for i, (c, n) in enumerate(hosts):
-        bufs = pre.next(c, n)
-        seen.append((bufs[0].sum().item() / 4000.0, bufs[1].sum().item() / 4000.0))      # consumer work on the current stream
-        pre.release(bufs)
-    assert seen[0] == (0.0, 0.0)
-    for i in range(1, 6):
-        assert seen[i] == (float(i - 1), float(-(i - 1))), (i, seen[i])
+    for clean, noisy in util.CudaPrefetcher(hosts, "cuda"):
+        big = torch.randn(2048, 2048, device="cuda") @ torch.randn(2048, 2048, device="cuda")   # keep the stream busy
+        seen.append((clean.mean().item(), noisy.mean().item(), tuple(clean.shape)))
+        del big
+    assert [s[0] for s in seen] == [float(i) for i in range(7)]
+    assert [s[1] for s in seen] == [float(-i) for i in range(7)]
+    assert seen[-1][2] == (3, 700)
+    assert list(util.CudaPrefetcher([], "cuda")) == []
 
 
 def test_loss_fn_end_to_end_matches_oracle():

@@ -138,12 +138,37 @@ def ptr(t):
     return t.data_ptr()
 
 
-def stream_ptr():
+def stream_ptr(device=None):
+    """The current torch stream of ``device`` (default: the current device).  Callers wrap the C call in
+    ``torch.cuda.device(device)`` so that the library's own cudaGetDevice-based state matches."""
     import torch
-    return torch.cuda.current_stream().cuda_stream
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def run(name, device, *args):
+    """One C-ABI call on ``device``: that device is made current for the call (the library keeps per-device state keyed
+    by cudaGetDevice), the work goes onto torch's current stream of that device, a non-zero status raises."""
+    import torch
+    with torch.cuda.device(device):
+        check(getattr(lib, name)(*args, torch.cuda.current_stream(device).cuda_stream), name)
+
+
+def same_device(*tensors):
+    """All given CUDA tensors live on one device: returns it."""
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise TruError("tensors on different devices: %s vs %s" % (dev, t.device))
+    return dev
 
 
 def require_cuda(*tensors):
+    """Every given tensor is a CUDA tensor and all of them are on one device."""
     for t in tensors:
         if t is not None and not t.is_cuda:
             raise TruError("tinyrecurrentunet_b200 ops need CUDA tensors (sm_100a); there is no CPU path")
+    same_device(*tensors)

@@ -17,7 +17,7 @@ class _CosSimFn(torch.autograd.Function):
     def forward(ctx, x, y, desc):
         stats = torch.empty((x.shape[0], desc.n_seg, 3), device=x.device, dtype=torch.float64)
         loss = torch.empty((), device=x.device, dtype=torch.float32)
-        L.check(L.lib.tru_cossim_fwd(C.byref(desc), L.ptr(x), L.ptr(y), L.ptr(stats), L.ptr(loss), L.stream_ptr()), "tru_cossim_fwd")
+        L.run("tru_cossim_fwd", x.device, C.byref(desc), L.ptr(x), L.ptr(y), L.ptr(stats), L.ptr(loss))
         ctx.desc = desc
         ctx.save_for_backward(x, y, stats)
         return loss
@@ -27,8 +27,7 @@ class _CosSimFn(torch.autograd.Function):
         x, y, stats = ctx.saved_tensors
         gx = torch.empty_like(x)
         gl = grad_loss.contiguous().float()
-        L.check(L.lib.tru_cossim_bwd(C.byref(ctx.desc), L.ptr(x), L.ptr(y), L.ptr(stats), L.ptr(gl), L.ptr(gx), L.stream_ptr()),
-                "tru_cossim_bwd")
+        L.run("tru_cossim_bwd", x.device, C.byref(ctx.desc), L.ptr(x), L.ptr(y), L.ptr(stats), L.ptr(gl), L.ptr(gx))
         return gx, None, None
 
 

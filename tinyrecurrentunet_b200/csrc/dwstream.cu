@@ -259,16 +259,14 @@ __global__ void __launch_bounds__(NT, 1) dw_bwd_stream_kernel(const __grid_const
 
 template <int K, int S>
 int launch_fwd_t(DwK& Kp, int grid, size_t smem, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) { TRU_CUDA(cudaFuncSetAttribute(dw_fwd_stream_kernel<K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX)); attr = true; }
+  TRU_SMEM_OPT_IN((dw_fwd_stream_kernel<K, S>), SMEM_MAX);
   TRU_CUDA(launch_pdl(dw_fwd_stream_kernel<K, S>, dim3(grid), dim3(NT), smem, st, Kp));
   TRU_LAUNCH_CHECK();
   return TRU_OK;
 }
 template <int K, int S>
 int launch_bwd_t(DwK& Kp, int grid, size_t smem, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) { TRU_CUDA(cudaFuncSetAttribute(dw_bwd_stream_kernel<K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX)); attr = true; }
+  TRU_SMEM_OPT_IN((dw_bwd_stream_kernel<K, S>), SMEM_MAX);
   TRU_CUDA(launch_pdl(dw_bwd_stream_kernel<K, S>, dim3(grid), dim3(NT), smem, st, Kp));
   TRU_LAUNCH_CHECK();
   return TRU_OK;

@@ -217,11 +217,7 @@ extern "C" int tru_frontend_fwd(const TruFrontendDesc* d, const float* audio, co
   p.counter = p.flags + (size_t)p.B * p.nchunks;
   cudaStream_t st = (cudaStream_t)stream;
   TRU_CUDA(cudaMemsetAsync(p.flags, 0, (size_t)p.B * p.nchunks * 4 + 4, st));
-  static bool attr_set = false;
-  if (!attr_set) {
-    TRU_CUDA(cudaFuncSetAttribute(frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FRONT_SMEM));
-    attr_set = true;
-  }
+  TRU_SMEM_OPT_IN(frontend_kernel, FRONT_SMEM);
   ProfScope prof("frontend", 4.0 * p.B * ((double)p.N + 4.0 * NB * p.T), 0.5 * p.B * p.T * 5.0 * NFFT * 9, st);
   frontend_kernel<<<p.B * p.nchunks, NT, FRONT_SMEM, st>>>(p);
   TRU_LAUNCH_CHECK();

@@ -436,11 +436,7 @@ int launch_igemm_simt(const IgemmParams& p, cudaStream_t st) {
   const int ktot_pad = ktot + BK;
   const size_t smem = ((size_t)ktot_pad * WS_LD + (size_t)BK * AS_LD) * sizeof(float);
   TRU_REQUIRE(smem <= 200 * 1024, TRU_ERR_ARG, "igemm: K too large (%d)", ktot);
-  static size_t max_set = 0;
-  if (smem > max_set) {
-    TRU_CUDA(cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    max_set = smem;
-  }
+  TRU_SMEM_OPT_IN(igemm_kernel, 200 * 1024);
   const long M = (long)p.BT * p.Lq;
   const int ntiles = (int)((M + BM - 1) / BM);
   const int per_sm = smem > 100 * 1024 ? 1 : 2;
@@ -463,52 +459,24 @@ static void wgrad_cost(const WgradParams& p, double& bytes, double& flops) {
   }
 }
 
+// Weight gradients of the shapes the streaming tensor-core kernel (tcwgrad2.cu) does not take: tiny products on the
+// small-shape kernel, bias-only jobs as column sums, everything else on the FFMA kernel.
 int launch_wgrad(const WgradParams& p, cudaStream_t st) {
-  if (!tc_enabled()) return launch_wgrad_simt(p, st);
-  WgradParams tcp{}, rest{};
-  tcp.BT = rest.BT = p.BT; tcp.Lq = rest.Lq = p.Lq;
-  WgradParams small{};
-  small.BT = p.BT; small.Lq = p.Lq;
+  WgradParams small{}, left{};
+  small.BT = left.BT = p.BT; small.Lq = left.Lq = p.Lq;
   for (int j = 0; j < p.njobs; ++j) {
-    if (small_wgrad_job(p.job[j])) small.job[small.njobs++] = p.job[j];
-    else if (p.job[j].a_src) tcp.job[tcp.njobs++] = p.job[j];
-    else rest.job[rest.njobs++] = p.job[j];
+    const WgradJob& J = p.job[j];
+    if (tc_enabled() && small_wgrad_job(J)) { small.job[small.njobs++] = J; continue; }
+    if (!J.a_src && J.db && J.z_mul == 1 && J.z_add == 0 && J.z_L == p.Lq) {
+      const int rc = launch_colsum(J.z_src, J.z_src2, J.z_p0, J.z_p1, J.z_p2, J.db, (long)p.BT * p.Lq, J.z_ld, J.z_coff, J.N, st);
+      if (rc) return rc;
+      continue;
+    }
+    left.job[left.njobs++] = J;
   }
   if (small.njobs) {
     const int rc = launch_wgrad_small(small, st);
     if (rc) return rc;
-  }
-  if (tcp.njobs) {
-    double bytes = 0, flops = 0;
-    if (prof_enabled()) wgrad_cost(tcp, bytes, flops);
-    int rc;
-    {
-      const char* nm = "wgrad_tc";
-      if (prof_enabled()) {
-        static std::map<std::string, const char*> names;
-        char buf[128];
-        snprintf(buf, sizeof(buf), "wgrad_tc:M=%ld,jobs=%d,C=%d,N=%d%s", (long)p.BT * p.Lq, tcp.njobs, tcp.job[0].C, tcp.job[0].N,
-                 tcp.job[0].z_src2 ? ",bnload" : "");
-        auto it = names.find(buf);
-        if (it == names.end()) it = names.emplace(buf, strdup(buf)).first;
-        nm = it->second;
-      }
-      ProfScope prof(nm, bytes, flops, st);
-      rc = launch_wgrad_tc(tcp, st);
-    }
-    if (rc == 1) return launch_wgrad_simt(p, st);      // (records an empty wgrad_tc interval; harmless)
-    if (rc) return rc;
-  }
-  WgradParams left{};
-  left.BT = p.BT; left.Lq = p.Lq;
-  for (int j = 0; j < rest.njobs; ++j) {
-    const WgradJob& J = rest.job[j];
-    if (!J.a_src && J.db && J.z_mul == 1 && J.z_add == 0 && J.z_L == p.Lq) {
-      const int rc = launch_colsum(J.z_src, J.z_src2, J.z_p0, J.z_p1, J.z_p2, J.db, (long)p.BT * p.Lq, J.z_ld, J.z_coff, J.N, st);
-      if (rc) return rc;
-    } else {
-      left.job[left.njobs++] = J;
-    }
   }
   if (left.njobs) return launch_wgrad_simt(left, st);
   return TRU_OK;

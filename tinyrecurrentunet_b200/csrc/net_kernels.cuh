@@ -40,7 +40,6 @@ bool igemm_tc_eligible(const IgemmParams& p);
 int launch_igemm_tc(const IgemmParams& p, cudaStream_t st);    // 0 launched, 1 not eligible, <0 error
 int launch_igemm_simt(const IgemmParams& p, cudaStream_t st);
 void set_tc_enabled(bool on);
-void set_tc_loader_warps(int n);
 int read_mbar_debug(unsigned* out, int n);   // debug builds (-DTRU_MBAR_TIMEOUT): stuck mbarrier waits of the GEMM kernel
 void set_tc_debug_flags(int f);  // ablation switches (tuning aid)   // 8 or 16 (tuning aid)
 bool tc_enabled();
@@ -54,8 +53,7 @@ struct WgradJob {
   float* db;
 };
 struct WgradParams { WgradJob job[8]; int njobs; int BT, Lq; };
-int launch_wgrad(const WgradParams& p, cudaStream_t st);        // tensor-core path for eligible jobs, FFMA for the rest
-int launch_wgrad_tc(const WgradParams& p, cudaStream_t st);     // 0 launched, 1 not eligible
+int launch_wgrad(const WgradParams& p, cudaStream_t st);        // shapes the streaming kernel below does not take: small-shape / column-sum / FFMA kernels
 int launch_wgrad_simt(const WgradParams& p, cudaStream_t st);
 
 // Streaming weight gradient of a conv layer (tcwgrad2.cu): up to two activation sources (skip concat) or up

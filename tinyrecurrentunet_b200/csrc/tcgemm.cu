@@ -621,11 +621,7 @@ bool plan(const IgemmParams& p, TcLayout& L, dim3& grid, size_t& smem_bytes) {
 
 template <int LW, bool LD2, int EPI>
 int launch_inst(const IgemmParams& p, const TcLayout& L, dim3 grid, size_t smem, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    TRU_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<LW, LD2, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
-    attr_done = true;
-  }
+  TRU_SMEM_OPT_IN((tc_igemm_kernel<LW, LD2, EPI>), SMEM_MAX);
   TRU_CUDA(launch_pdl(tc_igemm_kernel<LW, LD2, EPI>, grid, dim3(32 * (4 + LW + EW)), smem, st, p, L));
   TRU_LAUNCH_CHECK();
   return TRU_OK;
@@ -681,7 +677,6 @@ int read_mbar_debug(unsigned* out, int n) {
   return 0;
 #endif
 }
-void set_tc_loader_warps(int) {}    // kept for the debug ABI; the kernel has one loader layout now
 
 bool igemm_tc_eligible(const IgemmParams& p) {
   if (!shape_ok(p)) return false;

@@ -443,11 +443,7 @@ constexpr size_t SMEM_MAX = 227 * 1024;
 
 template <int IA, int IZ, int NTAP>
 int launch_variant(const WgK& K, int grid, size_t smem, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
-    TRU_CUDA(cudaFuncSetAttribute(tc_wgrad_stream_kernel<IA, IZ, NTAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
-    attr = true;
-  }
+  TRU_SMEM_OPT_IN((tc_wgrad_stream_kernel<IA, IZ, NTAP>), SMEM_MAX);
   TRU_CUDA(launch_pdl(tc_wgrad_stream_kernel<IA, IZ, NTAP>, dim3(grid), dim3(NT), smem, st, K));
   TRU_LAUNCH_CHECK();
   return TRU_OK;

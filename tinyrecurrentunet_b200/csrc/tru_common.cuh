@@ -70,6 +70,19 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// Opt a kernel in to more than 48 KB of dynamic shared memory.  Function attributes are per device (context), so the
+// "already done" flag is kept per device index, like the library's init state.
+#define TRU_SMEM_OPT_IN(kernel, bytes)                                                                        \
+  do {                                                                                                        \
+    static bool done__[64] = {};                                                                              \
+    int dev__ = 0;                                                                                            \
+    cudaGetDevice(&dev__);                                                                                    \
+    if (dev__ < 0 || dev__ >= 64 || !done__[dev__]) {                                                         \
+      TRU_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));      \
+      if (dev__ >= 0 && dev__ < 64) done__[dev__] = true;                                                     \
+    }                                                                                                         \
+  } while (0)
+
 static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <string>
 #include "net_kernels.cuh"
+#include "../../include/tru_b200_debug.h"
 
 namespace tru {
 namespace {
@@ -707,13 +708,12 @@ extern "C" int tru_debug_pw_bwd(const float* dy, const float* z, const float* q0
   return rc == 1 ? set_error(TRU_ERR_ARG, "debug_pw_bwd: shape not eligible for the tensor-core path") : rc;
 }
 extern "C" int tru_set_tensor_cores(int on) { set_tc_enabled(on != 0); return TRU_OK; }
-extern "C" int tru_debug_set_loader_warps(int n) { set_tc_loader_warps(n); return TRU_OK; }
 extern "C" int tru_debug_read_mbar(unsigned* out, int n) { return read_mbar_debug(out, n); }
 extern "C" int tru_debug_set_flags(int f) { set_tc_debug_flags(f); return TRU_OK; }
 
-// Test aid: dW (N,C) += z^T a for a (M,C), z (M,N) through either weight-gradient path.
-extern "C" int tru_debug_wgrad(const float* a, const float* z, float* dw, float* db, int M, int C, int N, int use_tc,
-                               void* stream) {
+// Test aid: dW (N,C) += z^T a for a (M,C), z (M,N) through the FFMA weight-gradient kernel (the parity reference of the
+// streaming tensor-core kernel below).
+extern "C" int tru_debug_wgrad(const float* a, const float* z, float* dw, float* db, int M, int C, int N, void* stream) {
   int rc = ensure_init();
   if (rc) return rc;
   WgradParams w{};
@@ -722,10 +722,6 @@ extern "C" int tru_debug_wgrad(const float* a, const float* z, float* dw, float*
   J.z_src = z; J.z_L = 1; J.z_ld = N; J.z_mul = 1; J.N = N;
   J.dW = dw; J.wsc = 1; J.wsn = C; J.db = db;
   w.njobs = 1; w.BT = M; w.Lq = 1;
-  if (use_tc) {
-    rc = launch_wgrad_tc(w, (cudaStream_t)stream);
-    return rc == 1 ? set_error(TRU_ERR_ARG, "debug_wgrad: not eligible for the tensor-core path") : rc;
-  }
   return launch_wgrad_simt(w, (cudaStream_t)stream);
 }
 

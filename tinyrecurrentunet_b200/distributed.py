@@ -3,18 +3,22 @@
 
 Same contract as the reference: the module is returned unchanged (no wrapper
 class), state is broadcast from rank 0 once, and after every backward the gradients
-are summed over ranks and divided by the world size, triggered by the reference's
-own mechanism (per-parameter hook -> engine callback -> one reduction).
+are averaged over the ranks, triggered by the reference's own mechanism
+(per-parameter hook -> engine callback -> one reduction).
 
 What is different is the data path.  TRUNet's backward (network._TRUNetFn) writes
-all 108 gradients into ONE flat fp32 buffer (1,525,888 B) and hands autograd views
-of it, so the reduction is a single in-place NCCL all-reduce of that buffer on the
-backward stream: no flatten (torch.cat), no 108 copy-backs, one collective launch.
-Modules whose grads are not views of one buffer take the reference path
-(flatten -> all_reduce -> copy back)."""
+all 108 gradients into ONE flat fp32 buffer (1,525,888 B + a 16-byte tail) and hands
+autograd views of it, so the reduction is a single in-place all-reduce of that buffer
+on the backward stream: no flatten (torch.cat), no 108 copy-backs, no separate divide
+kernel (NCCL: ReduceOp.AVG, exact for power-of-two world sizes), and the logging scalar
+of train.py:133 rides in the buffer's tail (``attach_loss``) instead of costing a second
+collective and a host sync.  A module whose gradients are not views of one densely
+packed buffer raises: this package has no second data path to fall back to."""
 import torch
 import torch.distributed as dist
 from torch.autograd import Variable
+
+LOSS_TAIL = 4           # floats appended to TRUNet's flat gradient buffer (network._TRUNetFn.backward): [loss, 0, 0, 0]
 
 
 def reduce_tensor(tensor, num_gpus):
@@ -35,21 +39,6 @@ def init_distributed(rank, num_gpus, group_name, dist_backend, dist_url):
                             group_name=group_name)
 
 
-def _flatten_dense_tensors(tensors):
-    if len(tensors) == 1:
-        return tensors[0].contiguous().view(-1)
-    return torch.cat([t.contiguous().view(-1) for t in tensors], dim=0)
-
-
-def _unflatten_dense_tensors(flat, tensors):
-    outputs, offset = [], 0
-    for tensor in tensors:
-        numel = tensor.numel()
-        outputs.append(flat.narrow(0, offset, numel).view_as(tensor))
-        offset += numel
-    return tuple(outputs)
-
-
 def broadcast_state(module, src=0):
     """Initial weight sync (distributed.py:105-108: 177 broadcasts) as one broadcast
     per dtype of a flat buffer."""
@@ -58,47 +47,62 @@ def broadcast_state(module, src=0):
         if torch.is_tensor(t):
             by_dtype.setdefault(t.dtype, []).append(t)
     for ts in by_dtype.values():
-        flat = _flatten_dense_tensors([t.data for t in ts])
+        flat = torch.cat([t.data.contiguous().view(-1) for t in ts], dim=0)
         dist.broadcast(flat, src)
-        for t, s in zip(ts, _unflatten_dense_tensors(flat, ts)):
-            t.data.copy_(s)
+        offset = 0
+        for t in ts:
+            t.data.copy_(flat.narrow(0, offset, t.numel()).view_as(t))
+            offset += t.numel()
 
 
 def _single_flat_buffer(grads):
-    """The flat tensor all grads are views of, in order and densely packed, else None."""
+    """The flat tensor all ``grads`` are views of - same storage, ascending, contiguous, at most 3 elements (the 16-byte
+    alignment padding) between neighbours - from the first gradient's offset to the end of the last one.  None if the
+    gradients are not laid out like that."""
     st = grads[0].untyped_storage()
-    base = st.data_ptr()
-    end = base
+    base, es = st.data_ptr(), grads[0].element_size()
+    start = grads[0].data_ptr()
+    end = start
     for g in grads:
-        if g.untyped_storage().data_ptr() != base or not g.is_contiguous() or g.data_ptr() < end:
+        if g.untyped_storage().data_ptr() != base or not g.is_contiguous() or g.data_ptr() < end or g.data_ptr() - end > 3 * es:
             return None
-        end = g.data_ptr() + g.numel() * g.element_size()
-    n = (end - base) // grads[0].element_size()
-    return torch.empty(0, dtype=grads[0].dtype, device=grads[0].device).set_(st, 0, (n,))
+        end = g.data_ptr() + g.numel() * es
+    return torch.empty(0, dtype=grads[0].dtype, device=grads[0].device).set_(st, (start - base) // es, ((end - start) // es,))
+
+
+def attach_loss(module, loss):
+    """Piggy-back the logging scalar of train.py:133 on the gradient bucket: call before ``loss.backward()``; after the
+    backward ``module.reduced_loss`` is a 0-d device tensor holding the mean of ``loss`` over the ranks (no extra
+    collective, no host sync until the caller reads it)."""
+    module._tru_loss = loss.detach()
 
 
 def allreduce_gradients(module):
-    """One reduction of all gradients of `module` (mean over ranks).  Returns the number
-    of collective calls issued (1 on the flat-buffer path)."""
+    """One reduction of all gradients of ``module`` (mean over ranks).  Returns the number of collective calls (1)."""
     world = dist.get_world_size()
-    buckets = {}
-    for p in module.parameters():
-        if p.requires_grad and p.grad is not None:
-            buckets.setdefault(p.grad.dtype, []).append(p.grad.data)
-    calls = 0
-    for grads in buckets.values():
-        flat = _single_flat_buffer(grads)
-        if flat is not None:
-            dist.all_reduce(flat)
-            flat /= world
-        else:                                   # reference path, distributed.py:127-134
-            coalesced = _flatten_dense_tensors(grads)
-            dist.all_reduce(coalesced)
-            coalesced /= world
-            for buf, synced in zip(grads, _unflatten_dense_tensors(coalesced, grads)):
-                buf.copy_(synced)
-        calls += 1
-    return calls
+    grads = [p.grad.data for p in module.parameters() if p.requires_grad and p.grad is not None]
+    if not grads:
+        return 0
+    flat = _single_flat_buffer(grads)
+    if flat is None:
+        raise RuntimeError("allreduce_gradients: the gradients are not views of one flat buffer (TRUNet's backward produces "
+                           "them that way; gradient accumulation over several backwards is not supported)")
+    # TRUNet's backward leaves its whole buffer (gradients + LOSS_TAIL floats) on the module: reduce the tail with it
+    own = getattr(module, "_tru_flat_grad", None)
+    loss = getattr(module, "_tru_loss", None)
+    tail = None
+    if own is not None and own.data_ptr() == flat.data_ptr() and 0 <= own.numel() - flat.numel() - LOSS_TAIL < 4:   # (< 4: padding of the last slice)
+        flat, tail = own, own[-LOSS_TAIL:]
+        if loss is not None:
+            tail[0].copy_(loss)
+    avg = dist.get_backend() == "nccl" and world & (world - 1) == 0       # 1/world is exact: same bits as SUM then divide
+    dist.all_reduce(flat, op=dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM)
+    if not avg:
+        flat /= world
+    if tail is not None and loss is not None:
+        module.reduced_loss = tail[0]
+    module._tru_loss = None
+    return 1
 
 
 def apply_gradient_allreduce(module):

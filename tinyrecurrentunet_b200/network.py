@@ -5,8 +5,9 @@ The module tree, constructor signatures and state-dict keys are the reference's
 train.py / distributed.py work unchanged (parameters are ordinary nn.Parameter
 leaves; gradients are delivered by autograd so per-parameter hooks fire).
 TRUNet.forward does NOT call the sub-modules: the whole network is one C-ABI call
-(csrc/trunet.cu) forward and one backward.  The block classes keep a plain
-``forward`` only so that code which instantiates them on their own keeps working.
+(csrc/trunet.cu) forward and one backward.  The block classes exist for the module
+tree / checkpoint schema; called on their own they raise (there is no cuDNN path in
+this package: the fused kernels only exist for the whole network).
 
 Wiring follows the repair decisions D4/D10/D11 of SURVEY.md section 0.2 (the reference's
 own forward does not run: defects X1-X6).
@@ -15,9 +16,14 @@ import ctypes as C
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import _lib as L
+
+
+def _no_standalone(self, *a, **k):
+    raise L.TruError("%s: the block classes of tinyrecurrentunet_b200.network carry parameters for TRUNet's fused CUDA "
+                     "forward / backward; they have no stand-alone forward (no cuDNN fallback in this package). "
+                     "Call TRUNet(...)" % type(self).__name__)
 
 
 class StandardConv1d(nn.Module):                     # network.py:9-21
@@ -27,8 +33,7 @@ class StandardConv1d(nn.Module):                     # network.py:9-21
             nn.Conv1d(in_channels, out_channels, kernel_size, stride=stride, padding=stride // 2),
             nn.ReLU(inplace=True))
 
-    def forward(self, x):
-        return self.StandardConv1d(x)
+    forward = _no_standalone
 
 
 class DepthwiseSeparableConv1d(nn.Module):           # network.py:24-43
@@ -41,8 +46,7 @@ class DepthwiseSeparableConv1d(nn.Module):           # network.py:24-43
                       groups=out_channels),
             nn.BatchNorm1d(out_channels), nn.ReLU(inplace=True))
 
-    def forward(self, x):
-        return self.DepthwiseSeparableConv1d(x)
+    forward = _no_standalone
 
 
 class GRUBlock(nn.Module):                           # network.py:45-58
@@ -53,9 +57,7 @@ class GRUBlock(nn.Module):                           # network.py:45-58
             nn.Conv1d(hidden_size * (2 if bidirectional == True else 1), out_channels, kernel_size=1),
             nn.BatchNorm1d(out_channels), nn.ReLU(inplace=True))
 
-    def forward(self, x):
-        output, h = self.GRU(x)
-        return self.conv(output.transpose(1, 2))
+    forward = _no_standalone
 
 
 def _tr(in_channels, out_channels, kernel_size, stride, last):
@@ -66,18 +68,12 @@ def _tr(in_channels, out_channels, kernel_size, stride, last):
     return nn.Sequential(*mods)
 
 
-def _pad_cat(x1, x2):                                # network.py:95-98
-    diff = x2.size()[2] - x1.size()[2]
-    return torch.cat((F.pad(x1, [diff // 2, diff - diff // 2, 0, 0]), x2), 1)
-
-
 class FirstTrCNN(nn.Module):                         # network.py:60-76
     def __init__(self, in_channels, out_channels, kernel_size, stride):
         super().__init__()
         self.FirstTrCNN = _tr(in_channels, out_channels, kernel_size, stride, False)
 
-    def forward(self, x):
-        return self.FirstTrCNN(x)
+    forward = _no_standalone
 
 
 class TrCNN(nn.Module):                              # network.py:79-100
@@ -85,8 +81,7 @@ class TrCNN(nn.Module):                              # network.py:79-100
         super().__init__()
         self.TrCNN = _tr(in_channels, out_channels, kernel_size, stride, False)
 
-    def forward(self, x1, x2):
-        return self.TrCNN(_pad_cat(x1, x2))
+    forward = _no_standalone                         # (pad / crop + concat of network.py:95-98: row maps in csrc/trunet.cu)
 
 
 class LastTrCNN(nn.Module):                          # network.py:102-120
@@ -94,8 +89,7 @@ class LastTrCNN(nn.Module):                          # network.py:102-120
         super().__init__()
         self.LastTrCNN = _tr(in_channels, out_channels, kernel_size, stride, True)
 
-    def forward(self, x1, x2):
-        return self.LastTrCNN(_pad_cat(x1, x2))
+    forward = _no_standalone
 
 
 def _param_order():
@@ -133,23 +127,28 @@ BN_ORDER = _bn_order()
 assert len(PARAM_ORDER) == 108 and len(BN_ORDER) == 23
 
 
+LOSS_TAIL = 4           # floats behind the last gradient in the flat buffer (distributed.attach_loss)
+
+
 class _TRUNetFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, h0, net, want_state, need_bwd, *params):
         B, T = x.shape[0], x.shape[1]
         training = net.training
-        desc = L.TruNetDesc(B, T, int(training), 1e-5, 0.1)
-        ws_bytes = L.lib.tru_trunet_workspace_bytes(C.byref(desc), int(need_bwd))
-        ws = torch.empty(ws_bytes, device=x.device, dtype=torch.uint8)
-        out = torch.empty((B, T, 8, 257), device=x.device, dtype=torch.float32)
-        hl = torch.empty((B * 16, 128), device=x.device, dtype=torch.float32) if want_state else None
-        pp = (C.c_void_p * 108)(*[p.data_ptr() for p in params])
-        rm, rv, nb = net._bn_ptrs()
-        L.check(L.lib.tru_trunet_forward(C.byref(desc), pp, rm, rv, nb, L.ptr(x), L.ptr(h0), L.ptr(out), L.ptr(hl),
-                                         L.ptr(ws), ws_bytes, L.stream_ptr()), "tru_trunet_forward")
+        eps, momentum = net._bn_hyper()
+        desc = L.TruNetDesc(B, T, int(training), eps, momentum)
+        with torch.cuda.device(x.device):
+            ws_bytes = L.lib.tru_trunet_workspace_bytes(C.byref(desc), int(need_bwd))
+            ws = torch.empty(ws_bytes, device=x.device, dtype=torch.uint8)
+            out = torch.empty((B, T, 8, 257), device=x.device, dtype=torch.float32)
+            hl = torch.empty((B * 16, 128), device=x.device, dtype=torch.float32) if want_state else None
+            pp = (C.c_void_p * 108)(*[p.data_ptr() for p in params])
+            rm, rv, nb = net._bn_ptrs(x.device)
+            L.check(L.lib.tru_trunet_forward(C.byref(desc), pp, rm, rv, nb, L.ptr(x), L.ptr(h0), L.ptr(out), L.ptr(hl),
+                                             L.ptr(ws), ws_bytes, L.stream_ptr(x.device)), "tru_trunet_forward")
         if net._debug_keep_ws:                         # test aid (tests/test_gpu_network.py)
             net._last_ws, net._last_desc = ws, desc
-        ctx.desc, ctx.ws_bytes, ctx.need_bwd, ctx.has_h0 = desc, ws_bytes, need_bwd, h0 is not None
+        ctx.desc, ctx.ws_bytes, ctx.need_bwd, ctx.has_h0, ctx.net = desc, ws_bytes, need_bwd, h0 is not None, net
         ctx.shapes = [p.shape for p in params]
         ctx.save_for_backward(x, ws, *params)
         if want_state:
@@ -160,7 +159,8 @@ class _TRUNetFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gout, *unused):
         if not ctx.need_bwd:
-            raise L.TruError("TRUNet backward needs a training-mode forward with grad enabled")
+            raise L.TruError("TRUNet backward needs a training-mode forward with grad enabled (eval-mode / frozen-BN "
+                             "fine-tuning is not supported: the backward kernels use the batch statistics)")
         if ctx.has_h0:
             raise L.TruError("TRUNet backward with a carried TGRU state (h0) is not supported")
         x, ws = ctx.saved_tensors[:2]
@@ -171,12 +171,16 @@ class _TRUNetFn(torch.autograd.Function):
         for n in sizes:
             offs.append(tot)
             tot += (n + 3) // 4 * 4                      # keep every slice 16-byte aligned
-        flat = torch.zeros(tot, device=x.device, dtype=torch.float32)
-        base = flat.data_ptr()
-        gp = (C.c_void_p * 108)(*[base + 4 * o for o in offs])
-        pp = (C.c_void_p * 108)(*[p.data_ptr() for p in params])
-        L.check(L.lib.tru_trunet_backward(C.byref(ctx.desc), pp, L.ptr(x), L.ptr(gout), gp, L.ptr(ws), ctx.ws_bytes,
-                                          L.stream_ptr()), "tru_trunet_backward")
+        with torch.cuda.device(x.device):
+            # one flat buffer for all gradients (+ the all-reduce's scalar tail).  It is a fresh zeroed block every time:
+            # the previous step's .grad tensors may still be alive (gradient accumulation), so it cannot be reused in place.
+            flat = torch.zeros(tot + LOSS_TAIL, device=x.device, dtype=torch.float32)
+            base = flat.data_ptr()
+            gp = (C.c_void_p * 108)(*[base + 4 * o for o in offs])
+            pp = (C.c_void_p * 108)(*[p.data_ptr() for p in params])
+            L.check(L.lib.tru_trunet_backward(C.byref(ctx.desc), pp, L.ptr(x), L.ptr(gout), gp, L.ptr(ws), ctx.ws_bytes,
+                                              L.stream_ptr(x.device)), "tru_trunet_backward")
+        ctx.net._tru_flat_grad = flat
         grads = [flat[o:o + n].view(s) for o, n, s in zip(offs, sizes, ctx.shapes)]
         return (None, None, None, None, None) + tuple(grads)
 
@@ -203,13 +207,40 @@ class TRUNet(nn.Module):
         self._debug_keep_ws = False
 
     # -- plumbing --
-    def _ordered_params(self):
-        d = dict(self.named_parameters())
-        return [d[n] for n in PARAM_ORDER]
+    def _ordered_params(self, device):
+        ps = self.__dict__.get("_plist")
+        if ps is None:                                 # Parameter objects keep their identity through .cuda() / .to() / load_state_dict
+            d = dict(self.named_parameters())
+            ps = self.__dict__["_plist"] = [d[n] for n in PARAM_ORDER]
+        for n, p in zip(PARAM_ORDER, ps):
+            if p.device != device or p.dtype != torch.float32 or not p.is_contiguous():
+                raise L.TruError("TRUNet parameter %s must be a contiguous float32 tensor on %s (it is %s on %s): the kernels "
+                                 "take raw pointers; move the model with .cuda() / .float()" % (n, device, p.dtype, p.device))
+        return ps
 
-    def _bn_ptrs(self):
-        mods = dict(self.named_modules())
-        bns = [mods[n] for n in BN_ORDER]
+    def _bn_modules(self):
+        bns = self.__dict__.get("_bnlist")
+        if bns is None:
+            mods = dict(self.named_modules())
+            bns = self.__dict__["_bnlist"] = [mods[n] for n in BN_ORDER]
+        return bns
+
+    def _bn_hyper(self):
+        """(eps, momentum) of the 23 BatchNorm1d layers: the kernels take one value for all of them."""
+        bns = self._bn_modules()
+        eps, mom = bns[0].eps, bns[0].momentum
+        for n, b in zip(BN_ORDER, bns):
+            if b.eps != eps or b.momentum != mom or b.momentum is None or not b.track_running_stats or not b.affine:
+                raise L.TruError("TRUNet: BatchNorm %s has eps/momentum/track_running_stats/affine settings the fused kernels do "
+                                 "not support (one eps and one numeric momentum for all layers, running statistics on)" % n)
+        return float(eps), float(mom)
+
+    def _bn_ptrs(self, device):
+        bns = self._bn_modules()
+        for n, b in zip(BN_ORDER, bns):
+            for t, dt in ((b.running_mean, torch.float32), (b.running_var, torch.float32), (b.num_batches_tracked, torch.int64)):
+                if t.device != device or t.dtype != dt or not t.is_contiguous():
+                    raise L.TruError("TRUNet buffer of %s must be contiguous %s on %s" % (n, dt, device))
         rm = (C.c_void_p * 23)(*[b.running_mean.data_ptr() for b in bns])
         rv = (C.c_void_p * 23)(*[b.running_var.data_ptr() for b in bns])
         nb = (C.c_void_p * 23)(*[b.num_batches_tracked.data_ptr() for b in bns])
@@ -229,7 +260,9 @@ class TRUNet(nn.Module):
             h0 = h0.reshape(-1, 128).contiguous()
             if h0.shape[0] != x.shape[0] * 16:
                 raise L.TruError("h0 must hold B*16 states of size 128")
-        params = self._ordered_params()
+        if h0 is not None and (h0.device != x.device or h0.dtype != torch.float32):
+            raise L.TruError("h0 must be float32 on the same device as x")
+        params = self._ordered_params(x.device)
         need_bwd = self.training and torch.is_grad_enabled() and any(p.requires_grad for p in params)
         res = _TRUNetFn.apply(x.detach(), h0, self, want_state, need_bwd, *params)
         out, hl = (res if want_state else (res, None))

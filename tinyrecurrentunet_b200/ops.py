@@ -35,8 +35,8 @@ def frontend(audio, pcen_state=None, return_state=False, pcen=None):
     ws = torch.empty(ws_bytes, device=audio.device, dtype=torch.uint8)
     st_in = _f32c(pcen_state) if pcen_state is not None else None
     st_out = torch.empty((B, NBINS), device=audio.device, dtype=torch.float32) if return_state else None
-    L.check(L.lib.tru_frontend_fwd(C.byref(d), L.ptr(audio), L.ptr(st_in), L.ptr(feats), L.ptr(st_out),
-                                   L.ptr(ws), ws_bytes, L.stream_ptr()), "tru_frontend_fwd")
+    L.run("tru_frontend_fwd", audio.device, C.byref(d), L.ptr(audio), L.ptr(st_in), L.ptr(feats), L.ptr(st_out),
+                                   L.ptr(ws), ws_bytes)
     return (feats, st_out) if return_state else feats
 
 
@@ -49,8 +49,7 @@ def frontend_step(frames, pcen_state, pcen=None):
     S = frames.shape[0]
     d = _front_desc(S, NFFT, pcen)
     feats = torch.empty((S, 4, NBINS), device=frames.device, dtype=torch.float32)
-    L.check(L.lib.tru_frontend_step(C.byref(d), L.ptr(frames), L.ptr(pcen_state), L.ptr(feats),
-                                    L.stream_ptr()), "tru_frontend_step")
+    L.run("tru_frontend_step", frames.device, C.byref(d), L.ptr(frames), L.ptr(pcen_state), L.ptr(feats))
     return feats
 
 
@@ -65,7 +64,7 @@ class _MaskISTFT(torch.autograd.Function):
             raise L.TruError("last dim must be 257 bins")
         d = L.TruBackendDesc(B, T, Cn, chans[0], chans[1], chans[2], chans[3], chans[4], int(use_mask), beta)
         audio = torch.empty((B, HOP * (T - 1)), device=x.device, dtype=torch.float32)
-        L.check(L.lib.tru_backend_fwd(C.byref(d), L.ptr(x), L.ptr(audio), L.stream_ptr()), "tru_backend_fwd")
+        L.run("tru_backend_fwd", x.device, C.byref(d), L.ptr(x), L.ptr(audio))
         ctx.save_for_backward(x)
         ctx.desc = d
         return audio
@@ -75,8 +74,7 @@ class _MaskISTFT(torch.autograd.Function):
         (x,) = ctx.saved_tensors
         g = _f32c(g)
         gx = torch.empty_like(x)
-        L.check(L.lib.tru_backend_bwd(C.byref(ctx.desc), L.ptr(x), L.ptr(g), L.ptr(gx), L.stream_ptr()),
-                "tru_backend_bwd")
+        L.run("tru_backend_bwd", x.device, C.byref(ctx.desc), L.ptr(x), L.ptr(g), L.ptr(gx))
         return gx, None, None, None
 
 
@@ -99,8 +97,8 @@ def mask_istft_step(net_out_frame, ola_state, frame_index, beta=0.5, flush=False
             raise L.TruError("net_out_frame must be (S,8,257) with S = ola_state.shape[0]")
     d = L.TruBackendDesc(S, 1, 8, 0, 2, 3, 6, 7, 1, float(beta))
     audio = torch.empty((S, HOP), device=ola_state.device, dtype=torch.float32)
-    L.check(L.lib.tru_backend_step(C.byref(d), L.ptr(x), L.ptr(ola_state), L.ptr(audio), int(frame_index),
-                                   0 if flush else 1, L.stream_ptr()), "tru_backend_step")
+    L.run("tru_backend_step", ola_state.device, C.byref(d), L.ptr(x), L.ptr(ola_state), L.ptr(audio), int(frame_index),
+                                   0 if flush else 1)
     return audio
 
 
@@ -129,8 +127,7 @@ class _MRSTFTL1(torch.autograd.Function):
         wptr = (C.c_void_p * 3)(*([w.data_ptr() for w in wins] + [None] * (3 - nres)))
         sums = torch.empty(16, device=x.device, dtype=torch.float64)
         out = torch.empty(3, device=x.device, dtype=torch.float32)
-        L.check(L.lib.tru_loss_fwd(C.byref(d), L.ptr(x), L.ptr(y), wptr, L.ptr(sums), L.ptr(out),
-                                   L.stream_ptr()), "tru_loss_fwd")
+        L.run("tru_loss_fwd", x.device, C.byref(d), L.ptr(x), L.ptr(y), wptr, L.ptr(sums), L.ptr(out))
         ctx.save_for_backward(x, y, sums, *wins)
         ctx.desc = d
         ctx.mark_non_differentiable(sums)
@@ -145,8 +142,7 @@ class _MRSTFTL1(torch.autograd.Function):
         gout = torch.stack([g if g is not None else zero for g in (g_l1, g_sc, g_mag)]).float().contiguous()
         wptr = (C.c_void_p * 3)(*([w.data_ptr() for w in wins] + [None] * (3 - len(wins))))
         gx = torch.empty_like(x)
-        L.check(L.lib.tru_loss_bwd(C.byref(d), L.ptr(x), L.ptr(y), wptr, L.ptr(sums), L.ptr(gout), L.ptr(gx),
-                                   L.stream_ptr()), "tru_loss_bwd")
+        L.run("tru_loss_bwd", x.device, C.byref(d), L.ptr(x), L.ptr(y), wptr, L.ptr(sums), L.ptr(gout), L.ptr(gx))
         return gx, None, None, None
 
 
@@ -163,8 +159,7 @@ def augment(noise, coef):
     if noise.dim() != 2 or coef.shape != (noise.shape[0], L.AUGMENT_NCOEF) or coef.dtype != torch.float32:
         raise L.TruError("augment: noise (B,N) and coef (B,%d) float32 expected" % L.AUGMENT_NCOEF)
     out = torch.empty_like(noise)
-    L.check(L.lib.tru_augment_fwd(noise.shape[0], noise.shape[1], L.ptr(noise), L.ptr(coef), L.ptr(out), L.stream_ptr()),
-            "tru_augment_fwd")
+    L.run("tru_augment_fwd", noise.device, noise.shape[0], noise.shape[1], L.ptr(noise), L.ptr(coef), L.ptr(out))
     return out
 
 
@@ -176,7 +171,7 @@ def mix_crop(clean, aug_noise, clean_start, noise_start, n_out):
     B = clean.shape[0]
     clean_out = torch.empty((B, n_out), device=clean.device, dtype=torch.float32)
     noisy_out = torch.empty_like(clean_out)
-    L.check(L.lib.tru_mix_crop(B, clean.shape[1], aug_noise.shape[1], n_out, L.ptr(clean), L.ptr(aug_noise),
+    L.run("tru_mix_crop", clean.device, B, clean.shape[1], aug_noise.shape[1], n_out, L.ptr(clean), L.ptr(aug_noise),
                                L.ptr(clean_start.contiguous()), L.ptr(noise_start.contiguous()), L.ptr(clean_out),
-                               L.ptr(noisy_out), L.stream_ptr()), "tru_mix_crop")
+                               L.ptr(noisy_out))
     return clean_out, noisy_out

@@ -161,9 +161,8 @@ class FlatAdamW(torch.optim.AdamW):
         beta1, beta2 = group["betas"]
         desc = L.TruAdamWDesc(fl["n"], t, float(group["lr"]), float(beta1), float(beta2), float(group["eps"]),
                               float(group["weight_decay"]), float(self.max_grad_norm or 0.0))
-        L.check(L.lib.tru_flat_adamw_step(C.byref(desc), L.ptr(fl["p"]), gbase, L.ptr(fl["m"]), L.ptr(fl["v"]),
-                                          L.ptr(fl["norm"]), L.ptr(fl["ws"]), fl["ws_bytes"], L.stream_ptr()),
-                "tru_flat_adamw_step")
+        L.run("tru_flat_adamw_step", fl["p"].device, C.byref(desc), L.ptr(fl["p"]), gbase, L.ptr(fl["m"]), L.ptr(fl["v"]),
+              L.ptr(fl["norm"]), L.ptr(fl["ws"]), fl["ws_bytes"])
         fl["step"] += 1
         self.grad_norm = fl["norm"]
         return loss
@@ -183,5 +182,5 @@ def grad_norm(parameters):
     ws_bytes = L.lib.tru_flat_adamw_workspace_bytes(C.byref(desc))
     ws = torch.empty(ws_bytes, device=flat.device, dtype=torch.uint8)
     out = torch.zeros((), device=flat.device, dtype=torch.float32)
-    L.check(L.lib.tru_flat_grad_norm(tot, L.ptr(flat), L.ptr(out), L.ptr(ws), ws_bytes, L.stream_ptr()), "tru_flat_grad_norm")
+    L.run("tru_flat_grad_norm", flat.device, tot, L.ptr(flat), L.ptr(out), L.ptr(ws), ws_bytes)
     return out

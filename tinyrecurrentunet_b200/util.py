@@ -26,46 +26,94 @@ def denoise(net, noisy_audio, beta=0.5):
 
 
 class CudaPrefetcher:
-    """Double-buffered host -> device staging of (clean, noisy) batches on a side stream, so the copy of batch i+1 overlaps
-    the training step of batch i (train.py:124-125 copies synchronously).  ``next(clean_host, noisy_host)`` returns device
-    tensors holding the batch passed in the PREVIOUS call (the first call copies and returns its own batch) and starts
-    the copy of the new one; host tensors must be pinned for the copy to be asynchronous."""
+    """Double-buffered host -> device staging on a side stream, so that the copy of batch i+1 overlaps the training step of
+    batch i (train.py:124-125 copies synchronously).  Wraps any iterable of host batches (tuples of tensors; pin them for
+    the copies to be asynchronous) and yields every batch exactly once, in order, as a tuple of device tensors:
 
-    def __init__(self, device="cuda"):
+        for clean, noisy in CudaPrefetcher(loader, device):
+            step(clean, noisy)
+
+    A yielded batch stays valid until the loop asks for the next one (the work the loop body enqueued on the current
+    stream is fenced with an event before its buffer is overwritten)."""
+
+    def __init__(self, batches, device="cuda"):
+        self.batches = batches
         self.device = torch.device(device)
         self.stream = torch.cuda.Stream(device=self.device)
         self.bufs = [None, None]
         self.ready = [torch.cuda.Event(), torch.cuda.Event()]
-        self.free = [torch.cuda.Event(), torch.cuda.Event()]
-        self.k = 0
-        self.primed = False
+        self.free = [None, None]                  # event after the last consumer of buffer k (None: never used)
 
-    def _issue(self, k, clean_h, noisy_h):
-        if self.bufs[k] is None or self.bufs[k][0].shape != clean_h.shape:
-            self.bufs[k] = (torch.empty(clean_h.shape, device=self.device, dtype=clean_h.dtype),
-                            torch.empty(noisy_h.shape, device=self.device, dtype=noisy_h.dtype))
+    def _issue(self, k, host):
+        cur = torch.cuda.current_stream(self.device)
+        old = self.bufs[k]
+        if old is None or len(old) != len(host) or any(o.shape != h.shape or o.dtype != h.dtype for o, h in zip(old, host)):
+            if old is not None:                   # a ragged batch: the old block may still be the target of an in-flight copy
+                for t in old:
+                    t.record_stream(self.stream)
+            self.bufs[k] = tuple(torch.empty(h.shape, device=self.device, dtype=h.dtype) for h in host)
+            fence = torch.cuda.Event()            # the block may be recycled memory that earlier work on `cur` still reads
+            fence.record(cur)
+            self.stream.wait_event(fence)
+        if self.free[k] is not None:
+            self.stream.wait_event(self.free[k])  # the step that last read this buffer has finished
         with torch.cuda.stream(self.stream):
-            self.stream.wait_event(self.free[k])          # the step that last read this buffer has finished
-            self.bufs[k][0].copy_(clean_h, non_blocking=True)
-            self.bufs[k][1].copy_(noisy_h, non_blocking=True)
+            for d, h in zip(self.bufs[k], host):
+                d.copy_(h, non_blocking=True)
             self.ready[k].record(self.stream)
 
-    def next(self, clean_h, noisy_h):
-        cur = torch.cuda.current_stream(self.device)
-        if not self.primed:
-            self.free[0].record(cur); self.free[1].record(cur)
-            self._issue(self.k, clean_h, noisy_h)
-            self.primed = True
-        k = self.k
-        self._issue(k ^ 1, clean_h, noisy_h)              # next batch goes into the other buffer while this one is used
-        cur.wait_event(self.ready[k])
-        self.k = k ^ 1
-        return self.bufs[k]
+    def __iter__(self):
+        it = iter(self.batches)
+        try:
+            self._issue(0, tuple(next(it)))
+        except StopIteration:
+            return
+        k, more = 0, True
+        while more:
+            try:
+                self._issue(k ^ 1, tuple(next(it)))      # the next batch travels while this one is used
+            except StopIteration:
+                more = False
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_event(self.ready[k])
+            yield self.bufs[k]
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            self.free[k] = ev
+            k ^= 1
 
-    def release(self, k_bufs):
-        """Call after the step that consumed ``k_bufs`` has been enqueued (marks the buffer reusable)."""
-        k = 0 if k_bufs is self.bufs[0] else 1
-        self.free[k].record(torch.cuda.current_stream(self.device))
+
+def denoise_host_batches(net, batches, device="cuda", beta=0.5):
+    """Offline batch denoising with host buffers on both sides (denoise.py:82-95's loop: load clip -> net -> write wav).
+    ``batches`` is an iterable of pinned host tensors (B,N); yields, for every batch in order, a pinned host tensor
+    (B,128*(N//128)) holding the denoised audio - complete when it is yielded.  Host->device copies run one batch ahead
+    on a side stream (CudaPrefetcher), device->host copies on a second side stream, so both overlap the kernels of the
+    neighbouring batches; the yielded tensor is one of two staging buffers and is overwritten two batches later."""
+    device = torch.device(device)
+    out_stream = torch.cuda.Stream(device=device)
+    host = [None, None]
+    done = [torch.cuda.Event(), torch.cuda.Event()]
+    pending = None
+    k = 0
+    with torch.no_grad():
+        for (noisy,) in CudaPrefetcher(((b,) for b in batches), device):
+            audio, _ = denoise(net, noisy, beta)
+            cur = torch.cuda.current_stream(device)
+            if host[k] is None or host[k].shape != audio.shape:
+                host[k] = torch.empty(audio.shape, dtype=audio.dtype, pin_memory=True)
+            out_stream.wait_stream(cur)
+            with torch.cuda.stream(out_stream):
+                host[k].copy_(audio, non_blocking=True)
+                done[k].record(out_stream)
+            audio.record_stream(out_stream)
+            if pending is not None:
+                done[pending].synchronize()
+                yield host[pending]
+            pending = k
+            k ^= 1
+    if pending is not None:
+        done[pending].synchronize()
+        yield host[pending]
 
 
 class StreamingDenoiser:
