@@ -79,7 +79,8 @@ def test_nccl_world1_real_trunet_takes_the_one_call_flat_path(monkeypatch):
         assert numel == pad + D.LOSS_TAIL and ptr == net._tru_flat_grad.data_ptr()
         assert op == dist.ReduceOp.AVG
         assert net._tru_flat_grad.data_ptr() <= first.grad.data_ptr() < ptr + 4 * numel
-        assert torch.equal(g1, g0)                                     # world size 1: the mean is the gradient itself
+        # world size 1: the mean is the gradient itself (two runs agree to a few ulp, not bit for bit: a few fp32 atomics)
+        assert (g1 - g0).abs().max().item() <= 1e-5 * g0.abs().max().item()
         assert abs(net.reduced_loss.item() - loss1.item()) == 0.0      # the piggy-backed logging scalar (train.py:133)
         assert abs(loss1.item() - loss0.item()) <= 1e-6 * abs(loss0.item())
     finally:

@@ -130,8 +130,9 @@ BN_OF = dict([("Zp%d" % i, 2 * (i - 1)) for i in range(1, 6)] + [("Zd%d" % i, 2 
              + [("ZFp", 21), ("ZTp", 22)])
 
 
-def compare_intermediate_grads(net, got, B, T):
-    """dZ (grad w.r.t. each pre-BN conv output) of the oracle vs q0*dY + q1*Z + q2 of the CUDA path."""
+def compare_intermediate_grads(net, got, B, T, quantile=None):
+    """dZ (grad w.r.t. each pre-BN conv output) of the oracle vs q0*dY + q1*Z + q2 of the CUDA path: max-norm relative error
+    per tensor; with ``quantile`` rows are (name, that quantile of |error| / max|ref|, max-norm error)."""
     rows = []
     small = gpu_buffer(net, "small", 0, (23, 7, 128))
     keys = ["ZDp5"] + [k for d in range(4, -1, -1) for k in ("ZDt%d" % d, "ZDp%d" % d)] + ["ZTp", "ZFp"]
@@ -147,7 +148,13 @@ def compare_intermediate_grads(net, got, B, T):
         z = gpu_buffer(net, name, idx, shape)
         Cn = shape[-1]
         q0, q1, q2 = (small[BN_OF[key], j, :Cn] for j in (4, 5, 6))
-        rows.append((key, rel(q0 * dy + q1 * z + q2, g)))
+        mine = q0 * dy + q1 * z + q2
+        if quantile is None:
+            rows.append((key, rel(mine, g)))
+        else:
+            e = (mine.double() - g.double()).abs().reshape(-1) / g.abs().max().clamp_min(1e-30).double()
+            k = max(1, int(quantile * e.numel()))
+            rows.append((key, e.kthvalue(k).values.item(), e.max().item()))
     return rows
 
 
@@ -337,7 +344,8 @@ def test_cuda_prefetcher_delivers_every_batch_once_in_order():
     seen = []
     for clean, noisy in util.CudaPrefetcher(hosts, "cuda"):
         big = torch.randn(2048, 2048, device="cuda") @ torch.randn(2048, 2048, device="cuda")   # keep the stream busy
-        seen.append((clean.mean().item(), noisy.mean().item(), tuple(clean.shape)))
+        assert clean.min().item() == clean.max().item() and noisy.min().item() == noisy.max().item()
+        seen.append((clean.max().item(), noisy.max().item(), tuple(clean.shape)))
         del big
     assert [s[0] for s in seen] == [float(i) for i in range(7)]
     assert [s[1] for s in seen] == [float(-i) for i in range(7)]
