@@ -207,7 +207,8 @@ __global__ void __launch_bounds__(NT) backend_bwd_kernel(BackParams p) {
 
 // Streaming step: one new network-output frame per stream.  ola (S,384) holds the overlap-add sums of
 // the three hops that still wait for later frames; adding frame t completes output block t-2 (two hops of
-// look-ahead, exactly the offline centre=True framing).  8 streams per CTA, two streams per complex transform.
+// look-ahead, exactly the offline centre=True framing).  4 streams per CTA, ONE stream per complex transform (Hermitian
+// extension of its own spectrum): streams are independent signals and must not share a transform (see frontend_step_kernel).
 __global__ void __launch_bounds__(NT) backend_step_kernel(BackParams p, float* __restrict__ ola, int frame_index, int add_frame) {
   __shared__ __align__(16) float fre[4 * FPAD];
   __shared__ __align__(16) float fim[4 * FPAD];
@@ -216,19 +217,18 @@ __global__ void __launch_bounds__(NT) backend_step_kernel(BackParams p, float* _
   for (int k = tid; k < NFFT; k += NT) tw[k] = p.tw[k * (2048 / NFFT)];
   float* re = fre + g * FPAD;
   float* im = fim + g * FPAD;
-  const int sa = blockIdx.x * 8 + g * 2, sb = sa + 1;
-  const bool va = sa < p.B, vb = sb < p.B;
+  const int sidx = blockIdx.x * 4 + g;
+  const bool valid = sidx < p.B;
   __syncthreads();
   if (add_frame) {
     for (int k = l; k <= NFFT / 2; k += 64) {
-      float ar = 0.f, ai = 0.f, br = 0.f, bi = 0.f;
-      if (va) bin_spectrum(p, p.net + (size_t)sa * p.C * NB, k, ar, ai);
-      if (vb) bin_spectrum(p, p.net + (size_t)sb * p.C * NB, k, br, bi);
-      if (k == 0 || k == NFFT / 2) {
-        re[TRU_FFT_IDX(k)] = ar; im[TRU_FFT_IDX(k)] = br;
+      float ar = 0.f, ai = 0.f;
+      if (valid) bin_spectrum(p, p.net + (size_t)sidx * p.C * NB, k, ar, ai);
+      if (k == 0 || k == NFFT / 2) {                 // c2r ignores Im of DC / Nyquist
+        re[TRU_FFT_IDX(k)] = ar; im[TRU_FFT_IDX(k)] = 0.f;
       } else {
-        re[TRU_FFT_IDX(k)] = ar - bi; im[TRU_FFT_IDX(k)] = ai + br;
-        re[TRU_FFT_IDX(NFFT - k)] = ar + bi; im[TRU_FFT_IDX(NFFT - k)] = br - ai;
+        re[TRU_FFT_IDX(k)] = ar; im[TRU_FFT_IDX(k)] = ai;
+        re[TRU_FFT_IDX(NFFT - k)] = ar; im[TRU_FFT_IDX(NFFT - k)] = -ai;
       }
     }
     fft_smem<NFFT, 1>(re, im, tw, l);
@@ -237,24 +237,20 @@ __global__ void __launch_bounds__(NT) backend_step_kernel(BackParams p, float* _
   const int newest = add_frame ? frame_index : frame_index - 1;
   const int cnt = newest - max(frame_index - 3, 0) + 1;
   const float invn = 1.0f / NFFT, invc = (frame_index >= 2 && cnt > 0) ? 1.0f / (float)cnt : 0.0f;
+  if (!valid) return;
+  float* o = ola + (size_t)sidx * 384;
+  float v[8];
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int sidx = h == 0 ? sa : sb;
-    if (h == 0 ? !va : !vb) continue;
-    float* o = ola + (size_t)sidx * 384;
-    float v[8];
+  for (int j = 0; j < 8; ++j) {
+    const int n = l + 64 * j;
+    const float x = add_frame ? re[TRU_FFT_IDX(n)] * invn : 0.0f;
+    v[j] = x + (n < 384 ? o[n] : 0.0f);
+  }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int n = l + 64 * j;
-      const float x = add_frame ? (h == 0 ? re[TRU_FFT_IDX(n)] : im[TRU_FFT_IDX(n)]) * invn : 0.0f;
-      v[j] = x + (n < 384 ? o[n] : 0.0f);
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int n = l + 64 * j;
-      if (n < HOP) p.audio[(size_t)sidx * HOP + n] = v[j] * invc;
-      else o[n - HOP] = v[j];
-    }
+  for (int j = 0; j < 8; ++j) {
+    const int n = l + 64 * j;
+    if (n < HOP) p.audio[(size_t)sidx * HOP + n] = v[j] * invc;
+    else o[n - HOP] = v[j];
   }
 }
 
@@ -290,7 +286,7 @@ extern "C" int tru_backend_step(const TruBackendDesc* d, const float* net_out, f
   TRU_REQUIRE(ola_state && audio && (net_out || !add_frame) && frame_index >= 0, TRU_ERR_ARG, "backend_step: null pointer / negative frame index");
   p.net = net_out; p.audio = audio;
   ProfScope prof("backend_step", 4.0 * p.B * ((double)p.C * NB + 2.0 * 384 + HOP), 0.5 * p.B * 5.0 * NFFT * 9, (cudaStream_t)stream);
-  backend_step_kernel<<<(p.B + 7) / 8, NT, 0, (cudaStream_t)stream>>>(p, ola_state, frame_index, add_frame);
+  backend_step_kernel<<<(p.B + 3) / 4, NT, 0, (cudaStream_t)stream>>>(p, ola_state, frame_index, add_frame);
   TRU_LAUNCH_CHECK();
   return TRU_OK;
 }

@@ -226,6 +226,11 @@ __global__ void __launch_bounds__(FNT) fgru_bwd_kernel(const __grid_constant__ G
 // independent FFMA chains (4 sequences x 64 deep) instead of 3 warps of 128-deep ones; the two half sums meet
 // in shared memory, where the gate phase reads them.
 constexpr int TH = 128, TL = 16, TNT = 768, TROWS = 384, TKH = 64;
+// Backward: a thread keeps a 2 x 32 register tile of W_hh (two columns, one of 12 row-chunks), so one 16-byte broadcast load of
+// the gate gradients feeds 4 FFMA2 (8 FMAs) instead of 2: ncu showed "short scoreboard" (waiting for shared-memory loads) as
+// the top stall at 8.0 warps per issue with the half-column layout.  The same tiling did not pay in the forward kernel
+// (1.43 vs 1.36 ms; with FFMA2 1.80 ms), which keeps one half row per thread.
+constexpr int TKQ = 32, TBQ = TROWS / TKQ;
 
 // Per-step operands (input gates / saved gates) are staged through shared memory with cp.async one step ahead:
 // register prefetches were spilled by the compiler, which turned every step into a synchronous wait for HBM.
@@ -336,13 +341,19 @@ template <int SC>
 __global__ void __launch_bounds__(TNT, 1) tgru_bwd_kernel(const __grid_constant__ GruParams p, int B, int T) {
   constexpr int NI = (SC * TH + TNT - 1) / TNT;
   constexpr int NCH = SC * 192;                        // 16-byte chunks per step: dH (32) + cache r,z,n,hn (128) + h_prev (32) per sequence
-  __shared__ __align__(16) float dgs[SC][3 * TH];
-  __shared__ float part[6][SC][TH];
-  __shared__ __align__(16) float sv[2][SC][6 * TH];     // staged: dh | r | z | n | hn | h_prev
-  const int tid = threadIdx.x, k = tid & (TH - 1), ph = tid >> 7, prt = ph % 3, half = ph / 3;   // ph: 0..5, warp-uniform
-  float w[TKH];                                         // w[jj] = W_hh[prt*128 + half*64 + jj][k]
+  // dynamic shared memory (55 KB): dgs[SC][384] | part[TBQ][SC][128] | sv[2][SC][768] (staged: dh | r | z | n | hn | h_prev)
+  extern __shared__ __align__(16) float tgru_bwd_smem[];
+  float (*dgs)[3 * TH] = (float (*)[3 * TH])tgru_bwd_smem;
+  float (*part)[SC][TH] = (float (*)[SC][TH])(tgru_bwd_smem + SC * 3 * TH);
+  float (*sv)[SC][6 * TH] = (float (*)[SC][6 * TH])(tgru_bwd_smem + SC * 3 * TH + TBQ * SC * TH);
+  const int tid = threadIdx.x, kp = tid & 63, jq = tid >> 6;      // jq: 0..11 (32 rows of W_hh each), warp-uniform
+  const int k0 = 2 * kp;                                // columns k0, k0 + 1 of W_hh, rows [32 jq, 32 jq + 32)
+  float w0[TKQ], w1[TKQ];
 #pragma unroll
-  for (int jj = 0; jj < TKH; ++jj) w[jj] = __ldg(p.whh[0] + (long)(prt * TH + half * TKH + jj) * TH + k);
+  for (int jj = 0; jj < TKQ; ++jj) {
+    const float2 v = __ldg((const float2*)(p.whh[0] + (long)(jq * TKQ + jj) * TH + k0));
+    w0[jj] = v.x; w1[jj] = v.y;
+  }
   const int nseq = B * TL;
   const int sbase = blockIdx.x * SC;
   auto stage = [&](int t, int buf) {
@@ -406,26 +417,31 @@ __global__ void __launch_bounds__(TNT, 1) tgru_bwd_kernel(const __grid_constant_
       }
     }
     __syncthreads();
-    float2 acc[SC];
+    float2 acc0[SC], acc1[SC];                            // packed over pairs of rows (FFMA2): the two lanes are added at the end
 #pragma unroll
-    for (int s = 0; s < SC; ++s) acc[s] = make_float2(0.f, 0.f);
+    for (int s = 0; s < SC; ++s) { acc0[s] = make_float2(0.f, 0.f); acc1[s] = make_float2(0.f, 0.f); }
 #pragma unroll
-    for (int j4 = 0; j4 < TKH / 4; ++j4) {
+    for (int j4 = 0; j4 < TKQ / 4; ++j4) {
 #pragma unroll
       for (int s = 0; s < SC; ++s) {
-        const float4 g = *(const float4*)&dgs[s][prt * TH + half * TKH + j4 * 4];
-        acc[s] = __ffma2_rn(make_float2(w[j4 * 4], w[j4 * 4 + 1]), make_float2(g.x, g.y), acc[s]);
-        acc[s] = __ffma2_rn(make_float2(w[j4 * 4 + 2], w[j4 * 4 + 3]), make_float2(g.z, g.w), acc[s]);
+        const float4 g = *(const float4*)&dgs[s][jq * TKQ + j4 * 4];
+        acc0[s] = __ffma2_rn(make_float2(w0[j4 * 4], w0[j4 * 4 + 1]), make_float2(g.x, g.y), acc0[s]);
+        acc1[s] = __ffma2_rn(make_float2(w1[j4 * 4], w1[j4 * 4 + 1]), make_float2(g.x, g.y), acc1[s]);
+        acc0[s] = __ffma2_rn(make_float2(w0[j4 * 4 + 2], w0[j4 * 4 + 3]), make_float2(g.z, g.w), acc0[s]);
+        acc1[s] = __ffma2_rn(make_float2(w1[j4 * 4 + 2], w1[j4 * 4 + 3]), make_float2(g.z, g.w), acc1[s]);
       }
     }
 #pragma unroll
-    for (int s = 0; s < SC; ++s) part[ph][s][k] = acc[s].x + acc[s].y;
+    for (int s = 0; s < SC; ++s) *(float2*)&part[jq][s][k0] = make_float2(acc0[s].x + acc0[s].y, acc1[s].x + acc1[s].y);
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < NI; ++r)
       if (tid + r * TNT < SC * TH) {
         const int s = is[r], u = iu[r];
-        carry[r] = dd[r] + ((part[0][s][u] + part[1][s][u]) + (part[2][s][u] + part[3][s][u])) + (part[4][s][u] + part[5][s][u]);
+        float sum = 0.f;
+#pragma unroll
+        for (int q = 0; q < TBQ; q += 4) sum += (part[q][s][u] + part[q + 1][s][u]) + (part[q + 2][s][u] + part[q + 3][s][u]);
+        carry[r] = dd[r] + sum;
       }
   }
 }
@@ -501,7 +517,10 @@ int launch_tgru_fwd(const GruParams& p, int B, int T, cudaStream_t st) {
 int launch_tgru_bwd(const GruParams& p, int B, int T, cudaStream_t st) {
   const int nseq = B * TL;
   ProfScope prof("tgru_bwd", 4.0 * nseq * T * (128 + 512 + 128 + 768), 2.0 * nseq * T * TH * 3 * TH, st);
-  tgru_bwd_kernel<4><<<(nseq + 3) / 4, TNT, 0, st>>>(p, B, T);
+  constexpr int SC = 4;
+  const size_t smem = (size_t)SC * (3 * TH + TBQ * TH + 2 * 6 * TH) * 4;     // dgs + part + sv: 55,296 B
+  TRU_SMEM_OPT_IN((tgru_bwd_kernel<SC>), smem);
+  tgru_bwd_kernel<SC><<<(nseq + SC - 1) / SC, TNT, smem, st>>>(p, B, T);
   TRU_LAUNCH_CHECK();
   return TRU_OK;
 }

@@ -38,7 +38,8 @@ using namespace tc;
 
 constexpr int BM = 128, KBLK = 32;
 constexpr int EW = 8;                                     // epilogue warps
-constexpr int A_TILE = BM * 128;                          // bytes of one hi (or lo) activation tile
+constexpr int AROWS = BM + 8;                             // rows of a staged activation tile: 128 + room for row-shifted reads
+constexpr int A_TILE = AROWS * 128;                       // bytes of one hi (or lo) activation tile (17 swizzle atoms of 1024 B)
 constexpr int STAGE = 2 * A_TILE;
 constexpr int MAXKB = 16, MAXCOEF = 12;
 constexpr int COEF_FLOATS = 96;                           // p0[32] p2[32] p1[32]
@@ -213,11 +214,12 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&mi.full[st], ph & 1, 200 + st * 10 + kb);
           tc_fence_after();
-          const uint32_t x_hi = a_base + st * (STAGE >> 4), x_lo = x_hi + (A_TILE >> 4);
+          const uint32_t x_hi = a_base + st * (STAGE >> 4) + ((Lo.dbg & 64) ? 8u : 0u), x_lo = x_hi + (A_TILE >> 4);
           const uint32_t w_hi = w_base + (uint32_t)kb * w_kb, w_lo = w_hi + w_lo_off;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const uint64_t dxh = dhi | (x_hi + 2 * j), dxl = dhi | (x_lo + 2 * j);
+            const uint64_t dxs = dhi | ((Lo.dbg & 128) ? (1ull << 49) : 0ull);     // (probe: matrix base offset = 1 row)
+            const uint64_t dxh = dxs | (x_hi + 2 * j), dxl = dxs | (x_lo + 2 * j);
             const uint64_t dwh = dhi | (w_hi + 2 * j), dwl = dhi | (w_lo + 2 * j);
             if (Lo.dbg & 1) continue;
             mma_tf32(d, dwl, dxh, idesc, (kb | j) != 0);
@@ -236,7 +238,8 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
     if (REG_LOAD < REG_LAUNCH) reg_dec<REG_LOAD>();
     constexpr int R = LD2 ? 4 : 8;                      // rows per thread and pass (LD2: two passes of 4 rows, two tensors)
     const int lt = tid - 128, g = lt >> 7, gt = lt & 127, chunk = gt & 7, rbase = gt >> 3;   // rows rbase + 16 i
-    const uint32_t st_off = (uint32_t)rbase * 128 + ((uint32_t)(chunk ^ (rbase & 7)) << 4);
+    const int prow = rbase + ((Lo.dbg & 64) ? 1 : 0);       // (probe: physical row = logical row + 1, read back through a shifted descriptor)
+    const uint32_t st_off = (uint32_t)prow * 128 + ((uint32_t)(chunk ^ (prow & 7)) << 4);
     const unsigned Lq = (unsigned)P.Lq, magic = Lo.lq_magic, Mu = (unsigned)M;
     int ti = 0, kb = g;
     while (kb >= nkb) { kb -= nkb; ++ti; }
