@@ -88,8 +88,9 @@ def test_gradients_per_parameter_at_multi_wave_size():
     for k, p in net.named_parameters():
         assert p.grad is not None, k
         g, r = p.grad.cpu(), gref[k].grad
-        if k in zero_bias:       # exactly-zero true gradient (conv bias in front of a training-mode BN): both sides hold rounding noise
-            rows.append((k, max(g.abs().max().item(), r.abs().max().item()) / (2e-5 * gmax) * GRAD_TOL))
+        if k in zero_bias:       # exactly-zero true gradient (conv bias in front of a training-mode BN): both sides hold the rounding
+            # noise of a fully cancelling sum over ~10^6 elements; require it to stay below 1e-4 of the largest gradient
+            rows.append((k, max(g.abs().max().item(), r.abs().max().item()) / (1e-4 * gmax) * GRAD_TOL))
             continue
         scale = max(r.abs().max().item(), 1e-3 * gmax)
         rows.append((k, (g - r).abs().max().item() / scale))
