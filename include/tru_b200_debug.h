@@ -23,9 +23,17 @@ int tru_debug_pw(const float* x, const float* p0, const float* p2, const float* 
 int tru_debug_pw_bwd(const float* dy, const float* z, const float* q0, const float* q1, const float* q2, const float* w,
                      float* dx, const float* zmask, const float* mp0, const float* mp2, const float* bmean,
                      const float* binv, double* bstats, const float* extra, int M, int K, int N, void* stream);
-/* Data gradient of ConvTranspose1d (network.py:67-73): dy (BT,Lout,Cout) channels-last, w (Cin,Cout,k) -> dx (BT,L,Cin). */
-int tru_debug_convt_bwd_data(const float* dy, const float* w, float* dx, int BT, int L, int Lout, int Cin, int Cout,
-                             int k, int s, void* stream);
+/* Data gradient of ConvTranspose1d (network.py:67-73): dy (BT,Lout,Cout) channels-last, w (Cin,Cout,k) -> dx (BT,L,Cin); with
+ * z / q0 / q1 / q2 (q0 != NULL) the gradient is dz = q0*dy + q1*z + q2 per channel, applied on load (BatchNorm backward).
+ * shared = 0: one gathered K-segment per tap; 1: the tap-shared launch (one staged tile, row-shifted descriptors per tap). */
+int tru_debug_convt_bwd_data(const float* dy, const float* z, const float* q0, const float* q1, const float* q2, const float* w,
+                             float* dx, const float* zmask, const float* mp0, const float* mp2, const float* bmean,
+                             const float* binv, double* bstats, int BT, int L, int Lout, int Cin, int Cout, int k, int s,
+                             int shared, void* stream);   /* zmask / bstats: the ReLU mask and BN-backward sums of tru_debug_pw_bwd */
+/* ConvTranspose1d forward: x (BT,L,Cin) channels-last, w (Cin,Cout,k), bias (Cout) -> out (BT,Lout,Cout), stride s, pad s/2;
+ * stats (2 Cout doubles, may be NULL) += column sums / sums of squares.  Takes the tap-shared launches where eligible. */
+int tru_debug_convt_fwd(const float* x, const float* w, const float* bias, float* out, double* stats, int BT, int L, int Lout,
+                        int Cin, int Cout, int k, int s, void* stream);
 /* Weight gradient dW (N,C) += z^T a, db (N) += column sums of z, a (M,C), z (M,N): the FFMA kernel (parity reference). */
 int tru_debug_wgrad(const float* a, const float* z, float* dw, float* db, int M, int C, int N, void* stream);
 /* The streaming tcgen05 weight-gradient kernel (csrc/tcwgrad2.cu): dz = q0*dy + q1*z + q2 (q0 NULL: dz = dy), rows in

@@ -58,6 +58,70 @@ def test_tensor_core_pointwise_conv(M, K, N):
         assert serr <= 1e-5, (affine, serr)
 
 
+# The transposed convs of the decoder (network.py:67-73): k3 s1 (dec2, dec4), k5 s2 (dec1, dec3), k3 s2 (dec0); 64 -> 64 channels.
+# Forward and data gradient run as TAP-SHARED launches (one staged tile, one row-shifted descriptor per tap); frame counts that
+# put tile boundaries at every position of a frame, and ragged last tiles.
+@pytest.mark.parametrize("BT,L,k,s", [(37, 64, 3, 1), (9, 128, 3, 1), (41, 32, 5, 2), (23, 64, 5, 2), (50, 16, 3, 2), (3, 5, 5, 2),
+                                      (252, 64, 5, 2), (252, 32, 5, 2), (1002, 64, 5, 2), (1002, 128, 3, 1)])
+def test_transposed_conv_forward_and_data_gradient(BT, L, k, s):
+    L_ = _lib()
+    torch.manual_seed(BT * 7 + L + k + s)
+    Cin = Cout = 64
+    pad = s // 2
+    Lout = (L - 1) * s - 2 * pad + k
+    x = torch.randn(BT, L, Cin, device="cuda")
+    w = torch.randn(Cin, Cout, k, device="cuda") / (Cin * k) ** 0.5
+    b = torch.randn(Cout, device="cuda")
+    ref = torch.nn.functional.conv_transpose1d(x.double().transpose(1, 2), w.double(), b.double(), stride=s, padding=pad)
+    ref = ref.transpose(1, 2).contiguous()                                   # (BT, Lout, Cout)
+    assert ref.shape == (BT, Lout, Cout)
+    fwd = L_.lib.tru_debug_convt_fwd
+    fwd.restype = C.c_int
+    fwd.argtypes = [C.c_void_p] * 5 + [C.c_int] * 7 + [C.c_void_p]
+    out = torch.full((BT, Lout, Cout), float("nan"), device="cuda")
+    st = torch.zeros(2 * Cout, device="cuda", dtype=torch.float64)
+    L_.check(fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), st.data_ptr(), BT, L, Lout, Cin, Cout, k, s, None), "convt_fwd")
+    torch.cuda.synchronize()
+    assert ((out.double() - ref).abs().max() / ref.abs().max()).item() <= 1e-5
+    s1, s2 = ref.sum((0, 1)), (ref * ref).sum((0, 1))
+    assert ((st[:Cout] - s1).abs().max() / s1.abs().max()).item() <= 1e-5
+    assert ((st[Cout:] - s2).abs().max() / s2.abs().max()).item() <= 1e-5
+    # data gradient: dx = conv1d(dz, w) (the adjoint), both launch forms, without and with the BatchNorm-backward affine on load
+    dy = torch.randn(BT, Lout, Cout, device="cuda")
+    z = torch.randn(BT, Lout, Cout, device="cuda")
+    q0 = torch.rand(Cout, device="cuda") + 0.5
+    q1 = torch.randn(Cout, device="cuda") * 0.1
+    q2 = torch.randn(Cout, device="cuda") * 0.1
+    bwd = L_.lib.tru_debug_convt_bwd_data
+    bwd.restype = C.c_int
+    bwd.argtypes = [C.c_void_p] * 13 + [C.c_int] * 8 + [C.c_void_p]
+    zm = torch.randn(BT, L, Cin, device="cuda")                     # pre-BN activation of the layer receiving the gradient
+    mp0, mp2 = torch.rand(Cin, device="cuda") + 0.5, torch.randn(Cin, device="cuda") * 0.3
+    bmean, binv = torch.randn(Cin, device="cuda") * 0.1, torch.rand(Cin, device="cuda") + 0.5
+    ptr = lambda t, on=True: t.data_ptr() if on else None
+    for bn in (False, True):
+        dz = (q0 * dy + q1 * z + q2).double() if bn else dy.double()
+        dref = torch.nn.functional.conv1d(dz.transpose(1, 2), w.double(), stride=s, padding=pad).transpose(1, 2)
+        assert dref.shape == (BT, L, Cin)
+        for shared in (0, 1):
+            for masked in (False, True):
+                want = dref * (zm.double() * mp0.double() + mp2.double() > 0) if masked else dref
+                dx = torch.full((BT, L, Cin), float("nan"), device="cuda")
+                bst = torch.zeros(2 * Cin, device="cuda", dtype=torch.float64)
+                L_.check(bwd(dy.data_ptr(), ptr(z, bn), ptr(q0, bn), ptr(q1, bn), ptr(q2, bn), w.data_ptr(), dx.data_ptr(),
+                             ptr(zm, masked), ptr(mp0, masked), ptr(mp2, masked), ptr(bmean, masked), ptr(binv, masked),
+                             ptr(bst, masked), BT, L, Lout, Cin, Cout, k, s, shared, None), "convt_bwd_data")
+                torch.cuda.synchronize()
+                err = ((dx.double() - want).abs().max() / want.abs().max()).item()
+                assert err <= 1e-5, (bn, shared, masked, err)
+                if masked:
+                    s1 = want.sum((0, 1))
+                    s2 = (want * (zm.double() - bmean.double())).sum((0, 1)) * binv.double()
+                    e1 = ((bst[:Cin] - s1).abs().max() / s1.abs().max()).item()
+                    e2 = ((bst[Cin:] - s2).abs().max() / s2.abs().max()).item()
+                    assert e1 <= 1e-4 and e2 <= 1e-4, (bn, shared, e1, e2)
+
+
 def _wgrad_stream(M, Lq, Cc, N, bn):
     L = _lib()
     fn = L.lib.tru_debug_wgrad_stream

@@ -19,6 +19,8 @@ struct Seg {
   const float* p0; const float* p1; const float* p2;   // per-channel coefficients, p0 == null: identity
   const float* W;        // weights of this segment: W[wbase + c*wsc + n*wsn]
   int Lsrc, ld, coff, C; // rows per frame, row stride (floats), first channel, channels
+  int fs;                // frame stride in floats (0: Lsrc * ld); tap-shared launches may view a frame as fewer, wider rows
+  int cmod;              // wide rows (several source rows side by side): per-channel coefficients repeat every cmod channels (0: no)
   int smul, sadd;        // source row li = q*smul + sadd (must satisfy 0 <= li < Lsrc, else zero row)
   int relu;
   int wbase, wsc, wsn;
@@ -34,6 +36,15 @@ struct IgemmParams {
   const float* zmask; const float* mp0; const float* mp2; int use_mask;   // ReLU mask of the layer receiving the gradient
   const float* bmean; const float* binv; double* bstats;                  // backward BN sums: sum g, sum g*xhat
   float src_frac;              // profiler only: fraction of each source this launch needs (0 -> 1)
+  // ---- tap-shared mode (transposed convs; tensor-core kernel only) -------------------------------------------
+  // ntap > 0: seg[0] is THE source.  Rows m = bt*Lq + q are VIRTUAL rows: the tile stages source row q of frame bt
+  // (zero where q >= the row limit of the channel block) for virtual rows [m0 + row_base, m0 + row_base + 128 + max shift) ONCE,
+  // and tap j multiplies channels [tap_c0[j], tap_c0[j] + tap_C[j]) of the rows shifted by tap_shift[j] (a row-shifted shared-memory
+  // descriptor) with W[tap_wbase[j] + c*wsc + n*wsn].  Virtual rows q >= Lvalid produce no output.  The caller chooses Lq so that a
+  // shifted read that leaves its frame lands on a zero row or feeds a discarded output (trunet.cu: convt_fwd / convt_bwd).
+  int ntap, tap_shift[5], tap_wbase[5], tap_c0[5], tap_C[5];
+  int row_base, Lvalid;        // Lvalid 0: every virtual row is an output row
+  int c_hi, lmax_hi;           // source channels >= c_hi exist for rows q < lmax_hi only (c_hi 0: Lsrc for all channels)
 };
 int launch_igemm(const IgemmParams& p, cudaStream_t st);       // tensor-core path when eligible, else FFMA
 bool igemm_tc_eligible(const IgemmParams& p);

@@ -38,20 +38,29 @@ using namespace tc;
 
 constexpr int BM = 128, KBLK = 32;
 constexpr int EW = 8;                                     // epilogue warps
-constexpr int AROWS = BM + 8;                             // rows of a staged activation tile: 128 + room for row-shifted reads
-constexpr int A_TILE = AROWS * 128;                       // bytes of one hi (or lo) activation tile (17 swizzle atoms of 1024 B)
-constexpr int STAGE = 2 * A_TILE;
-constexpr int MAXKB = 16, MAXCOEF = 12;
+constexpr int MAXKB = 16, MAXCOEF = 12, MAXWK = 16;
 constexpr int COEF_FLOATS = 96;                           // p0[32] p2[32] p1[32]
 
+// A tile of 128 gathered rows x 32 channels is staged ONCE per k-block (hi and lo tf32 planes, 128 B per row, SWIZZLE_128B) and
+// multiplied by one or several resident weight k-blocks.  Several = the taps of a transposed conv: tap j reads the same stage
+// through a descriptor whose start address is shifted by tap_shift[j] rows (the swizzle of a tcgen05 operand is a function of
+// the shared-memory ADDRESS bits - measured, profiles/r02_probe_desc_shift.log - so a row-shifted start, or a plane that does
+// not start on a 1024-byte boundary, reads correctly as long as the writer swizzles by address too).  The stage then holds
+// 128 + max shift rows.
 struct TcLayout {
   int MW;                       // MMA M = weight rows (output channels) per CTA: 64 or 128
-  int nkb, nstage, ncoef;
+  int nkb, nstage, ncoef, nwk;  // source k-blocks per tile, ring stages, coefficient rows, resident weight k-blocks
+  int arows, shared;            // rows of a staged plane; tap-shared mode
+  uint32_t atile, stage;        // bytes of one plane (arows * 128), bytes of a stage (hi + lo plane)
   unsigned lq_magic;            // ceil(2^32 / Lq) (0: Lq == 1) for the loaders' row decode
   int dbg;                      // ablation switches for bottleneck hunting (tru_debug_set_flags): 1 no MMA, 2 no global loads, 4 no smem stores, 8 no epilogue stores
   uint32_t a_off, coef_off, misc_off;                      // W tiles at offset 0
-  int8_t kb_seg[MAXKB], kb_coef[MAXKB], kb_relu[MAXKB];
+  int8_t kb_seg[MAXKB], kb_coef[MAXKB], kb_relu[MAXKB], kb_nw[MAXKB];   // kb_nw: weight k-blocks fed by this source k-block (consecutive in wk_*)
   int16_t kb_c0[MAXKB], kb_valid[MAXKB];
+  int kb_lmax[MAXKB];           // source rows li >= kb_lmax are zero rows
+  int8_t wk_seg[MAXWK], wk_shift[MAXWK];
+  int16_t wk_c0[MAXWK], wk_valid[MAXWK];
+  int wk_wbase[MAXWK];          // weight element of (channel c, output n) of weight k-block w: W[wk_wbase + (wk_c0 + c) * wsc + n * wsn]
   int8_t coef_seg[MAXCOEF];
   int16_t coef_c0[MAXCOEF];
 };
@@ -119,10 +128,9 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
   constexpr int REG_MMA = 24;
   constexpr int REG_LOAD = LW == 8 ? 104 : ((EPI == 2 && TRU_EPI2_REGS) ? 72 : 88);
   constexpr int REG_EPI = LW == 8 ? 120 : ((EPI == 2 && TRU_EPI2_REGS) ? 112 : 96);
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* Wsm = smem;                                 // [hi|lo][nkb][MW rows][128 B], swizzled
-  uint8_t* Asm = smem + Lo.a_off;                      // ring: [stage][hi|lo][128 rows][128 B]
+  extern __shared__ __align__(1024) uint8_t smem[];    // (1024-byte aligned: the weight tiles and the classic stages are whole swizzle atoms)
+  uint8_t* Wsm = smem;                                 // [hi|lo][nwk][MW rows][128 B], swizzled
+  uint8_t* Asm = smem + Lo.a_off;                      // ring: [stage][hi|lo][arows][128 B]
   float* coef = (float*)(smem + Lo.coef_off);          // [ncoef][p0 | p2 | p1][32]
   Misc& mi = *(Misc*)(smem + Lo.misc_off);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -131,43 +139,43 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
   const long M = (long)P.BT * P.Lq;
   const int ntiles = (int)((M + BM - 1) / BM);
   const int n_my = ((int)blockIdx.x < ntiles) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  if (smem_u32(smem) & 1023u) { if (tid == 0) printf("tc_igemm_kernel: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
 
   // ---- one-time setup: resident weight slice (hi/lo), affine coefficient table, barriers, TMEM ------
   pdl_trigger();       // the weights are parameters: nothing in the step writes them, so staging them may overlap the predecessor's tail
   {
-    const uint32_t wwords = (uint32_t)nkb * MW * 64;    // hi + lo, in 32-bit words
-    for (uint32_t i = tid; i < wwords / 4; i += NT) ((uint4*)Wsm)[i] = make_uint4(0u, 0u, 0u, 0u);
+    const int msh = MW == 64 ? 11 : 12;                 // log2(32 channels x MW rows)
+    const uint32_t nel = (uint32_t)Lo.nwk << msh;       // weight elements (one hi and one lo word each)
+    for (uint32_t i = tid; i < nel / 2; i += NT) ((uint4*)Wsm)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
-    const uint32_t lo_off = (uint32_t)nkb * MW * 128;
+    const uint32_t lo_off = nel * 4u;
     constexpr int WU = 8;          // weight loads in flight per thread (the prologue is on the critical path of every launch)
-    int kbb = 0;
-    for (int s = 0; s < P.nseg; ++s) {
-      const Seg& sg = P.seg[s];
-      const int tot = sg.C * MW;
-      for (int i0 = tid; i0 < tot; i0 += NT * WU) {
-        float v[WU];
-        int cc[WU], nn[WU];
+    for (uint32_t i0 = tid; i0 < nel; i0 += NT * WU) {
+      float v[WU];
+      uint32_t oo[WU];
 #pragma unroll
-        for (int u = 0; u < WU; ++u) {
-          const int i = i0 + u * NT;
-          int c = 0, n = MW;
-          if (i < tot) { if (sg.wsc == 1) { c = i % sg.C; n = i / sg.C; } else { n = i % MW; c = i / MW; } }
-          cc[u] = c; nn[u] = n;
-          v[u] = (n < MW && n0 + n < P.N) ? __ldg(sg.W + sg.wbase + (long)c * sg.wsc + (long)(n0 + n) * sg.wsn) : 0.f;
-        }
-#pragma unroll
-        for (int u = 0; u < WU; ++u) {
-          if (nn[u] < MW) {
-            const int c = cc[u], n = nn[u];
-            const int kb = kbb + (c >> 5), kk = c & 31;
-            const uint32_t off = (uint32_t)kb * MW * 128 + n * 128 + ((((kk >> 2) ^ (n & 7)) << 4) | ((kk & 3) << 2));
-            const uint32_t hi = f2tf32(v[u]);
-            *(uint32_t*)(Wsm + off) = hi;
-            *(float*)(Wsm + lo_off + off) = v[u] - __uint_as_float(hi);
+      for (int u = 0; u < WU; ++u) {
+        const uint32_t i = i0 + u * NT;
+        v[u] = 0.f; oo[u] = 0xffffffffu;
+        if (i < nel) {
+          const int w = (int)(i >> msh), rem = (int)(i & ((1u << msh) - 1u));
+          const Seg& sg = P.seg[Lo.wk_seg[w]];
+          int c, n;
+          if (sg.wsc == 1) { c = rem & 31; n = rem >> 5; } else { n = rem & (MW - 1); c = rem >> (msh - 5); }
+          if (c < Lo.wk_valid[w] && n0 + n < P.N) {
+            v[u] = __ldg(sg.W + Lo.wk_wbase[w] + (long)(Lo.wk_c0[w] + c) * sg.wsc + (long)(n0 + n) * sg.wsn);
+            oo[u] = (uint32_t)w * MW * 128 + n * 128 + ((((c >> 2) ^ (n & 7)) << 4) | ((c & 3) << 2));
           }
         }
       }
-      kbb += (sg.C + KBLK - 1) / KBLK;
+#pragma unroll
+      for (int u = 0; u < WU; ++u) {
+        if (oo[u] != 0xffffffffu) {
+          const uint32_t hi = f2tf32(v[u]);
+          *(uint32_t*)(Wsm + oo[u]) = hi;
+          *(float*)(Wsm + lo_off + oo[u]) = v[u] - __uint_as_float(hi);
+        }
+      }
     }
     pdl_wait();        // everything below reads what earlier kernels of the step produced (BN coefficients first)
     for (int i = tid; i < Lo.ncoef * 32; i += NT) {
@@ -175,9 +183,10 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
       const Seg& sg = P.seg[Lo.coef_seg[e]];
       const int c = Lo.coef_c0[e] + j;
       const bool ok = c < sg.C;
-      coef[e * COEF_FLOATS + j] = ok ? __ldg(sg.p0 + sg.coff + c) : 1.f;
-      coef[e * COEF_FLOATS + 32 + j] = ok ? __ldg(sg.p2 + sg.coff + c) : 0.f;
-      coef[e * COEF_FLOATS + 64 + j] = (ok && sg.p1) ? __ldg(sg.p1 + sg.coff + c) : 0.f;
+      const int cc = sg.coff + (sg.cmod ? c % sg.cmod : c);
+      coef[e * COEF_FLOATS + j] = ok ? __ldg(sg.p0 + cc) : 1.f;
+      coef[e * COEF_FLOATS + 32 + j] = ok ? __ldg(sg.p2 + cc) : 0.f;
+      coef[e * COEF_FLOATS + 64 + j] = (ok && sg.p1) ? __ldg(sg.p1 + cc) : 0.f;
     }
   }
   if (warp == 0) {
@@ -203,7 +212,8 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
       // descriptor = constant high word | 14-bit (address >> 4); K-steps advance the address by 32 B
       const uint64_t dhi = (uint64_t)(smem_desc_sw128(0, 16, 1024) >> 32) << 32 | (1ull << 16);
       const uint32_t a_base = smem_u32(Asm) >> 4, w_base = smem_u32(Wsm) >> 4;
-      const uint32_t w_lo_off = ((uint32_t)nkb * MW * 128) >> 4, w_kb = ((uint32_t)MW * 128) >> 4;
+      const uint32_t w_lo_off = ((uint32_t)Lo.nwk * MW * 128) >> 4, w_kb = ((uint32_t)MW * 128) >> 4;
+      const uint32_t stage16 = Lo.stage >> 4, atile16 = Lo.atile >> 4;
       int st = 0;
       uint32_t ph = 0;
       for (int ti = 0; ti < n_my; ++ti) {
@@ -211,20 +221,24 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
         mbar_wait(&mi.tempty[acc], ((ti >> 1) & 1) ^ 1, 100 + ti);
         tc_fence_after();
         const uint32_t d = tmem + acc * BM;
+        int w = 0;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&mi.full[st], ph & 1, 200 + st * 10 + kb);
           tc_fence_after();
-          const uint32_t x_hi = a_base + st * (STAGE >> 4) + ((Lo.dbg & 64) ? 8u : 0u), x_lo = x_hi + (A_TILE >> 4);
-          const uint32_t w_hi = w_base + (uint32_t)kb * w_kb, w_lo = w_hi + w_lo_off;
+          const uint32_t x_st = a_base + st * stage16;
+          for (int u = Lo.kb_nw[kb]; u > 0; --u, ++w) {
+            // tap w reads the stage from row wk_shift[w] on: start address + shift * 128 B (8 units of 16 B)
+            const uint32_t x_hi = x_st + (uint32_t)Lo.wk_shift[w] * 8u, x_lo = x_hi + atile16;
+            const uint32_t w_hi = w_base + (uint32_t)w * w_kb, w_lo = w_hi + w_lo_off;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint64_t dxs = dhi | ((Lo.dbg & 128) ? (1ull << 49) : 0ull);     // (probe: matrix base offset = 1 row)
-            const uint64_t dxh = dxs | (x_hi + 2 * j), dxl = dxs | (x_lo + 2 * j);
-            const uint64_t dwh = dhi | (w_hi + 2 * j), dwl = dhi | (w_lo + 2 * j);
-            if (Lo.dbg & 1) continue;
-            mma_tf32(d, dwl, dxh, idesc, (kb | j) != 0);
-            mma_tf32(d, dwh, dxl, idesc, 1);
-            mma_tf32(d, dwh, dxh, idesc, 1);
+            for (int j = 0; j < 4; ++j) {
+              const uint64_t dxh = dhi | (x_hi + 2 * j), dxl = dhi | (x_lo + 2 * j);
+              const uint64_t dwh = dhi | (w_hi + 2 * j), dwl = dhi | (w_lo + 2 * j);
+              if (Lo.dbg & 1) continue;
+              mma_tf32(d, dwl, dxh, idesc, (w | j) != 0);
+              mma_tf32(d, dwh, dxl, idesc, 1);
+              mma_tf32(d, dwh, dxh, idesc, 1);
+            }
           }
           mma_commit(&mi.empty[(ph & 1) * 8 + st]);
           if (++st == nstage) { st = 0; ++ph; }
@@ -238,9 +252,10 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
     if (REG_LOAD < REG_LAUNCH) reg_dec<REG_LOAD>();
     constexpr int R = LD2 ? 4 : 8;                      // rows per thread and pass (LD2: two passes of 4 rows, two tensors)
     const int lt = tid - 128, g = lt >> 7, gt = lt & 127, chunk = gt & 7, rbase = gt >> 3;   // rows rbase + 16 i
-    const int prow = rbase + ((Lo.dbg & 64) ? 1 : 0);       // (probe: physical row = logical row + 1, read back through a shifted descriptor)
-    const uint32_t st_off = (uint32_t)prow * 128 + ((uint32_t)(chunk ^ (prow & 7)) << 4);
     const unsigned Lq = (unsigned)P.Lq, magic = Lo.lq_magic, Mu = (unsigned)M;
+    const bool shared = Lo.shared != 0;
+    const int xrows = Lo.arows - BM;                    // tap-shared launches stage a few extra rows (the largest tap shift)
+    const uint32_t a_addr = smem_u32(Asm), stage_b = Lo.stage, atile_b = Lo.atile;
     int ti = 0, kb = g;
     while (kb >= nkb) { kb -= nkb; ++ti; }
     // Ring bookkeeping.  A group advances NG k-blocks at a time, which can be more than one turn of the ring,
@@ -252,32 +267,45 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
     while (st >= nstage) { st -= nstage; ++ph; }
     int cur = -1;
     unsigned bt0 = 0, qb = 0, qmax = 0;
+    int v0 = 0;                      // tap-shared: virtual row of the thread's first stage row
     constexpr bool CACHE_ROWS = TRU_CACHE_ROWS != 0;
     unsigned rbt[CACHE_ROWS ? 8 : 1], rqq[CACHE_ROWS ? 8 : 1];
     const float ninf = -__int_as_float(0x7f800000);
+    constexpr unsigned NOROW = 0x3fffffffu;              // row decode of a virtual row outside [0, M): fails every "li < rows" test
+    // (frame, position) of virtual / tile row vv; tap-shared launches stage rows in front of / behind the problem as zero rows,
+    // the classic path clamps rows beyond M (last tile only) to row M-1: they load valid memory and the epilogue drops them
+    auto decode = [&](int ii, unsigned& bt, unsigned& q) {
+      if (shared) {
+        const int vv = v0 + 16 * ii;
+        const bool in = (unsigned)vv < Mu;
+        const unsigned uv = in ? (unsigned)vv : 0u;
+        const unsigned bq = magic ? __umulhi(uv, magic) : uv;       // uv / Lq (exact: uv * Lq < 2^32)
+        bt = bq; q = in ? uv - bq * Lq : NOROW;
+      } else {
+        const unsigned qq = min(qb + 16u * ii, qmax);
+        const unsigned bq = magic ? __umulhi(qq, magic) : qq;        // qq / Lq (exact: qq * Lq < 2^32)
+        bt = bt0 + bq; q = qq - bq * Lq;
+      }
+    };
     while (ti < n_my) {
       if (ti != cur) {               // new tile: decode its first row once; the thread's rows follow by a small exact division
         const unsigned m0 = ((unsigned)blockIdx.x + (unsigned)ti * gridDim.x) * BM;
-        // rows beyond M (last tile only) are clamped to row M-1: they load valid memory and the epilogue drops them
         bt0 = m0 / Lq; qb = m0 - bt0 * Lq + rbase; qmax = Mu - 1u - bt0 * Lq;
+        v0 = (int)m0 + P.row_base + rbase;
         cur = ti;
         if (CACHE_ROWS) {            // the (frame, position) of the thread's 8 rows is the same for every k-block of the tile
 #pragma unroll
-          for (int ii = 0; ii < 8; ++ii) {
-            const unsigned qq = min(qb + 16u * ii, qmax);
-            const unsigned bq = magic ? __umulhi(qq, magic) : qq;
-            rbt[ii] = bt0 + bq; rqq[ii] = qq - bq * Lq;
-          }
+          for (int ii = 0; ii < 8; ++ii) decode(ii, rbt[ii], rqq[ii]);
         }
       }
       const Seg& sg = P.seg[Lo.kb_seg[kb]];
       const float* src = sg.src;
       const float* src2 = LD2 ? sg.src2 : nullptr;
-      const unsigned Lsrc = (unsigned)sg.Lsrc, ld = (unsigned)sg.ld;
+      const unsigned ld = (unsigned)sg.ld, fs = sg.fs ? (unsigned)sg.fs : (unsigned)sg.Lsrc * ld;
       const int smul = sg.smul, sadd = sg.sadd;
       const unsigned cb = (unsigned)(sg.coff + Lo.kb_c0[kb] + chunk * 4);
       const bool cok = chunk * 4 < Lo.kb_valid[kb] && !(Lo.dbg & 2);
-      const unsigned Lok = cok ? Lsrc : 0u;               // channel chunk beyond the segment: every row is a zero row
+      const unsigned Lok = cok ? (unsigned)Lo.kb_lmax[kb] : 0u;        // channel chunk beyond the segment: every row is a zero row
       const int e = Lo.kb_coef[kb];
       const float fl = Lo.kb_relu[kb] ? 0.f : ninf;
       float4 p0 = make_float4(1.f, 1.f, 1.f, 1.f), p1 = make_float4(0.f, 0.f, 0.f, 0.f), p2 = p1;
@@ -286,7 +314,33 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
         p0 = *(const float4*)ce; p2 = *(const float4*)(ce + 32);
         if (LD2) p1 = *(const float4*)(ce + 64);
       }
-      uint8_t* ah = Asm + st * STAGE + st_off;
+      // Swizzle by ADDRESS (bits 4-6 ^= bits 7-9): a plane of a tap-shared stage need not start on a 1024-byte boundary.
+      // Rows rbase + 16 i of a plane share their phase, so the two chunk offsets are per-k-block constants.
+      const uint32_t s_addr = a_addr + (uint32_t)st * stage_b;
+      const uint32_t sw_hi = (uint32_t)(chunk ^ (((s_addr >> 7) + rbase) & 7)) << 4;
+      const uint32_t sw_lo = (uint32_t)(chunk ^ ((((s_addr + atile_b) >> 7) + rbase) & 7)) << 4;
+      uint8_t* ah = Asm + (size_t)st * stage_b + (uint32_t)rbase * 128;
+      // transform (affine + ReLU, or BN-backward affine), truncating tf32 split, store row `row` of the stage
+      auto put = [&](float4 v, const float4& bz, bool keep, int row) {
+        if (e >= 0 && !(Lo.dbg & 32)) {
+          if (LD2) {
+            v.x = fmaf(p1.x, bz.x, fmaf(p0.x, v.x, p2.x)); v.y = fmaf(p1.y, bz.y, fmaf(p0.y, v.y, p2.y));
+            v.z = fmaf(p1.z, bz.z, fmaf(p0.z, v.z, p2.z)); v.w = fmaf(p1.w, bz.w, fmaf(p0.w, v.w, p2.w));
+          } else {
+            v.x = fmaf(p0.x, v.x, p2.x); v.y = fmaf(p0.y, v.y, p2.y); v.z = fmaf(p0.z, v.z, p2.z); v.w = fmaf(p0.w, v.w, p2.w);
+            v.x = fmaxf(v.x, fl); v.y = fmaxf(v.y, fl); v.z = fmaxf(v.z, fl); v.w = fmaxf(v.w, fl);
+          }
+        }
+        if (!keep) v = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint4 hi, lo;
+        hi.x = __float_as_uint(v.x) & 0xffffe000u; hi.y = __float_as_uint(v.y) & 0xffffe000u;
+        hi.z = __float_as_uint(v.z) & 0xffffe000u; hi.w = __float_as_uint(v.w) & 0xffffe000u;
+        lo.x = __float_as_uint(v.x - __uint_as_float(hi.x)); lo.y = __float_as_uint(v.y - __uint_as_float(hi.y));
+        lo.z = __float_as_uint(v.z - __uint_as_float(hi.z)); lo.w = __float_as_uint(v.w - __uint_as_float(hi.w));
+        if (Lo.dbg & 4) return;
+        *(uint4*)(ah + row * (16 * 128) + sw_hi) = hi;
+        *(uint4*)(ah + atile_b + row * (16 * 128) + sw_lo) = lo;
+      };
 #pragma unroll
       for (int h = 0; h < 8 / R; ++h) {
         float4 a[R], b[LD2 ? R : 1];
@@ -295,15 +349,10 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
         for (int i = 0; i < R; ++i) {
           const int ii = h * R + i;
           unsigned bt, q;
-          if (CACHE_ROWS) { bt = rbt[ii]; q = rqq[ii]; }
-          else {
-            const unsigned qq = min(qb + 16u * ii, qmax);
-            const unsigned bq = magic ? __umulhi(qq, magic) : qq;        // qq / Lq (exact: qq * Lq < 2^32)
-            bt = bt0 + bq; q = qq - bq * Lq;
-          }
+          if (CACHE_ROWS) { bt = rbt[ii]; q = rqq[ii]; } else decode(ii, bt, q);
           const unsigned li = (unsigned)((int)q * smul + sadd);
           const bool ok = li < Lok;
-          unsigned off = (bt * Lsrc + li) * ld + cb;
+          unsigned off = bt * fs + li * ld + cb;
           off = ok ? off : 0u;               // padding rows read element 0 (always mapped) and are zeroed below
           if (ok) msk |= 1u << i;
           a[i] = ldg4_off(src, off);
@@ -311,32 +360,23 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
         }
         if (h == 0 && ph > 0) mbar_wait(&mi.empty[((ph - 1) & 1) * 8 + st], ((ph - 1) >> 1) & 1, 300 + st * 10 + kb + 1000 * ti);
         const bool all_ok = __all_sync(0xffffffffu, msk == (1u << R) - 1u);
-        auto emit = [&](auto ZERO) {
-          constexpr bool zero = decltype(ZERO)::value;
+        if (all_ok) {
 #pragma unroll
-          for (int i = 0; i < R; ++i) {
-            float4 v = a[i];
-            if (e >= 0 && !(Lo.dbg & 32)) {
-              if (LD2) {
-                v.x = fmaf(p1.x, b[i].x, fmaf(p0.x, v.x, p2.x)); v.y = fmaf(p1.y, b[i].y, fmaf(p0.y, v.y, p2.y));
-                v.z = fmaf(p1.z, b[i].z, fmaf(p0.z, v.z, p2.z)); v.w = fmaf(p1.w, b[i].w, fmaf(p0.w, v.w, p2.w));
-              } else {
-                v.x = fmaf(p0.x, v.x, p2.x); v.y = fmaf(p0.y, v.y, p2.y); v.z = fmaf(p0.z, v.z, p2.z); v.w = fmaf(p0.w, v.w, p2.w);
-                v.x = fmaxf(v.x, fl); v.y = fmaxf(v.y, fl); v.z = fmaxf(v.z, fl); v.w = fmaxf(v.w, fl);
-              }
-            }
-            if (zero && !(msk & (1u << i))) v = make_float4(0.f, 0.f, 0.f, 0.f);
-            uint4 hi, lo;
-            hi.x = __float_as_uint(v.x) & 0xffffe000u; hi.y = __float_as_uint(v.y) & 0xffffe000u;
-            hi.z = __float_as_uint(v.z) & 0xffffe000u; hi.w = __float_as_uint(v.w) & 0xffffe000u;
-            lo.x = __float_as_uint(v.x - __uint_as_float(hi.x)); lo.y = __float_as_uint(v.y - __uint_as_float(hi.y));
-            lo.z = __float_as_uint(v.z - __uint_as_float(hi.z)); lo.w = __float_as_uint(v.w - __uint_as_float(hi.w));
-            if (Lo.dbg & 4) continue;
-            *(uint4*)(ah + (h * R + i) * (16 * 128)) = hi;
-            *(uint4*)(ah + A_TILE + (h * R + i) * (16 * 128)) = lo;
-          }
-        };
-        if (all_ok) emit(std::false_type{}); else emit(std::true_type{});
+          for (int i = 0; i < R; ++i) put(a[i], b[LD2 ? i : 0], true, h * R + i);
+        } else {
+#pragma unroll
+          for (int i = 0; i < R; ++i) put(a[i], b[LD2 ? i : 0], (msk >> i) & 1u, h * R + i);
+        }
+      }
+      if (shared && rbase < xrows) {         // stage rows 128 + rbase (rbase < largest tap shift): one more row for the first threads
+        unsigned bt, q;
+        decode(8, bt, q);
+        const unsigned li = (unsigned)((int)q * smul + sadd);
+        const bool ok = li < Lok;
+        const unsigned off = ok ? bt * fs + li * ld + cb : 0u;
+        const float4 a9 = ldg4_off(src, off);
+        const float4 b9 = (LD2 && src2) ? ldg4_off(src2, off) : make_float4(0.f, 0.f, 0.f, 0.f);
+        put(a9, b9, ok, 8);
       }
       fence_proxy_async();
       __syncwarp();
@@ -361,7 +401,7 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
     const int n = n0 + nl;
     const bool nok = n < P.N && !(Lo.dbg & 8);
     const int src64 = lane & 16;                        // M = 64: lanes 16-31 hold the second 16 rows of a chunk
-    const unsigned Mu = (unsigned)M, Lq = (unsigned)P.Lq;
+    const unsigned Mu = (unsigned)M, Lq = (unsigned)P.Lq;      // (P.Lvalid: the launcher sets it to Lq for classic launches)
     const float bias = (P.bias && nok) ? __ldg(P.bias + n) : 0.f;
     float mp0 = 1.f, mp2 = 0.f;
     const bool use_mask = EPI && P.use_mask, has_extra = EPI == 2 && P.extra != nullptr;
@@ -388,6 +428,7 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
           const unsigned lo = q * P.omul + P.oadd, r = bt * P.Lout + lo;
           ooff = P.planar ? bt * (unsigned)P.N * (unsigned)P.Lout + lo : r * (unsigned)P.ldo + P.ocoff;
           eoff = r * (unsigned)P.ext_ld;
+          if (q >= (unsigned)P.Lvalid) ooff = 0xffffffffu;   // (tap-shared launches: virtual rows that only exist to be read by shifted taps)
         }
       }
     };
@@ -444,7 +485,7 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
     zfetch(za, xx, oa, m64 ? src64 : 0);
     for (int ti = 0; ti < n_my; ++ti) {
       const int acc = ti & 1;
-      const bool part = (((unsigned)blockIdx.x + (unsigned)ti * gridDim.x) + 1u) * BM > Mu;    // tile has missing rows
+      const bool part = (((unsigned)blockIdx.x + (unsigned)ti * gridDim.x) + 1u) * BM > Mu || P.Lvalid < P.Lq;    // tile has missing rows
       row_offsets(ti, half * 2 + 1, ob, eb);
       mbar_wait(&mi.tfull[acc], (ti >> 1) & 1, 400 + ti);
       tc_fence_after();
@@ -546,6 +587,7 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
 }
 
 constexpr size_t SMEM_MAX = 227 * 1024;
+constexpr int STAGE = 2 * BM * 128;       // bytes of a classic stage (hi + lo plane of 128 rows)
 int g_dbg_flags = 0;        // ablation switches (tru_debug_set_flags)
 
 int total_kblocks(const IgemmParams& p) {
@@ -557,21 +599,29 @@ int total_kblocks(const IgemmParams& p) {
 bool shape_ok(const IgemmParams& p) {
   if (p.nseg < 1 || p.nseg > 5 || p.N < 1 || p.Lq < 1 || p.Lq > 32768) return false;
   for (int s = 0; s < p.nseg; ++s) {
-    if (p.seg[s].C % 4 != 0 || p.seg[s].ld % 4 != 0 || p.seg[s].coff % 4 != 0) return false;
+    if (p.seg[s].C % 4 != 0 || p.seg[s].ld % 4 != 0 || p.seg[s].coff % 4 != 0 || p.seg[s].fs % 4 != 0) return false;
     // 32-bit element offsets inside the kernel
-    if ((double)p.BT * p.seg[s].Lsrc * p.seg[s].ld >= 2147483648.0) return false;
+    const double fs = p.seg[s].fs ? p.seg[s].fs : (double)p.seg[s].Lsrc * p.seg[s].ld;
+    if ((double)p.BT * fs >= 2147483648.0) return false;
   }
-  if ((double)p.BT * p.Lout * std::max(p.ldo, 1) >= 4294967296.0 || (double)p.BT * p.Lq + BM >= 4294967296.0) return false;
+  if ((double)p.BT * p.Lout * std::max(p.ldo, 1) >= 4294967296.0 || (double)p.BT * p.Lq + BM >= 2147483648.0) return false;
   if (p.planar && (double)p.BT * p.N * p.Lout >= 4294967296.0) return false;
   if (p.extra && (p.ext_ld != p.ldo || p.planar)) return false;     // the added tensor shares the output's row offsets
+  if (p.ntap) {                // tap-shared mode: one source, whole 32-channel blocks, shifts inside the 8 spare rows, one N block
+    if (p.ntap > 5 || p.nseg != 1 || p.N > 128 || p.planar || p.seg[0].smul != 1 || p.seg[0].sadd != 0 || p.seg[0].C % KBLK != 0) return false;
+    if (p.Lvalid < 0 || p.Lvalid > p.Lq || p.row_base > 0 || p.row_base < -7) return false;
+    for (int j = 0; j < p.ntap; ++j)
+      if (p.tap_shift[j] < 0 || p.tap_shift[j] > 7 || p.tap_c0[j] % KBLK != 0 || p.tap_C[j] % KBLK != 0 || p.tap_C[j] < KBLK ||
+          p.tap_c0[j] < 0 || p.tap_c0[j] + p.tap_C[j] > p.seg[0].C) return false;
+  } else if (p.Lvalid != 0 && p.Lvalid != p.Lq) return false;
   return true;
 }
 
 int weight_rows(const IgemmParams& p) { return p.N <= 64 ? 64 : 128; }
 
-// the most k-blocks one launch can keep resident next to a 2-stage ring
+// the most k-blocks one classic launch can keep resident next to a 2-stage ring
 int max_kblocks(int MW) {
-  const size_t fixed = 1024 + 2 * STAGE + sizeof(Misc) + 64 + (size_t)MAXCOEF * COEF_FLOATS * 4;
+  const size_t fixed = 2 * STAGE + sizeof(Misc) + 64 + (size_t)MAXCOEF * COEF_FLOATS * 4;
   return (int)std::min<size_t>(MAXKB, (SMEM_MAX - fixed) / ((size_t)MW * 256));
 }
 
@@ -579,6 +629,7 @@ bool plan(const IgemmParams& p, TcLayout& L, dim3& grid, size_t& smem_bytes) {
   if (!shape_ok(p)) return false;
   memset(&L, 0, sizeof(L));
   L.MW = weight_rows(p);
+  L.shared = p.ntap > 0;
   int nkb = 0, ncoef = 0;
   for (int s = 0; s < p.nseg; ++s) {
     const Seg& sg = p.seg[s];
@@ -586,6 +637,7 @@ bool plan(const IgemmParams& p, TcLayout& L, dim3& grid, size_t& smem_bytes) {
       if (nkb >= MAXKB) return false;
       L.kb_seg[nkb] = (int8_t)s; L.kb_c0[nkb] = (int16_t)c0; L.kb_valid[nkb] = (int16_t)std::min(KBLK, sg.C - c0);
       L.kb_relu[nkb] = (int8_t)(sg.p0 && sg.relu);
+      L.kb_lmax[nkb] = (L.shared && p.c_hi > 0 && c0 >= p.c_hi) ? p.lmax_hi : sg.Lsrc;
       L.kb_coef[nkb] = -1;
       if (sg.p0) {
         int e = -1;
@@ -604,17 +656,39 @@ bool plan(const IgemmParams& p, TcLayout& L, dim3& grid, size_t& smem_bytes) {
       ++nkb;
     }
   }
-  L.nkb = nkb; L.ncoef = ncoef; L.dbg = g_dbg_flags;
+  // resident weight k-blocks, grouped by the source k-block that feeds them (the MMA thread walks them in this order)
+  int nwk = 0, maxshift = 0;
+  for (int kb = 0; kb < nkb; ++kb) {
+    if (!L.shared) {
+      const Seg& sg = p.seg[L.kb_seg[kb]];
+      L.wk_seg[nwk] = L.kb_seg[kb]; L.wk_shift[nwk] = 0; L.wk_c0[nwk] = L.kb_c0[kb]; L.wk_valid[nwk] = L.kb_valid[kb];
+      L.wk_wbase[nwk] = sg.wbase;
+      L.kb_nw[kb] = 1; ++nwk;
+      continue;
+    }
+    const int c0 = L.kb_c0[kb];
+    for (int j = 0; j < p.ntap; ++j) {
+      if (c0 < p.tap_c0[j] || c0 >= p.tap_c0[j] + p.tap_C[j]) continue;
+      if (nwk >= MAXWK) return false;
+      L.wk_seg[nwk] = 0; L.wk_shift[nwk] = (int8_t)p.tap_shift[j]; L.wk_c0[nwk] = (int16_t)(c0 - p.tap_c0[j]); L.wk_valid[nwk] = KBLK;
+      L.wk_wbase[nwk] = p.tap_wbase[j];
+      maxshift = std::max(maxshift, p.tap_shift[j]);
+      ++L.kb_nw[kb]; ++nwk;
+    }
+    if (L.kb_nw[kb] == 0) return false;       // a staged channel block no tap reads
+  }
+  L.nkb = nkb; L.ncoef = ncoef; L.nwk = nwk; L.dbg = g_dbg_flags;
+  L.arows = BM + maxshift; L.atile = (uint32_t)L.arows * 128; L.stage = 2 * L.atile;
   L.lq_magic = p.Lq == 1 ? 0u : (unsigned)((0x100000000ull + (unsigned)p.Lq - 1) / (unsigned)p.Lq);
-  const size_t w = (size_t)2 * nkb * L.MW * 128;
+  const size_t w = (size_t)2 * nwk * L.MW * 128;
   const size_t coefb = (size_t)ncoef * COEF_FLOATS * 4;
-  const size_t fixed = 1024 + coefb + sizeof(Misc) + 64;
-  if (fixed + w + 2 * STAGE > SMEM_MAX) return false;
-  L.nstage = (int)std::min<size_t>(6, (SMEM_MAX - fixed - w) / STAGE);
+  const size_t fixed = coefb + sizeof(Misc) + 64;
+  if (fixed + w + 2 * (size_t)L.stage > SMEM_MAX) return false;
+  L.nstage = (int)std::min<size_t>(6, (SMEM_MAX - fixed - w) / L.stage);
   L.a_off = (uint32_t)w;                                   // multiple of 1024
-  L.coef_off = L.a_off + L.nstage * STAGE;
+  L.coef_off = L.a_off + L.nstage * L.stage;               // multiple of 128
   L.misc_off = (uint32_t)align_up(L.coef_off + coefb, 16);
-  smem_bytes = 1024 + L.misc_off + sizeof(Misc);
+  smem_bytes = L.misc_off + sizeof(Misc);
   const int ny = (p.N + L.MW - 1) / L.MW;
   const long M = (long)p.BT * p.Lq;
   const int ntiles = (int)((M + BM - 1) / BM);
@@ -640,11 +714,13 @@ int launch_one(const IgemmParams& p, const TcLayout& L, dim3 grid, size_t smem, 
   return epi == 0 ? launch_inst<12, false, 0>(p, L, grid, smem, st) : epi == 1 ? launch_inst<12, false, 1>(p, L, grid, smem, st) : launch_inst<12, false, 2>(p, L, grid, smem, st);
 }
 
-int launch_planned(const IgemmParams& p, cudaStream_t st) {
+int launch_planned(const IgemmParams& p0, cudaStream_t st) {
   TcLayout L;
   dim3 grid;
   size_t smem = 0;
-  if (!plan(p, L, grid, smem)) return 1;
+  if (!plan(p0, L, grid, smem)) return 1;
+  IgemmParams p = p0;
+  if (p.Lvalid == 0) p.Lvalid = p.Lq;        // classic launches: every row is an output row
   return launch_one(p, L, grid, smem, st);
 }
 
@@ -683,6 +759,7 @@ int read_mbar_debug(unsigned* out, int n) {
 
 bool igemm_tc_eligible(const IgemmParams& p) {
   if (!shape_ok(p)) return false;
+  if (p.ntap) { TcLayout L; dim3 g; size_t s = 0; return plan(p, L, g, s); }      // tap-shared launches are never split
   const int nkb = total_kblocks(p), cap = max_kblocks(weight_rows(p));
   if (nkb <= cap) { TcLayout L; dim3 g; size_t s = 0; return plan(p, L, g, s); }
   return !p.planar && cap >= 1 && (nkb + cap - 1) / cap <= 4;
@@ -695,7 +772,7 @@ bool igemm_tc_eligible(const IgemmParams& p) {
 int launch_igemm_tc(const IgemmParams& p, cudaStream_t st) {
   if (!igemm_tc_eligible(p)) return 1;
   const int nkb = total_kblocks(p), cap = max_kblocks(weight_rows(p));
-  if (nkb <= cap) return launch_planned(p, st);
+  if (p.ntap || nkb <= cap) return launch_planned(p, st);
   const int npass = (nkb + cap - 1) / cap, per = (nkb + npass - 1) / npass;
   for (int i = 0; i < npass; ++i) {
     IgemmParams q = slice_kblocks(p, i * per, std::min(nkb, (i + 1) * per));

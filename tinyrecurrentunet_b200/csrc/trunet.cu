@@ -6,6 +6,7 @@
 // consumers on load.  The host code below is the only "runtime": one C call walks
 // the whole layer list and enqueues every kernel on the caller's stream.
 #include <algorithm>
+#include <stdlib.h>
 #include <string>
 #include "net_kernels.cuh"
 #include "../../include/tru_b200_debug.h"
@@ -165,7 +166,31 @@ int pw_fwd(Ctx& c, const Act& x1, int padL, const Act* skip, const float* W, con
   return launch_igemm(p, c.st);
 }
 
+// Tap-shared launch parameters common to the transposed-conv forward and data gradient (net_kernels.cuh: IgemmParams::ntap):
+// taps (delta_j, channel slice, weight offset); virtual rows per frame Lq_v chosen by the caller.
+struct Tap { int delta, c0, C, wbase; };
+// TRU_TAP_SHARED_OFF (bit 0: forward, bit 1: data gradient) sends the transposed convs down the one-segment-per-tap launches (A/B aid)
+int tap_shared_off() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("TRU_TAP_SHARED_OFF"); v = e ? atoi(e) : 0; }
+  return v;
+}
+void set_taps(IgemmParams& p, const Tap* taps, int ntap) {
+  int dmin = 0;
+  for (int j = 0; j < ntap; ++j) dmin = std::min(dmin, taps[j].delta);
+  p.ntap = ntap; p.row_base = dmin;
+  for (int j = 0; j < ntap; ++j) {
+    p.tap_shift[j] = taps[j].delta - dmin; p.tap_c0[j] = taps[j].c0; p.tap_C[j] = taps[j].C; p.tap_wbase[j] = taps[j].wbase;
+  }
+}
+
 // transposed conv (weight (Cin,Cout,k), stride s, pad s/2): x [BT][L][Cin] -> out [BT][Lout][Cout]
+//   out[lo] = sum_j x[(lo + pad - j) / s] W_j  over the taps j with (lo + pad - j) divisible by s.
+// Per output-row parity class (lo = s q + par) the taps read source rows q + delta_j, delta_j = (par + pad - j) / s.  With two or
+// more taps the launch is TAP-SHARED: rows m = (bt, q) are virtual rows, Lq_v per frame; the kernel stages source row q of every
+// virtual row once (zero for q >= L) and each tap reads the stage shifted by delta_j rows.  Lq_v = max(Lq + max delta, L - min delta)
+// makes every shifted read that leaves its frame land on a zero row (q >= L of the neighbouring frame) or belong to a virtual
+// row beyond the Lq real ones, which is not stored.
 int convt_fwd(Ctx& c, const Act& x, const float* W, const float* bias, int Cout, int k, int s, int Lout, float* out,
               double* stats, int planar) {
   const int pad = s / 2;
@@ -173,6 +198,8 @@ int convt_fwd(Ctx& c, const Act& x, const float* W, const float* bias, int Cout,
     return launch_convt_small_fwd(x.z, x.p0, x.p2, W, bias, out, (int)c.BT, x.L, Lout, planar, c.st);
   for (int par = 0; par < s; ++par) {
     IgemmParams p{};
+    Tap taps[5];
+    int nt = 0, dmax = 0, dmin = 0;
     p.nseg = 0;
     for (int j = 0; j < k; ++j) {
       if (((par + pad - j) % s + s) % s != 0) continue;
@@ -180,11 +207,22 @@ int convt_fwd(Ctx& c, const Act& x, const float* W, const float* bias, int Cout,
       const int num = par + pad - j;
       const int add = num >= 0 ? num / s : -((-num) / s);
       p.seg[p.nseg++] = fwd_seg(x, W, j, Cout * k, k, 1, add);
+      taps[nt++] = Tap{add, 0, x.C, j};
+      dmax = std::max(dmax, add); dmin = std::min(dmin, add);
     }
-    p.BT = (int)c.BT; p.Lq = (Lout - par + s - 1) / s; p.N = Cout; p.bias = bias;
+    const int Lq = (Lout - par + s - 1) / s;
+    p.BT = (int)c.BT; p.Lq = Lq; p.N = Cout; p.bias = bias;
     p.out = out; p.Lout = Lout; p.ldo = Cout; p.ocoff = 0; p.omul = s; p.oadd = par; p.planar = planar;
     p.stats = stats; p.src_frac = 1.0f / s;
-    if (p.Lq > 0 && p.nseg > 0) TRY(launch_igemm(p, c.st));
+    if (Lq <= 0 || p.nseg == 0) continue;
+    if (nt >= 2 && !planar && tc_enabled() && !(tap_shared_off() & 1)) {
+      IgemmParams q = p;
+      q.nseg = 1; q.seg[0] = fwd_seg(x, W, 0, Cout * k, k, 1, 0);
+      set_taps(q, taps, nt);
+      q.Lq = std::max(Lq + dmax, x.L - dmin); q.Lvalid = Lq;
+      if (igemm_tc_eligible(q)) { TRY(launch_igemm(q, c.st)); continue; }
+    }
+    TRY(launch_igemm(p, c.st));
   }
   return TRU_OK;
 }
@@ -363,6 +401,38 @@ int pw_bwd(Ctx& c, const Grad& g, const Act& x1, int padL, const Act* skip, int 
   return TRU_OK;
 }
 
+// Tap-shared form of a transposed conv's data gradient: dX[li] = sum_j dZ[s li + j - pad] W_j^T.  The gradient rows of a frame are
+// viewed as g.L / s "wide rows" of s consecutive rows (s * Cout channels: one contiguous run), wide row r = rows s r .. s r + s - 1;
+// tap j reads wide row li + delta_j, delta_j = floor((j - pad) / s), channels [h Cout, (h + 1) Cout) with h = (j - pad) - s delta_j.
+// When g.L is not a multiple of s the last wide row is incomplete: channel blocks >= c_hi exist for fewer rows (lmax_hi).
+// Virtual rows per frame Lq_v = max(L + max delta, rows of the slice a negative-delta tap reads - delta): a tap that leaves its
+// frame finds a zero (non-existent) wide row, or feeds one of the Lq_v - L virtual rows that are not stored.
+// p = the classic launch (one segment per tap) of the same product; returns false if the tensor-core kernel does not take q.
+bool convt_dgrad_shared(IgemmParams& q, const IgemmParams& p, const Grad& g, int xL, int Cout, int k, int s, const float* W) {
+  const int pad = s / 2;
+  if (!(k >= 2 && k <= 5 && tc_enabled() && (s == 1 || s == 2) && Cout % 32 == 0) || (tap_shared_off() & 2)) return false;
+  q = p;
+  q.nseg = 1;
+  q.seg[0] = bwd_seg(g, 0, s * Cout, s * Cout, W, 0, k, Cout * k, 1, 0);
+  const int wide_full = g.L / s, wide_any = (g.L + s - 1) / s;      // wide rows with all s rows / with at least the first
+  q.seg[0].Lsrc = wide_any; q.seg[0].fs = g.L * Cout; q.seg[0].cmod = Cout;
+  if (wide_full != wide_any) { q.c_hi = Cout; q.lmax_hi = wide_full; }     // (s = 2: the second half of the last wide row is missing)
+  Tap taps[5];
+  int dmax = 0, Lqv = xL;
+  for (int j = 0; j < k; ++j) {
+    const int t = j - pad;
+    const int delta = t >= 0 ? t / s : -((-t + s - 1) / s);
+    const int h = t - s * delta;
+    taps[j] = Tap{delta, h * Cout, Cout, j};
+    dmax = std::max(dmax, delta);
+    if (delta < 0) Lqv = std::max(Lqv, (h == 0 ? wide_any : wide_full) - delta);
+  }
+  Lqv = std::max(Lqv, xL + dmax);
+  set_taps(q, taps, k);
+  q.Lq = Lqv; q.Lvalid = xL;
+  return igemm_tc_eligible(q);
+}
+
 // transposed conv backward: g = grad of the convT output (Lout rows, Cout ch), x = its input activation
 int convt_bwd(Ctx& c, const Grad& g, const Act& x, int ct_param, int k, int s, float* dX, const float* planar_dy = nullptr) {
   const float* W = c.prm[ct_param];
@@ -412,6 +482,8 @@ int convt_bwd(Ctx& c, const Grad& g, const Act& x, int ct_param, int k, int s, f
   p.nseg = k; p.BT = (int)c.BT; p.Lq = x.L; p.N = Cin;
   p.out = dX; p.Lout = x.L; p.ldo = Cin; p.omul = 1;
   set_mask(p, c, x, true);
+  IgemmParams q;
+  if (convt_dgrad_shared(q, p, g, x.L, Cout, k, s, W)) return launch_igemm(q, c.st);
   return launch_igemm(p, c.st);
 }
 
@@ -657,18 +729,40 @@ extern "C" long long tru_trunet_buffer_offset(const TruNetDesc* d, const char* n
   return -1;
 }
 
-// Test aid: raw transposed-conv data gradient through the implicit-GEMM path.
-// dy (BT, Lout, Cout) channels-last, w (Cin, Cout, k) -> dx (BT, L, Cin); no BN, no mask.
-extern "C" int tru_debug_convt_bwd_data(const float* dy, const float* w, float* dx, int BT, int L, int Lout,
-                                        int Cin, int Cout, int k, int s, void* stream) {
+// Test aid: transposed-conv data gradient through the implicit-GEMM path.
+// dy (BT, Lout, Cout) channels-last, w (Cin, Cout, k) -> dx (BT, L, Cin); with z / q0 / q1 / q2 the gradient is
+// dz = q0*dy + q1*z + q2 per channel (the BatchNorm-backward affine applied on load); with zmask / mp0 / mp2 the result is
+// masked by relu'(mp0*zmask + mp2) and bstats (2 Cin doubles) += sum g, invstd * sum g*(zmask - mean) (the epilogue of the
+// in-network launches).
+extern "C" int tru_debug_convt_bwd_data(const float* dy, const float* z, const float* q0, const float* q1, const float* q2,
+                                        const float* w, float* dx, const float* zmask, const float* mp0, const float* mp2,
+                                        const float* bmean, const float* binv, double* bstats, int BT, int L, int Lout,
+                                        int Cin, int Cout, int k, int s, int shared, void* stream) {
   int rc = ensure_init();
   if (rc) return rc;
   IgemmParams p{};
-  Grad g{dy, nullptr, nullptr, nullptr, nullptr, Lout, Cout};
+  Grad g{dy, q0 ? z : nullptr, q0, q1, q2, Lout, Cout};
   for (int j = 0; j < k; ++j) p.seg[j] = bwd_seg(g, 0, Cout, Cout, w, j, k, Cout * k, s, j - s / 2);
   p.nseg = k; p.BT = BT; p.Lq = L; p.N = Cin;
   p.out = dx; p.Lout = L; p.ldo = Cin; p.omul = 1;
+  if (zmask) { p.use_mask = 1; p.zmask = zmask; p.mp0 = mp0; p.mp2 = mp2; }
+  if (bstats) { p.bstats = bstats; p.bmean = bmean; p.binv = binv; }
+  IgemmParams q;
+  if (shared && convt_dgrad_shared(q, p, g, L, Cout, k, s, w)) return launch_igemm(q, (cudaStream_t)stream);
+  if (shared) return set_error(TRU_ERR_ARG, "debug_convt_bwd_data: shape not eligible for the tap-shared path");
   return launch_igemm(p, (cudaStream_t)stream);
+}
+
+// Test aid: ConvTranspose1d forward through the implicit-GEMM path (tap-shared launches where eligible).
+extern "C" int tru_debug_convt_fwd(const float* x, const float* w, const float* bias, float* out, double* stats, int BT, int L,
+                                   int Lout, int Cin, int Cout, int k, int s, void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  TRU_REQUIRE(Lout == (L - 1) * s - 2 * (s / 2) + k, TRU_ERR_ARG, "debug_convt_fwd: Lout does not match (L-1)s - 2 pad + k");
+  Ctx c{};
+  c.BT = BT; c.st = (cudaStream_t)stream;
+  Act a{x, L, Cin, nullptr, nullptr, -1};
+  return convt_fwd(c, a, w, bias, Cout, k, s, Lout, out, stats, 0);
 }
 
 // Test aid: pointwise conv y = act(x) W^T + b through either GEMM path.  x (M,K), w (N,K), out (M,N).
