@@ -39,6 +39,7 @@ using namespace tc;
 constexpr int BM = 128, KBLK = 32;
 constexpr int EW = 8;                                     // epilogue warps
 constexpr int MAXKB = 16, MAXCOEF = 12, MAXWK = 16;
+constexpr uint32_t ATILE_C = BM * 128, STAGE_C = 2 * ATILE_C;    // classic launches: 128 rows per plane
 constexpr int COEF_FLOATS = 96;                           // p0[32] p2[32] p1[32]
 
 // A tile of 128 gathered rows x 32 channels is staged ONCE per k-block (hi and lo tf32 planes, 128 B per row, SWIZZLE_128B) and
@@ -115,7 +116,9 @@ __device__ __forceinline__ float4 ldg4_off(const float* base, unsigned off) {
 //     parallelism comes from the groups working on different k-blocks, not from register slots.
 //   * the epilogue addresses rows with one 32-bit element offset (lane j computes row j's, broadcast by
 //     shuffle) and IMAD.WIDE + STG; full tiles skip the per-row validity test.
-template <int LW, bool LD2, int EPI>
+// SH: tap-shared launch (compile-time, so that the classic launches keep their constant stage geometry, their per-thread
+// constant swizzle and one weight k-block per staged k-block: the generalised loader cost them ~10 % when it was a run-time mode)
+template <int LW, bool LD2, int EPI, bool SH>
 __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const __grid_constant__ IgemmParams P,
                                                          const __grid_constant__ TcLayout Lo) {
   // register budgets per role (launch value 72 for 28 warps): 4*24 + 16*64 + 8*112 = 2016 = 28*72
@@ -213,7 +216,7 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
       const uint64_t dhi = (uint64_t)(smem_desc_sw128(0, 16, 1024) >> 32) << 32 | (1ull << 16);
       const uint32_t a_base = smem_u32(Asm) >> 4, w_base = smem_u32(Wsm) >> 4;
       const uint32_t w_lo_off = ((uint32_t)Lo.nwk * MW * 128) >> 4, w_kb = ((uint32_t)MW * 128) >> 4;
-      const uint32_t stage16 = Lo.stage >> 4, atile16 = Lo.atile >> 4;
+      const uint32_t stage16 = (SH ? Lo.stage : STAGE_C) >> 4, atile16 = (SH ? Lo.atile : ATILE_C) >> 4;
       int st = 0;
       uint32_t ph = 0;
       for (int ti = 0; ti < n_my; ++ti) {
@@ -226,9 +229,9 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
           mbar_wait(&mi.full[st], ph & 1, 200 + st * 10 + kb);
           tc_fence_after();
           const uint32_t x_st = a_base + st * stage16;
-          for (int u = Lo.kb_nw[kb]; u > 0; --u, ++w) {
+          for (int u = SH ? Lo.kb_nw[kb] : 1; u > 0; --u, ++w) {
             // tap w reads the stage from row wk_shift[w] on: start address + shift * 128 B (8 units of 16 B)
-            const uint32_t x_hi = x_st + (uint32_t)Lo.wk_shift[w] * 8u, x_lo = x_hi + atile16;
+            const uint32_t x_hi = x_st + (SH ? (uint32_t)Lo.wk_shift[w] * 8u : 0u), x_lo = x_hi + atile16;
             const uint32_t w_hi = w_base + (uint32_t)w * w_kb, w_lo = w_hi + w_lo_off;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -253,9 +256,10 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
     constexpr int R = LD2 ? 4 : 8;                      // rows per thread and pass (LD2: two passes of 4 rows, two tensors)
     const int lt = tid - 128, g = lt >> 7, gt = lt & 127, chunk = gt & 7, rbase = gt >> 3;   // rows rbase + 16 i
     const unsigned Lq = (unsigned)P.Lq, magic = Lo.lq_magic, Mu = (unsigned)M;
-    const bool shared = Lo.shared != 0;
-    const int xrows = Lo.arows - BM;                    // tap-shared launches stage a few extra rows (the largest tap shift)
-    const uint32_t a_addr = smem_u32(Asm), stage_b = Lo.stage, atile_b = Lo.atile;
+    constexpr bool shared = SH;
+    const int xrows = SH ? Lo.arows - BM : 0;           // tap-shared launches stage a few extra rows (the largest tap shift)
+    const uint32_t a_addr = smem_u32(Asm), stage_b = SH ? Lo.stage : STAGE_C, atile_b = SH ? Lo.atile : ATILE_C;
+    const uint32_t sw_c = (uint32_t)(chunk ^ (rbase & 7)) << 4;      // classic stages are whole 1024-byte atoms: constant swizzle
     int ti = 0, kb = g;
     while (kb >= nkb) { kb -= nkb; ++ti; }
     // Ring bookkeeping.  A group advances NG k-blocks at a time, which can be more than one turn of the ring,
@@ -317,8 +321,8 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
       // Swizzle by ADDRESS (bits 4-6 ^= bits 7-9): a plane of a tap-shared stage need not start on a 1024-byte boundary.
       // Rows rbase + 16 i of a plane share their phase, so the two chunk offsets are per-k-block constants.
       const uint32_t s_addr = a_addr + (uint32_t)st * stage_b;
-      const uint32_t sw_hi = (uint32_t)(chunk ^ (((s_addr >> 7) + rbase) & 7)) << 4;
-      const uint32_t sw_lo = (uint32_t)(chunk ^ ((((s_addr + atile_b) >> 7) + rbase) & 7)) << 4;
+      const uint32_t sw_hi = SH ? (uint32_t)(chunk ^ (((s_addr >> 7) + rbase) & 7)) << 4 : sw_c;
+      const uint32_t sw_lo = SH ? (uint32_t)(chunk ^ ((((s_addr + atile_b) >> 7) + rbase) & 7)) << 4 : sw_c;
       uint8_t* ah = Asm + (size_t)st * stage_b + (uint32_t)rbase * 128;
       // transform (affine + ReLU, or BN-backward affine), truncating tf32 split, store row `row` of the stage
       auto put = [&](float4 v, const float4& bz, bool keep, int row) {
@@ -428,7 +432,7 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
           const unsigned lo = q * P.omul + P.oadd, r = bt * P.Lout + lo;
           ooff = P.planar ? bt * (unsigned)P.N * (unsigned)P.Lout + lo : r * (unsigned)P.ldo + P.ocoff;
           eoff = r * (unsigned)P.ext_ld;
-          if (q >= (unsigned)P.Lvalid) ooff = 0xffffffffu;   // (tap-shared launches: virtual rows that only exist to be read by shifted taps)
+          if (SH && q >= (unsigned)P.Lvalid) ooff = 0xffffffffu;   // (tap-shared launches: virtual rows that only exist to be read by shifted taps)
         }
       }
     };
@@ -485,7 +489,7 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
     zfetch(za, xx, oa, m64 ? src64 : 0);
     for (int ti = 0; ti < n_my; ++ti) {
       const int acc = ti & 1;
-      const bool part = (((unsigned)blockIdx.x + (unsigned)ti * gridDim.x) + 1u) * BM > Mu || P.Lvalid < P.Lq;    // tile has missing rows
+      const bool part = (((unsigned)blockIdx.x + (unsigned)ti * gridDim.x) + 1u) * BM > Mu || (SH && P.Lvalid < P.Lq);    // tile has missing rows
       row_offsets(ti, half * 2 + 1, ob, eb);
       mbar_wait(&mi.tfull[acc], (ti >> 1) & 1, 400 + ti);
       tc_fence_after();
@@ -696,10 +700,10 @@ bool plan(const IgemmParams& p, TcLayout& L, dim3& grid, size_t& smem_bytes) {
   return smem_bytes <= SMEM_MAX;
 }
 
-template <int LW, bool LD2, int EPI>
+template <int LW, bool LD2, int EPI, bool SH>
 int launch_inst(const IgemmParams& p, const TcLayout& L, dim3 grid, size_t smem, cudaStream_t st) {
-  TRU_SMEM_OPT_IN((tc_igemm_kernel<LW, LD2, EPI>), SMEM_MAX);
-  TRU_CUDA(launch_pdl(tc_igemm_kernel<LW, LD2, EPI>, grid, dim3(32 * (4 + LW + EW)), smem, st, p, L));
+  TRU_SMEM_OPT_IN((tc_igemm_kernel<LW, LD2, EPI, SH>), SMEM_MAX);
+  TRU_CUDA(launch_pdl(tc_igemm_kernel<LW, LD2, EPI, SH>, grid, dim3(32 * (4 + LW + EW)), smem, st, p, L));
   TRU_LAUNCH_CHECK();
   return TRU_OK;
 }
@@ -708,10 +712,17 @@ int launch_one(const IgemmParams& p, const TcLayout& L, dim3 grid, size_t smem, 
   const int epi = p.extra != nullptr ? 2 : ((p.use_mask || p.bstats != nullptr) ? 1 : 0);
   bool ld2 = false;
   for (int s = 0; s < p.nseg; ++s) ld2 |= (p.seg[s].src2 != nullptr);
+  if (L.shared) {        // transposed convs: forward (affine + ReLU on load, plain / statistics epilogue), data gradient (masked)
+    if (!ld2 && epi == 0) return launch_inst<12, false, 0, true>(p, L, grid, smem, st);
+    if (ld2 && epi == 0) return launch_inst<12, true, 0, true>(p, L, grid, smem, st);
+    if (ld2 && epi == 1) return launch_inst<8, true, 1, true>(p, L, grid, smem, st);
+    if (!ld2 && epi == 1) return launch_inst<12, false, 1, true>(p, L, grid, smem, st);     // (no BN behind the conv: tests only)
+    return set_error(TRU_ERR_ARG, "igemm_tc: no tap-shared kernel variant for this loader / epilogue combination");
+  }
   if (ld2 && epi >= 1 && p.nseg == 1)      // masked backward of a pointwise conv: the epilogue is the slow role, 8 loader warps leave it more registers
-    return epi == 1 ? launch_inst<8, true, 1>(p, L, grid, smem, st) : launch_inst<8, true, 2>(p, L, grid, smem, st);
-  if (ld2) return epi == 0 ? launch_inst<12, true, 0>(p, L, grid, smem, st) : epi == 1 ? launch_inst<12, true, 1>(p, L, grid, smem, st) : launch_inst<12, true, 2>(p, L, grid, smem, st);
-  return epi == 0 ? launch_inst<12, false, 0>(p, L, grid, smem, st) : epi == 1 ? launch_inst<12, false, 1>(p, L, grid, smem, st) : launch_inst<12, false, 2>(p, L, grid, smem, st);
+    return epi == 1 ? launch_inst<8, true, 1, false>(p, L, grid, smem, st) : launch_inst<8, true, 2, false>(p, L, grid, smem, st);
+  if (ld2) return epi == 0 ? launch_inst<12, true, 0, false>(p, L, grid, smem, st) : epi == 1 ? launch_inst<12, true, 1, false>(p, L, grid, smem, st) : launch_inst<12, true, 2, false>(p, L, grid, smem, st);
+  return epi == 0 ? launch_inst<12, false, 0, false>(p, L, grid, smem, st) : epi == 1 ? launch_inst<12, false, 1, false>(p, L, grid, smem, st) : launch_inst<12, false, 2, false>(p, L, grid, smem, st);
 }
 
 int launch_planned(const IgemmParams& p0, cudaStream_t st) {
