@@ -37,8 +37,11 @@ __device__ __forceinline__ void bin_features(float re, float im, float& lm, floa
 }
 
 __device__ __forceinline__ float pcen_out(float x, float M, const FrontParams& p) {
-  // dataset.py:73: (x / (M + eps)^alpha + delta)^r - delta^r
-  return powf(x / powf(M + p.eps, p.alpha) + p.delta, p.r) - p.delta_r;
+  // dataset.py:73: (x / (M + eps)^alpha + delta)^r - delta^r.  The powers as exp2f(y log2f(x)): 2 + 2 special-function ops instead
+  // of two full powf calls (the error of log2f is ~1 ulp, amplified by |alpha log2(M + eps)| <= 20: ~5e-6 relative, well inside the
+  // 1e-4 feature tolerance); r = 0.5 (the reference's default) is a square root.
+  const float d = x * exp2f(-p.alpha * log2f(M + p.eps)) + p.delta;
+  return (p.r == 0.5f ? sqrtf(d) : exp2f(p.r * log2f(d))) - p.delta_r;
 }
 
 __global__ void __launch_bounds__(NT) frontend_kernel(FrontParams p) {
@@ -116,17 +119,27 @@ __global__ void __launch_bounds__(NT) frontend_kernel(FrontParams p) {
   for (int cc = tid; cc < c; cc += NT)
     while (ld_acquire(p.flags + b * p.nchunks + cc) == 0) { }
   __syncthreads();
+  // The smoother is a serial chain per bin (16 FMAs per chunk); the compression (two powers per element) is not: the chain writes
+  // M_t into the FFT scratch planes, which are free by now, and ALL threads then compress the chunk's nfr x 257 elements in
+  // parallel (the previous version ran both inside the per-bin loop: 257 threads, one of them with two bins, each with 16
+  // dependent pow pairs - ncu showed the kernel waiting at barriers behind those chains).
+  float* mbuf = fre;                                   // [TC][NB] (4112 floats <= 8 FPAD)
   for (int f = tid; f < NB; f += NT) {
     float M = p.state_in ? __ldg(p.state_in + (size_t)b * NB + f) : 0.0f;
     const float* pa = p.agg + (size_t)b * p.nchunks * NB + f;
 #pragma unroll 8
     for (int cc = 0; cc < c; ++cc) M = p.decay_chunk * M + __ldcg(pa + (size_t)cc * NB);
     for (int t = 0; t < nfr; ++t) {
-      const float xm = tile[t * FEAT + NB + f];
-      M = p.oms * M + p.s * xm;                     // dataset.py:66-68
-      tile[t * FEAT + NB + f] = pcen_out(xm, M, p);
+      M = p.oms * M + p.s * tile[t * FEAT + NB + f];  // dataset.py:66-68
+      mbuf[t * NB + f] = M;
     }
     if (p.state_out && c == p.nchunks - 1) p.state_out[(size_t)b * NB + f] = M;
+  }
+  __syncthreads();
+  for (int i = tid; i < nfr * NB; i += NT) {
+    const int t = i / NB, f = i - t * NB;
+    float* o = tile + t * FEAT + NB + f;
+    *o = pcen_out(*o, mbuf[i], p);
   }
   __syncthreads();
 
