@@ -715,7 +715,7 @@ int launch_one(const IgemmParams& p, const TcLayout& L, dim3 grid, size_t smem, 
   if (L.shared) {        // transposed convs: forward (affine + ReLU on load, plain / statistics epilogue), data gradient (masked)
     if (!ld2 && epi == 0) return launch_inst<12, false, 0, true>(p, L, grid, smem, st);
     if (ld2 && epi == 0) return launch_inst<12, true, 0, true>(p, L, grid, smem, st);
-    if (ld2 && epi == 1) return launch_inst<8, true, 1, true>(p, L, grid, smem, st);
+    if (ld2 && epi == 1) return launch_inst<8, true, 1, true>(p, L, grid, smem, st);      // (12 loader warps measured slower: 0.57 vs 0.51 ms on dec4 - the masked epilogue is the slow role)
     if (!ld2 && epi == 1) return launch_inst<12, false, 1, true>(p, L, grid, smem, st);     // (no BN behind the conv: tests only)
     return set_error(TRU_ERR_ARG, "igemm_tc: no tap-shared kernel variant for this loader / epilogue combination");
   }
