@@ -393,7 +393,7 @@ def measure_inference(args, dev, state_dict, world, rank, dist):
                           "gpu_ms": round(statistics.median(lat[5:]), 3), "gpu_rtf": round(4000.0 / statistics.median(lat[5:]), 1),
                           "gpu_single_frame_step_ms": round(statistics.median(lat1[10:]), 3),
                           "single_frame_note": "rt.py:20-27: one stream, one frame per call, state carried; hop = 8 ms of audio"}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # (at N > 1 the other ranks keep the host cores busy)
             cores = os.cpu_count() or 1
             out["latency"]["cpu_ms"] = cpu_forward_latency_ms(cores)
             out["latency"]["cpu_threads"] = cores
