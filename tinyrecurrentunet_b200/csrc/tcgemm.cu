@@ -57,6 +57,8 @@ struct TcLayout {
   int dbg;                      // ablation switches for bottleneck hunting (tru_debug_set_flags): 1 no MMA, 2 no global loads, 4 no smem stores, 8 no epilogue stores
   uint32_t a_off, coef_off, misc_off;                      // W tiles at offset 0
   int8_t kb_seg[MAXKB], kb_coef[MAXKB], kb_relu[MAXKB], kb_nw[MAXKB];   // kb_nw: weight k-blocks fed by this source k-block (consecutive in wk_*)
+  int8_t kb_pf[MAXKB];          // rows of this k-block's source are contiguous in tile order (row m at (m + sadd) * ld): the loaders can
+                                // prefetch the CTA's next tile into L2 with plain address arithmetic
   int16_t kb_c0[MAXKB], kb_valid[MAXKB];
   int kb_lmax[MAXKB];           // source rows li >= kb_lmax are zero rows
   int8_t wk_seg[MAXWK], wk_shift[MAXWK];
@@ -84,6 +86,9 @@ __device__ __forceinline__ float ldg_off(const float* base, unsigned off) {
   asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %2, 4, %1;\n\tld.global.nc.f32 %0, [a];\n\t}" : "=f"(v) : "l"(base), "r"(off));
   return v;
 }
+__device__ __forceinline__ void prefetch_l2_off(const float* base, unsigned off) {
+  asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %1, 4, %0;\n\tprefetch.global.L2 [a];\n\t}" ::"l"(base), "r"(off));
+}
 __device__ __forceinline__ float4 ldg4_off(const float* base, unsigned off) {
   float4 v;
   asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %5, 4, %4;\n\tld.global.nc.v4.f32 {%0,%1,%2,%3}, [a];\n\t}"
@@ -93,6 +98,9 @@ __device__ __forceinline__ float4 ldg4_off(const float* base, unsigned off) {
 
 #ifndef TRU_CACHE_ROWS
 #define TRU_CACHE_ROWS 1
+#endif
+#ifndef TRU_L2_PREFETCH
+#define TRU_L2_PREFETCH 1
 #endif
 #ifndef TRU_EPI2_PIPE
 #define TRU_EPI2_PIPE 1
@@ -372,6 +380,23 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
           for (int i = 0; i < R; ++i) put(a[i], b[LD2 ? i : 0], (msk >> i) & 1u, h * R + i);
         }
       }
+      // L2 prefetch of the same k-block of the CTA's NEXT tile (one 128-byte line per row: the chunk-0 threads issue it).  The
+      // loaders keep 8 (LD2: 2 x 4) 16-byte loads per thread in flight - ~32-48 KB per SM, borderline for 22 B/clk x ~1,000 cycles
+      // of loaded DRAM latency - and more would cost registers; a prefetch costs none and turns the next tile's loads into L2 hits.
+      // (measured: the same prefetch for gathered rows - skip alignment, tap-shared virtual rows; with a row decode per line or as
+      // a linear sweep from the tile's first row - gained nothing, and for the epilogue's mask / added-tensor rows of 128-channel
+      // layers it cost more than it hid: 0.95 -> 1.06 ms on the masked 128 -> 128 data gradient; the epilogue prefetch pays for
+      // <= 64 output channels only, see below)
+      if (!SH && TRU_L2_PREFETCH && Lo.kb_pf[kb] && chunk == 0 && ti + 1 < n_my) {
+        const unsigned m1 = ((unsigned)blockIdx.x + (unsigned)(ti + 1) * gridDim.x) * BM + rbase;
+#pragma unroll
+        for (int ii = 0; ii < 8; ++ii) {
+          const unsigned mm = min(m1 + 16u * ii, Mu - 1u);
+          const unsigned off = (unsigned)((int)mm + sadd) * ld + cb;
+          prefetch_l2_off(src, off);
+          if (LD2 && src2) prefetch_l2_off(src2, off);
+        }
+      }
       if (shared && rbase < xrows) {         // stage rows 128 + rbase (rbase < largest tap shift): one more row for the first threads
         unsigned bt, q;
         decode(8, bt, q);
@@ -491,6 +516,21 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
       const int acc = ti & 1;
       const bool part = (((unsigned)blockIdx.x + (unsigned)ti * gridDim.x) + 1u) * BM > Mu || (SH && P.Lvalid < P.Lq);    // tile has missing rows
       row_offsets(ti, half * 2 + 1, ob, eb);
+      if (TRU_L2_PREFETCH && EPI && m64 && (use_mask || has_extra) && ti + 1 < n_my && !P.planar) {
+        // L2 prefetch of the NEXT tile's mask / added-tensor rows of this warp (64 rows x one 128-byte line of 32 channels; lane j
+        // takes rows j and j + 32 of the warp's half tile)
+        const int cbase = lg * 16;                                     // first channel of the warp's 16 (M = 64 accumulators only: measured)
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          const unsigned m = ((unsigned)blockIdx.x + (unsigned)(ti + 1) * gridDim.x) * BM + half * 64 + rr * 32 + lane;
+          if (m < Mu) {
+            const unsigned bt = m / Lq, q = m - bt * Lq;
+            const unsigned off = (bt * P.Lout + q * P.omul + P.oadd) * (unsigned)P.ldo + P.ocoff + n0 + cbase;
+            if (use_mask) prefetch_l2_off(P.zmask, off);
+            if (has_extra) prefetch_l2_off(P.extra - P.ocoff, off);
+          }
+        }
+      }
       mbar_wait(&mi.tfull[acc], (ti >> 1) & 1, 400 + ti);
       tc_fence_after();
       const uint32_t taddr = tmem + ((uint32_t)(lg * 32) << 16) + acc * BM + half * 64;
@@ -642,6 +682,7 @@ bool plan(const IgemmParams& p, TcLayout& L, dim3& grid, size_t& smem_bytes) {
       L.kb_seg[nkb] = (int8_t)s; L.kb_c0[nkb] = (int16_t)c0; L.kb_valid[nkb] = (int16_t)std::min(KBLK, sg.C - c0);
       L.kb_relu[nkb] = (int8_t)(sg.p0 && sg.relu);
       L.kb_lmax[nkb] = (L.shared && p.c_hi > 0 && c0 >= p.c_hi) ? p.lmax_hi : sg.Lsrc;
+      L.kb_pf[nkb] = (int8_t)(!L.shared && sg.smul == 1 && sg.Lsrc == p.Lq && (sg.fs == 0 || sg.fs == sg.Lsrc * sg.ld));
       L.kb_coef[nkb] = -1;
       if (sg.p0) {
         int e = -1;
