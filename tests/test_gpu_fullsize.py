@@ -207,8 +207,10 @@ def test_two_identical_training_steps_give_identical_gradients():
     """run-to-run reproducibility of loss and gradients of a B = 8 x 4-s training step.  The overlap-adds and
     the weight-gradient reduction are ordered; BatchNorm statistics are fp64 atomic sums of fp32 partials (the order can move
     the fp64 sum by ~1e-16 relative, i.e. an fp32 coefficient by at most one ulp once in a while) and a few fp32 atomics remain
-    (overlap-add of the loss gradient, bias-gradient column sums), so the bound is ~100 ulp of each tensor's scale (10^3 times
-    inside the 1e-3 gradient tolerance), and bit-identity is reported."""
+    (overlap-add of the loss gradient: 4e-7 run to run on d loss / d network output; bias / depthwise weight-gradient column sums), so
+    the bound is 1e-5 of each tensor's scale (measured 1.8e-6; 100 times inside the 1e-3 gradient tolerance).  The conv biases in front
+    of a training-mode BatchNorm have an exactly-zero true gradient: what is stored there is cancellation noise (~1e-8 of the largest
+    gradient), different on every run, and reported separately."""
     from tinyrecurrentunet_b200 import stft_loss
     _, net = make_pair(3)
     net.train()
@@ -226,10 +228,15 @@ def test_two_identical_training_steps_give_identical_gradients():
     # BatchNorm has an exactly-zero true gradient: what is stored there is cancellation noise, different on every run)
     per = [((a - b).abs().max() / max(a.abs().max().item(), 1e-3 * gmax)).item() for a, b in zip(g1, g2)]
     names = [k for k, _ in net.named_parameters()]
+    zero_bias = {"encoder.%d.DepthwiseSeparableConv1d.%d.bias" % (i, j) for i in range(1, 6) for j in (0, 3)}
+    zero_bias |= {"decoder.%d.%s.0.bias" % (d, c) for d, c in enumerate(["FirstTrCNN"] + ["TrCNN"] * 4 + ["LastTrCNN"])}
+    zero_bias |= {"decoder.%d.%s.3.bias" % (d, c) for d, c in enumerate(["FirstTrCNN"] + ["TrCNN"] * 4)}
+    zero_bias |= {"FGRU.conv.0.bias", "TGRU.conv.0.bias"}
     for v, k in sorted(zip(per, names), reverse=True)[:8]:
-        print("  %-55s %.3e" % (k, v))
-    worst = max(per)
-    print("bit-identical gradient tensors: %d / %d, worst relative difference %.3e, loss %r vs %r"
-          % (identical, len(g1), worst, l1.item(), l2.item()))
+        print("  %-55s %.3e%s" % (k, v, "  (exactly-zero true gradient: cancellation noise)" if k in zero_bias else ""))
+    worst = max(v for v, k in zip(per, names) if k not in zero_bias)
+    worst_zero = max(v for v, k in zip(per, names) if k in zero_bias)
+    print("bit-identical gradient tensors: %d / %d, worst relative difference %.3e (zero-gradient biases: %.3e of 1e-3 of the largest "
+          "gradient), loss %r vs %r" % (identical, len(g1), worst, worst_zero, l1.item(), l2.item()))
     assert abs(l1.item() - l2.item()) <= 2e-7 * abs(l1.item())
-    assert worst <= 2e-4, worst
+    assert worst <= 1e-5 and worst_zero <= 1.0, (worst, worst_zero)
