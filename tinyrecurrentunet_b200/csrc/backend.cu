@@ -77,8 +77,7 @@ __global__ void __launch_bounds__(NT) backend_fwd_kernel(BackParams p) {
   const int tfirst = q0 - 1;                         // first frame touching block q0
   const int nfr = nq + 3;
   for (int k = tid; k < NFFT; k += NT) tw[k] = p.tw[k * (2048 / NFFT)];
-  float* re = fre + g * FPAD;
-  float* im = fim + g * FPAD;
+  float* z = fre + g * (2 * FPAD);                      // interleaved (re, im) pairs, tru_fft.cuh
   const float* net = p.net + (size_t)b * p.T * p.C * NB;
   const float invn = 1.0f / NFFT;
 
@@ -92,10 +91,10 @@ __global__ void __launch_bounds__(NT) backend_fwd_kernel(BackParams p) {
     // stall when every bin loaded and then computed its atan2 / exp chain), then the arithmetic; bin 256 is thread 0's extra
     auto put_bin = [&](int k, float ar, float ai, float br, float bi) {
       if (k == 0 || k == NFFT / 2) {                 // c2r ignores Im of DC / Nyquist
-        re[TRU_FFT_IDX(k)] = ar; im[TRU_FFT_IDX(k)] = br;
+        TRU_FFT_RE(z, k) = ar; TRU_FFT_IM(z, k) = br;
       } else {
-        re[TRU_FFT_IDX(k)] = ar - bi; im[TRU_FFT_IDX(k)] = ai + br;
-        re[TRU_FFT_IDX(NFFT - k)] = ar + bi; im[TRU_FFT_IDX(NFFT - k)] = br - ai;
+        TRU_FFT_RE(z, k) = ar - bi; TRU_FFT_IM(z, k) = ai + br;
+        TRU_FFT_RE(z, NFFT - k) = ar + bi; TRU_FFT_IM(z, NFFT - k) = br - ai;
       }
     };
     const float* fa = net + (size_t)ta * p.C * NB;
@@ -119,12 +118,12 @@ __global__ void __launch_bounds__(NT) backend_fwd_kernel(BackParams p) {
       if (vb) bin_spectrum(p, fb, NFFT / 2, br, bi);
       put_bin(NFFT / 2, ar, ai, br, bi);
     }
-    fft_smem<NFFT, 1>(re, im, tw, l);
+    fft_smem<NFFT, 1>(z, tw, l);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int n = l + 64 * j;
-      if (la < nfr) td[la * NFFT + n] = va ? re[TRU_FFT_IDX(n)] * invn : 0.0f;
-      if (lb < nfr) td[lb * NFFT + n] = vb ? im[TRU_FFT_IDX(n)] * invn : 0.0f;
+      if (la < nfr) td[la * NFFT + n] = va ? TRU_FFT_RE(z, n) * invn : 0.0f;
+      if (lb < nfr) td[lb * NFFT + n] = vb ? TRU_FFT_IM(z, n) * invn : 0.0f;
     }
   }
   __syncthreads();
@@ -153,8 +152,7 @@ __global__ void __launch_bounds__(NT) backend_bwd_kernel(BackParams p) {
   const int nfr = min(TCB, p.T - t0);
   const int NOUT = (p.T - 1) * HOP;
   for (int k = tid; k < NFFT; k += NT) tw[k] = p.tw[k * (2048 / NFFT)];
-  float* re = fre + g * FPAD;
-  float* im = fim + g * FPAD;
+  float* z = fre + g * (2 * FPAD);                      // interleaved (re, im) pairs, tru_fft.cuh
   const float* ga = p.gaudio + (size_t)b * NOUT;
   const float ln10_20x50 = 2.302585092994046f / 20.0f * 50.0f;
 
@@ -175,16 +173,16 @@ __global__ void __launch_bounds__(NT) backend_bwd_kernel(BackParams p) {
         const int pp = tb * HOP + n, o = pp - NFFT / 2;
         if (o >= 0 && o < NOUT) xb = __ldg(ga + o) / (float)frames_covering(pp, p.T);
       }
-      re[TRU_FFT_IDX(n)] = xa; im[TRU_FFT_IDX(n)] = xb;
+      TRU_FFT_RE(z, n) = xa; TRU_FFT_IM(z, n) = xb;
     }
-    fft_smem<NFFT, -1>(re, im, tw, l);
+    fft_smem<NFFT, -1>(z, tw, l);
     // (loading all 40 values of the thread's bins ahead of the chain rule, as the forward kernel does, was measured slower here:
     // 0.15 -> 0.19 ms at 121 registers - the kernel writes 8 channels per bin and lives on occupancy)
     // gradient of bin k of frame t (h = 0: the frame in the real part of the packed transform, 1: imaginary part)
     auto do_bin = [&](int k, int h, int t, const float (&x)[5]) {
       const int kn = (NFFT - k) & (NFFT - 1);
-      const float zr = re[TRU_FFT_IDX(k)], zi = im[TRU_FFT_IDX(k)];
-      const float wr = re[TRU_FFT_IDX(kn)], wi = im[TRU_FFT_IDX(kn)];
+      const float zr = TRU_FFT_RE(z, k), zi = TRU_FFT_IM(z, k);
+      const float wr = TRU_FFT_RE(z, kn), wi = TRU_FFT_IM(z, kn);
       const bool edge = (k == 0 || k == NFFT / 2);
       const float ck = (edge ? 1.0f : 2.0f) / NFFT;
       // G = FFT(g)[k]; dL/dRe Y = ck Re G, dL/dIm Y = ck Im G (0 at DC / Nyquist)
@@ -237,13 +235,11 @@ __global__ void __launch_bounds__(NT) backend_bwd_kernel(BackParams p) {
 // look-ahead, exactly the offline centre=True framing).  4 streams per CTA, ONE stream per complex transform (Hermitian
 // extension of its own spectrum): streams are independent signals and must not share a transform (see frontend_step_kernel).
 __global__ void __launch_bounds__(NT) backend_step_kernel(BackParams p, float* __restrict__ ola, int frame_index, int add_frame) {
-  __shared__ __align__(16) float fre[4 * FPAD];
-  __shared__ __align__(16) float fim[4 * FPAD];
+  __shared__ __align__(16) float fre[8 * FPAD];
   __shared__ float2 tw[NFFT];
   const int tid = threadIdx.x, g = tid >> 6, l = tid & 63;
   for (int k = tid; k < NFFT; k += NT) tw[k] = p.tw[k * (2048 / NFFT)];
-  float* re = fre + g * FPAD;
-  float* im = fim + g * FPAD;
+  float* z = fre + g * (2 * FPAD);                      // interleaved (re, im) pairs, tru_fft.cuh
   const int sidx = blockIdx.x * 4 + g;
   const bool valid = sidx < p.B;
   __syncthreads();
@@ -252,13 +248,13 @@ __global__ void __launch_bounds__(NT) backend_step_kernel(BackParams p, float* _
       float ar = 0.f, ai = 0.f;
       if (valid) bin_spectrum(p, p.net + (size_t)sidx * p.C * NB, k, ar, ai);
       if (k == 0 || k == NFFT / 2) {                 // c2r ignores Im of DC / Nyquist
-        re[TRU_FFT_IDX(k)] = ar; im[TRU_FFT_IDX(k)] = 0.f;
+        TRU_FFT_RE(z, k) = ar; TRU_FFT_IM(z, k) = 0.f;
       } else {
-        re[TRU_FFT_IDX(k)] = ar; im[TRU_FFT_IDX(k)] = ai;
-        re[TRU_FFT_IDX(NFFT - k)] = ar; im[TRU_FFT_IDX(NFFT - k)] = -ai;
+        TRU_FFT_RE(z, k) = ar; TRU_FFT_IM(z, k) = ai;
+        TRU_FFT_RE(z, NFFT - k) = ar; TRU_FFT_IM(z, NFFT - k) = -ai;
       }
     }
-    fft_smem<NFFT, 1>(re, im, tw, l);
+    fft_smem<NFFT, 1>(z, tw, l);
   }
   // frames contributing to block q = frame_index - 2 are q-1 .. q+2 = frame_index-3 .. frame_index (those that exist)
   const int newest = add_frame ? frame_index : frame_index - 1;
@@ -270,7 +266,7 @@ __global__ void __launch_bounds__(NT) backend_step_kernel(BackParams p, float* _
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int n = l + 64 * j;
-    const float x = add_frame ? re[TRU_FFT_IDX(n)] * invn : 0.0f;
+    const float x = add_frame ? TRU_FFT_RE(z, n) * invn : 0.0f;
     v[j] = x + (n < 384 ? o[n] : 0.0f);
   }
 #pragma unroll

@@ -70,8 +70,7 @@ __global__ void __launch_bounds__(NT) frontend_kernel(FrontParams p) {
 
   // ---- STFT: two frames per complex FFT, 4 groups x 64 threads ----------------
   const int g = tid >> 6, l = tid & 63;
-  float* re = fre + g * FPAD;
-  float* im = fim + g * FPAD;
+  float* z = fre + g * (2 * FPAD);                      // interleaved (re, im) pairs, tru_fft.cuh
   const int npairs = (nfr + 1) >> 1;
   for (int round = 0; round * 4 < npairs; ++round) {
     const int pair = round * 4 + g;
@@ -80,15 +79,15 @@ __global__ void __launch_bounds__(NT) frontend_kernel(FrontParams p) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int n = l + 64 * j;
-      re[TRU_FFT_IDX(n)] = (ta < nfr) ? stage[ta * HOP + n] : 0.0f;
-      im[TRU_FFT_IDX(n)] = (tb < nfr) ? stage[tb * HOP + n] : 0.0f;
+      TRU_FFT_RE(z, n) = (ta < nfr) ? stage[ta * HOP + n] : 0.0f;
+      TRU_FFT_IM(z, n) = (tb < nfr) ? stage[tb * HOP + n] : 0.0f;
     }
-    fft_smem<NFFT, -1>(re, im, tw, l);
+    fft_smem<NFFT, -1>(z, tw, l);
     if (ta < nfr) {
       for (int k = l; k <= NFFT / 2; k += 64) {
         const int kn = (NFFT - k) & (NFFT - 1);
-        const float zr = re[TRU_FFT_IDX(k)], zi = im[TRU_FFT_IDX(k)];
-        const float wr = re[TRU_FFT_IDX(kn)], wi = im[TRU_FFT_IDX(kn)];
+        const float zr = TRU_FFT_RE(z, k), zi = TRU_FFT_IM(z, k);
+        const float wr = TRU_FFT_RE(z, kn), wi = TRU_FFT_IM(z, kn);
         float lm, mg, sn, cs;
         bin_features(0.5f * (zr + wr), 0.5f * (zi - wi), lm, mg, sn, cs);
         float* o = tile + ta * FEAT + k;
@@ -161,20 +160,19 @@ __global__ void __launch_bounds__(NT) frontend_step_kernel(FrontParams p, const 
   float2* tw = (float2*)(fim + 4 * FPAD);
   const int tid = threadIdx.x, g = tid >> 6, l = tid & 63;
   for (int k = tid; k < NFFT; k += NT) tw[k] = p.tw[k * (2048 / NFFT)];
-  float* re = fre + g * FPAD;
-  float* im = fim + g * FPAD;
+  float* z = fre + g * (2 * FPAD);                      // interleaved (re, im) pairs, tru_fft.cuh
   const int sidx = blockIdx.x * 4 + g;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int n = l + 64 * j;
-    re[TRU_FFT_IDX(n)] = (sidx < S) ? __ldg(frames + (size_t)sidx * NFFT + n) : 0.0f;
-    im[TRU_FFT_IDX(n)] = 0.0f;
+    TRU_FFT_RE(z, n) = (sidx < S) ? __ldg(frames + (size_t)sidx * NFFT + n) : 0.0f;
+    TRU_FFT_IM(z, n) = 0.0f;
   }
-  fft_smem<NFFT, -1>(re, im, tw, l);
+  fft_smem<NFFT, -1>(z, tw, l);
   if (sidx >= S) return;
   for (int k = l; k <= NFFT / 2; k += 64) {
     float lm, mg, sn, cs;
-    bin_features(re[TRU_FFT_IDX(k)], im[TRU_FFT_IDX(k)], lm, mg, sn, cs);
+    bin_features(TRU_FFT_RE(z, k), TRU_FFT_IM(z, k), lm, mg, sn, cs);
     float* st = p.state_out + (size_t)sidx * NB + k;
     const float M = p.oms * (*st) + p.s * mg;
     *st = M;

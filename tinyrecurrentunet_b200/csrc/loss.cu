@@ -46,7 +46,7 @@ __device__ __forceinline__ void block_add(double* dst, float v0, float v1, float
 // load frame t of (x,y), windowed, into (re, im)
 template <int N>
 __device__ __forceinline__ void load_frame(const LossParams& p, int r, int b, int t, bool valid,
-                                           float* re, float* im, int l) {
+                                           float* z, int l) {
   const int left = (N - p.wlen[r]) >> 1;
   const float* x = p.x + (size_t)b * p.N;
   const float* y = p.y + (size_t)b * p.N;
@@ -61,14 +61,14 @@ __device__ __forceinline__ void load_frame(const LossParams& p, int r, int b, in
       const float wv = __ldg(w + wi);
       a = wv * __ldg(x + src); c = wv * __ldg(y + src);
     }
-    re[TRU_FFT_IDX(n)] = a; im[TRU_FFT_IDX(n)] = c;
+    TRU_FFT_RE(z, n) = a; TRU_FFT_IM(z, n) = c;
   }
 }
 
-__device__ __forceinline__ void split_xy(const float* re, const float* im, int k, int kn,
+__device__ __forceinline__ void split_xy(const float* z, int k, int kn,
                                          float& xr, float& xi, float& yr, float& yi) {
-  const float zr = re[TRU_FFT_IDX(k)], zi = im[TRU_FFT_IDX(k)];
-  const float wr = re[TRU_FFT_IDX(kn)], wi = im[TRU_FFT_IDX(kn)];
+  const float zr = TRU_FFT_RE(z, k), zi = TRU_FFT_IM(z, k);
+  const float wr = TRU_FFT_RE(z, kn), wi = TRU_FFT_IM(z, kn);
   xr = 0.5f * (zr + wr); xi = 0.5f * (zi - wi);
   yr = 0.5f * (zi + wi); yi = -0.5f * (zr - wr);
 }
@@ -78,19 +78,18 @@ __device__ void loss_fwd_block(const LossParams& p, int r, int blk, float* fre, 
   constexpr int GT = N / 8, NG = NT / GT, PADN = TRU_FFT_PAD(N);
   const int tid = threadIdx.x, g = tid / GT, l = tid % GT;
   const int b = blk / p.bpc[r], t0 = (blk % p.bpc[r]) * p.fpb[r];
-  float* re = fre + g * PADN;
-  float* im = fim + g * PADN;
+  float* z = fre + g * (2 * PADN);                      // interleaved (re, im) pairs, tru_fft.cuh
   float a0 = 0.f, a1 = 0.f, a2 = 0.f;
   for (int round = 0; round * NG < p.fpb[r]; ++round) {
     const int t = t0 + round * NG + g;
     const bool valid = t < p.T[r];
     __syncthreads();
-    load_frame<N>(p, r, b, t, valid, re, im, l);
-    fft_smem<N, -1>(re, im, tw, l);
+    load_frame<N>(p, r, b, t, valid, z, l);
+    fft_smem<N, -1>(z, tw, l);
     if (valid) {
       for (int k = l; k <= N / 2; k += GT) {
         float xr, xi, yr, yi;
-        split_xy(re, im, k, (N - k) & (N - 1), xr, xi, yr, yi);
+        split_xy(z, k, (N - k) & (N - 1), xr, xi, yr, yi);
         const float mx = sqrtf(fmaxf(xr * xr + xi * xi, 1e-7f));     // stft_loss.py:30
         const float my = sqrtf(fmaxf(yr * yr + yi * yi, 1e-7f));
         const float d = my - mx;
@@ -144,8 +143,7 @@ __device__ void loss_bwd_block(const LossParams& p, int r, int blk, float* fre, 
   constexpr int GT = N / 8, NG = NT / GT, PADN = TRU_FFT_PAD(N), NBIN = N / 2 + 1;
   const int tid = threadIdx.x, g = tid / GT, l = tid % GT;
   const int b = blk / p.bpc[r], t0 = (blk % p.bpc[r]) * p.fpb[r];
-  float* re = fre + g * PADN;
-  float* im = fim + g * PADN;
+  float* z = fre + g * (2 * PADN);                      // interleaved (re, im) pairs, tru_fft.cuh
   float* dre = dbuf + g * 4 * NBIN;                     // [2][NBIN]
   float* dim = dre + 2 * NBIN;
   const double A = p.csums[4 * r], Bn = p.csums[4 * r + 1];
@@ -162,13 +160,13 @@ __device__ void loss_bwd_block(const LossParams& p, int r, int blk, float* fre, 
       const int t = ta + h;
       const bool valid = t < p.T[r];
       __syncthreads();
-      load_frame<N>(p, r, b, t, valid, re, im, l);
-      fft_smem<N, -1>(re, im, tw, l);
+      load_frame<N>(p, r, b, t, valid, z, l);
+      fft_smem<N, -1>(z, tw, l);
       for (int k = l; k <= N / 2; k += GT) {
         float dr = 0.f, di = 0.f;
         if (valid) {
           float xr, xi, yr, yi;
-          split_xy(re, im, k, (N - k) & (N - 1), xr, xi, yr, yi);
+          split_xy(z, k, (N - k) & (N - 1), xr, xi, yr, yi);
           const float px = xr * xr + xi * xi;
           if (px >= 1e-7f) {                           // clamp passes gradient only above the floor
             const float mx = sqrtf(px);
@@ -188,13 +186,13 @@ __device__ void loss_bwd_block(const LossParams& p, int r, int blk, float* fre, 
     for (int k = l; k <= N / 2; k += GT) {
       const float ar = dre[k], ai = dim[k], br = dre[NBIN + k], bi = dim[NBIN + k];
       if (k == 0 || k == N / 2) {
-        re[TRU_FFT_IDX(k)] = ar; im[TRU_FFT_IDX(k)] = br;
+        TRU_FFT_RE(z, k) = ar; TRU_FFT_IM(z, k) = br;
       } else {
-        re[TRU_FFT_IDX(k)] = 0.5f * (ar - bi); im[TRU_FFT_IDX(k)] = 0.5f * (ai + br);
-        re[TRU_FFT_IDX(N - k)] = 0.5f * (ar + bi); im[TRU_FFT_IDX(N - k)] = 0.5f * (br - ai);
+        TRU_FFT_RE(z, k) = 0.5f * (ar - bi); TRU_FFT_IM(z, k) = 0.5f * (ai + br);
+        TRU_FFT_RE(z, N - k) = 0.5f * (ar + bi); TRU_FFT_IM(z, N - k) = 0.5f * (br - ai);
       }
     }
-    fft_smem<N, 1>(re, im, tw, l);
+    fft_smem<N, 1>(z, tw, l);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int n = l + GT * j;
@@ -202,9 +200,9 @@ __device__ void loss_bwd_block(const LossParams& p, int r, int blk, float* fre, 
       if (wi >= 0 && wi < p.wlen[r]) {
         const float wv = __ldg(p.win[r] + wi);
         if (ta < p.T[r])
-          atomicAdd(gx + reflect_idx(ta * p.hop[r] + n - N / 2, p.N), wv * re[TRU_FFT_IDX(n)]);
+          atomicAdd(gx + reflect_idx(ta * p.hop[r] + n - N / 2, p.N), wv * TRU_FFT_RE(z, n));
         if (ta + 1 < p.T[r])
-          atomicAdd(gx + reflect_idx((ta + 1) * p.hop[r] + n - N / 2, p.N), wv * im[TRU_FFT_IDX(n)]);
+          atomicAdd(gx + reflect_idx((ta + 1) * p.hop[r] + n - N / 2, p.N), wv * TRU_FFT_IM(z, n));
       }
     }
   }

@@ -1,10 +1,12 @@
 // Shared-memory Stockham FFT building blocks (radix 8/4, in-register butterflies).
 //
-// One complex FFT of size N is carried out by N/8 threads; data lives in two
-// padded float arrays (re/im, index a -> a + a/8, which makes the strided
-// writes of the first two passes bank-conflict free).  The per-thread halves of
-// a pass (load+twiddle+butterfly, then store) are plain inline functions so the
-// exact same code is exercised on the host by tests/host_fft_test.cpp.
+// One complex FFT of size N is carried out by N/8 threads; data lives in ONE padded array of interleaved (re, im) pairs
+// (element a at pair index a + a/16), so every butterfly operand is one 8-byte shared-memory access: ncu had the FFT-bound
+// kernels (loss_fwd / loss_bwd) stalled on "mio throttle" - the shared-memory instruction rate - with separate re / im
+// planes (16 + 16 four-byte accesses per radix-8 pass and thread); the padding keeps the 8-byte loads conflict-free per
+// half warp and leaves 2-way conflicts on one store pass only.  The per-thread halves of a pass (load+twiddle+butterfly,
+// then store) are plain inline functions so the exact same code is exercised on the host by tests/host/host_fft_test.cpp.
+// Buffers are declared as float z[2 * TRU_FFT_PAD(N)] (a little more than the 2 * (N + N/16) floats in use).
 //
 // Used by: frontend.cu (STFT-512, dataset.py:260-264), backend.cu (irFFT-512,
 // dataset.py:293-296), loss.cu (STFT 512/1024/2048, stft_loss.py:21-23).
@@ -15,11 +17,13 @@
 #define TRU_HD __host__ __device__ __forceinline__
 #else
 #define TRU_HD inline
-struct float2 { float x, y; };
+struct alignas(8) float2 { float x, y; };
 #endif
 
-#define TRU_FFT_IDX(a) ((a) + ((a) >> 3))
+#define TRU_FFT_IDX(a) ((a) + ((a) >> 4))
 #define TRU_FFT_PAD(n) ((n) + ((n) >> 3))
+#define TRU_FFT_RE(z, a) (z)[2 * TRU_FFT_IDX(a)]
+#define TRU_FFT_IM(z, a) (z)[2 * TRU_FFT_IDX(a) + 1]
 
 namespace tru {
 
@@ -76,14 +80,15 @@ TRU_HD void dft8(float (&r)[8], float (&i)[8]) {
 // One radix-R butterfly (index i in [0, N/R)) of the Stockham pass with current
 // sub-transform length p.  tw[k] = exp(-2*pi*i*k/N), k < N.
 template <int N, int R, int DIR>
-TRU_HD void fft_butterfly_load(const float* re, const float* im, const float2* tw,
+TRU_HD void fft_butterfly_load(const float* z, const float2* tw,
                                int p, int i, float (&ur)[R], float (&ui)[R]) {
   const int k = i & (p - 1);
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int a = i + r * (N / R);
-    ur[r] = re[TRU_FFT_IDX(a)];
-    ui[r] = im[TRU_FFT_IDX(a)];
+    const float2 v = *(const float2*)(z + 2 * TRU_FFT_IDX(a));
+    ur[r] = v.x;
+    ui[r] = v.y;
   }
   if (p > 1) {
     const int step = k * (N / (p * R));
@@ -99,15 +104,16 @@ TRU_HD void fft_butterfly_load(const float* re, const float* im, const float2* t
 }
 
 template <int N, int R>
-TRU_HD void fft_butterfly_store(float* re, float* im, int p, int i,
+TRU_HD void fft_butterfly_store(float* z, int p, int i,
                                 const float (&ur)[R], const float (&ui)[R]) {
   const int k = i & (p - 1);
   const int j0 = (i - k) * R + k;
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int a = j0 + r * p;
-    re[TRU_FFT_IDX(a)] = ur[r];
-    im[TRU_FFT_IDX(a)] = ui[r];
+    float2 v;
+    v.x = ur[r]; v.y = ui[r];
+    *(float2*)(z + 2 * TRU_FFT_IDX(a)) = v;
   }
 }
 
@@ -122,16 +128,16 @@ template <> struct FftPlan<2048> { static constexpr int n8 = 3, n4 = 1; };
 // call it (it contains __syncthreads).  Data must be in place before the call
 // (a __syncthreads is issued on entry); result is visible to all on return.
 template <int N, int DIR>
-__device__ __forceinline__ void fft_smem(float* re, float* im, const float2* tw, int tid) {
+__device__ __forceinline__ void fft_smem(float* z, const float2* tw, int tid) {
   int p = 1;
   __syncthreads();
 #pragma unroll
   for (int s = 0; s < FftPlan<N>::n8; ++s) {
     float ur[8], ui[8];
-    fft_butterfly_load<N, 8, DIR>(re, im, tw, p, tid, ur, ui);
+    fft_butterfly_load<N, 8, DIR>(z, tw, p, tid, ur, ui);
     dft8<DIR>(ur, ui);
     __syncthreads();
-    fft_butterfly_store<N, 8>(re, im, p, tid, ur, ui);
+    fft_butterfly_store<N, 8>(z, p, tid, ur, ui);
     __syncthreads();
     p *= 8;
   }
@@ -140,13 +146,13 @@ __device__ __forceinline__ void fft_smem(float* re, float* im, const float2* tw,
     float ur[2][4], ui[2][4];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      fft_butterfly_load<N, 4, DIR>(re, im, tw, p, tid + h * (N / 8), ur[h], ui[h]);
+      fft_butterfly_load<N, 4, DIR>(z, tw, p, tid + h * (N / 8), ur[h], ui[h]);
       dft4<DIR>(ur[h][0], ui[h][0], ur[h][1], ui[h][1], ur[h][2], ui[h][2], ur[h][3], ui[h][3]);
     }
     __syncthreads();
 #pragma unroll
     for (int h = 0; h < 2; ++h)
-      fft_butterfly_store<N, 4>(re, im, p, tid + h * (N / 8), ur[h], ui[h]);
+      fft_butterfly_store<N, 4>(z, p, tid + h * (N / 8), ur[h], ui[h]);
     __syncthreads();
     p *= 4;
   }
