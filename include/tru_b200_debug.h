@@ -44,6 +44,7 @@ int tru_debug_wgrad_stream(const float* a, const float* dy, const float* z, cons
 /* Process-wide switches (tuning aids; defaults: tensor cores on, flags 0). */
 int tru_set_tensor_cores(int on);          /* 0: every GEMM-shaped launch takes the FFMA kernels */
 int tru_debug_set_flags(int flags);        /* ablation bits of tc_igemm_kernel (results are garbage when set) */
+int tru_debug_set_eval_fusion(int on);     /* 0: inference keeps the layer-by-layer schedule (pointwise outputs written; default 1: depthwise conv in the GEMM epilogue) */
 int tru_debug_read_mbar(unsigned* out, int n);   /* -DTRU_MBAR_TIMEOUT builds: log of stuck mbarrier waits */
 
 #ifdef __cplusplus

@@ -13,27 +13,31 @@ import pytest
 import torch
 
 from oracle import tru_oracle as O
-from test_gpu_network import (GRAD_TOL, OUT_TOL, compare_intermediate_grads, compare_intermediates, feats_like, force_relu_masks,
-                              gpu_relu_masks, make_pair, oracle_intermediates, rel, relu_mask_mismatches)
+from test_gpu_network import (FORWARD_MODES, GRAD_TOL, OUT_TOL, compare_intermediate_grads, compare_intermediates, feats_like,
+                              force_relu_masks, forward_mode, gpu_relu_masks, make_pair, oracle_intermediates, rel,
+                              relu_mask_mismatches)
+from tinyrecurrentunet_b200 import _lib as L
 from test_gpu_dsp import check_feats
 
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("training", [True, False])
-def test_forward_per_layer_at_4s_clip_length(training):
+@pytest.mark.parametrize("mode", FORWARD_MODES)
+def test_forward_per_layer_at_4s_clip_length(mode):
     """every pre-BN conv output and GRU output of a B = 4, T' = 501 forward (2004 frames: 16 to 2004 row
     tiles per layer, several waves of the persistent GEMM grid) against the oracle's, layer by layer."""
     ref, net = make_pair(11)
     B, T = 4, 501
     x = feats_like(B, T, 20)
-    ref.train(training)
-    net.train(training)
+    training, skip = forward_mode(net, ref, mode)
     net._debug_keep_ws = True
-    with torch.no_grad():
-        y_ref, inter = oracle_intermediates(ref, x)
-        y = net(x.cuda())
-    rows = compare_intermediates(net, inter, B, T)
+    try:
+        with torch.no_grad():
+            y_ref, inter = oracle_intermediates(ref, x)
+            y = net(x.cuda())
+    finally:
+        L.lib.tru_debug_set_eval_fusion(1)
+    rows = compare_intermediates(net, inter, B, T, skip)
     print("\n".join("%-6s %.3e" % r for r in rows))
     bad = [r for r in rows if not r[1] <= OUT_TOL]
     assert not bad, bad

@@ -83,7 +83,7 @@ def gpu_buffer(net, name, index, shape):
     return net._last_ws[off:off + 4 * n].view(torch.float32).view(shape).cpu()
 
 
-def compare_intermediates(net, got, B, T):
+def compare_intermediates(net, got, B, T, skip=()):
     rows = []
     names = [("A0", "A0", 0)] + [("Zp%d" % i, "Zp", i) for i in range(1, 6)] + [("Zd%d" % i, "Zd", i) for i in range(1, 6)]
     names += [("HF", "HF", 0), ("ZFp", "ZFp", 0), ("HT", "HT", 0), ("ZTp", "ZTp", 0)]
@@ -93,24 +93,45 @@ def compare_intermediates(net, got, B, T):
         order += ["ZDp%d" % d] + (["ZDt%d" % d] if d < 5 else [])
     lut = {a: (b, c) for a, b, c in names}
     for key in order:
+        if key in skip:
+            continue
         ref = got[key]
         mine = gpu_buffer(net, lut[key][0], lut[key][1], tuple(ref.shape))
         rows.append((key, rel(mine, ref)))
     return rows
 
 
-@pytest.mark.parametrize("training", [False, True])
-def test_forward_matches_oracle(training):
+# inference fuses the encoder blocks' depthwise conv into the pointwise GEMM's epilogue (tcgemm.cu, EPI 3): the pointwise outputs
+# Zp1..Zp5 are then never written.  "eval-unfused" (tru_debug_set_eval_fusion(0)) keeps the layer-by-layer schedule and checks them too.
+EVAL_FUSED_SKIP = tuple("Zp%d" % i for i in range(1, 6))
+FORWARD_MODES = ["eval", "eval-unfused", "train"]
+
+
+def forward_mode(net, ref, mode):
+    """-> (training, intermediates not to compare); call L.lib.tru_debug_set_eval_fusion(1) when done"""
+    from tinyrecurrentunet_b200 import _lib as L
+    training = mode == "train"
+    ref.train(training)
+    net.train(training)
+    L.lib.tru_debug_set_eval_fusion(0 if mode == "eval-unfused" else 1)
+    return training, (EVAL_FUSED_SKIP if mode == "eval" else ())
+
+
+@pytest.mark.parametrize("mode", FORWARD_MODES)
+def test_forward_matches_oracle(mode):
+    from tinyrecurrentunet_b200 import _lib as L
     ref, net = make_pair(1)
     B, T = 2, 7
     x = feats_like(B, T, 3)
-    ref.train(training)
-    net.train(training)
+    training, skip = forward_mode(net, ref, mode)
     net._debug_keep_ws = True
-    with torch.no_grad():
-        y_ref, inter = oracle_intermediates(ref, x)
-        y = net(x.cuda())
-    rows = compare_intermediates(net, inter, B, T)
+    try:
+        with torch.no_grad():
+            y_ref, inter = oracle_intermediates(ref, x)
+            y = net(x.cuda())
+    finally:
+        L.lib.tru_debug_set_eval_fusion(1)
+    rows = compare_intermediates(net, inter, B, T, skip)
     print("\n".join("%-6s %.3e" % r for r in rows))
     bad = [r for r in rows if not r[1] <= OUT_TOL]
     assert not bad, bad

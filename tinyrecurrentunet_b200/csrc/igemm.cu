@@ -400,7 +400,8 @@ static void igemm_cost(const IgemmParams& p, double& bytes, double& flops) {
   }
   const double Mout = p.ntap && p.Lvalid > 0 ? (double)p.BT * p.Lvalid : (double)M;      // tap-shared: virtual rows produce no output
   if (p.ntap) { ktot = 0; for (int j = 0; j < p.ntap; ++j) ktot += p.tap_C[j]; bytes += 4.0 * ktot * p.N; }
-  bytes += 4.0 * Mout * p.N * (1 + (p.use_mask ? 1 : 0) + (p.extra ? 1 : 0));
+  if (p.dw_k) bytes += 4.0 * p.BT * p.Lout * p.N;        // depthwise epilogue: only the depthwise output is written
+  else bytes += 4.0 * Mout * p.N * (1 + (p.use_mask ? 1 : 0) + (p.extra ? 1 : 0));
   flops = 2.0 * Mout * ktot * p.N;
 }
 
@@ -411,8 +412,8 @@ static const char* shape_name(const char* kind, const IgemmParams& p) {
   for (int s = 0; s < p.nseg; ++s) ktot += p.seg[s].C;
   char buf[128];
   if (p.ntap) { ktot = 0; for (int j = 0; j < p.ntap; ++j) ktot += p.tap_C[j]; }
-  snprintf(buf, sizeof(buf), "%s:M=%ld,K=%d,N=%d,%s=%d%s%s", kind, (long)p.BT * p.Lq, ktot, p.N, p.ntap ? "taps" : "seg",
-           p.ntap ? p.ntap : p.nseg, p.seg[0].src2 ? ",bnload" : "", p.use_mask ? ",mask" : "");
+  snprintf(buf, sizeof(buf), "%s:M=%ld,K=%d,N=%d,%s=%d%s%s%s", kind, (long)p.BT * p.Lq, ktot, p.N, p.ntap ? "taps" : "seg",
+           p.ntap ? p.ntap : p.nseg, p.seg[0].src2 ? ",bnload" : "", p.use_mask ? ",mask" : "", p.dw_k ? ",dw" : "");
   auto it = names.find(buf);
   if (it == names.end()) it = names.emplace(buf, strdup(buf)).first;
   return it->second;
@@ -430,6 +431,7 @@ int launch_igemm(const IgemmParams& p, cudaStream_t st) {
 
 int launch_igemm_simt(const IgemmParams& p, cudaStream_t st) {
   TRU_REQUIRE(p.ntap == 0, TRU_ERR_ARG, "igemm: tap-shared launches exist on the tensor-core kernel only (the caller checks igemm_tc_eligible)");
+  TRU_REQUIRE(p.dw_k == 0, TRU_ERR_ARG, "igemm: the depthwise epilogue exists on the tensor-core kernel only (the caller checks igemm_tc_eligible)");
   TRU_REQUIRE(p.nseg >= 1 && p.nseg <= 5 && p.N % 4 == 0 && p.BT > 0 && p.Lq > 0, TRU_ERR_ARG, "igemm: bad params");
   int ktot = 0;
   for (int s = 0; s < p.nseg; ++s) {

@@ -45,6 +45,11 @@ struct IgemmParams {
   int ntap, tap_shift[5], tap_wbase[5], tap_c0[5], tap_C[5];
   int row_base, Lvalid;        // Lvalid 0: every virtual row is an output row
   int c_hi, lmax_hi;           // source channels >= c_hi exist for rows q < lmax_hi only (c_hi 0: Lsrc for all channels)
+  // ---- depthwise epilogue (inference, encoder blocks network.py:28-40; tensor-core kernel only) ---------------------------
+  // dw_k > 0: the product (+bias) is NOT stored.  The epilogue applies a = relu(mp0*z + mp2) (the folded BatchNorm of the pointwise
+  // conv) and the depthwise conv over the frame's rows,  out[bt][lo][n] = dw_b[n] + sum_j dw_w[n*dw_k + j] a[bt][lo*dw_s - dw_k/2 + j][n]
+  // (zero padding), Lout rows per frame: the pointwise output never reaches HBM.  Needs Lq in {16,32,64,128}, 64 < N <= 128.
+  const float* dw_w; const float* dw_b; int dw_k, dw_s;
 };
 int launch_igemm(const IgemmParams& p, cudaStream_t st);       // tensor-core path when eligible, else FFMA
 bool igemm_tc_eligible(const IgemmParams& p);

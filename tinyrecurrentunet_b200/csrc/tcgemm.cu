@@ -415,6 +415,103 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
       st += NG;
       while (st >= nstage) { st -= nstage; ++ph; }
     }
+  } else if constexpr (EPI == 3) {
+    // ====================== epilogue with the depthwise conv (inference) ======================
+    // Encoder block network.py:28-40 in eval mode: pointwise conv -> BN -> ReLU -> depthwise conv.  The accumulator is
+    // D[channel][row] and a thread owns one channel, so the rows of a frame are CONSECUTIVE REGISTERS of the thread and the
+    // 3 / 5-tap depthwise filter along the frame is register-local: a = relu(mp0 * (acc + bias) + mp2) (the folded BatchNorm,
+    // the same two roundings as the consumers' load-time affine), out[lo] = dw_b + sum_j w[j] a[lo*S - K/2 + j], zero padding.
+    // Frames (Lq rows, Lq | 128, 16 | Lq) never straddle a tile; a warp walks its 64 tile rows in chunks of 16 carrying the
+    // last 4 activations (e[0..3]); a chunk emits the outputs whose window ENDS in it, the frame's last chunk also the output
+    // whose window ends in the padding.  The warp of the second half tile starts mid-frame when Lq = 128: it reads its 4-row
+    // halo from TMEM.  The pointwise output never reaches HBM (halves the encoder traffic of an inference pass).
+    reg_inc<REG_EPI>();
+    const int ew = warp - 4 - LW, lg = warp & 3, half = ew >> 2;
+    const int n = n0 + lg * 32 + lane;
+    const bool nok = n < P.N;
+    const float bias = (P.bias && nok) ? __ldg(P.bias + n) : 0.f;
+    const float a0 = (P.mp0 && nok) ? __ldg(P.mp0 + n) : 1.f, a2 = (P.mp2 && nok) ? __ldg(P.mp2 + n) : 0.f;
+    const float dwb = (P.dw_b && nok) ? __ldg(P.dw_b + n) : 0.f;
+    float* outb = P.out + (size_t)n + P.ocoff;
+    const unsigned Lq = (unsigned)P.Lq, Lout = (unsigned)P.Lout, BT = (unsigned)P.BT, ldo = (unsigned)P.ldo;
+    auto act = [&](uint32_t v) { return fmaxf(fmaf(__uint_as_float(v) + bias, a0, a2), 0.f); };
+    auto run = [&](auto KK, auto SS) {
+      constexpr int K = decltype(KK)::value, S = decltype(SS)::value, PD = K / 2;
+      constexpr int D = -((PD) / S);                    // first output of a chunk at q: lo = q/S + D  (ceil(-PD / S))
+      constexpr int I0 = D * S - PD + 4;                // its window starts at e[I0]
+      constexpr int NO = 16 / S;
+      static_assert(I0 >= 0 && I0 + (NO - 1) * S + K - 1 <= 19, "window outside the 4 + 16 register buffer");
+      float w[K];
+#pragma unroll
+      for (int j = 0; j < K; ++j) w[j] = nok ? __ldg(P.dw_w + (size_t)n * K + j) : 0.f;
+      for (int ti = 0; ti < n_my; ++ti) {
+        const int acc = ti & 1;
+        const unsigned m0 = ((unsigned)blockIdx.x + (unsigned)ti * gridDim.x) * BM + half * 64;
+        unsigned bt = m0 / Lq, q = m0 - bt * Lq;
+        mbar_wait(&mi.tfull[acc], (ti >> 1) & 1, 400 + ti);
+        tc_fence_after();
+        const uint32_t taddr = tmem + ((uint32_t)(lg * 32) << 16) + acc * BM + half * 64;
+        float e[20];
+        uint32_t va[16], vb[16];
+        tmem_ld16_issue(taddr, va);
+        if (q != 0) {
+          uint32_t h[4];
+          tmem_ld4(taddr - 4, h);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) e[j] = act(h[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) e[j] = 0.f;
+        }
+        auto chunk = [&](uint32_t (&v)[16]) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) e[4 + j] = act(v[j]);
+          const bool ok = nok && bt < BT;               // (rows beyond M: the last tile of the problem only)
+          const int lo0 = (int)(q / S) + D;
+          const unsigned rb = bt * Lout;
+#pragma unroll
+          for (int i = 0; i < NO; ++i) {
+            float o = dwb;
+#pragma unroll
+            for (int j = 0; j < K; ++j) o = fmaf(w[j], e[I0 + i * S + j], o);
+            const int lo = lo0 + i;
+            if (ok && lo >= 0) outb[(size_t)((rb + (unsigned)lo) * ldo)] = o;
+          }
+          q += 16;
+          if (q == Lq) {                                // frame complete: the output whose window ends in the padding, then a new frame
+            if (D < 0) {
+              float o = dwb;
+#pragma unroll
+              for (int j = 0; j < K; ++j)
+                if (I0 + j < 4) o = fmaf(w[j], e[16 + I0 + j], o);
+              if (ok) outb[(size_t)((bt * Lout + Lout - 1u) * ldo)] = o;
+            }
+            q = 0; ++bt;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) e[j] = 0.f;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) e[j] = e[16 + j];
+          }
+        };
+        tmem_ld_wait(va);
+        tmem_ld16_issue(taddr + 16, vb);
+        chunk(va);
+        tmem_ld_wait(vb);
+        tmem_ld16_issue(taddr + 32, va);
+        chunk(vb);
+        tmem_ld_wait(va);
+        tmem_ld16_issue(taddr + 48, vb);
+        chunk(va);
+        tmem_ld_wait(vb);
+        tc_fence_before();
+        mbar_arrive(&mi.tempty[acc]);
+        chunk(vb);
+      }
+    };
+    if (P.dw_k == 5) run(std::integral_constant<int, 5>{}, std::integral_constant<int, 2>{});
+    else if (P.dw_s == 1) run(std::integral_constant<int, 3>{}, std::integral_constant<int, 1>{});
+    else run(std::integral_constant<int, 3>{}, std::integral_constant<int, 2>{});
   } else {
     // ================================== epilogue ===================================
     // Thread = one output channel (TMEM lane); per tile a warp drains 2 chunks of 32 tile rows
@@ -640,6 +737,8 @@ int total_kblocks(const IgemmParams& p) {
   return nkb;
 }
 
+int max_kblocks(int MW);
+
 bool shape_ok(const IgemmParams& p) {
   if (p.nseg < 1 || p.nseg > 5 || p.N < 1 || p.Lq < 1 || p.Lq > 32768) return false;
   for (int s = 0; s < p.nseg; ++s) {
@@ -658,6 +757,13 @@ bool shape_ok(const IgemmParams& p) {
       if (p.tap_shift[j] < 0 || p.tap_shift[j] > 7 || p.tap_c0[j] % KBLK != 0 || p.tap_C[j] % KBLK != 0 || p.tap_C[j] < KBLK ||
           p.tap_c0[j] < 0 || p.tap_c0[j] + p.tap_C[j] > p.seg[0].C) return false;
   } else if (p.Lvalid != 0 && p.Lvalid != p.Lq) return false;
+  if (p.dw_k) {                // depthwise epilogue: whole frames per half tile, one 128-lane accumulator, nothing else in the epilogue
+    if (p.ntap || p.planar || p.extra || p.use_mask || p.stats || p.bstats || !p.dw_w || p.N <= 64 || p.N > 128) return false;
+    if (!((p.dw_k == 5 && p.dw_s == 2) || (p.dw_k == 3 && (p.dw_s == 1 || p.dw_s == 2)))) return false;
+    if (p.Lq < 16 || p.Lq % 16 != 0 || 128 % p.Lq != 0) return false;
+    if (p.Lout != (p.Lq + 2 * (p.dw_k / 2) - p.dw_k) / p.dw_s + 1) return false;
+    if (total_kblocks(p) > max_kblocks(128)) return false;       // (never split into k passes)
+  }
   return true;
 }
 
@@ -753,6 +859,7 @@ int launch_one(const IgemmParams& p, const TcLayout& L, dim3 grid, size_t smem, 
   const int epi = p.extra != nullptr ? 2 : ((p.use_mask || p.bstats != nullptr) ? 1 : 0);
   bool ld2 = false;
   for (int s = 0; s < p.nseg; ++s) ld2 |= (p.seg[s].src2 != nullptr);
+  if (p.dw_k) return launch_inst<12, false, 3, false>(p, L, grid, smem, st);      // inference: pointwise conv with the depthwise conv in the epilogue
   if (L.shared) {        // transposed convs: forward (affine + ReLU on load, plain / statistics epilogue), data gradient (masked)
     if (!ld2 && epi == 0) return launch_inst<12, false, 0, true>(p, L, grid, smem, st);
     if (ld2 && epi == 0) return launch_inst<12, true, 0, true>(p, L, grid, smem, st);

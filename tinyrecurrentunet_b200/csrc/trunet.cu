@@ -169,6 +169,7 @@ int pw_fwd(Ctx& c, const Act& x1, int padL, const Act* skip, const float* W, con
 // Tap-shared launch parameters common to the transposed-conv forward and data gradient (net_kernels.cuh: IgemmParams::ntap):
 // taps (delta_j, channel slice, weight offset); virtual rows per frame Lq_v chosen by the caller.
 struct Tap { int delta, c0, C, wbase; };
+int g_eval_fusion = 1;          // tru_debug_set_eval_fusion: 0 keeps the layer-by-layer schedule in inference (A/B aid; tests that read the pointwise outputs)
 // TRU_TAP_SHARED_OFF (bit 0: forward, bit 1: data gradient) sends the transposed convs down the one-segment-per-tap launches (A/B aid)
 int tap_shared_off() {
   static int v = -1;
@@ -238,6 +239,21 @@ int forward(Ctx& c, const float* x, const float* h0, float* out, float* hlast) {
   for (int i = 1; i <= 5; ++i) {
     const int Lin = ENC_L[i - 1], Lo = ENC_L[i];
     const int b1 = BN_ENC(i, 0), b2 = BN_ENC(i, 1);
+    if (!c.d->training && g_eval_fusion && tc_enabled()) {
+      // inference: no batch statistics between the two convs -> the depthwise conv runs in the pointwise GEMM's epilogue and
+      // the pointwise output (the block's largest tensor) is never written (tcgemm.cu, EPI 3)
+      IgemmParams p{};
+      p.seg[0] = fwd_seg(cur, c.prm[P_ENC(i, 0)], 0, 1, cur.C, 1, 0);
+      p.nseg = 1; p.BT = (int)BT; p.Lq = Lin; p.N = 128; p.bias = c.prm[P_ENC(i, 1)];
+      p.mp0 = c.bn[b1].p0; p.mp2 = c.bn[b1].p2;
+      p.dw_w = c.prm[P_ENC(i, 4)]; p.dw_b = c.prm[P_ENC(i, 5)]; p.dw_k = ENC_K[i]; p.dw_s = ENC_S[i];
+      p.out = c.F(P.Zd[i]); p.Lout = Lo; p.ldo = 128; p.omul = 1;
+      if (igemm_tc_eligible(p)) {
+        TRY(launch_igemm(p, c.st));
+        cur = c.act(P.Zd[i], Lo, 128, b2);
+        continue;
+      }
+    }
     TRY(pw_fwd(c, cur, 0, nullptr, c.prm[P_ENC(i, 0)], c.prm[P_ENC(i, 1)], 128, Lin, c.F(P.Zp[i]), 128, 0, c.bn[b1].stats));
     TRY(bn_fin(c, b1, 128, BT * Lin, c.prm[P_ENC(i, 2)], c.prm[P_ENC(i, 3)]));
     DwParams dp{};
@@ -804,6 +820,7 @@ extern "C" int tru_debug_pw_bwd(const float* dy, const float* z, const float* q0
 extern "C" int tru_set_tensor_cores(int on) { set_tc_enabled(on != 0); return TRU_OK; }
 extern "C" int tru_debug_read_mbar(unsigned* out, int n) { return read_mbar_debug(out, n); }
 extern "C" int tru_debug_set_flags(int f) { set_tc_debug_flags(f); return TRU_OK; }
+extern "C" int tru_debug_set_eval_fusion(int on) { g_eval_fusion = on != 0; return TRU_OK; }
 
 // Test aid: dW (N,C) += z^T a for a (M,C), z (M,N) through the FFMA weight-gradient kernel (the parity reference of the
 // streaming tensor-core kernel below).
