@@ -59,6 +59,8 @@ struct TcLayout {
   int8_t kb_seg[MAXKB], kb_coef[MAXKB], kb_relu[MAXKB], kb_nw[MAXKB];   // kb_nw: weight k-blocks fed by this source k-block (consecutive in wk_*)
   int8_t kb_pf[MAXKB];          // rows of this k-block's source are contiguous in tile order (row m at (m + sadd) * ld): the loaders can
                                 // prefetch the CTA's next tile into L2 with plain address arithmetic
+  int8_t kb_lin[MAXKB];         // ... and sadd == 0, all 32 channels exist: problem row m IS source row m, no row decode / validity test
+  int all_lin;                  // every k-block is linear: the per-tile row decode is skipped altogether
   int16_t kb_c0[MAXKB], kb_valid[MAXKB];
   int kb_lmax[MAXKB];           // source rows li >= kb_lmax are zero rows
   int8_t wk_seg[MAXWK], wk_shift[MAXWK];
@@ -101,6 +103,9 @@ __device__ __forceinline__ float4 ldg4_off(const float* base, unsigned off) {
 #endif
 #ifndef TRU_L2_PREFETCH
 #define TRU_L2_PREFETCH 1
+#endif
+#ifndef TRU_LINEAR_ROWS
+#define TRU_LINEAR_ROWS 1
 #endif
 #ifndef TRU_EPI2_PIPE
 #define TRU_EPI2_PIPE 1
@@ -305,7 +310,7 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
         bt0 = m0 / Lq; qb = m0 - bt0 * Lq + rbase; qmax = Mu - 1u - bt0 * Lq;
         v0 = (int)m0 + P.row_base + rbase;
         cur = ti;
-        if (CACHE_ROWS) {            // the (frame, position) of the thread's 8 rows is the same for every k-block of the tile
+        if (CACHE_ROWS && (SH || !Lo.all_lin)) {            // the (frame, position) of the thread's 8 rows is the same for every k-block of the tile
 #pragma unroll
           for (int ii = 0; ii < 8; ++ii) decode(ii, rbt[ii], rqq[ii]);
         }
@@ -353,6 +358,25 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
         *(uint4*)(ah + row * (16 * 128) + sw_hi) = hi;
         *(uint4*)(ah + atile_b + row * (16 * 128) + sw_lo) = lo;
       };
+      if (!SH && Lo.kb_lin[kb]) {
+        // LINEAR k-block (pointwise convs and their data gradients: the bulk of the step): problem row m is source row m, every
+        // row and channel exists - no row decode, no validity mask (rows beyond M, last tile only, re-read row M-1; the epilogue
+        // drops them).  The profile had ~480 instructions per warp and k-block in this loop for 150 of loads, math and stores.
+        const unsigned mr = ((unsigned)blockIdx.x + (unsigned)ti * gridDim.x) * BM + rbase;
+#pragma unroll
+        for (int h = 0; h < 8 / R; ++h) {
+          float4 a[R], b[LD2 ? R : 1];
+#pragma unroll
+          for (int i = 0; i < R; ++i) {
+            const unsigned off = min(mr + 16u * (h * R + i), Mu - 1u) * ld + cb;
+            a[i] = ldg4_off(src, off);
+            if (LD2) b[i] = src2 ? ldg4_off(src2, off) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          if (h == 0 && ph > 0) mbar_wait(&mi.empty[((ph - 1) & 1) * 8 + st], ((ph - 1) >> 1) & 1, 300 + st * 10 + kb + 1000 * ti);
+#pragma unroll
+          for (int i = 0; i < R; ++i) put(a[i], b[LD2 ? i : 0], true, h * R + i);
+        }
+      } else {
 #pragma unroll
       for (int h = 0; h < 8 / R; ++h) {
         float4 a[R], b[LD2 ? R : 1];
@@ -380,6 +404,7 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
           for (int i = 0; i < R; ++i) put(a[i], b[LD2 ? i : 0], (msk >> i) & 1u, h * R + i);
         }
       }
+      }
       // L2 prefetch of the same k-block of the CTA's NEXT tile (one 128-byte line per row: the chunk-0 threads issue it).  The
       // loaders keep 8 (LD2: 2 x 4) 16-byte loads per thread in flight - ~32-48 KB per SM, borderline for 22 B/clk x ~1,000 cycles
       // of loaded DRAM latency - and more would cost registers; a prefetch costs none and turns the next tile's loads into L2 hits.
@@ -387,15 +412,13 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
       // a linear sweep from the tile's first row - gained nothing, and for the epilogue's mask / added-tensor rows of 128-channel
       // layers it cost more than it hid: 0.95 -> 1.06 ms on the masked 128 -> 128 data gradient; the epilogue prefetch pays for
       // <= 64 output channels only, see below)
-      if (!SH && TRU_L2_PREFETCH && Lo.kb_pf[kb] && chunk == 0 && ti + 1 < n_my) {
-        const unsigned m1 = ((unsigned)blockIdx.x + (unsigned)(ti + 1) * gridDim.x) * BM + rbase;
-#pragma unroll
-        for (int ii = 0; ii < 8; ++ii) {
-          const unsigned mm = min(m1 + 16u * ii, Mu - 1u);
-          const unsigned off = (unsigned)((int)mm + sadd) * ld + cb;
-          prefetch_l2_off(src, off);
-          if (LD2 && src2) prefetch_l2_off(src2, off);
-        }
+      if (!SH && TRU_L2_PREFETCH && Lo.kb_pf[kb] && ti + 1 < n_my) {
+        // (one line per LANE: the warp's 32 rows are (lane >> 3) + 4 (warp of the group) + 16 ii; lane j takes ii = j & 7)
+        const unsigned m1 = ((unsigned)blockIdx.x + (unsigned)(ti + 1) * gridDim.x) * BM + (unsigned)(rbase + 16 * chunk);
+        const unsigned mm = min(m1, Mu - 1u);
+        const unsigned off = (unsigned)((int)mm + sadd) * ld + (unsigned)(sg.coff + Lo.kb_c0[kb]);
+        prefetch_l2_off(src, off);
+        if (LD2 && src2) prefetch_l2_off(src2, off);
       }
       if (shared && rbase < xrows) {         // stage rows 128 + rbase (rbase < largest tap shift): one more row for the first threads
         unsigned bt, q;
@@ -789,6 +812,7 @@ bool plan(const IgemmParams& p, TcLayout& L, dim3& grid, size_t& smem_bytes) {
       L.kb_relu[nkb] = (int8_t)(sg.p0 && sg.relu);
       L.kb_lmax[nkb] = (L.shared && p.c_hi > 0 && c0 >= p.c_hi) ? p.lmax_hi : sg.Lsrc;
       L.kb_pf[nkb] = (int8_t)(!L.shared && sg.smul == 1 && sg.Lsrc == p.Lq && (sg.fs == 0 || sg.fs == sg.Lsrc * sg.ld));
+      L.kb_lin[nkb] = (int8_t)(L.kb_pf[nkb] && sg.sadd == 0 && L.kb_valid[nkb] == KBLK && TRU_LINEAR_ROWS);
       L.kb_coef[nkb] = -1;
       if (sg.p0) {
         int e = -1;
@@ -829,6 +853,8 @@ bool plan(const IgemmParams& p, TcLayout& L, dim3& grid, size_t& smem_bytes) {
     if (L.kb_nw[kb] == 0) return false;       // a staged channel block no tap reads
   }
   L.nkb = nkb; L.ncoef = ncoef; L.nwk = nwk; L.dbg = g_dbg_flags;
+  L.all_lin = 1;
+  for (int kb = 0; kb < nkb; ++kb) L.all_lin &= L.kb_lin[kb];
   L.arows = BM + maxshift; L.atile = (uint32_t)L.arows * 128; L.stage = 2 * L.atile;
   L.lq_magic = p.Lq == 1 ? 0u : (unsigned)((0x100000000ull + (unsigned)p.Lq - 1) / (unsigned)p.Lq);
   const size_t w = (size_t)2 * nwk * L.MW * 128;
