@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the global-batch-256 strong-scaling point")
     ap.add_argument("--streams", type=int, default=4096, help="concurrent streams of the streaming measurement (configs[3])")
     ap.add_argument("--offline-clips", type=int, default=1250, help="10-s clips per GPU of the offline measurement (configs[4])")
+    ap.add_argument("--offline-batch", type=int, default=37,
+                    help="clips per offline batch: 37 x 16 TGRU sequences = 148 CTAs of 4, one full wave of the recurrence kernel")
     return ap.parse_args()
 
 
@@ -399,14 +401,14 @@ def measure_inference(args, dev, state_dict, world, rank, dist):
             out["latency"]["cpu_threads"] = cores
             out["latency"]["cpu_1thread_ms"] = cpu_forward_latency_ms(1)
     # ---- configs[4] (every rank) ---------------------------------------------------------------------------------
-    Bo = 25
-    nclips = max(Bo, args.offline_clips // Bo * Bo)
-    pool = [(0.1 * torch.randn(Bo, LONG_SAMPLES, generator=g)).pin_memory() for _ in range(2)]   # 50 distinct clips, cycled
+    Bo = max(1, args.offline_batch)
+    nclips = max(Bo, args.offline_clips)
+    pool = [(0.1 * torch.randn(Bo, LONG_SAMPLES, generator=g)).pin_memory() for _ in range(2)]   # 2 x Bo distinct clips, cycled
 
-    def host_batches(n):
-        for i in range(n):
-            yield pool[i & 1]
-    for _ in util.denoise_host_batches(net, host_batches(2), dev):      # warm-up (allocations, pinned staging)
+    def host_batches(n):                                                # n clips: full batches, then the ragged rest
+        for i in range((n + Bo - 1) // Bo):
+            yield pool[i & 1][:min(Bo, n - i * Bo)]
+    for _ in util.denoise_host_batches(net, host_batches(2 * Bo + nclips % Bo), dev):      # warm-up (allocations, pinned staging of both batch sizes)
         pass
     if world > 1:
         dist.barrier()
@@ -415,7 +417,7 @@ def measure_inference(args, dev, state_dict, world, rank, dist):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     checksum = 0.0
-    for host_audio in util.denoise_host_batches(net, host_batches(nclips // Bo), dev):
+    for host_audio in util.denoise_host_batches(net, host_batches(nclips), dev):
         checksum += float(host_audio[0, 1000])                         # the consumer touches every result
     e1.record()
     sync()
@@ -437,8 +439,8 @@ def measure_inference(args, dev, state_dict, world, rank, dist):
                           "roofline": {"bound": "hbm", "algorithmic_bytes_per_batch": alg, "achieved": round(alg / dev_ms / 1e6, 1),
                                        "peak": peak, "unit": "GB/s", "frac": round(alg / dev_ms / 1e6 / peak, 4)},
                           "workload": "configs[4]: %d x 10-s clips per GPU on %d GPU(s) in batches of %d, pinned host buffers in and "
-                                      "out every batch (util.denoise_host_batches), 50 distinct clips cycled; no collective"
-                                      % (nclips, world, Bo)}
+                                      "out every batch (util.denoise_host_batches), %d distinct clips cycled; no collective"
+                                      % (nclips, world, Bo, 2 * Bo)}
     return out
 
 

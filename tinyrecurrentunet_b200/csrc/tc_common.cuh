@@ -66,6 +66,23 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint6
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// same with the A operand (M x 8 tf32: row i in TMEM lane i, the 8 K elements in consecutive 32-bit columns) read from TENSOR MEMORY
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// registers -> TMEM: thread i of the warp writes lane (base + i), columns c..c+15; tmem_st_wait before anything depends on it
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // arrive on an mbarrier once all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -172,6 +189,27 @@ __device__ __forceinline__ void split_tf32(const float4& v, uint4& hi, uint4& lo
   hi.x = f2tf32(v.x); hi.y = f2tf32(v.y); hi.z = f2tf32(v.z); hi.w = f2tf32(v.w);
   lo.x = __float_as_uint(v.x - __uint_as_float(hi.x)); lo.y = __float_as_uint(v.y - __uint_as_float(hi.y));
   lo.z = __float_as_uint(v.z - __uint_as_float(hi.z)); lo.w = __float_as_uint(v.w - __uint_as_float(hi.w));
+}
+
+// (volatile: the loads must stay where they are written - they are prefetches issued ahead of a wait)
+// st.global / ld.global with a 64-bit base and a 32-bit element offset: IMAD.WIDE + STG/LDG (the
+// compiler's own addressing of base[off] re-materialised the base from the constant bank per element).
+__device__ __forceinline__ void stg_off(float* base, unsigned off, float v) {
+  asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %1, 4, %0;\n\tst.global.f32 [a], %2;\n\t}" ::"l"(base), "r"(off), "f"(v) : "memory");
+}
+__device__ __forceinline__ float ldg_off(const float* base, unsigned off) {
+  float v;
+  asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %2, 4, %1;\n\tld.global.nc.f32 %0, [a];\n\t}" : "=f"(v) : "l"(base), "r"(off));
+  return v;
+}
+__device__ __forceinline__ void prefetch_l2_off(const float* base, unsigned off) {
+  asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %1, 4, %0;\n\tprefetch.global.L2 [a];\n\t}" ::"l"(base), "r"(off));
+}
+__device__ __forceinline__ float4 ldg4_off(const float* base, unsigned off) {
+  float4 v;
+  asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %5, 4, %4;\n\tld.global.nc.v4.f32 {%0,%1,%2,%3}, [a];\n\t}"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(base), "r"(off));
+  return v;
 }
 
 }  // namespace tc

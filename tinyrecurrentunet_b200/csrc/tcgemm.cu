@@ -61,6 +61,7 @@ struct TcLayout {
                                 // prefetch the CTA's next tile into L2 with plain address arithmetic
   int8_t kb_lin[MAXKB];         // ... and sadd == 0, all 32 channels exist: problem row m IS source row m, no row decode / validity test
   int all_lin;                  // every k-block is linear: the per-tile row decode is skipped altogether
+  int wtmem;                    // the weight slice (hi | lo, 2 x 32 nwk columns) lives in TENSOR MEMORY behind the two accumulators, not in shared memory
   int16_t kb_c0[MAXKB], kb_valid[MAXKB];
   int kb_lmax[MAXKB];           // source rows li >= kb_lmax are zero rows
   int8_t wk_seg[MAXWK], wk_shift[MAXWK];
@@ -77,32 +78,15 @@ struct Misc {
 
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldg((const float4*)p); }
 
-// (volatile: the loads must stay where they are written - they are prefetches issued ahead of a wait)
-// st.global / ld.global with a 64-bit base and a 32-bit element offset: IMAD.WIDE + STG/LDG (the
-// compiler's own addressing of base[off] re-materialised the base from the constant bank per element).
-__device__ __forceinline__ void stg_off(float* base, unsigned off, float v) {
-  asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %1, 4, %0;\n\tst.global.f32 [a], %2;\n\t}" ::"l"(base), "r"(off), "f"(v) : "memory");
-}
-__device__ __forceinline__ float ldg_off(const float* base, unsigned off) {
-  float v;
-  asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %2, 4, %1;\n\tld.global.nc.f32 %0, [a];\n\t}" : "=f"(v) : "l"(base), "r"(off));
-  return v;
-}
-__device__ __forceinline__ void prefetch_l2_off(const float* base, unsigned off) {
-  asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %1, 4, %0;\n\tprefetch.global.L2 [a];\n\t}" ::"l"(base), "r"(off));
-}
-__device__ __forceinline__ float4 ldg4_off(const float* base, unsigned off) {
-  float4 v;
-  asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %5, 4, %4;\n\tld.global.nc.v4.f32 {%0,%1,%2,%3}, [a];\n\t}"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(base), "r"(off));
-  return v;
-}
 
 #ifndef TRU_CACHE_ROWS
 #define TRU_CACHE_ROWS 1
 #endif
 #ifndef TRU_L2_PREFETCH
 #define TRU_L2_PREFETCH 1
+#endif
+#ifndef TRU_W_IN_TMEM
+#define TRU_W_IN_TMEM 1
 #endif
 #ifndef TRU_LINEAR_ROWS
 #define TRU_LINEAR_ROWS 1
@@ -159,7 +143,7 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
 
   // ---- one-time setup: resident weight slice (hi/lo), affine coefficient table, barriers, TMEM ------
   pdl_trigger();       // the weights are parameters: nothing in the step writes them, so staging them may overlap the predecessor's tail
-  {
+  if (!Lo.wtmem) {
     const int msh = MW == 64 ? 11 : 12;                 // log2(32 channels x MW rows)
     const uint32_t nel = (uint32_t)Lo.nwk << msh;       // weight elements (one hi and one lo word each)
     for (uint32_t i = tid; i < nel / 2; i += NT) ((uint4*)Wsm)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -193,6 +177,8 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
         }
       }
     }
+  }
+  auto load_coef = [&]() {
     pdl_wait();        // everything below reads what earlier kernels of the step produced (BN coefficients first)
     for (int i = tid; i < Lo.ncoef * 32; i += NT) {
       const int e = i >> 5, j = i & 31;
@@ -204,7 +190,8 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
       coef[e * COEF_FLOATS + 32 + j] = ok ? __ldg(sg.p2 + cc) : 0.f;
       coef[e * COEF_FLOATS + 64 + j] = (ok && sg.p1) ? __ldg(sg.p1 + cc) : 0.f;
     }
-  }
+  };
+  if (!Lo.wtmem) load_coef();
   if (warp == 0) {
     if (lane == 0) {
       for (int s = 0; s < nstage; ++s) { mbar_init(&mi.full[s], LW / NG); mbar_init(&mi.empty[s], 1); mbar_init(&mi.empty[8 + s], 1); }
@@ -212,13 +199,47 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(&mi.tmem_base, 2 * BM);
+    tmem_alloc(&mi.tmem_base, Lo.wtmem ? 512 : 2 * BM);
   }
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = mi.tmem_base;
+  if (Lo.wtmem) {
+    // Weights as the MMA's A operand IN TENSOR MEMORY (M = 128 launches with <= 128 reduction channels): row n of the slice in
+    // lane n, its channels in consecutive columns - hi plane at column 256, lo plane behind it.  The MMAs then read only the
+    // gathered rows from shared memory (per 128 x 128 x 128 tile the operand reads drop from 384 KB to 192 KB of a 512 KB total:
+    // the pipe was ~55 % of the shared-memory bandwidth), and the 128 KB the slice occupied become ring stages.
+    // A warp writes the 32 lanes of its quadrant (warp & 3); the 6 warps of a quadrant share the 16-column groups.
+    const int q = warp & 3, n = q * 32 + lane, ngrp = Lo.nwk * 4;              // groups: [hi | lo][nwk][2 x 16 channels]
+    const bool nok = n0 + n < P.N;
+    for (int gi = warp >> 2; gi < ngrp; gi += NT / 128) {
+      const int plane = gi >= 2 * Lo.nwk, gg = gi - plane * 2 * Lo.nwk, w = gg >> 1, c0 = (gg & 1) * 16;
+      const Seg& sg = P.seg[Lo.wk_seg[w]];
+      const float* wp = sg.W + Lo.wk_wbase[w] + (long)(Lo.wk_c0[w] + c0) * sg.wsc + (long)(n0 + n) * sg.wsn;
+      uint32_t v[16];
+      float x[16];
+      if (sg.wsc == 1 && nok && c0 + 16 <= Lo.wk_valid[w] && (((size_t)wp) & 15) == 0) {      // the thread's 16 channels are contiguous: 4 x 16 bytes
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { const float4 t = __ldg((const float4*)wp + c); x[4 * c] = t.x; x[4 * c + 1] = t.y; x[4 * c + 2] = t.z; x[4 * c + 3] = t.w; }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) x[c] = (nok && c0 + c < Lo.wk_valid[w]) ? __ldg(wp + (long)c * sg.wsc) : 0.f;
+      }
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        const uint32_t hi = f2tf32(x[c]);
+        v[c] = plane ? __float_as_uint(x[c] - __uint_as_float(hi)) : hi;
+      }
+      tmem_st16(tmem + ((uint32_t)(q * 32) << 16) + 2 * BM + (uint32_t)plane * Lo.nwk * 32 + (uint32_t)w * 32 + c0, v);
+    }
+    tmem_st_wait();
+    load_coef();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
 
   if (warp < 4) {
     // ================================ MMA issuer ==================================
@@ -246,6 +267,18 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
             // tap w reads the stage from row wk_shift[w] on: start address + shift * 128 B (8 units of 16 B)
             const uint32_t x_hi = x_st + (SH ? (uint32_t)Lo.wk_shift[w] * 8u : 0u), x_lo = x_hi + atile16;
             const uint32_t w_hi = w_base + (uint32_t)w * w_kb, w_lo = w_hi + w_lo_off;
+            if (Lo.wtmem) {
+              const uint32_t t_hi = tmem + 2 * BM + (uint32_t)w * 32, t_lo = t_hi + (uint32_t)Lo.nwk * 32;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint64_t dxh = dhi | (x_hi + 2 * j), dxl = dhi | (x_lo + 2 * j);
+                if (Lo.dbg & 1) continue;
+                mma_tf32_ts(d, t_lo + 8 * j, dxh, idesc, (w | j) != 0);
+                mma_tf32_ts(d, t_hi + 8 * j, dxl, idesc, 1);
+                mma_tf32_ts(d, t_hi + 8 * j, dxh, idesc, 1);
+              }
+              continue;
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint64_t dxh = dhi | (x_hi + 2 * j), dxl = dhi | (x_lo + 2 * j);
@@ -746,7 +779,7 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem, 2 * BM);
+    tmem_dealloc(tmem, Lo.wtmem ? 512 : 2 * BM);
   }
 }
 
@@ -796,6 +829,13 @@ int weight_rows(const IgemmParams& p) { return p.N <= 64 ? 64 : 128; }
 int max_kblocks(int MW) {
   const size_t fixed = 2 * STAGE + sizeof(Misc) + 64 + (size_t)MAXCOEF * COEF_FLOATS * 4;
   return (int)std::min<size_t>(MAXKB, (SMEM_MAX - fixed) / ((size_t)MW * 256));
+}
+
+// TRU_W_TMEM_OFF=1 keeps the weight slice in shared memory (A/B aid)
+bool wtmem_off() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("TRU_W_TMEM_OFF"); v = (e && atoi(e)) ? 1 : 0; }
+  return v != 0;
 }
 
 bool plan(const IgemmParams& p, TcLayout& L, dim3& grid, size_t& smem_bytes) {
@@ -857,7 +897,8 @@ bool plan(const IgemmParams& p, TcLayout& L, dim3& grid, size_t& smem_bytes) {
   for (int kb = 0; kb < nkb; ++kb) L.all_lin &= L.kb_lin[kb];
   L.arows = BM + maxshift; L.atile = (uint32_t)L.arows * 128; L.stage = 2 * L.atile;
   L.lq_magic = p.Lq == 1 ? 0u : (unsigned)((0x100000000ull + (unsigned)p.Lq - 1) / (unsigned)p.Lq);
-  const size_t w = (size_t)2 * nwk * L.MW * 128;
+  L.wtmem = (TRU_W_IN_TMEM && !wtmem_off() && L.MW == 128 && nwk * 64 <= 512 - 2 * BM) ? 1 : 0;
+  const size_t w = L.wtmem ? 0 : (size_t)2 * nwk * L.MW * 128;
   const size_t coefb = (size_t)ncoef * COEF_FLOATS * 4;
   const size_t fixed = coefb + sizeof(Misc) + 64;
   if (fixed + w + 2 * (size_t)L.stage > SMEM_MAX) return false;

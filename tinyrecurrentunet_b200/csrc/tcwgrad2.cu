@@ -49,6 +49,7 @@ struct WgK {
   int n_split; float* dW2; float* db2;
   float* scratch;                // per-CTA partial accumulators [CTA][Mmma][QWt] (null: atomics straight into dW)
   int BT, Lq; unsigned units_total, units_per_cta;
+  int dbg;                       // ablation switches (env TRU_WG_DBG, tuning aid; results are garbage when set): 1 no MMAs, 2 no transform math / stores, 4 no proxy fence
 };
 
 struct StageFlags { uint32_t amask[2]; uint32_t zmask[2]; };
@@ -186,6 +187,7 @@ __global__ void __launch_bounds__(NT, 1) tc_wgrad_stream_kernel(const __grid_con
 #pragma unroll
           for (int g = 0; g < UR / 8; ++g) {                    // k-steps of 8 rows = 2 atoms
             const uint32_t po = g * NBp * 64, qo = g * NBq * 64 + b0 * 32;     // (bytes >> 4)
+            if (K.dbg & 1) continue;
             mma_tf32(d, dP | (p_lo + po), dQ | (q_hi + qo), idesc, (u | g) != 0);
             mma_tf32(d, dP | (p_hi + po), dQ | (q_lo + qo), idesc, 1);
             mma_tf32(d, dP | (p_hi + po), dQ | (q_hi + qo), idesc, 1);
@@ -345,6 +347,7 @@ __global__ void __launch_bounds__(NT, 1) tc_wgrad_stream_kernel(const __grid_con
         }
       mbar_wait(&mi.op_empty[os], ((u >> 1) & 1) ^ 1);
       uint8_t* op = ops + (size_t)os * K.op_stage;
+      if (!(K.dbg & 2)) {
 #pragma unroll
       for (int k = 0; k < IA; ++k) {
         if (a_raw[k] != NONE) {
@@ -383,7 +386,8 @@ __global__ void __launch_bounds__(NT, 1) tc_wgrad_stream_kernel(const __grid_con
             if (NTAP == 1 || z_dst[k][j] != NONE) { *(uint4*)(op + z_dst[k][j]) = hi; *(uint4*)(op + z_dst[k][j] + z_lo) = lo; }
         }
       }
-      fence_proxy_async();
+      }
+      if (!(K.dbg & 4)) fence_proxy_async();
       __syncwarp();
       if (lane == 0) { mbar_arrive(&mi.op_full[os]); mbar_arrive(&mi.raw_empty[rs]); }
       if (++rs == nraw) { rs = 0; ph ^= 1; }
@@ -454,6 +458,7 @@ int launch_variant(const WgK& K, int grid, size_t smem, cudaStream_t st) {
 // returns TRU_OK if launched, 1 if the job does not fit this kernel (caller uses the per-job kernels)
 int launch_wgrad_stream(const WgStream& w, cudaStream_t st) {
   WgK K{};
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("TRU_WG_DBG"); dbg = e ? atoi(e) : 0; } K.dbg = dbg; }
   if (w.nsrc < 1 || w.nsrc > 2 || w.ntap < 1 || w.ntap > 5 || w.Lq % UR != 0 || w.N % 4 != 0 || w.N > (w.ntap == 1 ? 384 : 128)) return 1;
   if (w.nsrc == 2 && w.ntap > 1) return 1;
   int Ca = 0;
