@@ -55,7 +55,7 @@ __device__ __forceinline__ void reduce_channels(float* red, const float (&v)[4],
 struct DwK {
   DwParams p;
   int nstage, upf;                    // stages, units per frame
-  uint32_t stage_bytes, in2_off, in3_off, red_off, misc_off;
+  uint32_t stage_bytes, in2_off, in3_off, red_off, misc_off, coef_off;
   unsigned units;
 };
 
@@ -157,6 +157,11 @@ __global__ void __launch_bounds__(NT, 1) dw_bwd_stream_kernel(const __grid_const
     fence_barrier_init();
   }
   pdl_wait();                                            // barrier setup above overlaps the predecessor's tail
+  // Per-channel coefficients that are used once per row live in shared memory, not in registers: 17 warps put five on one SM
+  // sub-partition, which caps the kernel at 96 registers, and with q0-q2, the taps and the K + 3 sums resident the compiler spilled
+  // the RING STATE - ncu's source view had 21 % of the warp time waiting on local-memory reloads of the stage index and phase.
+  float* cf = (float*)(smem + Kp.coef_off);              // [mp0 | mp2 | bmean][DC]
+  for (int i = tid; i < DC; i += NT) { cf[i] = __ldg(p.mp0 + i); cf[DC + i] = __ldg(p.mp2 + i); cf[2 * DC + i] = __ldg(p.bmean + i); }
   __syncthreads();
   const unsigned n_my = Kp.units > blockIdx.x ? (Kp.units - 1 - blockIdx.x) / gridDim.x + 1 : 0;
   auto lo_range = [&](int li0, int& la, int& lb) {
@@ -189,15 +194,22 @@ __global__ void __launch_bounds__(NT, 1) dw_bwd_stream_kernel(const __grid_const
   } else {
     const int cw = warp - 1, c4 = lane * 4;
     const float4 q0 = ld4(p.p0 + c4), q1 = ld4(p.p1 + c4), q2 = ld4(p.p2 + c4);
-    const float4 mp0 = ld4(p.mp0 + c4), mp2 = ld4(p.mp2 + c4), bmean = ld4(p.bmean + c4);
+    const uint32_t cfa = smem_u32(cf + c4);
+    auto lds4 = [](uint32_t a) {                         // (volatile: the load stays next to its use)
+      float4 v;
+      asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+      return v;
+    };
     float w[4][K];
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
       for (int t = 0; t < K; ++t) w[j][t] = __ldg(p.w + (c4 + j) * K + t);
-    float acc[K + 3][4];             // 0..K-1: dw taps, K: db, K+1: sum g, K+2: sum g*(z - mean)
+    // (the depthwise bias gradient - exactly zero in front of a training-mode BatchNorm - is produced by bn_bwd_finalize from the
+    // sums it already has, like the transposed convs': no per-row accumulation here)
+    float acc[K + 2][4];             // 0..K-1: dw taps, K: sum g, K+1: sum g*(z - mean)
 #pragma unroll
-    for (int t = 0; t < K + 3; ++t)
+    for (int t = 0; t < K + 2; ++t)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[t][j] = 0.f;
     int st = 0; uint32_t ph = 0;
@@ -214,6 +226,7 @@ __global__ void __launch_bounds__(NT, 1) dw_bwd_stream_kernel(const __grid_const
       for (int r = cw; r < RI; r += CW) {
         const int li = li0 + r;
         const float4 z = *(const float4*)(zp + r * DC + c4);
+        const float4 mp0 = lds4(cfa), mp2 = lds4(cfa + DC * 4);
         float4 a;
         a.x = fmaxf(fmaf(z.x, mp0.x, mp2.x), 0.f); a.y = fmaxf(fmaf(z.y, mp0.y, mp2.y), 0.f);
         a.z = fmaxf(fmaf(z.z, mp0.z, mp2.z), 0.f); a.w = fmaf(z.w, mp0.w, mp2.w); a.w = fmaxf(a.w, 0.f);
@@ -232,28 +245,27 @@ __global__ void __launch_bounds__(NT, 1) dw_bwd_stream_kernel(const __grid_const
               g.z = fmaf(w[2][t], v.z, g.z); g.w = fmaf(w[3][t], v.w, g.w);
               acc[t][0] = fmaf(v.x, a.x, acc[t][0]); acc[t][1] = fmaf(v.y, a.y, acc[t][1]);
               acc[t][2] = fmaf(v.z, a.z, acc[t][2]); acc[t][3] = fmaf(v.w, a.w, acc[t][3]);
-              if (t == PAD) { acc[K][0] += v.x; acc[K][1] += v.y; acc[K][2] += v.z; acc[K][3] += v.w; }
             }
           }
         }
         g.x = a.x > 0.f ? g.x : 0.f; g.y = a.y > 0.f ? g.y : 0.f; g.z = a.z > 0.f ? g.z : 0.f; g.w = a.w > 0.f ? g.w : 0.f;
         *(float4*)(p.out + ((size_t)bt * p.Lin + li) * DC + c4) = g;
-        acc[K + 1][0] += g.x; acc[K + 1][1] += g.y; acc[K + 1][2] += g.z; acc[K + 1][3] += g.w;
-        acc[K + 2][0] = fmaf(g.x, z.x - bmean.x, acc[K + 2][0]); acc[K + 2][1] = fmaf(g.y, z.y - bmean.y, acc[K + 2][1]);
-        acc[K + 2][2] = fmaf(g.z, z.z - bmean.z, acc[K + 2][2]); acc[K + 2][3] = fmaf(g.w, z.w - bmean.w, acc[K + 2][3]);
+        acc[K][0] += g.x; acc[K][1] += g.y; acc[K][2] += g.z; acc[K][3] += g.w;
+        const float4 bmean = lds4(cfa + 2 * DC * 4);
+        acc[K + 1][0] = fmaf(g.x, z.x - bmean.x, acc[K + 1][0]); acc[K + 1][1] = fmaf(g.y, z.y - bmean.y, acc[K + 1][1]);
+        acc[K + 1][2] = fmaf(g.z, z.z - bmean.z, acc[K + 1][2]); acc[K + 1][3] = fmaf(g.w, z.w - bmean.w, acc[K + 1][3]);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&mi.empty[st]);
       if (++st == nst) { st = 0; ph ^= 1; }
     }
     const float4 binv = ld4(p.binv + c4);
-    acc[K + 2][0] *= binv.x; acc[K + 2][1] *= binv.y; acc[K + 2][2] *= binv.z; acc[K + 2][3] *= binv.w;
+    acc[K + 1][0] *= binv.x; acc[K + 1][1] *= binv.y; acc[K + 1][2] *= binv.z; acc[K + 1][3] *= binv.w;
     float* red = (float*)(smem + Kp.red_off);
 #pragma unroll
     for (int t = 0; t < K; ++t) reduce_channels(red, acc[t], cw, c4, nullptr, p.dw + t, K);
-    reduce_channels(red, acc[K], cw, c4, p.bstats + 2 * DC, nullptr, 0);        // db: fp64 scratch, folded in by bn_bwd_finalize
-    reduce_channels(red, acc[K + 1], cw, c4, p.bstats, nullptr, 0);
-    reduce_channels(red, acc[K + 2], cw, c4, p.bstats + DC, nullptr, 0);
+    reduce_channels(red, acc[K], cw, c4, p.bstats, nullptr, 0);
+    reduce_channels(red, acc[K + 1], cw, c4, p.bstats + DC, nullptr, 0);
   }
 }
 
@@ -290,11 +302,13 @@ bool layout(DwK& Kp, bool bwd, size_t& smem) {
     stage = zb + 2 * db;
   }
   Kp.stage_bytes = (uint32_t)stage;
-  Kp.nstage = (int)std::min<size_t>(MAXST, (SMEM_MAX - redb - miscb - 128) / stage);
+  const size_t coefb = bwd ? (size_t)3 * DC * 4 : 0;          // backward: ReLU-mask affine + BN mean of the layer in front (see the kernel)
+  Kp.nstage = (int)std::min<size_t>(MAXST, (SMEM_MAX - redb - miscb - coefb - 128) / stage);
   if (Kp.nstage < 2) return false;
   Kp.red_off = (uint32_t)(Kp.nstage * stage);
   Kp.misc_off = (uint32_t)(Kp.red_off + redb);
-  smem = Kp.misc_off + miscb;
+  Kp.coef_off = (uint32_t)(Kp.misc_off + miscb);
+  smem = Kp.coef_off + coefb;
   Kp.units = (unsigned)p.BT * Kp.upf;
   return true;
 }

@@ -649,7 +649,7 @@ int backward(Ctx& c, const float* x, const float* gout) {
   for (int i = 5; i >= 1; --i) {
     const int Lin = ENC_L[i - 1], Lo = ENC_L[i];
     const int b1 = BN_ENC(i, 0), b2 = BN_ENC(i, 1);
-    TRY(bn_bfin(c, b2, 128, BT * Lo, P_ENC(i, 6)));
+    TRY(bn_bfin(c, b2, 128, BT * Lo, P_ENC(i, 6), -1, P_ENC(i, 5)));   // (+ the depthwise bias gradient, from the sums: it cancels exactly)
     DwParams dp{};
     dp.src = c.F(P.dZd[i]); dp.src2 = c.F(P.Zd[i]); dp.p0 = c.bn[b2].q0; dp.p1 = c.bn[b2].q1; dp.p2 = c.bn[b2].q2;
     dp.w = c.prm[P_ENC(i, 4)]; dp.out = c.F(P.dZp[i]);
@@ -659,7 +659,7 @@ int backward(Ctx& c, const float* x, const float* gout) {
     dp.a_src = c.F(P.Zp[i]); dp.a_p0 = c.bn[b1].p0; dp.a_p2 = c.bn[b1].p2;
     dp.dw = c.grd[P_ENC(i, 4)]; dp.db = c.grd[P_ENC(i, 5)];
     TRY(launch_dw_bwd_fused(dp, c.st));
-    TRY(bn_bfin(c, b1, 128, BT * Lin, P_ENC(i, 2), P_ENC(i, 5)));   // also folds the fp64 depthwise-bias sums into db
+    TRY(bn_bfin(c, b1, 128, BT * Lin, P_ENC(i, 2)));
     Grad gp = c.grad(P.dZp[i], P.Zp[i], Lin, 128, b1);
     if (i >= 2) {
       Act xin = c.act(P.Zd[i - 1], Lin, 128, BN_ENC(i - 1, 1));
