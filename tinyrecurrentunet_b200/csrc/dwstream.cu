@@ -161,7 +161,11 @@ __global__ void __launch_bounds__(NT, 1) dw_bwd_stream_kernel(const __grid_const
   // sub-partition, which caps the kernel at 96 registers, and with q0-q2, the taps and the K + 3 sums resident the compiler spilled
   // the RING STATE - ncu's source view had 21 % of the warp time waiting on local-memory reloads of the stage index and phase.
   float* cf = (float*)(smem + Kp.coef_off);              // [mp0 | mp2 | bmean][DC]
-  for (int i = tid; i < DC; i += NT) { cf[i] = __ldg(p.mp0 + i); cf[DC + i] = __ldg(p.mp2 + i); cf[2 * DC + i] = __ldg(p.bmean + i); }
+  for (int i = tid; i < DC; i += NT) {
+    cf[i] = __ldg(p.mp0 + i); cf[DC + i] = __ldg(p.mp2 + i); cf[2 * DC + i] = __ldg(p.bmean + i);
+    if (K == 5)                                          // (five taps x four channels are 20 more registers: tap-major copy, read per use)
+      for (int t = 0; t < K; ++t) cf[(3 + t) * DC + i] = __ldg(p.w + i * K + t);
+  }
   __syncthreads();
   const unsigned n_my = Kp.units > blockIdx.x ? (Kp.units - 1 - blockIdx.x) / gridDim.x + 1 : 0;
   auto lo_range = [&](int li0, int& la, int& lb) {
@@ -200,11 +204,13 @@ __global__ void __launch_bounds__(NT, 1) dw_bwd_stream_kernel(const __grid_const
       asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
       return v;
     };
-    float w[4][K];
+    float w[4][K == 5 ? 1 : K];
+    if (K != 5) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+      for (int j = 0; j < 4; ++j)
 #pragma unroll
-      for (int t = 0; t < K; ++t) w[j][t] = __ldg(p.w + (c4 + j) * K + t);
+        for (int t = 0; t < (K == 5 ? 1 : K); ++t) w[j][t] = __ldg(p.w + (c4 + j) * K + t);
+    }
     // (the depthwise bias gradient - exactly zero in front of a training-mode BatchNorm - is produced by bn_bwd_finalize from the
     // sums it already has, like the transposed convs': no per-row accumulation here)
     float acc[K + 2][4];             // 0..K-1: dw taps, K: sum g, K+1: sum g*(z - mean)
@@ -241,8 +247,13 @@ __global__ void __launch_bounds__(NT, 1) dw_bwd_stream_kernel(const __grid_const
               float4 v;
               v.x = fmaf(q1.x, zz.x, fmaf(q0.x, y.x, q2.x)); v.y = fmaf(q1.y, zz.y, fmaf(q0.y, y.y, q2.y));
               v.z = fmaf(q1.z, zz.z, fmaf(q0.z, y.z, q2.z)); v.w = fmaf(q1.w, zz.w, fmaf(q0.w, y.w, q2.w));
-              g.x = fmaf(w[0][t], v.x, g.x); g.y = fmaf(w[1][t], v.y, g.y);
-              g.z = fmaf(w[2][t], v.z, g.z); g.w = fmaf(w[3][t], v.w, g.w);
+              if (K == 5) {
+                const float4 wt = lds4(cfa + (3 + t) * DC * 4);
+                g.x = fmaf(wt.x, v.x, g.x); g.y = fmaf(wt.y, v.y, g.y); g.z = fmaf(wt.z, v.z, g.z); g.w = fmaf(wt.w, v.w, g.w);
+              } else {
+                g.x = fmaf(w[0][K == 5 ? 0 : t], v.x, g.x); g.y = fmaf(w[1][K == 5 ? 0 : t], v.y, g.y);
+                g.z = fmaf(w[2][K == 5 ? 0 : t], v.z, g.z); g.w = fmaf(w[3][K == 5 ? 0 : t], v.w, g.w);
+              }
               acc[t][0] = fmaf(v.x, a.x, acc[t][0]); acc[t][1] = fmaf(v.y, a.y, acc[t][1]);
               acc[t][2] = fmaf(v.z, a.z, acc[t][2]); acc[t][3] = fmaf(v.w, a.w, acc[t][3]);
             }
@@ -302,7 +313,7 @@ bool layout(DwK& Kp, bool bwd, size_t& smem) {
     stage = zb + 2 * db;
   }
   Kp.stage_bytes = (uint32_t)stage;
-  const size_t coefb = bwd ? (size_t)3 * DC * 4 : 0;          // backward: ReLU-mask affine + BN mean of the layer in front (see the kernel)
+  const size_t coefb = bwd ? (size_t)(3 + 5) * DC * 4 : 0;    // backward: ReLU-mask affine + BN mean of the layer in front, 5-tap weights (see the kernel)
   Kp.nstage = (int)std::min<size_t>(MAXST, (SMEM_MAX - redb - miscb - coefb - 128) / stage);
   if (Kp.nstage < 2) return false;
   Kp.red_off = (uint32_t)(Kp.nstage * stage);
