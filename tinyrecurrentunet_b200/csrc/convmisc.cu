@@ -304,7 +304,8 @@ __global__ void __launch_bounds__(256) dw_bwd_data_kernel(const __grid_constant_
 // (t == pad, li == lo*s) visits every output row exactly once, so it also carries db.  a() is the same
 // tensor as the ReLU mask (Zp with BN1's affine), so every operand is read once per use site and the
 // weight-gradient pass over dY / Zd / Zp of dw_wgrad_kernel disappears.  db (whose true value is 0 in
-// front of a training-mode BN: pure cancellation) is summed in fp64 next to the BN sums.
+// front of a training-mode BN: pure cancellation) is summed in fp64 next to the BN sums (scratch; the network path takes the
+// gradient from bn_bwd_finalize's conv_db, which derives it from the BN sums - trunet.cu, encoder blocks).
 __global__ void __launch_bounds__(256, 2) dw_bwd_fused_kernel(const __grid_constant__ DwParams p) {
   __shared__ float red[DW_ROWS][DW_C];
   const int c4 = (threadIdx.x & 31) * 4, rl = threadIdx.x >> 5;
@@ -362,7 +363,7 @@ __global__ void __launch_bounds__(256, 2) dw_bwd_fused_kernel(const __grid_const
       double s = 0.0;
       for (int r = 0; r < DW_ROWS; ++r) s += (double)red[r][threadIdx.x];
       if (t < 5) atomicAdd(p.dw + threadIdx.x * p.k + t, (float)s);
-      else if (t == 5) atomicAdd(p.bstats + 2 * DW_C + threadIdx.x, s);     // db: fp64 scratch, folded in by bn_bwd_finalize
+      else if (t == 5) atomicAdd(p.bstats + 2 * DW_C + threadIdx.x, s);     // db: fp64 scratch (see above)
       else atomicAdd(p.bstats + (t - 6) * DW_C + threadIdx.x, s);
     }
   }
