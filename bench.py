@@ -245,8 +245,53 @@ class ClockSampler:
         self.path = tempfile.mktemp(suffix=".csv")
         self.proc = None
         self.idx = gpu_index
+        self.nvml = None
+
+    # NVML from a thread (first sample within a millisecond; an `nvidia-smi -lms` child needs most of a 0.5-s timed region to start
+    # and sometimes delivered no sample at all); the nvidia-smi loop is the fallback when the binding is missing
+    def _nvml_start(self):
+        import threading
+        import pynvml as N
+        N.nvmlInit()
+        h = None
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.idx).uuid)
+            h = N.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            h = N.nvmlDeviceGetHandleByIndex(self.idx)
+        self.nvml = {"N": N, "h": h, "sm": [], "reasons": 0, "stop": False}
+        self.nvml["max"] = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+
+        def loop():
+            st = self.nvml
+            get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not st["stop"]:
+                try:
+                    st["sm"].append(float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
+                    st["reasons"] |= int(get_reasons(h))
+                except Exception:
+                    pass
+                time.sleep(0.02)
+        self.thread = threading.Thread(target=loop, daemon=True)
+        self.thread.start()
+
+    def _nvml_stop(self):
+        st = self.nvml
+        st["stop"] = True
+        self.thread.join(timeout=2)
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        out = {"sm_mhz": None, "sm_max_mhz": st["max"], "reasons": sorted(k for k, b in bits.items() if st["reasons"] & b)}
+        if st["sm"]:
+            out.update(sm_mhz=statistics.median(st["sm"]), samples=len(st["sm"]), source="nvml, 20 ms period")
+        return out
 
     def start(self):
+        try:
+            self._nvml_start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.fh = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
@@ -256,6 +301,8 @@ class ClockSampler:
             self.proc = None
 
     def stop(self):
+        if self.nvml is not None:
+            return self._nvml_stop()
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.proc is None:
             return out
