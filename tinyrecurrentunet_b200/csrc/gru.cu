@@ -18,7 +18,19 @@ namespace tru {
 namespace {
 
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldg((const float4*)p); }
+// Gate non-linearities from the two SFU primitives (ex2.approx, rcp.approx: ~2 ulp each; absolute error ~1e-7 on outputs in
+// [-1, 1], parity tolerance 1e-4).  libm's expf / tanhf and the IEEE division are ~130 instructions per hidden unit, on the serial
+// path of every recurrence step.  (Round 1 tried __expf / __frcp_rn and measured a loss: __frcp_rn is a correctly-rounded software
+// reciprocal.)  TRU_GRU_LIBM=1 at compile time restores libm.
+#ifndef TRU_GRU_LIBM
+__device__ __forceinline__ float ex2a(float x) { float y; asm("ex2.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcpa(float x) { float y; asm("rcp.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoidf_(float x) { return rcpa(1.0f + ex2a(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float tanhf_(float x) { return fmaf(-2.0f, rcpa(1.0f + ex2a(2.8853900817779268f * x)), 1.0f); }
+#else
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float tanhf_(float x) { return tanhf(x); }
+#endif
 
 // =============================== FGRU ========================================
 constexpr int FH = 64, FL = 16, FSEQ = 64, FNT = 256;
@@ -108,7 +120,7 @@ __global__ void __launch_bounds__(FNT) fgru_fwd_kernel(const __grid_constant__ G
       for (int u = 0; u < 4; ++u) {
         r[u] = sigmoidf_(gr[u] + acc[s][0][u]);
         z[u] = sigmoidf_(gz[u] + acc[s][1][u]);
-        n[u] = tanhf(gn[u] + r[u] * acc[s][2][u]);
+        n[u] = tanhf_(gn[u] + r[u] * acc[s][2][u]);
         hown[s][u] = (1.0f - z[u]) * n[u] + z[u] * hown[s][u];
       }
       const float4 hv = make_float4(hown[s][0], hown[s][1], hown[s][2], hown[s][3]);
@@ -314,7 +326,7 @@ __global__ void __launch_bounds__(TNT, 1) tgru_fwd_kernel(const __grid_constant_
         const float hn = hid[0][s][2 * TH + u] + hid[1][s][2 * TH + u];
         const float rr = sigmoidf_(g[u] + (hid[0][s][u] + hid[1][s][u]));
         const float zz = sigmoidf_(g[TH + u] + (hid[0][s][TH + u] + hid[1][s][TH + u]));
-        const float nn = tanhf(g[2 * TH + u] + rr * hn);
+        const float nn = tanhf_(g[2 * TH + u] + rr * hn);
         const float hnew = (1.0f - zz) * nn + zz * hprev[r];
         hprev[r] = hnew;
         hs[s][u] = hnew;
@@ -468,7 +480,7 @@ __global__ void __launch_bounds__(256) tgru_step_gates_kernel(const float* __res
     hr = ld4(bhh + u); hz = ld4(bhh + TH + u); hn = ld4(bhh + 2 * TH + u);
   }
   float4 o;
-#define TRU_GATE(c) { const float rr = sigmoidf_(ir.c + hr.c), zz = sigmoidf_(iz.c + hz.c), nn = tanhf(in.c + rr * hn.c); \
+#define TRU_GATE(c) { const float rr = sigmoidf_(ir.c + hr.c), zz = sigmoidf_(iz.c + hz.c), nn = tanhf_(in.c + rr * hn.c); \
                       o.c = (1.0f - zz) * nn + zz * hp.c; }
   TRU_GATE(x) TRU_GATE(y) TRU_GATE(z) TRU_GATE(w)
 #undef TRU_GATE
