@@ -43,6 +43,10 @@ __device__ __forceinline__ void block_add(double* dst, float v0, float v1, float
   }
 }
 
+__device__ __forceinline__ float sqrta(float x) { float y; asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rsqrta(float x) { float y; asm("rsqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2a(float x) { float y; asm("lg2.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 // load frame t of (x,y), windowed, into (re, im)
 template <int N>
 __device__ __forceinline__ void load_frame(const LossParams& p, int r, int b, int t, bool valid,
@@ -90,10 +94,12 @@ __device__ void loss_fwd_block(const LossParams& p, int r, int blk, float* fre, 
       for (int k = l; k <= N / 2; k += GT) {
         float xr, xi, yr, yi;
         split_xy(z, k, (N - k) & (N - 1), xr, xi, yr, yi);
-        const float mx = sqrtf(fmaxf(xr * xr + xi * xi, 1e-7f));     // stft_loss.py:30
-        const float my = sqrtf(fmaxf(yr * yr + yi * yi, 1e-7f));
+        // (SFU sqrt / log2, ~2 ulp: the per-bin arithmetic with libm's logf and the IEEE sqrt was a third of this kernel's
+        // instructions; |log my - log mx| = ln2 / 2 * |log2 my^2 - log2 mx^2|)
+        const float px = fmaxf(xr * xr + xi * xi, 1e-7f), py = fmaxf(yr * yr + yi * yi, 1e-7f);     // stft_loss.py:30 (clamp on the power)
+        const float mx = sqrta(px), my = sqrta(py);
         const float d = my - mx;
-        a0 += d * d; a1 += my * my; a2 += fabsf(logf(my) - logf(mx));
+        a0 += d * d; a1 += py; a2 += 0.34657359027997264f * fabsf(lg2a(py) - lg2a(px));
       }
     }
   }
@@ -169,12 +175,12 @@ __device__ void loss_bwd_block(const LossParams& p, int r, int blk, float* fre, 
           split_xy(z, k, (N - k) & (N - 1), xr, xi, yr, yi);
           const float px = xr * xr + xi * xi;
           if (px >= 1e-7f) {                           // clamp passes gradient only above the floor
-            const float mx = sqrtf(px);
-            const float my = sqrtf(fmaxf(yr * yr + yi * yi, 1e-7f));
-            const float dl = logf(my) - logf(mx);
+            const float inv = rsqrta(px), mx = px * inv;                       // (SFU rsqrt / sqrt instead of IEEE sqrt + two divisions)
+            const float my = sqrta(fmaxf(yr * yr + yi * yi, 1e-7f));
+            const float dl = my - mx;                                          // sign(log my - log mx): the logarithm is monotone
             const float sg = dl > 0.f ? 1.f : (dl < 0.f ? -1.f : 0.f);
-            const float dmx = csc * (my - mx) - cmg * sg / mx;
-            const float sc = dmx / mx;
+            const float dmx = csc * dl - cmg * sg * inv;
+            const float sc = dmx * inv;
             dr = sc * xr; di = sc * xi;
           }
         }
