@@ -49,6 +49,7 @@ struct WgK {
   int n_split; float* dW2; float* db2;
   float* scratch;                // per-CTA partial accumulators [CTA][Mmma][QWt] (null: atomics straight into dW)
   int BT, Lq; unsigned units_total, units_per_cta;
+  int ur;                        // rows per unit: 16, or 32 for narrow layers (few bytes per row: the per-unit hand-offs, not the bytes, set the pace)
   int dbg;                       // ablation switches (env TRU_WG_DBG, tuning aid; results are garbage when set): 1 no MMAs, 2 no transform math / stores, 4 no proxy fence
 };
 
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const __grid_constant
 
 // IA / IZ: per-thread item slots (activation / dz float4s per unit), NTAP: taps (compile-time so that unused
 // slots and taps cost nothing; with one slot each the BN coefficients live in registers)
-template <int IA, int IZ, int NTAP>
+template <int IA, int IZ, int NTAP, int URT>
 __global__ void __launch_bounds__(NT, 1) tc_wgrad_stream_kernel(const __grid_constant__ WgK K) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(NT, 1) tc_wgrad_stream_kernel(const __grid_con
           const uint32_t idesc = idesc_tf32(K.Mmma, nb * 32, 1, 1);
           const uint32_t d = tmem + b0 * 32;
 #pragma unroll
-          for (int g = 0; g < UR / 8; ++g) {                    // k-steps of 8 rows = 2 atoms
+          for (int g = 0; g < URT / 8; ++g) {                  // k-steps of 8 rows = 2 atoms
             const uint32_t po = g * NBp * 64, qo = g * NBq * 64 + b0 * 32;     // (bytes >> 4)
             if (K.dbg & 1) continue;
             mma_tf32(d, dP | (p_lo + po), dQ | (q_hi + qo), idesc, (u | g) != 0);
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(NT, 1) tc_wgrad_stream_kernel(const __grid_con
       Run r{0, 0, 0, nullptr, 0u, 0u};
       if (o < K.nsrc) {
         const int l0 = (int)q0 + K.a_add[o];
-        r.lo = max(0, -l0); r.hi = min(UR, K.a_L[o] - l0);
+        r.lo = max(0, -l0); r.hi = min(URT, K.a_L[o] - l0);
         r.rowb = (uint32_t)K.a_C[o] * 4u; r.ld = K.a_ld[o];
         r.src = K.a_src[o] + ((size_t)bt * K.a_L[o] + (l0 + r.lo)) * r.ld + K.a_coff[o];
         r.dst = K.raw_a[o] + (uint32_t)r.lo * r.rowb;
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(NT, 1) tc_wgrad_stream_kernel(const __grid_con
     uint32_t ph = 0;
     while (rs >= nraw) { rs -= nraw; ph ^= 1; }
     for (unsigned u = pw; pw < NPW && u < nun; u += NPW) {
-      const unsigned m0 = (u0 + u) * UR, bt = m0 / Lq, q0 = m0 - bt * Lq;
+      const unsigned m0 = (u0 + u) * URT, bt = m0 / Lq, q0 = m0 - bt * Lq;
       const Run r = plan(lane, bt, q0);              // lane o < 4 plans operand o (lanes >= 4: empty run)
       const bool has = lane < 4 && r.hi > r.lo;
       const uint32_t mybytes = has ? (uint32_t)(r.hi - r.lo) * r.rowb : 0u;
@@ -280,7 +281,7 @@ __global__ void __launch_bounds__(NT, 1) tc_wgrad_stream_kernel(const __grid_con
     constexpr uint32_t NONE = 0xffffffffu;
     uint32_t a_raw[IA], a_dst[IA], a_cb[IA];          // a_cb: channel | row << 16 | source << 24
     uint32_t z_raw[IZ], z_cb[IZ], z_dst[IZ][NTAP];    // z_cb: channel | t << 16
-    const int nA = UR * NBa * 8, nZ = ((K.NZ + 3) & ~3) * NBz * 8;
+    const int nA = URT * NBa * 8, nZ = ((K.NZ + 3) & ~3) * NBz * 8;
 #pragma unroll
     for (int k = 0; k < IA; ++k) {
       const int it = tt + k * NTR;
@@ -310,7 +311,7 @@ __global__ void __launch_bounds__(NT, 1) tc_wgrad_stream_kernel(const __grid_con
 #pragma unroll
           for (int j = 0; j < NTAP; ++j) {
             const int d = t - j;
-            if (d >= 0 && d % K.zs == 0 && d / K.zs < UR) z_dst[k][j] = z_tile + tile_off(d / K.zs, j * K.N + c, NBzt);
+            if (d >= 0 && d % K.zs == 0 && d / K.zs < URT) z_dst[k][j] = z_tile + tile_off(d / K.zs, j * K.N + c, NBzt);
           }
         }
       }
@@ -445,10 +446,10 @@ __global__ void __launch_bounds__(NT, 1) tc_wgrad_stream_kernel(const __grid_con
 
 constexpr size_t SMEM_MAX = 227 * 1024;
 
-template <int IA, int IZ, int NTAP>
+template <int IA, int IZ, int NTAP, int URT = UR>
 int launch_variant(const WgK& K, int grid, size_t smem, cudaStream_t st) {
-  TRU_SMEM_OPT_IN((tc_wgrad_stream_kernel<IA, IZ, NTAP>), SMEM_MAX);
-  TRU_CUDA(launch_pdl(tc_wgrad_stream_kernel<IA, IZ, NTAP>, dim3(grid), dim3(NT), smem, st, K));
+  TRU_SMEM_OPT_IN((tc_wgrad_stream_kernel<IA, IZ, NTAP, URT>), SMEM_MAX);
+  TRU_CUDA(launch_pdl(tc_wgrad_stream_kernel<IA, IZ, NTAP, URT>, dim3(grid), dim3(NT), smem, st, K));
   TRU_LAUNCH_CHECK();
   return TRU_OK;
 }
@@ -460,6 +461,24 @@ int launch_wgrad_stream(const WgStream& w, cudaStream_t st) {
   WgK K{};
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("TRU_WG_DBG"); dbg = e ? atoi(e) : 0; } K.dbg = dbg; }
   if (w.nsrc < 1 || w.nsrc > 2 || w.ntap < 1 || w.ntap > 5 || w.Lq % UR != 0 || w.N % 4 != 0 || w.N > (w.ntap == 1 ? 384 : 128)) return 1;
+  // Narrow layers take 32-row units: a 16-row unit of e.g. the 128 -> 8 layer is 9 KB, 0.2 us of HBM time, while the transform ->
+  // fence -> MMA -> commit hand-off of a unit is ~0.5 us on two operand stages (ablation: 0.30 ms skeleton, 0.51 ms full)
+  static int ur32_on = -1;
+  if (ur32_on < 0) { const char* e = getenv("TRU_WG_UR32_OFF"); ur32_on = (e && atoi(e)) ? 0 : 1; }
+  int ca_all = 0;
+  for (int s = 0; s < w.nsrc; ++s) ca_all += w.a_C[s];
+  const bool narrow = ca_all + w.N * w.zs * (w.z_p0 && w.z_src2 ? 2 : 1) <= 192;
+  int ur = (ur32_on && narrow && w.Lq % 32 == 0 && 31 * w.zs + w.ntap <= 64) ? 32 : UR;
+  if (ur == 32) {               // (only where a kernel variant exists for the slot counts of 32-row units)
+    const int nz32 = 31 * w.zs + w.ntap;
+    const int ia32 = (32 * ((ca_all + 31) / 32) * 8 + NTR - 1) / NTR, iz32 = (((nz32 + 3) & ~3) * ((w.N + 31) / 32) * 8 + NTR - 1) / NTR;
+    const int key32 = ia32 * 100 + iz32 * 10 + (w.ntap == 1 ? 1 : (w.ntap <= 3 ? 3 : 5));
+    const int have[] = {111, 211, 123};                  // (the 32-row instantiations below)
+    bool okk = false;
+    for (int k : have) okk |= (k == key32);
+    if (!okk) ur = UR;
+  }
+  K.ur = ur;
   if (w.nsrc == 2 && w.ntap > 1) return 1;
   int Ca = 0;
   for (int s = 0; s < w.nsrc; ++s) {
@@ -475,7 +494,7 @@ int launch_wgrad_stream(const WgStream& w, cudaStream_t st) {
   K.z_L = w.z_L; K.z_ld = w.z_ld; K.z_coff = w.z_coff; K.N = w.N;
   K.strided = (w.z_ld != w.N ? (4 | (K.z_src2 ? 8 : 0)) : 0);
   for (int s = 0; s < w.nsrc; ++s) if (w.a_ld[s] != w.a_C[s]) K.strided |= 1 << s; K.ntap = w.ntap; K.zs = w.zs; K.zpad = w.zpad;
-  K.NZ = (UR - 1) * w.zs + w.ntap;
+  K.NZ = (ur - 1) * w.zs + w.ntap;
   if (K.NZ > 64) return 1;
   const int Zcols = w.ntap * w.N;
   K.p_is_z = (w.ntap == 1 && w.N <= 128 && (Ca > 128 || w.N > Ca)) ? 1 : 0;
@@ -483,17 +502,17 @@ int launch_wgrad_stream(const WgStream& w, cudaStream_t st) {
   if (Pc > 128 || Qc > 384) return 1;
   K.Mmma = Pc <= 64 ? 64 : 128; K.PWt = K.Mmma; K.QWt = (Qc + 31) / 32 * 32; K.Pvalid = Pc; K.Qvalid = Qc;
   K.tmem_cols = K.QWt <= 32 ? 32 : K.QWt <= 64 ? 64 : K.QWt <= 128 ? 128 : K.QWt <= 256 ? 256 : 512;
-  const int nA = UR * ((Ca + 31) / 32) * 8, nZ = ((K.NZ + 3) & ~3) * ((w.N + 31) / 32) * 8;
+  const int nA = ur * ((Ca + 31) / 32) * 8, nZ = ((K.NZ + 3) & ~3) * ((w.N + 31) / 32) * 8;
   const int ia = (nA + NTR - 1) / NTR, iz = (nZ + NTR - 1) / NTR, nt = w.ntap == 1 ? 1 : (w.ntap <= 3 ? 3 : 5);
   if (ia > 2 || iz > 3) return 1;
   if (w.db && w.ntap != 1) return 1;
   K.db = w.db;
-  K.p_tile = (uint32_t)UR * K.PWt * 4; K.q_tile = (uint32_t)UR * K.QWt * 4;
+  K.p_tile = (uint32_t)ur * K.PWt * 4; K.q_tile = (uint32_t)ur * K.QWt * 4;
   K.op_stage = (uint32_t)align_up(2 * K.p_tile + 2 * K.q_tile, 1024);
   if (w.z_ld < w.N + w.z_coff) return 1;
   for (int s = 0; s < w.nsrc; ++s) if (w.a_ld[s] < w.a_C[s] + w.a_coff[s]) return 1;
-  K.raw_a[0] = 0; K.raw_a[1] = (uint32_t)UR * K.a_C[0] * 4;
-  K.raw_dy = (uint32_t)align_up((size_t)UR * Ca * 4, 128);
+  K.raw_a[0] = 0; K.raw_a[1] = (uint32_t)ur * K.a_C[0] * 4;
+  K.raw_dy = (uint32_t)align_up((size_t)ur * Ca * 4, 128);
   K.raw_z = K.raw_dy + (uint32_t)align_up((size_t)K.NZ * w.N * 4, 128);
   K.raw_stage = (uint32_t)align_up(K.raw_z + (K.z_src2 ? (size_t)K.NZ * w.N * 4 : 0), 1024);
   const size_t coefb = align_up((size_t)(3 * Ca + 3 * w.N) * 4, 128), miscb = align_up(sizeof(WMisc2), 128);
@@ -510,7 +529,7 @@ int launch_wgrad_stream(const WgStream& w, cudaStream_t st) {
   K.BT = w.BT; K.Lq = w.Lq;
   const long M = (long)w.BT * w.Lq;
   if ((double)w.BT * w.z_L * w.z_ld >= 1.8e19) return 1;
-  K.units_total = (unsigned)(M / UR);
+  K.units_total = (unsigned)(M / ur);
   const int grid = (int)std::min<long>(sm_count(), K.units_total);
   K.units_per_cta = (K.units_total + grid - 1) / grid;
   const char* nm = "wgrad_stream";
@@ -524,9 +543,12 @@ int launch_wgrad_stream(const WgStream& w, cudaStream_t st) {
   }
   ProfScope prof(nm, 4.0 * M * (Ca + (double)w.N * w.zs * (K.z_src2 ? 2 : 1)), 2.0 * M * Ca * (double)w.N * w.ntap, st);
   K.scratch = (w.scratch && w.scratch_floats >= (size_t)grid * K.Mmma * K.QWt) ? w.scratch : nullptr;
-  const int key = ia * 100 + iz * 10 + nt;
+  const int key = ia * 100 + iz * 10 + nt + (ur == 32 ? 1000 : 0);
   int rc;
   switch (key) {
+    case 1111: rc = launch_variant<1, 1, 1, 32>(K, grid, smem, st); break;
+    case 1211: rc = launch_variant<2, 1, 1, 32>(K, grid, smem, st); break;
+    case 1123: rc = launch_variant<1, 2, 3, 32>(K, grid, smem, st); break;
     case 111: rc = launch_variant<1, 1, 1>(K, grid, smem, st); break;
     case 113: rc = launch_variant<1, 1, 3>(K, grid, smem, st); break;
     case 115: rc = launch_variant<1, 1, 5>(K, grid, smem, st); break;
