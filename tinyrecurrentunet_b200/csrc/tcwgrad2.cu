@@ -461,22 +461,30 @@ int launch_wgrad_stream(const WgStream& w, cudaStream_t st) {
   WgK K{};
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("TRU_WG_DBG"); dbg = e ? atoi(e) : 0; } K.dbg = dbg; }
   if (w.nsrc < 1 || w.nsrc > 2 || w.ntap < 1 || w.ntap > 5 || w.Lq % UR != 0 || w.N % 4 != 0 || w.N > (w.ntap == 1 ? 384 : 128)) return 1;
-  // Narrow layers take 32-row units: a 16-row unit of e.g. the 128 -> 8 layer is 9 KB, 0.2 us of HBM time, while the transform ->
-  // fence -> MMA -> commit hand-off of a unit is ~0.5 us on two operand stages (ablation: 0.30 ms skeleton, 0.51 ms full)
+  // 32-row units wherever two operand stages of 32 rows leave room for >= 3 raw stages and a kernel variant exists: a 16-row unit
+  // of e.g. the 128 -> 8 layer is 9 KB, 0.2 us of HBM time, while the transform -> fence -> MMA -> commit hand-off of a unit is
+  // ~0.5 us on two operand stages (ablation: 0.30 ms skeleton, 0.51 ms full)
   static int ur32_on = -1;
   if (ur32_on < 0) { const char* e = getenv("TRU_WG_UR32_OFF"); ur32_on = (e && atoi(e)) ? 0 : 1; }
   int ca_all = 0;
   for (int s = 0; s < w.nsrc; ++s) ca_all += w.a_C[s];
-  const bool narrow = ca_all + w.N * w.zs * (w.z_p0 && w.z_src2 ? 2 : 1) <= 192;
-  int ur = (ur32_on && narrow && w.Lq % 32 == 0 && 31 * w.zs + w.ntap <= 64) ? 32 : UR;
-  if (ur == 32) {               // (only where a kernel variant exists for the slot counts of 32-row units)
+  int ur = UR;
+  if (ur32_on && w.Lq % 32 == 0 && 31 * w.zs + w.ntap <= 64) {
     const int nz32 = 31 * w.zs + w.ntap;
     const int ia32 = (32 * ((ca_all + 31) / 32) * 8 + NTR - 1) / NTR, iz32 = (((nz32 + 3) & ~3) * ((w.N + 31) / 32) * 8 + NTR - 1) / NTR;
     const int key32 = ia32 * 100 + iz32 * 10 + (w.ntap == 1 ? 1 : (w.ntap <= 3 ? 3 : 5));
-    const int have[] = {111, 211, 123};                  // (the 32-row instantiations below)
+    const int have[] = {111, 211, 123, 121, 221, 131};    // (the 32-row instantiations below)
     bool okk = false;
     for (int k : have) okk |= (k == key32);
-    if (!okk) ur = UR;
+    // shared memory of the 32-row layout (same formulas as below)
+    const bool pz = (w.ntap == 1 && w.N <= 128 && (ca_all > 128 || w.N > ca_all));
+    const int Pc = pz ? w.N : ca_all, Qc = pz ? ca_all : w.ntap * w.N;
+    const size_t pw = Pc <= 64 ? 64 : 128, qw = (size_t)(Qc + 31) / 32 * 32;
+    const size_t op32 = align_up(2 * 32 * pw * 4 + 2 * 32 * qw * 4, 1024);
+    const size_t zb = align_up((size_t)nz32 * w.N * 4, 128);
+    const size_t raw32 = align_up(align_up((size_t)32 * ca_all * 4, 128) + zb + ((w.z_p0 && w.z_src2) ? (size_t)nz32 * w.N * 4 : 0), 1024);
+    const size_t fixed32 = 1024 + 2 * op32 + align_up((size_t)(3 * ca_all + 3 * w.N) * 4, 128) + align_up(sizeof(WMisc2), 128);
+    if (okk && Pc <= 128 && Qc <= 384 && fixed32 + 3 * raw32 <= SMEM_MAX) ur = 32;
   }
   K.ur = ur;
   if (w.nsrc == 2 && w.ntap > 1) return 1;
@@ -549,6 +557,9 @@ int launch_wgrad_stream(const WgStream& w, cudaStream_t st) {
     case 1111: rc = launch_variant<1, 1, 1, 32>(K, grid, smem, st); break;
     case 1211: rc = launch_variant<2, 1, 1, 32>(K, grid, smem, st); break;
     case 1123: rc = launch_variant<1, 2, 3, 32>(K, grid, smem, st); break;
+    case 1121: rc = launch_variant<1, 2, 1, 32>(K, grid, smem, st); break;
+    case 1221: rc = launch_variant<2, 2, 1, 32>(K, grid, smem, st); break;
+    case 1131: rc = launch_variant<1, 3, 1, 32>(K, grid, smem, st); break;
     case 111: rc = launch_variant<1, 1, 1>(K, grid, smem, st); break;
     case 113: rc = launch_variant<1, 1, 3>(K, grid, smem, st); break;
     case 115: rc = launch_variant<1, 1, 5>(K, grid, smem, st); break;
