@@ -33,7 +33,7 @@ def report(title, fn, reps):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--streams", type=int, default=4096)
-    ap.add_argument("--offline-batch", type=int, default=25)
+    ap.add_argument("--offline-batch", type=int, default=37)
     ap.add_argument("--fusion", type=int, default=1)
     a = ap.parse_args()
     dev = torch.device("cuda:0")
