@@ -85,6 +85,11 @@ __device__ __forceinline__ float4 ld4(const float* p) { return __ldg((const floa
 #ifndef TRU_L2_PREFETCH
 #define TRU_L2_PREFETCH 1
 #endif
+#ifndef TRU_REG_MMA12
+#define TRU_REG_MMA12 40
+#define TRU_REG_LOAD12 88
+#define TRU_REG_EPI12 88
+#endif
 #ifndef TRU_W_IN_TMEM
 #define TRU_W_IN_TMEM 1
 #endif
@@ -125,9 +130,13 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
   //   LW = 12: 24 warps x 80 = 1920 >= 4*24 + 12*88 + 8*96      (EPI 2: 4*24 + 12*72 + 8*112 = 1856)
   //   LW =  8: 20 warps x 96 = 1920 >= 4*24 +  8*104 + 8*120
   constexpr int REG_LAUNCH = LW == 8 ? 96 : 80;
-  constexpr int REG_MMA = 24;
-  constexpr int REG_LOAD = LW == 8 ? 104 : ((EPI == 2 && TRU_EPI2_REGS) ? 72 : 88);
-  constexpr int REG_EPI = LW == 8 ? 120 : ((EPI == 2 && TRU_EPI2_REGS) ? 112 : 96);
+  // (the issuing thread is the critical role of the 12-loader-warp launches - ncu's source view has it busy 3/4 of the time - and at
+  // 24 registers its loop spilled in the tap-shared variants (local-memory reloads in front of the MMAs) and any change of the
+  // prologue pushed the forward variants over the edge (15-40 % slower, twice).  The 12-warp variants give the MMA warps 40 registers
+  // and take them from the epilogue (96 -> 88): 4 x 40 + 12 x 88 + 8 x 88 = 1920 = 24 x 80)
+  constexpr int REG_MMA = LW == 8 ? 24 : ((EPI == 2 && TRU_EPI2_REGS) ? 40 : TRU_REG_MMA12);
+  constexpr int REG_LOAD = LW == 8 ? 104 : ((EPI == 2 && TRU_EPI2_REGS) ? 72 : TRU_REG_LOAD12);
+  constexpr int REG_EPI = LW == 8 ? 120 : ((EPI == 2 && TRU_EPI2_REGS) ? 112 : TRU_REG_EPI12);
   extern __shared__ __align__(1024) uint8_t smem[];    // (1024-byte aligned: the weight tiles and the classic stages are whole swizzle atoms)
   uint8_t* Wsm = smem;                                 // [hi|lo][nwk][MW rows][128 B], swizzled
   uint8_t* Asm = smem + Lo.a_off;                      // ring: [stage][hi|lo][arows][128 B]
