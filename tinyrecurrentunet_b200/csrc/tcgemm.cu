@@ -221,8 +221,9 @@ __global__ void __launch_bounds__(32 * (4 + LW + EW), 1) tc_igemm_kernel(const _
     // gathered rows from shared memory (per 128 x 128 x 128 tile the operand reads drop from 384 KB to 192 KB of a 512 KB total:
     // the pipe was ~55 % of the shared-memory bandwidth), and the 128 KB the slice occupied become ring stages.
     // A warp writes the 32 lanes of its quadrant (warp & 3); the 6 warps of a quadrant share the 16-column groups.
-    const int q = warp & 3, n = q * 32 + lane, ngrp = Lo.nwk * 4;              // groups: [hi | lo][nwk][2 x 16 channels]
-    const bool nok = n0 + n < P.N;
+    // (M = 64: row n of the slice lives in lane 32 (n / 16) + n % 16, the accumulator's own lane mapping; lanes 16-31 of a quadrant hold zeros)
+    const int q = warp & 3, n = MW == 64 ? q * 16 + (lane & 15) : q * 32 + lane, ngrp = Lo.nwk * 4;      // groups: [hi | lo][nwk][2 x 16 channels]
+    const bool nok = n0 + n < P.N && (MW == 128 || lane < 16);
     for (int gi = warp >> 2; gi < ngrp; gi += NT / 128) {
       const int plane = gi >= 2 * Lo.nwk, gg = gi - plane * 2 * Lo.nwk, w = gg >> 1, c0 = (gg & 1) * 16;
       const Seg& sg = P.seg[Lo.wk_seg[w]];
@@ -906,7 +907,7 @@ bool plan(const IgemmParams& p, TcLayout& L, dim3& grid, size_t& smem_bytes) {
   for (int kb = 0; kb < nkb; ++kb) L.all_lin &= L.kb_lin[kb];
   L.arows = BM + maxshift; L.atile = (uint32_t)L.arows * 128; L.stage = 2 * L.atile;
   L.lq_magic = p.Lq == 1 ? 0u : (unsigned)((0x100000000ull + (unsigned)p.Lq - 1) / (unsigned)p.Lq);
-  L.wtmem = (TRU_W_IN_TMEM && !wtmem_off() && L.MW == 128 && nwk * 64 <= 512 - 2 * BM) ? 1 : 0;
+  L.wtmem = (TRU_W_IN_TMEM && !wtmem_off() && !L.shared && nwk * 64 <= 512 - 2 * BM) ? 1 : 0;
   const size_t w = L.wtmem ? 0 : (size_t)2 * nwk * L.MW * 128;
   const size_t coefb = (size_t)ncoef * COEF_FLOATS * 4;
   const size_t fixed = coefb + sizeof(Misc) + 64;
