@@ -907,7 +907,7 @@ bool plan(const IgemmParams& p, TcLayout& L, dim3& grid, size_t& smem_bytes) {
   for (int kb = 0; kb < nkb; ++kb) L.all_lin &= L.kb_lin[kb];
   L.arows = BM + maxshift; L.atile = (uint32_t)L.arows * 128; L.stage = 2 * L.atile;
   L.lq_magic = p.Lq == 1 ? 0u : (unsigned)((0x100000000ull + (unsigned)p.Lq - 1) / (unsigned)p.Lq);
-  L.wtmem = (TRU_W_IN_TMEM && !wtmem_off() && !L.shared && nwk * 64 <= 512 - 2 * BM) ? 1 : 0;
+  L.wtmem = (TRU_W_IN_TMEM && !wtmem_off() && nwk * 64 <= 512 - 2 * BM) ? 1 : 0;
   const size_t w = L.wtmem ? 0 : (size_t)2 * nwk * L.MW * 128;
   const size_t coefb = (size_t)ncoef * COEF_FLOATS * 4;
   const size_t fixed = coefb + sizeof(Misc) + 64;
