@@ -417,6 +417,19 @@ def measure_inference(args, dev, state_dict, world, rank, dist):
                          "workload": "configs[3]: %d concurrent streams, 1 frame (hop 128 @16 kHz) per stream and step, "
                                      "PCEN / TGRU / overlap-add state carried" % S}
         del sd
+        try:                               # the same step replayed as one CUDA graph (util.StreamingDenoiser(cuda_graph=True))
+            sdg = util.StreamingDenoiser(net, S, device=dev, cuda_graph=True)
+            ms_g = device_ms(lambda: sdg.step(frames_d), 30, 6, sync)
+
+            def e2e_stream_graph():
+                audio_h.copy_(sdg.step(frames_h.to(dev, non_blocking=True)), non_blocking=True)
+            ms_ge = device_ms(e2e_stream_graph, 30, 3, sync)
+            out["stream"]["cuda_graph"] = {"ms_per_step": round(ms_g, 4), "rtf": round(S * 0.008 / (ms_g / 1000.0), 1),
+                                           "e2e_ms_per_step": round(ms_ge, 4), "e2e_rtf": round(S * 0.008 / (ms_ge / 1000.0), 1),
+                                           "frac": round(alg / ms_g / 1e6 / peak, 4)}
+            del sdg
+        except Exception as exc:           # reported, never hidden: the launch-by-launch numbers above stand on their own
+            out["stream"]["cuda_graph"] = {"error": repr(exc)[:300]}
         # ---- configs[0] ------------------------------------------------------------------------------------------
         one_h = synthetic_batch(1, CLIP_SAMPLES)[1].pin_memory()
         res_h = torch.empty(1, CLIP_SAMPLES).pin_memory()
@@ -437,11 +450,26 @@ def measure_inference(args, dev, state_dict, world, rank, dist):
             sd1.step(fr1)
             sync()
             lat1.append(1000.0 * (time.perf_counter() - t0))
+        lat1g = []
+        try:
+            sd1g = util.StreamingDenoiser(net, 1, device=dev, cuda_graph=True)
+            for it in range(60):
+                sync()
+                t0 = time.perf_counter()
+                sd1g.step(fr1)
+                sync()
+                lat1g.append(1000.0 * (time.perf_counter() - t0))
+            del sd1g
+        except Exception as exc:
+            lat1g = repr(exc)[:300]
         out["latency"] = {"workload": "configs[0]: one 4-s clip, batch 1: features + network + mask + iSTFT, host buffer in and out, "
                                       "synchronous (wall clock, median of 20)",
                           "gpu_ms": round(statistics.median(lat[5:]), 3), "gpu_rtf": round(4000.0 / statistics.median(lat[5:]), 1),
                           "gpu_single_frame_step_ms": round(statistics.median(lat1[10:]), 3),
-                          "single_frame_note": "rt.py:20-27: one stream, one frame per call, state carried; hop = 8 ms of audio"}
+                          "gpu_single_frame_step_cuda_graph_ms": (round(statistics.median(lat1g[10:]), 3)
+                                                                  if isinstance(lat1g, list) else lat1g),
+                          "single_frame_note": "rt.py:20-27: one stream, one frame per call, state carried; hop = 8 ms of audio; "
+                                               "cuda_graph = the same step replayed as one captured graph"}
         if not args.no_cpu_baseline and world == 1:      # (at N > 1 the other ranks keep the host cores busy)
             cores = os.cpu_count() or 1
             out["latency"]["cpu_ms"] = cpu_forward_latency_ms(cores)

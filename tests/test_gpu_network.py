@@ -357,6 +357,29 @@ def test_streaming_denoiser_equals_offline_denoise():
     assert rel(streamed, offline) <= OUT_TOL
 
 
+@pytest.mark.parametrize("S", [1, 5])
+def test_streaming_cuda_graph_replay_is_bit_identical_to_the_eager_steps(S):
+    """StreamingDenoiser(cuda_graph=True): from the fourth frame on the step is ONE replayed CUDA graph (two graphs, the
+    TGRU state ping-pongs); every block, the flushed tail and all carried states equal the launch-by-launch path bit for bit."""
+    from tinyrecurrentunet_b200 import util
+    _, net = make_pair(7)
+    net.eval()
+    T = 14
+    _, noisy = O.synthetic_batch(S, n=128 * (T - 1), first=11)
+    xp = torch.nn.functional.pad(noisy.cuda().unsqueeze(1), (256, 256), mode="reflect").squeeze(1)
+    eager, graph = util.StreamingDenoiser(net, S), util.StreamingDenoiser(net, S, cuda_graph=True)
+    for t in range(T):
+        fr = xp[:, 128 * t:128 * t + 512].contiguous()
+        a, b = eager.step(fr), graph.step(fr)
+        assert torch.equal(a, b), "block %d" % t
+    assert graph._graphs is not None and len(graph._graphs) == 2
+    assert torch.equal(eager.h, graph.h) and torch.equal(eager.pcen, graph.pcen) and torch.equal(eager.ola, graph.ola)
+    assert torch.equal(eager.flush(), graph.flush())
+    graph.reset_graph()                                            # re-capture (as after moved weights) continues the streams
+    fr = xp[:, :512].contiguous()
+    assert torch.equal(eager.step(fr), graph.step(fr))
+
+
 def test_streaming_feed_loop_equals_offline_denoise():
     """The real-time loop (stream.py:83-109 intent): raw audio fed one hop at a time through StreamingDenoiser.feed /
     finish - which keeps the 512-sample window and does the reflect framing itself - gives the offline result, block for

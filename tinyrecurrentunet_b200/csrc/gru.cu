@@ -305,13 +305,39 @@ __global__ void __launch_bounds__(TNT, 1) tgru_fwd_kernel(const __grid_constant_
     float acc[SC];             // (packed FFMA2 was slower here: measured 1.85 vs 1.35 ms; it does pay in the backward kernel)
 #pragma unroll
     for (int s = 0; s < SC; ++s) acc[s] = bj;
+    if constexpr (SC >= 4) {
 #pragma unroll
-    for (int k4 = 0; k4 < TKH / 4; ++k4) {
+      for (int k4 = 0; k4 < TKH / 4; ++k4) {
+#pragma unroll
+        for (int s = 0; s < SC; ++s) {
+          const float4 h = *(const float4*)&hs[s][kh * TKH + k4 * 4];
+          acc[s] = fmaf(w[k4 * 4], h.x, acc[s]); acc[s] = fmaf(w[k4 * 4 + 1], h.y, acc[s]);
+          acc[s] = fmaf(w[k4 * 4 + 2], h.z, acc[s]); acc[s] = fmaf(w[k4 * 4 + 3], h.w, acc[s]);
+        }
+      }
+    } else {
+      // few sequences per CTA (small batches: the step is pure latency): 4 / SC independent chains per sequence instead of
+      // one 64-deep dependent FFMA chain
+      constexpr int NCHAIN = 4 / SC;
+      float part[SC][NCHAIN];
+#pragma unroll
+      for (int s = 0; s < SC; ++s)
+#pragma unroll
+        for (int c = 0; c < NCHAIN; ++c) part[s][c] = 0.f;
+#pragma unroll
+      for (int k4 = 0; k4 < TKH / 4; ++k4) {
+#pragma unroll
+        for (int s = 0; s < SC; ++s) {
+          const float4 h = *(const float4*)&hs[s][kh * TKH + k4 * 4];
+          float& a = part[s][k4 % NCHAIN];
+          a = fmaf(w[k4 * 4], h.x, a); a = fmaf(w[k4 * 4 + 1], h.y, a);
+          a = fmaf(w[k4 * 4 + 2], h.z, a); a = fmaf(w[k4 * 4 + 3], h.w, a);
+        }
+      }
 #pragma unroll
       for (int s = 0; s < SC; ++s) {
-        const float4 h = *(const float4*)&hs[s][kh * TKH + k4 * 4];
-        acc[s] = fmaf(w[k4 * 4], h.x, acc[s]); acc[s] = fmaf(w[k4 * 4 + 1], h.y, acc[s]);
-        acc[s] = fmaf(w[k4 * 4 + 2], h.z, acc[s]); acc[s] = fmaf(w[k4 * 4 + 3], h.w, acc[s]);
+        if constexpr (NCHAIN == 4) acc[s] += (part[s][0] + part[s][1]) + (part[s][2] + part[s][3]);
+        else acc[s] += part[s][0] + part[s][1];
       }
     }
 #pragma unroll
@@ -518,10 +544,22 @@ int launch_fgru_bwd(const GruParams& p, cudaStream_t st) {
   return TRU_OK;
 }
 
+// Sequences per CTA of the TGRU recurrence kernels: the kernels hold one CTA per SM (768 threads), every step is a latency
+// chain, and a step costs less the fewer sequences the CTA carries - so small batches (one clip = 16 sequences: configs[0],
+// rt.py:20-27) spread over more SMs; from 2 x SMs sequences up it is 4 per CTA (B = 32: 128 CTAs, B = 37: one full wave).
+static int tgru_seqs_per_cta(int nseq) {
+  const int sms = sm_count();
+  return nseq <= sms ? 1 : (nseq <= 2 * sms ? 2 : 4);
+}
+
 int launch_tgru_fwd(const GruParams& p, int B, int T, cudaStream_t st) {
   const int nseq = B * TL;
   ProfScope prof("tgru_fwd", 4.0 * nseq * T * (384 + 128 + 512), 2.0 * nseq * T * TH * 3 * TH, st);
-  tgru_fwd_kernel<4><<<(nseq + 3) / 4, TNT, 0, st>>>(p, B, T);
+  switch (tgru_seqs_per_cta(nseq)) {
+    case 1: tgru_fwd_kernel<1><<<nseq, TNT, 0, st>>>(p, B, T); break;
+    case 2: tgru_fwd_kernel<2><<<(nseq + 1) / 2, TNT, 0, st>>>(p, B, T); break;
+    default: tgru_fwd_kernel<4><<<(nseq + 3) / 4, TNT, 0, st>>>(p, B, T); break;
+  }
   TRU_LAUNCH_CHECK();
   return TRU_OK;
 }
@@ -529,10 +567,16 @@ int launch_tgru_fwd(const GruParams& p, int B, int T, cudaStream_t st) {
 int launch_tgru_bwd(const GruParams& p, int B, int T, cudaStream_t st) {
   const int nseq = B * TL;
   ProfScope prof("tgru_bwd", 4.0 * nseq * T * (128 + 512 + 128 + 768), 2.0 * nseq * T * TH * 3 * TH, st);
-  constexpr int SC = 4;
-  const size_t smem = (size_t)SC * (3 * TH + TBQ * TH + 2 * 6 * TH) * 4;     // dgs + part + sv: 55,296 B
-  TRU_SMEM_OPT_IN((tgru_bwd_kernel<SC>), smem);
-  tgru_bwd_kernel<SC><<<(nseq + SC - 1) / SC, TNT, smem, st>>>(p, B, T);
+  const int sc = tgru_seqs_per_cta(nseq);
+  const size_t smem = (size_t)sc * (3 * TH + TBQ * TH + 2 * 6 * TH) * 4;     // dgs + part + sv: 55,296 B at 4 sequences per CTA
+  if (sc == 1) {
+    tgru_bwd_kernel<1><<<nseq, TNT, smem, st>>>(p, B, T);
+  } else if (sc == 2) {
+    tgru_bwd_kernel<2><<<(nseq + 1) / 2, TNT, smem, st>>>(p, B, T);
+  } else {
+    TRU_SMEM_OPT_IN((tgru_bwd_kernel<4>), smem);
+    tgru_bwd_kernel<4><<<(nseq + 3) / 4, TNT, smem, st>>>(p, B, T);
+  }
   TRU_LAUNCH_CHECK();
   return TRU_OK;
 }

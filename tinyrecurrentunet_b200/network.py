@@ -141,7 +141,15 @@ class _TRUNetFn(torch.autograd.Function):
             ws_bytes = L.lib.tru_trunet_workspace_bytes(C.byref(desc), int(need_bwd))
             ws = torch.empty(ws_bytes, device=x.device, dtype=torch.uint8)
             out = torch.empty((B, T, 8, 257), device=x.device, dtype=torch.float32)
-            hl = torch.empty((B * 16, 128), device=x.device, dtype=torch.float32) if want_state else None
+            given = torch.is_tensor(want_state)            # step(): the caller's own state buffer (CUDA-graph replay needs fixed addresses)
+            if given:
+                hl = want_state
+                if hl.shape != (B * 16, 128) or hl.dtype != torch.float32 or hl.device != x.device or not hl.is_contiguous():
+                    raise L.TruError("h_out must be a contiguous float32 (B*16,128) tensor on the input's device")
+                if h0 is not None and hl.data_ptr() == h0.data_ptr():
+                    raise L.TruError("h_out must not alias h (the step reads the old state while it writes the new one)")
+            else:
+                hl = torch.empty((B * 16, 128), device=x.device, dtype=torch.float32) if want_state else None
             pp = (C.c_void_p * 108)(*[p.data_ptr() for p in params])
             rm, rv, nb = net._bn_ptrs(x.device)
             L.check(L.lib.tru_trunet_forward(C.byref(desc), pp, rm, rv, nb, L.ptr(x), L.ptr(h0), L.ptr(out), L.ptr(hl),
@@ -151,6 +159,8 @@ class _TRUNetFn(torch.autograd.Function):
         ctx.desc, ctx.ws_bytes, ctx.need_bwd, ctx.has_h0, ctx.net = desc, ws_bytes, need_bwd, h0 is not None, net
         ctx.shapes = [p.shape for p in params]
         ctx.save_for_backward(x, ws, *params)
+        if given:
+            return out                                 # the state went into the caller's buffer
         if want_state:
             ctx.mark_non_differentiable(hl)
             return out, hl
@@ -265,19 +275,23 @@ class TRUNet(nn.Module):
         params = self._ordered_params(x.device)
         need_bwd = self.training and torch.is_grad_enabled() and any(p.requires_grad for p in params)
         res = _TRUNetFn.apply(x.detach(), h0, self, want_state, need_bwd, *params)
-        out, hl = (res if want_state else (res, None))
+        if torch.is_tensor(want_state):
+            out, hl = res, want_state
+        else:
+            out, hl = (res if want_state else (res, None))
         if squeeze:
             out = out.squeeze(0)
-        return (out, hl) if want_state else out
+        return (out, hl) if (torch.is_tensor(want_state) or want_state) else out
 
     def forward(self, x, h0=None, return_state=False):
         """x (T,4,257) or (B,T,4,257) float32 CUDA -> (...,8,257)."""
         return self._run(x, h0, return_state)
 
     @torch.no_grad()
-    def step(self, frame_feats, h):
-        """Streaming (D11): frame_feats (S,4,257), h (S*16,128) -> (out (S,8,257), h')."""
+    def step(self, frame_feats, h, h_out=None):
+        """Streaming (D11): frame_feats (S,4,257), h (S*16,128) -> (out (S,8,257), h').  ``h_out``: write h' into this
+        (S*16,128) buffer (not ``h`` itself) instead of a new tensor - fixed addresses for CUDA-graph replay."""
         if self.training:
             raise L.TruError("step() is an inference call: put the model in eval() mode")
-        out, h2 = self._run(frame_feats.unsqueeze(1), h, True)
+        out, h2 = self._run(frame_feats.unsqueeze(1), h, True if h_out is None else h_out)
         return out[:, 0], h2

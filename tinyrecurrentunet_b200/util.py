@@ -123,21 +123,69 @@ class StreamingDenoiser:
     reflect framing) and returns the 128 output samples that became final (block t-2; zeros for the first two
     steps); ``flush()`` returns the last block after the final frame.  Output equals the offline ``denoise``."""
 
-    def __init__(self, net, n_streams, beta=0.5, device="cuda"):
+    def __init__(self, net, n_streams, beta=0.5, device="cuda", cuda_graph=False):
+        """``cuda_graph=True``: from the fourth frame on (the back end's normalisation depends on the frame index until then)
+        the whole step - ~35 kernels of three C calls - is replayed as ONE captured CUDA graph instead of being launched
+        one by one: the step of a few streams is launch-bound (rt.py:20-27: one stream, one frame per call).  The graphs
+        hold the addresses of the weights: call ``reset_graph()`` after anything that re-allocates them
+        (``optim.FlatAdamW`` re-points ``p.data``; ``load_state_dict`` copies in place and is fine)."""
         if net.training:
             raise ValueError("StreamingDenoiser needs net.eval()")
         self.net, self.beta, self.t = net, beta, 0
         self.pcen = torch.zeros(n_streams, 257, device=device)
         self.h = torch.zeros(n_streams * 16, 128, device=device)
         self.ola = torch.zeros(n_streams, 384, device=device)
+        self.cuda_graph, self._graphs = bool(cuda_graph), None
+
+    GRAPH_FROM = 3          # backend_step_kernel: 1 / (number of frames overlapping the emitted block) is constant from here on
 
     @torch.no_grad()
     def step(self, frames):
+        if self.cuda_graph and self.t >= self.GRAPH_FROM:
+            return self._graph_step(frames)
         feats = ops.frontend_step(frames, self.pcen)
         out, self.h = self.net.step(feats, self.h)
         audio = ops.mask_istft_step(out, self.ola, self.t, self.beta)
         self.t += 1
         return audio
+
+    # -- CUDA-graph replay of the steady-state step --------------------------------------------------------------
+    def _capture_one(self, graph, pool, h_in, h_out):
+        with torch.cuda.graph(graph, pool=pool, capture_error_mode="thread_local"):
+            feats = ops.frontend_step(self._g_frames, self.pcen)              # PCEN state updated in place
+            out, _ = self.net.step(feats, h_in, h_out=h_out)
+            audio = ops.mask_istft_step(out, self.ola, self.GRAPH_FROM, self.beta)   # overlap-add tail updated in place
+        return audio                    # lives in the graph's pool; everything else allocated in the capture is released to it
+
+    def _graph_step(self, frames):
+        if frames.shape != (self.pcen.shape[0], 512) or frames.dtype != torch.float32 or not frames.is_cuda:
+            raise ValueError("step() takes the (S,512) float32 CUDA frames of the S streams")
+        if self._graphs is None:
+            # two graphs, because the TGRU state ping-pongs between two buffers: graph k reads hs[k] and writes hs[1 - k].
+            # The eager steps before GRAPH_FROM have already run every kernel once (lazy per-device initialisation, dynamic
+            # shared-memory opt-ins), so nothing but launches and memsets is recorded here.
+            self._g_frames = torch.empty_like(frames)
+            self._g_h = (self.h.contiguous(), torch.empty_like(self.h))
+            torch.cuda.current_stream(frames.device).synchronize()
+            graphs, pool = [], None
+            for k in range(2):
+                g = torch.cuda.CUDAGraph()
+                audio = self._capture_one(g, pool, self._g_h[k], self._g_h[1 - k])
+                pool = g.pool()
+                graphs.append((g, audio))
+            self._graphs, self._g_k = graphs, 0
+            self.h = self._g_h[0]
+        g, audio = self._graphs[self._g_k]
+        self._g_frames.copy_(frames, non_blocking=True)
+        g.replay()
+        self._g_k ^= 1
+        self.h = self._g_h[self._g_k]
+        self.t += 1
+        return audio.clone()            # the graph's own output buffer is overwritten by its next replay
+
+    def reset_graph(self):
+        """Drop the captured graphs (the next step captures again): needed after the weights moved to other addresses."""
+        self._graphs = None
 
     @torch.no_grad()
     def flush(self):
