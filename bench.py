@@ -396,6 +396,20 @@ def measure_inference(args, dev, state_dict, world, rank, dist):
         def e2e_stream():
             audio_h.copy_(sd.step(frames_h.to(dev, non_blocking=True)), non_blocking=True)
         ms_e = device_ms(e2e_stream, 30, 3, sync)
+
+        def pipelined_ms(sdx, n=60):
+            """n hops through util.stream_host_frames (upload of hop t+1 and download of hop t-1 overlap hop t), wall clock
+            from the first upload to the last block on the host, every block touched by the consumer."""
+            for _ in util.stream_host_frames(sdx, (frames_h for _ in range(6)), dev):
+                pass
+            sync()
+            t0 = time.perf_counter()
+            chk = 0.0
+            for blk in util.stream_host_frames(sdx, (frames_h for _ in range(n)), dev):
+                chk += float(blk[0, 0])
+            sync()
+            return 1000.0 * (time.perf_counter() - t0) / n
+        ms_p = pipelined_ms(sd)
         L.profile_enable(True)
         for _ in range(5):
             sd.step(frames_d)
@@ -410,7 +424,10 @@ def measure_inference(args, dev, state_dict, world, rank, dist):
         out["stream"] = {"streams": S, "ms_per_step": round(ms, 4), "audio_ms_per_step": 8.0,
                          "rtf": round(S * 0.008 / (ms / 1000.0), 1),
                          "e2e": {"ms_per_step": round(ms_e, 4), "rtf": round(S * 0.008 / (ms_e / 1000.0), 1),
-                                 "h2d_bytes_per_step": S * 512 * 4, "d2h_bytes_per_step": S * 128 * 4},
+                                 "h2d_bytes_per_step": S * 512 * 4, "d2h_bytes_per_step": S * 128 * 4,
+                                 "pipelined_ms_per_step": round(ms_p, 4), "pipelined_rtf": round(S * 0.008 / (ms_p / 1000.0), 1),
+                                 "pipelined_note": "util.stream_host_frames: same copies every hop, on side streams, one hop of "
+                                                   "pipeline latency; wall clock over 60 hops"},
                          "roofline": {"bound": "hbm", "algorithmic_bytes_per_step": alg, "achieved": round(alg / ms / 1e6, 1),
                                       "peak": peak, "unit": "GB/s", "frac": round(alg / ms / 1e6 / peak, 4)},
                          "kernels_ms": {k: [round(v[0], 4), v[1]] for k, v in sorted(fam.items(), key=lambda kv: -kv[1][0])},
@@ -424,8 +441,11 @@ def measure_inference(args, dev, state_dict, world, rank, dist):
             def e2e_stream_graph():
                 audio_h.copy_(sdg.step(frames_h.to(dev, non_blocking=True)), non_blocking=True)
             ms_ge = device_ms(e2e_stream_graph, 30, 3, sync)
+            ms_gp = pipelined_ms(sdg)
             out["stream"]["cuda_graph"] = {"ms_per_step": round(ms_g, 4), "rtf": round(S * 0.008 / (ms_g / 1000.0), 1),
                                            "e2e_ms_per_step": round(ms_ge, 4), "e2e_rtf": round(S * 0.008 / (ms_ge / 1000.0), 1),
+                                           "e2e_pipelined_ms_per_step": round(ms_gp, 4),
+                                           "e2e_pipelined_rtf": round(S * 0.008 / (ms_gp / 1000.0), 1),
                                            "frac": round(alg / ms_g / 1e6 / peak, 4)}
             del sdg
         except Exception as exc:           # reported, never hidden: the launch-by-launch numbers above stand on their own
@@ -441,6 +461,18 @@ def measure_inference(args, dev, state_dict, world, rank, dist):
                 res_h.copy_(util.denoise(net, one_h.to(dev, non_blocking=True))[0], non_blocking=True)
                 sync()
                 lat.append(1000.0 * (time.perf_counter() - t0))
+        latg = []
+        try:
+            gd = util.GraphedDenoise(net, 1, CLIP_SAMPLES, device=dev)
+            for it in range(25):
+                sync()
+                t0 = time.perf_counter()
+                res_h.copy_(gd(one_h.to(dev, non_blocking=True))[0], non_blocking=True)
+                sync()
+                latg.append(1000.0 * (time.perf_counter() - t0))
+            del gd
+        except Exception as exc:
+            latg = repr(exc)[:300]
         sd1 = util.StreamingDenoiser(net, 1, device=dev)
         fr1 = torch.zeros(1, 512, device=dev)
         lat1 = []
@@ -465,6 +497,7 @@ def measure_inference(args, dev, state_dict, world, rank, dist):
         out["latency"] = {"workload": "configs[0]: one 4-s clip, batch 1: features + network + mask + iSTFT, host buffer in and out, "
                                       "synchronous (wall clock, median of 20)",
                           "gpu_ms": round(statistics.median(lat[5:]), 3), "gpu_rtf": round(4000.0 / statistics.median(lat[5:]), 1),
+                          "gpu_cuda_graph_ms": round(statistics.median(latg[5:]), 3) if isinstance(latg, list) else latg,
                           "gpu_single_frame_step_ms": round(statistics.median(lat1[10:]), 3),
                           "gpu_single_frame_step_cuda_graph_ms": (round(statistics.median(lat1g[10:]), 3)
                                                                   if isinstance(lat1g, list) else lat1g),

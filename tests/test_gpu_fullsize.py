@@ -59,9 +59,21 @@ def test_gradients_per_parameter_at_multi_wave_size():
     this size).  Here the oracle is made to differentiate the same piecewise-linear function instead: its ReLUs are replaced
     by the branch masks the CUDA forward took (force_relu_masks), which changes its forward by ~1e-6 at those ~30 elements
     and nothing else."""
-    B, T = 2, 126
-    ref, net = make_pair(7)
-    x = feats_like(B, T, 31)
+    gradient_parity(2, 126, 7, 31)
+
+
+@pytest.mark.parametrize("B", [10, 19])
+def test_gradients_with_two_and_four_tgru_sequences_per_cta(B):
+    """The TGRU recurrence kernels carry 1, 2 or 4 sequences per CTA depending on the batch (gru.cu tgru_seqs_per_cta: up to
+    148 / 296 / more sequences; 16 sequences per clip).  Every other parity test runs B <= 5 (1 per CTA) or B = 32 (4 per CTA,
+    compared with a replicated small batch); here B = 10 takes the 2-per-CTA and B = 19 the 4-per-CTA kernels, forward and
+    BPTT, against the oracle - all intermediates and all 108 parameter gradients, same method as the test above."""
+    gradient_parity(B, 5, 9, 61)
+
+
+def gradient_parity(B, T, seed, xseed):
+    ref, net = make_pair(seed)
+    x = feats_like(B, T, xseed)
     ref.train()
     net.train()
     net._debug_keep_ws = True
@@ -72,7 +84,7 @@ def test_gradients_per_parameter_at_multi_wave_size():
     print("ReLU mask mismatches between the two plain forwards:", flips)
     assert flips <= 200, flips
     assert rel(y, y_plain) <= OUT_TOL
-    ref2, _ = make_pair(7)                                  # fresh running statistics
+    ref2, _ = make_pair(seed)                               # fresh running statistics
     ref2.train()
     force_relu_masks(ref2, gpu_relu_masks(net, B, T))
     y_ref, inter = oracle_intermediates(ref2, x, keep_graph=True)

@@ -380,6 +380,44 @@ def test_streaming_cuda_graph_replay_is_bit_identical_to_the_eager_steps(S):
     assert torch.equal(eager.step(fr), graph.step(fr))
 
 
+@pytest.mark.parametrize("graph", [False, True])
+def test_stream_host_frames_pipeline_equals_step_by_step(graph):
+    """util.stream_host_frames (pinned host frames in, pinned host blocks out, copies one hop ahead / behind on side
+    streams) yields exactly the blocks of step() called hop by hop - with and without CUDA-graph replay."""
+    from tinyrecurrentunet_b200 import util
+    _, net = make_pair(8)
+    net.eval()
+    S, T = 3, 12
+    _, noisy = O.synthetic_batch(S, n=128 * (T - 1), first=21)
+    xp = torch.nn.functional.pad(noisy.unsqueeze(1), (256, 256), mode="reflect").squeeze(1)
+    frames = [xp[:, 128 * t:128 * t + 512].contiguous().pin_memory() for t in range(T)]
+    ref = util.StreamingDenoiser(net, S)
+    want = [ref.step(f.cuda()).cpu() for f in frames]
+    sd = util.StreamingDenoiser(net, S, cuda_graph=graph)
+    got = [blk.clone() for blk in util.stream_host_frames(sd, iter(frames))]
+    assert len(got) == T
+    for t in range(T):
+        assert torch.equal(got[t], want[t]), "hop %d" % t
+
+
+def test_graphed_denoise_equals_denoise():
+    """util.GraphedDenoise: front end + network + mask / iSTFT of one input shape replayed as a CUDA graph gives what the
+    launch-by-launch denoise gives, for every new input copied into its buffer."""
+    from tinyrecurrentunet_b200 import util
+    _, net = make_pair(9)
+    net.eval()
+    B, N = 2, 128 * 40
+    gd = util.GraphedDenoise(net, B, N)
+    for first in (70, 80, 90):
+        _, noisy = O.synthetic_batch(B, n=N, first=first)
+        with torch.no_grad():
+            want, want_out = util.denoise(net, noisy.cuda())
+        got, got_out = gd(noisy.cuda())
+        assert rel(got_out, want_out) <= 1e-6 and rel(got, want) <= 1e-6
+    with pytest.raises(ValueError):
+        gd(torch.zeros(B, N + 128, device="cuda"))
+
+
 def test_streaming_feed_loop_equals_offline_denoise():
     """The real-time loop (stream.py:83-109 intent): raw audio fed one hop at a time through StreamingDenoiser.feed /
     finish - which keeps the 512-sample window and does the reflect framing itself - gives the offline result, block for

@@ -25,6 +25,32 @@ def denoise(net, noisy_audio, beta=0.5):
     return ops.mask_istft(out, beta), out
 
 
+class GraphedDenoise:
+    """``denoise`` for ONE input shape, captured once as a CUDA graph and replayed: the ~45 launches of a small batch
+    (rt.py:80-89: one clip at a time) cost more on the host than on the device.  ``g = GraphedDenoise(net, B, N)``;
+    ``audio, net_out = g(noisy)`` - both results live in the graph's own buffers and are overwritten by the next call.
+    The graph holds the addresses of the weights (see StreamingDenoiser.reset_graph): build a new object after they moved."""
+
+    def __init__(self, net, batch, n_samples, beta=0.5, device="cuda"):
+        if net.training:
+            raise ValueError("GraphedDenoise needs net.eval()")
+        device = torch.device(device)
+        self.noisy = torch.zeros(batch, n_samples, device=device)
+        with torch.no_grad():
+            denoise(net, self.noisy, beta)                     # lazy initialisation and shared-memory opt-ins happen here
+            torch.cuda.current_stream(device).synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+                self.audio, self.net_out = denoise(net, self.noisy, beta)
+
+    def __call__(self, noisy_audio):
+        if noisy_audio.shape != self.noisy.shape:
+            raise ValueError("GraphedDenoise was captured for input shape %s" % (tuple(self.noisy.shape),))
+        self.noisy.copy_(noisy_audio, non_blocking=True)
+        self.graph.replay()
+        return self.audio, self.net_out
+
+
 class CudaPrefetcher:
     """Double-buffered host -> device staging on a side stream, so that the copy of batch i+1 overlaps the training step of
     batch i (train.py:124-125 copies synchronously).  Wraps any iterable of host batches (tuples of tensors; pin them for
@@ -83,12 +109,11 @@ class CudaPrefetcher:
             k ^= 1
 
 
-def denoise_host_batches(net, batches, device="cuda", beta=0.5):
-    """Offline batch denoising with host buffers on both sides (denoise.py:82-95's loop: load clip -> net -> write wav).
-    ``batches`` is an iterable of pinned host tensors (B,N); yields, for every batch in order, a pinned host tensor
-    (B,128*(N//128)) holding the denoised audio - complete when it is yielded.  Host->device copies run one batch ahead
-    on a side stream (CudaPrefetcher), device->host copies on a second side stream, so both overlap the kernels of the
-    neighbouring batches; the yielded tensor is one of two staging buffers and is overwritten two batches later."""
+def _host_pipeline(fn, batches, device):
+    """For every pinned host tensor of ``batches``: device copy (one item ahead, side stream: CudaPrefetcher) -> ``fn`` on the
+    current stream -> copy of its result into one of two pinned staging buffers on a second side stream.  Yields the staged
+    results in order, each complete when yielded (it is overwritten two items later); item i is yielded after item i+1 has
+    been enqueued, so both copies overlap the kernels of the neighbouring items."""
     device = torch.device(device)
     out_stream = torch.cuda.Stream(device=device)
     host = [None, None]
@@ -96,16 +121,16 @@ def denoise_host_batches(net, batches, device="cuda", beta=0.5):
     pending = None
     k = 0
     with torch.no_grad():
-        for (noisy,) in CudaPrefetcher(((b,) for b in batches), device):
-            audio, _ = denoise(net, noisy, beta)
+        for (x,) in CudaPrefetcher(((b,) for b in batches), device):
+            y = fn(x)
             cur = torch.cuda.current_stream(device)
-            if host[k] is None or host[k].shape != audio.shape:
-                host[k] = torch.empty(audio.shape, dtype=audio.dtype, pin_memory=True)
+            if host[k] is None or host[k].shape != y.shape:
+                host[k] = torch.empty(y.shape, dtype=y.dtype, pin_memory=True)
             out_stream.wait_stream(cur)
             with torch.cuda.stream(out_stream):
-                host[k].copy_(audio, non_blocking=True)
+                host[k].copy_(y, non_blocking=True)
                 done[k].record(out_stream)
-            audio.record_stream(out_stream)
+            y.record_stream(out_stream)
             if pending is not None:
                 done[pending].synchronize()
                 yield host[pending]
@@ -114,6 +139,23 @@ def denoise_host_batches(net, batches, device="cuda", beta=0.5):
     if pending is not None:
         done[pending].synchronize()
         yield host[pending]
+
+
+def denoise_host_batches(net, batches, device="cuda", beta=0.5):
+    """Offline batch denoising with host buffers on both sides (denoise.py:82-95's loop: load clip -> net -> write wav).
+    ``batches`` is an iterable of pinned host tensors (B,N); yields, for every batch in order, a pinned host tensor
+    (B,128*(N//128)) holding the denoised audio - complete when it is yielded.  Host->device copies run one batch ahead
+    on a side stream (CudaPrefetcher), device->host copies on a second side stream, so both overlap the kernels of the
+    neighbouring batches; the yielded tensor is one of two staging buffers and is overwritten two batches later."""
+    return _host_pipeline(lambda noisy: denoise(net, noisy, beta)[0], batches, device)
+
+
+def stream_host_frames(denoiser, frames, device="cuda"):
+    """The serving loop of a StreamingDenoiser with host buffers on both sides (stream.py:83-109: hop in from the sound
+    card -> net -> hop out): ``frames`` is an iterable of pinned host tensors (S,512), one analysis frame per stream and
+    hop; yields the pinned host block (S,128) of every step in order.  The upload of hop t+1 and the download of hop t-1
+    overlap the kernels of hop t (one extra hop of pipeline latency for the copies to hide behind)."""
+    return _host_pipeline(denoiser.step, frames, device)
 
 
 class StreamingDenoiser:
