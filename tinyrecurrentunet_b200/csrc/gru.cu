@@ -375,6 +375,129 @@ __global__ void __launch_bounds__(TNT, 1) tgru_fwd_kernel(const __grid_constant_
   }
 }
 
+// ---- forward, second layout (round 2, late) ---------------------------------------------------------------------------
+// SASS of the kernel above at its 80-register cap (768 threads): ONE float4 of h in flight per thread - LDS.128, four
+// FFMAs that chain on one accumulator, the next LDS.128 into the same registers - so every warp runs a serial
+// load-latency + 4 x FMA-latency chain 64 times per step and six warps per scheduler cannot cover it: 2.56 us per step at
+// 4 sequences per CTA, linear in the sequence count (tools/probe_tgru.py), 3x the FFMA issue time.
+// Here: 512 threads (128 registers each), thread = (hidden unit j, k-slice kq): the THREE gate rows j, 128 + j, 256 + j
+// of W_hh over columns [32 kq, 32 kq + 32) = 96 weights.  One float4 of h feeds 12 FFMAs on 3 independent accumulators
+// (x SC sequences), the loads of the next sequence are in flight meanwhile.  The four k-slices of a unit are adjacent
+// lanes: a two-stage shuffle reduce-scatter leaves lane kq with the three gate sums of SEQUENCE kq, which then does that
+// sequence's gate arithmetic in registers - no partial sums through shared memory, ONE barrier per step (h is double
+// buffered, the input gates are staged two steps ahead in a three-buffer ring).
+constexpr int T3NT = 512;
+constexpr int T3_HLD = TH + 12;       // h row: k-slice kq starts at 36 kq floats (16-byte aligned, the four float4s of a warp's load hit disjoint banks)
+constexpr int T3_GLD = 3 * TH + 8;    // input-gate row stride: the 4 sequences of a warp's gate phase read disjoint banks
+__device__ __forceinline__ int t3_hidx(int k) { return k + (k >> 5) * 4; }
+
+template <int SC>
+__global__ void __launch_bounds__(T3NT, 1) tgru_fwd3_kernel(const __grid_constant__ GruParams p, int B, int T) {
+  pdl_trigger();
+  constexpr int NCH = SC * 96;                         // 16-byte chunks of one step's input gates
+  __shared__ __align__(16) float hs[2][SC][T3_HLD];
+  __shared__ __align__(16) float gin[3][SC][T3_GLD];
+  const int tid = threadIdx.x, j = tid >> 2, kq = tid & 3;
+  float w[3][32];
+#pragma unroll
+  for (int g = 0; g < 3; ++g)
+#pragma unroll
+    for (int k4 = 0; k4 < 8; ++k4) {
+      const float4 v = ld4(p.whh[0] + (long)(g * TH + j) * TH + kq * 32 + k4 * 4);
+      w[g][k4 * 4] = v.x; w[g][k4 * 4 + 1] = v.y; w[g][k4 * 4 + 2] = v.z; w[g][k4 * 4 + 3] = v.w;
+    }
+  const int nseq = B * TL;
+  const int sbase = blockIdx.x * SC;
+  const int sidx = sbase + kq;                         // the sequence whose gates this lane computes
+  const bool gate = kq < SC, ok = gate && sidx < nseq;
+  const long ibase = ok ? ((long)(sidx / TL) * T) * TL + sidx % TL : 0;      // row(t) = ibase + 16 t
+  const float b_r = gate ? __ldg(p.bhh[0] + j) : 0.f, b_z = gate ? __ldg(p.bhh[0] + TH + j) : 0.f,
+              b_n = gate ? __ldg(p.bhh[0] + 2 * TH + j) : 0.f;
+  float hprev = (ok && p.h0) ? __ldg(p.h0 + (long)sidx * TH + j) : 0.f;
+  if (gate) hs[0][kq][t3_hidx(j)] = hprev;
+  // copy plan (one 16-byte chunk per thread and step): chunk tid -> sequence tid / 96, chunk tid % 96 of its 384-float gate row
+  static_assert(NCH <= T3NT, "one chunk per thread");
+  const int cs = tid / 96, cq = tid % 96, csi = sbase + cs;
+  const bool cok = tid < NCH && csi < nseq;
+  const float* csrc = cok ? p.G + (((long)(csi / TL) * T) * TL + csi % TL) * (3 * TH) + cq * 4 : nullptr;   // step 0; + 16 rows per step
+  const int cdst = cs * T3_GLD + cq * 4;
+  auto stage = [&](int t, int buf) {
+    if (cok) cp_async16(&gin[buf][0][0] + cdst, csrc + (long)t * (TL * 3 * TH));
+    cp_async_commit();
+  };
+  stage(0, 0);
+  if (T > 1) stage(1, 1); else cp_async_commit();
+  cp_async_wait<1>();
+  __syncthreads();
+  const int b0 = kq & 1, b1 = kq >> 1;
+  int gb = 0, nb = 2;                                  // ring slots of step t and of step t + 2
+  for (int t = 0; t < T; ++t) {
+    if (t + 2 < T) stage(t + 2, nb); else cp_async_commit();      // always one group per step (uniform wait below)
+    const float* hcur = &hs[t & 1][0][0] + kq * 36;
+    float acc[3][SC];
+#pragma unroll
+    for (int g = 0; g < 3; ++g)
+#pragma unroll
+      for (int s = 0; s < SC; ++s) acc[g][s] = 0.f;
+#pragma unroll
+    for (int k4 = 0; k4 < 8; ++k4) {
+#pragma unroll
+      for (int s = 0; s < SC; ++s) {
+        const float4 h = *(const float4*)(hcur + s * T3_HLD + k4 * 4);
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          acc[g][s] = fmaf(w[g][k4 * 4], h.x, acc[g][s]); acc[g][s] = fmaf(w[g][k4 * 4 + 1], h.y, acc[g][s]);
+          acc[g][s] = fmaf(w[g][k4 * 4 + 2], h.z, acc[g][s]); acc[g][s] = fmaf(w[g][k4 * 4 + 3], h.w, acc[g][s]);
+        }
+      }
+    }
+    // reduce over the 4 k-slices (lanes kq = 0..3 of a unit), scattered: lane kq ends with the sums of sequence kq.
+    // The pairing is (slice kq + slice kq^1) + (slice kq^2 + slice kq^3) for every sequence and every SC.
+    float tot[3];
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+      if constexpr (SC == 4) {
+        const float m0 = b0 ? acc[g][1] : acc[g][0], s0 = b0 ? acc[g][0] : acc[g][1];
+        const float m1 = b0 ? acc[g][3] : acc[g][2], s1 = b0 ? acc[g][2] : acc[g][3];
+        const float k0 = m0 + __shfl_xor_sync(0xffffffffu, s0, 1);          // sequence b0, slices {kq, kq^1}
+        const float k1 = m1 + __shfl_xor_sync(0xffffffffu, s1, 1);          // sequence 2 + b0
+        const float mine = b1 ? k1 : k0, send = b1 ? k0 : k1;
+        tot[g] = mine + __shfl_xor_sync(0xffffffffu, send, 2);             // sequence 2 b1 + b0 = kq
+      } else if constexpr (SC == 2) {
+        const float mine = b0 ? acc[g][1] : acc[g][0], send = b0 ? acc[g][0] : acc[g][1];
+        const float k = mine + __shfl_xor_sync(0xffffffffu, send, 1);       // sequence b0
+        tot[g] = k + __shfl_xor_sync(0xffffffffu, k, 2);
+      } else {
+        const float k = acc[g][0] + __shfl_xor_sync(0xffffffffu, acc[g][0], 1);
+        tot[g] = k + __shfl_xor_sync(0xffffffffu, k, 2);
+      }
+    }
+    if (gate) {
+      const float* gi = gin[gb][kq];
+      const float hn = tot[2] + b_n;
+      const float rr = sigmoidf_(gi[j] + (tot[0] + b_r));
+      const float zz = sigmoidf_(gi[TH + j] + (tot[1] + b_z));
+      const float nn = tanhf_(gi[2 * TH + j] + rr * hn);
+      const float hnew = (1.0f - zz) * nn + zz * hprev;
+      hprev = hnew;
+      hs[(t + 1) & 1][kq][t3_hidx(j)] = hnew;
+      if (ok) {
+        const long row = ibase + (long)t * TL;
+        p.H[row * TH + j] = hnew;
+        if (p.cache) {
+          float* c = p.cache + row * (4 * TH) + j;
+          c[0] = rr; c[TH] = zz; c[2 * TH] = nn; c[3 * TH] = hn;
+        }
+      }
+    }
+    cp_async_wait<1>();                                 // the gates of step t + 1 (staged one step ago) have landed
+    __syncthreads();                                    // ... for everybody; and h of step t + 1 is complete
+    gb = gb == 2 ? 0 : gb + 1;
+    nb = nb == 2 ? 0 : nb + 1;
+  }
+  if (ok && p.hlast) p.hlast[(long)sidx * TH + j] = hprev;
+}
+
 template <int SC>
 __global__ void __launch_bounds__(TNT, 1) tgru_bwd_kernel(const __grid_constant__ GruParams p, int B, int T) {
   constexpr int NI = (SC * TH + TNT - 1) / TNT;
@@ -555,10 +678,20 @@ static int tgru_seqs_per_cta(int nseq) {
 int launch_tgru_fwd(const GruParams& p, int B, int T, cudaStream_t st) {
   const int nseq = B * TL;
   ProfScope prof("tgru_fwd", 4.0 * nseq * T * (384 + 128 + 512), 2.0 * nseq * T * TH * 3 * TH, st);
-  switch (tgru_seqs_per_cta(nseq)) {
-    case 1: tgru_fwd_kernel<1><<<nseq, TNT, 0, st>>>(p, B, T); break;
-    case 2: tgru_fwd_kernel<2><<<(nseq + 1) / 2, TNT, 0, st>>>(p, B, T); break;
-    default: tgru_fwd_kernel<4><<<(nseq + 3) / 4, TNT, 0, st>>>(p, B, T); break;
+  static const int old_layout = [] { const char* e = getenv("TRU_TGRU_OLD"); return e ? atoi(e) : 0; }();   // A/B switch
+  const int sc = tgru_seqs_per_cta(nseq);
+  if (old_layout) {
+    switch (sc) {
+      case 1: tgru_fwd_kernel<1><<<nseq, TNT, 0, st>>>(p, B, T); break;
+      case 2: tgru_fwd_kernel<2><<<(nseq + 1) / 2, TNT, 0, st>>>(p, B, T); break;
+      default: tgru_fwd_kernel<4><<<(nseq + 3) / 4, TNT, 0, st>>>(p, B, T); break;
+    }
+  } else {
+    switch (sc) {
+      case 1: tgru_fwd3_kernel<1><<<nseq, T3NT, 0, st>>>(p, B, T); break;
+      case 2: tgru_fwd3_kernel<2><<<(nseq + 1) / 2, T3NT, 0, st>>>(p, B, T); break;
+      default: tgru_fwd3_kernel<4><<<(nseq + 3) / 4, T3NT, 0, st>>>(p, B, T); break;
+    }
   }
   TRU_LAUNCH_CHECK();
   return TRU_OK;

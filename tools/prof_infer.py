@@ -12,8 +12,11 @@ sys.path.insert(0, ROOT)
 from tinyrecurrentunet_b200 import _lib as L, network, util  # noqa: E402
 
 
+WARM = 3
+
+
 def report(title, fn, reps):
-    for _ in range(3):
+    for _ in range(WARM):
         fn()
     torch.cuda.synchronize()
     L.profile_enable(True)
@@ -35,19 +38,23 @@ def main():
     ap.add_argument("--streams", type=int, default=4096)
     ap.add_argument("--offline-batch", type=int, default=37)
     ap.add_argument("--fusion", type=int, default=1)
+    ap.add_argument("--ncu", action="store_true", help="one warm-up and one measured pass per path (for an ncu launch list)")
     a = ap.parse_args()
+    global WARM
+    if a.ncu:
+        WARM = 1
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
     net = network.TRUNet().to(dev).eval()
     L.lib.tru_debug_set_eval_fusion(a.fusion)
     frames = 0.1 * torch.randn(a.streams, 512, device=dev)
     sd = util.StreamingDenoiser(net, a.streams, device=dev)
-    report("streaming step, %d streams" % a.streams, lambda: sd.step(frames), 5)
+    report("streaming step, %d streams" % a.streams, lambda: sd.step(frames), 1 if a.ncu else 5)
     del sd
     if a.offline_batch:
         clips = 0.1 * torch.randn(a.offline_batch, 160000, device=dev)
         with torch.no_grad():
-            report("offline batch, %d x 10-s clips" % a.offline_batch, lambda: util.denoise(net, clips), 3)
+            report("offline batch, %d x 10-s clips" % a.offline_batch, lambda: util.denoise(net, clips), 1 if a.ncu else 3)
 
 
 if __name__ == "__main__":
