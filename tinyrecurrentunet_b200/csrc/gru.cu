@@ -607,6 +607,150 @@ __global__ void __launch_bounds__(TNT, 1) tgru_bwd_kernel(const __grid_constant_
   }
 }
 
+// ---- backward, second layout (same idea as tgru_fwd3_kernel) ----------------------------------------------------------------
+// 512 threads, thread = (4 consecutive outputs k = 4 kp .. 4 kp + 3, j-slice jq of 16): W_hh[24 jq .. 24 jq + 24)[4 kp .. + 4) =
+// 96 weights; one float4 of gate gradients feeds 16 FFMAs.  The 16 j-slices of an output group are the lanes of a half warp:
+// four shuffle scatter stages (xor 1, 2: the four outputs; xor 4, 8: the sequences) leave every lane with dh_prev of ONE
+// (sequence, unit) = (jq >> 2, 4 kp + (jq & 3)), and that lane also does this element's gate-gradient arithmetic: its carry
+// never leaves the register.  Gate gradients are double buffered, the per-step operands (dH | r | z | n | hn | h_prev) are staged
+// two steps ahead in a three-slot ring: ONE barrier per step (three before).
+constexpr int TB_DLD = 3 * TH + 64;   // gate-gradient row: j-slice jq starts at 28 jq floats
+constexpr int TB_SLD = 6 * TH + 8;    // staged-operand row stride: the sequences of a warp's element phase read disjoint banks
+__device__ __forceinline__ int tb_didx(int j) { return j + (j / 24) * 4; }
+
+template <int N>
+__device__ __forceinline__ void tb_scatter(const float (&in)[2 * N], float (&out)[N], int bit, int lane_xor) {
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+    const float keep = bit ? in[2 * n + 1] : in[2 * n], send = bit ? in[2 * n] : in[2 * n + 1];
+    out[n] = keep + __shfl_xor_sync(0xffffffffu, send, lane_xor);
+  }
+}
+
+template <int SC>
+__global__ void __launch_bounds__(T3NT, 1) tgru_bwd3_kernel(const __grid_constant__ GruParams p, int B, int T) {
+  extern __shared__ __align__(16) float tgru_bwd_smem[];
+  float (*dgs)[SC][TB_DLD] = (float (*)[SC][TB_DLD])tgru_bwd_smem;                        // [2]
+  float (*sv)[SC][TB_SLD] = (float (*)[SC][TB_SLD])(tgru_bwd_smem + 2 * SC * TB_DLD);     // [3]
+  const int tid = threadIdx.x, kp = tid >> 4, jq = tid & 15;
+  float w[24][4];
+#pragma unroll
+  for (int jj = 0; jj < 24; ++jj) {
+    const float4 v = ld4(p.whh[0] + (long)(24 * jq + jj) * TH + 4 * kp);
+    w[jj][0] = v.x; w[jj][1] = v.y; w[jj][2] = v.z; w[jj][3] = v.w;
+  }
+  const int nseq = B * TL;
+  const int sbase = blockIdx.x * SC;
+  const int c0 = jq & 1, c1 = (jq >> 1) & 1, c2 = (jq >> 2) & 1, c3 = jq >> 3;
+  // the element this lane owns
+  const int own_s = SC == 4 ? (jq >> 2) : (SC == 2 ? c2 : 0);
+  const int own_u = 4 * kp + (jq & 3);
+  const bool owner = SC == 4 ? true : (SC == 2 ? c3 == 0 : (jq >> 2) == 0);
+  const int sidx = sbase + own_s;
+  const bool ok = owner && sidx < nseq;
+  const long ibase = ok ? ((long)(sidx / TL) * T) * TL + sidx % TL : 0;
+  // copy plan (stage() is called for t = T - 1, T - 2, ... in order, so the source offsets just run backwards; 32-bit, in float4 units):
+  //   A: every thread < 128 SC: cache chunk (sequence tid >> 7, float4 tid & 127) -> r | z | n | hn
+  //   B: threads < 32 SC: dH chunk (sequence tid >> 5, float4 tid & 31); threads in [32 SC, 64 SC): the same of h_prev = H of step t - 1
+  static_assert(SC * 128 <= T3NT, "one cache chunk per thread");
+  const int sA = tid >> 7, qA = tid & 127;
+  const bool okA = tid < SC * 128 && sbase + sA < nseq;
+  const bool isHp = tid >= 32 * SC;
+  const int tB = isHp ? tid - 32 * SC : tid, sB = tB >> 5, qB = tB & 31;
+  const bool okB = tid < 64 * SC && sbase + sB < nseq;
+  int offA = 0, offB = 0;
+  if (okA) { const int si = sbase + sA; offA = (((si / TL) * T + (T - 1)) * TL + si % TL) * 128 + qA; }
+  if (okB) { const int si = sbase + sB; offB = (((si / TL) * T + (T - 1)) * TL + si % TL - (isHp ? TL : 0)) * 32 + qB; }
+  const float* baseB = isHp ? p.H : p.dH;
+  const int dA = sA * TB_SLD + TH + qA * 4, dB = sB * TB_SLD + (isHp ? 5 * TH : 0) + qB * 4;
+  auto stage = [&](int t, int buf) {
+    float* s0 = &sv[buf][0][0];
+    if (okA) cp_async16(s0 + dA, p.cache + 4 * (long)offA);
+    if (okB) {
+      if (isHp && t == 0) {                              // the state before the first step: h0 or zero
+        if (p.h0) cp_async16(s0 + dB, p.h0 + (long)(sbase + sB) * TH + qB * 4);
+        else *(float4*)(s0 + dB) = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        cp_async16(s0 + dB, baseB + 4 * (long)offB);
+      }
+    }
+    offA -= TL * 128; offB -= TL * 32;
+    cp_async_commit();
+  };
+  const int d0 = tb_didx(own_u), d1 = tb_didx(TH + own_u), d2 = tb_didx(2 * TH + own_u);
+  float* gi = p.dGi + (ibase + (long)(T - 1) * TL) * (3 * TH) + own_u;          // the owner's output row of step t, running backwards
+  const long ghd = p.dGh - p.dGi;
+  float carry = 0.f;
+  stage(T - 1, 0);
+  if (T > 1) stage(T - 2, 1); else cp_async_commit();
+  cp_async_wait<1>();
+  __syncthreads();
+  int gb = 0, nb = 2;                                  // ring slots of step t and of step t - 2
+  for (int t = T - 1; t >= 0; --t) {
+    if (t >= 2) stage(t - 2, nb); else cp_async_commit();
+    float dd = 0.f;
+    if (owner) {
+      const float* v = &sv[gb][own_s][own_u];
+      const float v_dh = v[0], v_r = v[TH], v_z = v[2 * TH], v_n = v[3 * TH], v_hn = v[4 * TH], v_hp = v[5 * TH];
+      const float dh = v_dh + carry;
+      const float dn = dh * (1.0f - v_z) * (1.0f - v_n * v_n);
+      const float dr = dn * v_hn * v_r * (1.0f - v_r);
+      const float dz = dh * (v_hp - v_n) * v_z * (1.0f - v_z);
+      const float dhn = dn * v_r;
+      dd = dh * v_z;
+      float* d = &dgs[t & 1][own_s][0];
+      d[d0] = dr; d[d1] = dz; d[d2] = dhn;
+      if (ok) {
+        gi[0] = dr; gi[TH] = dz; gi[2 * TH] = dn;
+        float* gh = gi + ghd;
+        gh[0] = dr; gh[TH] = dz; gh[2 * TH] = dhn;
+        gi -= TL * 3 * TH;
+      }
+    }
+    cp_async_wait<1>();                                 // the operands of step t - 1 (staged one step ago) have landed
+    __syncthreads();                                    // ... for everybody; and this step's gate gradients are complete
+    const float* dcur = &dgs[t & 1][0][0] + 28 * jq;
+    float acc[SC * 4];
+#pragma unroll
+    for (int i = 0; i < SC * 4; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int q6 = 0; q6 < 6; ++q6) {
+#pragma unroll
+      for (int s = 0; s < SC; ++s) {
+        const float4 g = *(const float4*)(dcur + s * TB_DLD + q6 * 4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float a = acc[s * 4 + i];
+          a = fmaf(w[q6 * 4][i], g.x, a); a = fmaf(w[q6 * 4 + 1][i], g.y, a);
+          a = fmaf(w[q6 * 4 + 2][i], g.z, a); a = fmaf(w[q6 * 4 + 3][i], g.w, a);
+          acc[s * 4 + i] = a;
+        }
+      }
+    }
+    // reduce over the 16 j-slices, scattered: xor 1 / 2 pick the output (jq & 3), xor 4 / 8 the sequence (jq >> 2)
+    float r1[SC * 2], r2[SC];
+    tb_scatter<SC * 2>(acc, r1, c0, 1);
+    tb_scatter<SC>(r1, r2, c1, 2);
+    float dhp;
+    if constexpr (SC == 4) {
+      float r3[2], r4[1];
+      tb_scatter<2>(r2, r3, c2, 4);
+      tb_scatter<1>(r3, r4, c3, 8);
+      dhp = r4[0];
+    } else if constexpr (SC == 2) {
+      float r3[1];
+      tb_scatter<1>(r2, r3, c2, 4);
+      dhp = r3[0] + __shfl_xor_sync(0xffffffffu, r3[0], 8);
+    } else {
+      const float k = r2[0] + __shfl_xor_sync(0xffffffffu, r2[0], 4);
+      dhp = k + __shfl_xor_sync(0xffffffffu, k, 8);
+    }
+    carry = dd + dhp;
+    gb = gb == 2 ? 0 : gb + 1;
+    nb = nb == 2 ? 0 : nb + 1;
+  }
+}
+
 // Single-step TGRU (streaming inference, T = 1): the hidden projection G_h = h W_hh^T + b_hh is one dense GEMM over all
 // sequences (done by the caller on the tensor-core kernel) instead of nseq / 4 CTAs each pulling the 192 KB W_hh
 // through L2; this kernel is the gate arithmetic.  Thread = (sequence, 4 hidden units).
@@ -680,7 +824,7 @@ int launch_tgru_fwd(const GruParams& p, int B, int T, cudaStream_t st) {
   ProfScope prof("tgru_fwd", 4.0 * nseq * T * (384 + 128 + 512), 2.0 * nseq * T * TH * 3 * TH, st);
   static const int old_layout = [] { const char* e = getenv("TRU_TGRU_OLD"); return e ? atoi(e) : 0; }();   // A/B switch
   const int sc = tgru_seqs_per_cta(nseq);
-  if (old_layout) {
+  if (old_layout == 1) {
     switch (sc) {
       case 1: tgru_fwd_kernel<1><<<nseq, TNT, 0, st>>>(p, B, T); break;
       case 2: tgru_fwd_kernel<2><<<(nseq + 1) / 2, TNT, 0, st>>>(p, B, T); break;
@@ -701,6 +845,20 @@ int launch_tgru_bwd(const GruParams& p, int B, int T, cudaStream_t st) {
   const int nseq = B * TL;
   ProfScope prof("tgru_bwd", 4.0 * nseq * T * (128 + 512 + 128 + 768), 2.0 * nseq * T * TH * 3 * TH, st);
   const int sc = tgru_seqs_per_cta(nseq);
+  static const int old_layout = [] { const char* e = getenv("TRU_TGRU_OLD"); return e ? atoi(e) : 0; }();   // A/B switch
+  if (!old_layout) {
+    const size_t smem3 = (size_t)sc * (2 * TB_DLD + 3 * TB_SLD) * 4;          // gate gradients x 2 + staged operands x 3: 12,896 B per sequence
+    if (sc == 1) {
+      tgru_bwd3_kernel<1><<<nseq, T3NT, smem3, st>>>(p, B, T);
+    } else if (sc == 2) {
+      tgru_bwd3_kernel<2><<<(nseq + 1) / 2, T3NT, smem3, st>>>(p, B, T);
+    } else {
+      TRU_SMEM_OPT_IN((tgru_bwd3_kernel<4>), smem3);
+      tgru_bwd3_kernel<4><<<(nseq + 3) / 4, T3NT, smem3, st>>>(p, B, T);
+    }
+    TRU_LAUNCH_CHECK();
+    return TRU_OK;
+  }
   const size_t smem = (size_t)sc * (3 * TH + TBQ * TH + 2 * 6 * TH) * 4;     // dgs + part + sv: 55,296 B at 4 sequences per CTA
   if (sc == 1) {
     tgru_bwd_kernel<1><<<nseq, TNT, smem, st>>>(p, B, T);

@@ -13,9 +13,11 @@ dev = torch.device("cuda:0")
 torch.manual_seed(0)
 net = network.TRUNet().to(dev)
 T = 501
-for B in (1, 9, 18, 36):
+BS = [int(v) for v in os.environ.get("PROBE_B", "1,9,18,36").split(",")]
+MODES = os.environ.get("PROBE_MODE", "eval,train").split(",")
+for B in BS:
     x = torch.randn(B, T, 4, 257, device=dev)
-    for mode in ("eval", "train"):
+    for mode in MODES:
         net.train(mode == "train")
 
         def run():
