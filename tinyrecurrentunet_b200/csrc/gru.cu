@@ -232,155 +232,26 @@ __global__ void __launch_bounds__(FNT) fgru_bwd_kernel(const __grid_constant__ G
 }
 
 // =============================== TGRU ========================================
-// One CTA carries SC sequences through all T steps.  The recurrence is a latency chain (T strictly sequential
-// steps of a 384 x 128 mat-vec per sequence), so the kernel is organised for issue rate per step: 768 threads,
-// thread (j, kh) keeps HALF a row of W_hh (64 floats) in registers, so each scheduler has 6 warps of
-// independent FFMA chains (4 sequences x 64 deep) instead of 3 warps of 128-deep ones; the two half sums meet
-// in shared memory, where the gate phase reads them.
-constexpr int TH = 128, TL = 16, TNT = 768, TROWS = 384, TKH = 64;
-// Backward: a thread keeps a 2 x 32 register tile of W_hh (two columns, one of 12 row-chunks), so one 16-byte broadcast load of
-// the gate gradients feeds 4 FFMA2 (8 FMAs) instead of 2: ncu showed "short scoreboard" (waiting for shared-memory loads) as
-// the top stall at 8.0 warps per issue with the half-column layout.  The same tiling did not pay in the forward kernel
-// (1.43 vs 1.36 ms; with FFMA2 1.80 ms), which keeps one half row per thread.
-constexpr int TKQ = 32, TBQ = TROWS / TKQ;
+// One CTA carries SC sequences (1, 2 or 4: tgru_seqs_per_cta) through all T steps; W_hh (384 x 128) lives in the registers of its
+// 512 threads (96 weights each) for the whole launch.  The first layout of this round - 768 threads at the 80-register cap,
+// half a row of W_hh per thread - left room for ONE float4 of h per thread: SASS had LDS.128 -> four FFMAs chained on one
+// accumulator -> the next LDS.128 into the same registers, a serial load-latency + FMA-latency chain 64 times per step that six
+// warps per scheduler could not cover (2.56 us per step at 4 sequences per CTA, linear in the sequence count:
+// profiles/r02_tgru_probe_old_layout.log).  The kernels below give every thread 128 registers, feed 12 / 16 FFMAs on 3 / 4
+// independent accumulators from every float4 loaded, reduce across the k- / j-slices with shuffles so that one lane OWNS each
+// (sequence, unit) element - its gate arithmetic, previous state and carry stay in registers - and need one barrier per step.
+constexpr int TH = 128, TL = 16;
 
-// Per-step operands (input gates / saved gates) are staged through shared memory with cp.async one step ahead:
-// register prefetches were spilled by the compiler, which turned every step into a synchronous wait for HBM.
+// Per-step operands (input gates / saved gates) are staged through shared memory with cp.async two steps ahead
+// (register prefetches were spilled by the compiler, which turned every step into a synchronous wait for HBM).
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int SC>
-__global__ void __launch_bounds__(TNT, 1) tgru_fwd_kernel(const __grid_constant__ GruParams p, int B, int T) {
-  pdl_trigger();                               // a PDL-launched successor (GEMM) may stage its weights while this runs
-  constexpr int NI = (SC * TH + TNT - 1) / TNT;        // (s,u) items per thread
-  constexpr int NCH = SC * 96;                         // 16-byte chunks of one step's input gates (384 floats per sequence)
-  __shared__ __align__(16) float hs[SC][TH];
-  __shared__ __align__(16) float hid[2][SC][3 * TH];
-  __shared__ __align__(16) float gin[2][SC][3 * TH];
-  const int tid = threadIdx.x, j = tid % TROWS, kh = tid / TROWS;     // kh is warp-uniform (384 = 12 warps)
-  float w[TKH];
-#pragma unroll
-  for (int k4 = 0; k4 < TKH / 4; ++k4) {
-    const float4 v = ld4(p.whh[0] + (long)j * TH + kh * TKH + k4 * 4);
-    w[k4 * 4] = v.x; w[k4 * 4 + 1] = v.y; w[k4 * 4 + 2] = v.z; w[k4 * 4 + 3] = v.w;
-  }
-  const float bj = kh == 0 ? __ldg(p.bhh[0] + j) : 0.f;
-  const int nseq = B * TL;
-  const int sbase = blockIdx.x * SC;
-  // copy plan: chunk c = tid + i*TNT -> sequence c / 96, 16-byte chunk c % 96 of its 384-float gate row
-  auto stage = [&](int t, int buf) {
-#pragma unroll
-    for (int i = 0; i < (NCH + TNT - 1) / TNT; ++i) {
-      const int c = tid + i * TNT;
-      if (c < NCH) {
-        const int s = c / 96, q = c % 96, sidx = sbase + s;
-        if (sidx < nseq) {
-          const long row = ((long)(sidx / TL) * T + t) * TL + sidx % TL;
-          cp_async16(&gin[buf][s][q * 4], p.G + row * (3 * TH) + q * 4);
-        }
-      }
-    }
-    cp_async_commit();
-  };
-  int is[NI], iu[NI]; long ibase[NI]; bool iok[NI]; float hprev[NI];
-#pragma unroll
-  for (int r = 0; r < NI; ++r) {
-    const int it = tid + r * TNT;
-    is[r] = it / TH; iu[r] = it % TH;
-    const int sidx = sbase + is[r];
-    iok[r] = it < SC * TH && sidx < nseq;
-    const int b = iok[r] ? sidx / TL : 0, l = iok[r] ? sidx % TL : 0;
-    ibase[r] = ((long)b * T) * TL + l;                  // row(t) = ibase + t*16
-    hprev[r] = (iok[r] && p.h0) ? __ldg(p.h0 + (long)sidx * TH + iu[r]) : 0.f;
-    if (it < SC * TH) hs[is[r]][iu[r]] = hprev[r];
-  }
-  stage(0, 0);
-  __syncthreads();
-
-  for (int t = 0; t < T; ++t) {
-    if (t + 1 < T) stage(t + 1, (t + 1) & 1); else cp_async_commit();     // always one group per step (uniform wait below)
-    float acc[SC];             // (packed FFMA2 was slower here: measured 1.85 vs 1.35 ms; it does pay in the backward kernel)
-#pragma unroll
-    for (int s = 0; s < SC; ++s) acc[s] = bj;
-    if constexpr (SC >= 4) {
-#pragma unroll
-      for (int k4 = 0; k4 < TKH / 4; ++k4) {
-#pragma unroll
-        for (int s = 0; s < SC; ++s) {
-          const float4 h = *(const float4*)&hs[s][kh * TKH + k4 * 4];
-          acc[s] = fmaf(w[k4 * 4], h.x, acc[s]); acc[s] = fmaf(w[k4 * 4 + 1], h.y, acc[s]);
-          acc[s] = fmaf(w[k4 * 4 + 2], h.z, acc[s]); acc[s] = fmaf(w[k4 * 4 + 3], h.w, acc[s]);
-        }
-      }
-    } else {
-      // few sequences per CTA (small batches: the step is pure latency): 4 / SC independent chains per sequence instead of
-      // one 64-deep dependent FFMA chain
-      constexpr int NCHAIN = 4 / SC;
-      float part[SC][NCHAIN];
-#pragma unroll
-      for (int s = 0; s < SC; ++s)
-#pragma unroll
-        for (int c = 0; c < NCHAIN; ++c) part[s][c] = 0.f;
-#pragma unroll
-      for (int k4 = 0; k4 < TKH / 4; ++k4) {
-#pragma unroll
-        for (int s = 0; s < SC; ++s) {
-          const float4 h = *(const float4*)&hs[s][kh * TKH + k4 * 4];
-          float& a = part[s][k4 % NCHAIN];
-          a = fmaf(w[k4 * 4], h.x, a); a = fmaf(w[k4 * 4 + 1], h.y, a);
-          a = fmaf(w[k4 * 4 + 2], h.z, a); a = fmaf(w[k4 * 4 + 3], h.w, a);
-        }
-      }
-#pragma unroll
-      for (int s = 0; s < SC; ++s) {
-        if constexpr (NCHAIN == 4) acc[s] += (part[s][0] + part[s][1]) + (part[s][2] + part[s][3]);
-        else acc[s] += part[s][0] + part[s][1];
-      }
-    }
-#pragma unroll
-    for (int s = 0; s < SC; ++s) hid[kh][s][j] = acc[s];
-    cp_async_wait<1>();                                 // this step's gates (staged one step ago) have landed
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < NI; ++r) {
-      if (tid + r * TNT < SC * TH) {
-        const int s = is[r], u = iu[r];
-        const float* g = gin[t & 1][s];
-        const float hn = hid[0][s][2 * TH + u] + hid[1][s][2 * TH + u];
-        const float rr = sigmoidf_(g[u] + (hid[0][s][u] + hid[1][s][u]));
-        const float zz = sigmoidf_(g[TH + u] + (hid[0][s][TH + u] + hid[1][s][TH + u]));
-        const float nn = tanhf_(g[2 * TH + u] + rr * hn);
-        const float hnew = (1.0f - zz) * nn + zz * hprev[r];
-        hprev[r] = hnew;
-        hs[s][u] = hnew;
-        if (iok[r]) {
-          const long row = ibase[r] + (long)t * TL;
-          p.H[row * TH + u] = hnew;
-          if (p.cache) {
-            float* c = p.cache + row * (4 * TH) + u;
-            c[0] = rr; c[TH] = zz; c[2 * TH] = nn; c[3 * TH] = hn;
-          }
-        }
-      }
-    }
-    __syncthreads();
-  }
-  if (p.hlast) {
-#pragma unroll
-    for (int r = 0; r < NI; ++r)
-      if (iok[r]) p.hlast[(long)(sbase + is[r]) * TH + iu[r]] = hprev[r];
-  }
-}
-
-// ---- forward, second layout (round 2, late) ---------------------------------------------------------------------------
-// SASS of the kernel above at its 80-register cap (768 threads): ONE float4 of h in flight per thread - LDS.128, four
-// FFMAs that chain on one accumulator, the next LDS.128 into the same registers - so every warp runs a serial
-// load-latency + 4 x FMA-latency chain 64 times per step and six warps per scheduler cannot cover it: 2.56 us per step at
-// 4 sequences per CTA, linear in the sequence count (tools/probe_tgru.py), 3x the FFMA issue time.
-// Here: 512 threads (128 registers each), thread = (hidden unit j, k-slice kq): the THREE gate rows j, 128 + j, 256 + j
+// ---- forward -----------------------------------------------------------------------------------------------------------------
+// 512 threads (128 registers each), thread = (hidden unit j, k-slice kq): the THREE gate rows j, 128 + j, 256 + j
 // of W_hh over columns [32 kq, 32 kq + 32) = 96 weights.  One float4 of h feeds 12 FFMAs on 3 independent accumulators
 // (x SC sequences), the loads of the next sequence are in flight meanwhile.  The four k-slices of a unit are adjacent
 // lanes: a two-stage shuffle reduce-scatter leaves lane kq with the three gate sums of SEQUENCE kq, which then does that
@@ -498,116 +369,7 @@ __global__ void __launch_bounds__(T3NT, 1) tgru_fwd3_kernel(const __grid_constan
   if (ok && p.hlast) p.hlast[(long)sidx * TH + j] = hprev;
 }
 
-template <int SC>
-__global__ void __launch_bounds__(TNT, 1) tgru_bwd_kernel(const __grid_constant__ GruParams p, int B, int T) {
-  constexpr int NI = (SC * TH + TNT - 1) / TNT;
-  constexpr int NCH = SC * 192;                        // 16-byte chunks per step: dH (32) + cache r,z,n,hn (128) + h_prev (32) per sequence
-  // dynamic shared memory (55 KB): dgs[SC][384] | part[TBQ][SC][128] | sv[2][SC][768] (staged: dh | r | z | n | hn | h_prev)
-  extern __shared__ __align__(16) float tgru_bwd_smem[];
-  float (*dgs)[3 * TH] = (float (*)[3 * TH])tgru_bwd_smem;
-  float (*part)[SC][TH] = (float (*)[SC][TH])(tgru_bwd_smem + SC * 3 * TH);
-  float (*sv)[SC][6 * TH] = (float (*)[SC][6 * TH])(tgru_bwd_smem + SC * 3 * TH + TBQ * SC * TH);
-  const int tid = threadIdx.x, kp = tid & 63, jq = tid >> 6;      // jq: 0..11 (32 rows of W_hh each), warp-uniform
-  const int k0 = 2 * kp;                                // columns k0, k0 + 1 of W_hh, rows [32 jq, 32 jq + 32)
-  float w0[TKQ], w1[TKQ];
-#pragma unroll
-  for (int jj = 0; jj < TKQ; ++jj) {
-    const float2 v = __ldg((const float2*)(p.whh[0] + (long)(jq * TKQ + jj) * TH + k0));
-    w0[jj] = v.x; w1[jj] = v.y;
-  }
-  const int nseq = B * TL;
-  const int sbase = blockIdx.x * SC;
-  auto stage = [&](int t, int buf) {
-#pragma unroll
-    for (int i = 0; i < (NCH + TNT - 1) / TNT; ++i) {
-      const int c = tid + i * TNT;
-      if (c < NCH) {
-        const int s = c / 192, q = c % 192, sidx = sbase + s;
-        if (sidx < nseq) {
-          const long row = ((long)(sidx / TL) * T + t) * TL + sidx % TL;
-          if (q < 32) cp_async16(&sv[buf][s][q * 4], p.dH + row * TH + q * 4);
-          else if (q < 160) cp_async16(&sv[buf][s][TH + (q - 32) * 4], p.cache + row * (4 * TH) + (q - 32) * 4);
-          else if (t > 0) cp_async16(&sv[buf][s][5 * TH + (q - 160) * 4], p.H + (row - TL) * TH + (q - 160) * 4);
-          else if (p.h0) cp_async16(&sv[buf][s][5 * TH + (q - 160) * 4], p.h0 + (long)sidx * TH + (q - 160) * 4);
-          else *(float4*)&sv[buf][s][5 * TH + (q - 160) * 4] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-    }
-    cp_async_commit();
-  };
-  int is[NI], iu[NI]; long ibase[NI]; bool iok[NI]; float carry[NI];
-#pragma unroll
-  for (int r = 0; r < NI; ++r) {
-    const int it = tid + r * TNT;
-    is[r] = it / TH; iu[r] = it % TH;
-    const int sidx = sbase + is[r];
-    iok[r] = it < SC * TH && sidx < nseq;
-    const int b = iok[r] ? sidx / TL : 0, l = iok[r] ? sidx % TL : 0;
-    ibase[r] = ((long)b * T) * TL + l;
-    carry[r] = 0.f;
-  }
-  stage(T - 1, (T - 1) & 1);
-
-  for (int t = T - 1; t >= 0; --t) {
-    if (t > 0) stage(t - 1, (t - 1) & 1); else cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();                                     // step t's operands visible; also orders the previous step's part[] reads
-    float dd[NI];
-#pragma unroll
-    for (int r = 0; r < NI; ++r) {
-      dd[r] = 0.f;
-      if (tid + r * TNT < SC * TH) {
-        const int s = is[r], u = iu[r];
-        const float* v = sv[t & 1][s];
-        float v_dh = 0.f, v_r = 0.f, v_z = 0.f, v_n = 0.f, v_hn = 0.f, v_hp = 0.f;
-        if (iok[r]) { v_dh = v[u]; v_r = v[TH + u]; v_z = v[2 * TH + u]; v_n = v[3 * TH + u]; v_hn = v[4 * TH + u]; v_hp = v[5 * TH + u]; }
-        const float dh = v_dh + carry[r];
-        const float dn = dh * (1.0f - v_z) * (1.0f - v_n * v_n);
-        const float dr = dn * v_hn * v_r * (1.0f - v_r);
-        const float dz = dh * (v_hp - v_n) * v_z * (1.0f - v_z);
-        const float dhn = dn * v_r;
-        dd[r] = dh * v_z;
-        dgs[s][u] = dr; dgs[s][TH + u] = dz; dgs[s][2 * TH + u] = dhn;
-        if (iok[r]) {
-          const long row = ibase[r] + (long)t * TL;
-          float* gi = p.dGi + row * (3 * TH) + u;
-          float* gh = p.dGh + row * (3 * TH) + u;
-          gi[0] = dr; gi[TH] = dz; gi[2 * TH] = dn;
-          gh[0] = dr; gh[TH] = dz; gh[2 * TH] = dhn;
-        }
-      }
-    }
-    __syncthreads();
-    float2 acc0[SC], acc1[SC];                            // packed over pairs of rows (FFMA2): the two lanes are added at the end
-#pragma unroll
-    for (int s = 0; s < SC; ++s) { acc0[s] = make_float2(0.f, 0.f); acc1[s] = make_float2(0.f, 0.f); }
-#pragma unroll
-    for (int j4 = 0; j4 < TKQ / 4; ++j4) {
-#pragma unroll
-      for (int s = 0; s < SC; ++s) {
-        const float4 g = *(const float4*)&dgs[s][jq * TKQ + j4 * 4];
-        acc0[s] = __ffma2_rn(make_float2(w0[j4 * 4], w0[j4 * 4 + 1]), make_float2(g.x, g.y), acc0[s]);
-        acc1[s] = __ffma2_rn(make_float2(w1[j4 * 4], w1[j4 * 4 + 1]), make_float2(g.x, g.y), acc1[s]);
-        acc0[s] = __ffma2_rn(make_float2(w0[j4 * 4 + 2], w0[j4 * 4 + 3]), make_float2(g.z, g.w), acc0[s]);
-        acc1[s] = __ffma2_rn(make_float2(w1[j4 * 4 + 2], w1[j4 * 4 + 3]), make_float2(g.z, g.w), acc1[s]);
-      }
-    }
-#pragma unroll
-    for (int s = 0; s < SC; ++s) *(float2*)&part[jq][s][k0] = make_float2(acc0[s].x + acc0[s].y, acc1[s].x + acc1[s].y);
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < NI; ++r)
-      if (tid + r * TNT < SC * TH) {
-        const int s = is[r], u = iu[r];
-        float sum = 0.f;
-#pragma unroll
-        for (int q = 0; q < TBQ; q += 4) sum += (part[q][s][u] + part[q + 1][s][u]) + (part[q + 2][s][u] + part[q + 3][s][u]);
-        carry[r] = dd[r] + sum;
-      }
-  }
-}
-
-// ---- backward, second layout (same idea as tgru_fwd3_kernel) ----------------------------------------------------------------
+// ---- backward (same idea as tgru_fwd3_kernel) --------------------------------------------------------------------------------
 // 512 threads, thread = (4 consecutive outputs k = 4 kp .. 4 kp + 3, j-slice jq of 16): W_hh[24 jq .. 24 jq + 24)[4 kp .. + 4) =
 // 96 weights; one float4 of gate gradients feeds 16 FFMAs.  The 16 j-slices of an output group are the lanes of a half warp:
 // four shuffle scatter stages (xor 1, 2: the four outputs; xor 4, 8: the sequences) leave every lane with dh_prev of ONE
@@ -811,9 +573,10 @@ int launch_fgru_bwd(const GruParams& p, cudaStream_t st) {
   return TRU_OK;
 }
 
-// Sequences per CTA of the TGRU recurrence kernels: the kernels hold one CTA per SM (768 threads), every step is a latency
-// chain, and a step costs less the fewer sequences the CTA carries - so small batches (one clip = 16 sequences: configs[0],
-// rt.py:20-27) spread over more SMs; from 2 x SMs sequences up it is 4 per CTA (B = 32: 128 CTAs, B = 37: one full wave).
+// Sequences per CTA of the TGRU recurrence kernels: one CTA per SM (512 threads x 128 registers), and a step costs
+// 0.70 / 1.03 / 1.88 us forward (0.68 / 1.15 / 2.28 backward) with 1 / 2 / 4 sequences (tools/probe_tgru.py) - so small batches
+// (one clip = 16 sequences: configs[0], rt.py:20-27) spread over more SMs; from 2 x SMs sequences up it is 4 per CTA (B = 32:
+// 128 CTAs, B = 37: one full wave).
 static int tgru_seqs_per_cta(int nseq) {
   const int sms = sm_count();
   return nseq <= sms ? 1 : (nseq <= 2 * sms ? 2 : 4);
@@ -822,20 +585,10 @@ static int tgru_seqs_per_cta(int nseq) {
 int launch_tgru_fwd(const GruParams& p, int B, int T, cudaStream_t st) {
   const int nseq = B * TL;
   ProfScope prof("tgru_fwd", 4.0 * nseq * T * (384 + 128 + 512), 2.0 * nseq * T * TH * 3 * TH, st);
-  static const int old_layout = [] { const char* e = getenv("TRU_TGRU_OLD"); return e ? atoi(e) : 0; }();   // A/B switch
-  const int sc = tgru_seqs_per_cta(nseq);
-  if (old_layout == 1) {
-    switch (sc) {
-      case 1: tgru_fwd_kernel<1><<<nseq, TNT, 0, st>>>(p, B, T); break;
-      case 2: tgru_fwd_kernel<2><<<(nseq + 1) / 2, TNT, 0, st>>>(p, B, T); break;
-      default: tgru_fwd_kernel<4><<<(nseq + 3) / 4, TNT, 0, st>>>(p, B, T); break;
-    }
-  } else {
-    switch (sc) {
-      case 1: tgru_fwd3_kernel<1><<<nseq, T3NT, 0, st>>>(p, B, T); break;
-      case 2: tgru_fwd3_kernel<2><<<(nseq + 1) / 2, T3NT, 0, st>>>(p, B, T); break;
-      default: tgru_fwd3_kernel<4><<<(nseq + 3) / 4, T3NT, 0, st>>>(p, B, T); break;
-    }
+  switch (tgru_seqs_per_cta(nseq)) {
+    case 1: tgru_fwd3_kernel<1><<<nseq, T3NT, 0, st>>>(p, B, T); break;
+    case 2: tgru_fwd3_kernel<2><<<(nseq + 1) / 2, T3NT, 0, st>>>(p, B, T); break;
+    default: tgru_fwd3_kernel<4><<<(nseq + 3) / 4, T3NT, 0, st>>>(p, B, T); break;
   }
   TRU_LAUNCH_CHECK();
   return TRU_OK;
@@ -845,28 +598,14 @@ int launch_tgru_bwd(const GruParams& p, int B, int T, cudaStream_t st) {
   const int nseq = B * TL;
   ProfScope prof("tgru_bwd", 4.0 * nseq * T * (128 + 512 + 128 + 768), 2.0 * nseq * T * TH * 3 * TH, st);
   const int sc = tgru_seqs_per_cta(nseq);
-  static const int old_layout = [] { const char* e = getenv("TRU_TGRU_OLD"); return e ? atoi(e) : 0; }();   // A/B switch
-  if (!old_layout) {
-    const size_t smem3 = (size_t)sc * (2 * TB_DLD + 3 * TB_SLD) * 4;          // gate gradients x 2 + staged operands x 3: 12,896 B per sequence
-    if (sc == 1) {
-      tgru_bwd3_kernel<1><<<nseq, T3NT, smem3, st>>>(p, B, T);
-    } else if (sc == 2) {
-      tgru_bwd3_kernel<2><<<(nseq + 1) / 2, T3NT, smem3, st>>>(p, B, T);
-    } else {
-      TRU_SMEM_OPT_IN((tgru_bwd3_kernel<4>), smem3);
-      tgru_bwd3_kernel<4><<<(nseq + 3) / 4, T3NT, smem3, st>>>(p, B, T);
-    }
-    TRU_LAUNCH_CHECK();
-    return TRU_OK;
-  }
-  const size_t smem = (size_t)sc * (3 * TH + TBQ * TH + 2 * 6 * TH) * 4;     // dgs + part + sv: 55,296 B at 4 sequences per CTA
+  const size_t smem = (size_t)sc * (2 * TB_DLD + 3 * TB_SLD) * 4;            // gate gradients x 2 + staged operands x 3: 12,896 B per sequence
   if (sc == 1) {
-    tgru_bwd_kernel<1><<<nseq, TNT, smem, st>>>(p, B, T);
+    tgru_bwd3_kernel<1><<<nseq, T3NT, smem, st>>>(p, B, T);
   } else if (sc == 2) {
-    tgru_bwd_kernel<2><<<(nseq + 1) / 2, TNT, smem, st>>>(p, B, T);
+    tgru_bwd3_kernel<2><<<(nseq + 1) / 2, T3NT, smem, st>>>(p, B, T);
   } else {
-    TRU_SMEM_OPT_IN((tgru_bwd_kernel<4>), smem);
-    tgru_bwd_kernel<4><<<(nseq + 3) / 4, TNT, smem, st>>>(p, B, T);
+    TRU_SMEM_OPT_IN((tgru_bwd3_kernel<4>), smem);
+    tgru_bwd3_kernel<4><<<(nseq + 3) / 4, T3NT, smem, st>>>(p, B, T);
   }
   TRU_LAUNCH_CHECK();
   return TRU_OK;
