@@ -137,6 +137,14 @@ if d.get("inference"):
           "host memory and its audio copied back: %.3f ms -> RTF %.0f; %.3f of the HBM roofline on %.2f GB algorithmic bytes per step"
           % (s["streams"], s["ms_per_step"], s["rtf"], s["e2e"]["ms_per_step"], s["e2e"]["rtf"], s["roofline"]["frac"],
              s["roofline"]["algorithmic_bytes_per_step"] / 1e9))
+        if "pipelined_ms_per_step" in s["e2e"]:
+            w("  * the same copies on side streams, one hop ahead / behind (`util.stream_host_frames`): %.3f ms per hop -> RTF %.0f"
+              % (s["e2e"]["pipelined_ms_per_step"], s["e2e"]["pipelined_rtf"]))
+        g = s.get("cuda_graph")
+        if g and "ms_per_step" in g:
+            w("  * step replayed as ONE CUDA graph (`StreamingDenoiser(cuda_graph=True)`): %.3f ms device-resident (RTF %.0f), %.3f ms with "
+              "serial copies, %.3f ms with pipelined copies (RTF %.0f)" % (g["ms_per_step"], g["rtf"], g["e2e_ms_per_step"],
+                                                                          g["e2e_pipelined_ms_per_step"], g["e2e_pipelined_rtf"]))
     if "offline" in i:
         o = i["offline"]
         w("* offline (configs[4]): %d x 10-s clips per GPU on %d GPU(s), host buffers in and out: %.3f s -> **RTF %.0f** (%.0f per GPU); "
@@ -147,6 +155,9 @@ if d.get("inference"):
         w("* latency (configs[0]): one 4-s clip, host to host: GPU %.2f ms (RTF %.0f), CPU oracle %s ms on %s threads / %s ms on one; "
           "one stream, one frame: %.3f ms per 8-ms hop" % (l["gpu_ms"], l["gpu_rtf"], l.get("cpu_ms"), l.get("cpu_threads"), l.get("cpu_1thread_ms"),
                                                            l["gpu_single_frame_step_ms"]))
+        if "gpu_cuda_graph_ms" in l:
+            w("  * as captured CUDA graphs: the 4-s clip (`util.GraphedDenoise`) %s ms, the single-frame step %s ms"
+              % (l["gpu_cuda_graph_ms"], l.get("gpu_single_frame_step_cuda_graph_ms")))
 r = d["roofline"]
 w("* roofline of the dominant kernel family (`%s`): %.0f GB/s algorithmic = **%.3f** of the measured %.0f GB/s copy peak; "
   "ncu DRAM traffic per launch %s B vs %.0f B algorithmic" % (r["kernel"], r["achieved"], r["frac"], peak, r.get("traffic"), r.get("algorithmic_bytes_per_launch", 0)))
