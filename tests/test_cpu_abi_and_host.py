@@ -93,7 +93,8 @@ def test_reference_api_names_exist():
                        (stft_loss, ["stft", "SpectralConvergenceLoss", "LogSTFTMagnitudeLoss", "STFTLoss",
                                     "MultiResolutionSTFTLoss"]),
                        (dataset, ["ProcessAudio", "pcenfunc", "unwrap", "diff", "DataAugment"]),
-                       (util, ["loss_fn", "sampling", "find_max_epoch", "LinearWarmupCosineDecay"]),
+                       (util, ["loss_fn", "sampling", "find_max_epoch", "LinearWarmupCosineDecay", "denoise", "denoise_host_batches",
+                               "StreamingDenoiser", "GraphedDenoise", "stream_host_frames", "CudaPrefetcher"]),
                        (cos_loss, ["CosSimLoss"]),
                        (optim, ["FlatAdamW"]),
                        (distributed, ["init_distributed", "apply_gradient_allreduce", "reduce_tensor"])):
@@ -247,3 +248,27 @@ def test_fold_batchnorm_export_keeps_the_eval_outputs():
         y2 = ref2(x)
     assert ((y2 - y).abs().max() / y.abs().max()).item() <= 1e-5
     assert not torch.equal(folded["encoder.1.DepthwiseSeparableConv1d.0.weight"], sd["encoder.1.DepthwiseSeparableConv1d.0.weight"])
+
+
+def test_cuda_graph_threshold_is_the_first_frame_with_a_full_overlap_add_window():
+    """StreamingDenoiser replays its step as a CUDA graph from frame GRAPH_FROM on.  The only step argument that depends
+    on the frame index is the back end's 1 / (number of frames overlapping the emitted block) (backend.cu,
+    backend_step_kernel; block frame_index - 2 of the centre-framed iSTFT of dataset.py:293-296): it must be constant
+    from GRAPH_FROM on and not before.  Checked against the overlap-add envelope torch.istft itself divides by."""
+    from tinyrecurrentunet_b200 import util
+    T = 12
+    spec = torch.stft(torch.ones(128 * (T - 1)), 512, hop_length=128, window=torch.ones(512), center=True,
+                      pad_mode="reflect", return_complex=True)
+    assert spec.shape[1] == T
+    frames = torch.ones(T, 512)                                         # every frame contributes 1 to each sample it covers
+    env = torch.nn.functional.fold(frames.t().unsqueeze(0), (1, 128 * (T - 1) + 512), (1, 512), stride=(1, 128))[0, 0, 0]
+    env = env[256:256 + 128 * (T - 1)]                                  # centre trimming
+    per_block = env.view(T - 1, 128)
+    assert all(len(set(b.tolist())) == 1 for b in per_block[1:T - 3]), "interior blocks have one count each"
+    counts = [int(b[0]) for b in per_block]                             # frames overlapping block q (first sample)
+    first_full = next(q for q, c in enumerate(counts) if c == 4)
+    assert util.StreamingDenoiser.GRAPH_FROM == first_full + 2          # block q is emitted by the step of frame q + 2
+    assert all(c == 4 for c in counts[first_full:T - 3])
+    # the kernel's own formula for an added frame: newest - max(frame_index - 3, 0) + 1
+    kernel_cnt = [fi - max(fi - 3, 0) + 1 for fi in range(T)]
+    assert kernel_cnt[util.StreamingDenoiser.GRAPH_FROM - 1] != 4 and all(c == 4 for c in kernel_cnt[util.StreamingDenoiser.GRAPH_FROM:])
