@@ -170,7 +170,9 @@ class StreamingDenoiser:
         the whole step - ~35 kernels of three C calls - is replayed as ONE captured CUDA graph instead of being launched
         one by one: the step of a few streams is launch-bound (rt.py:20-27: one stream, one frame per call).  The graphs
         hold the addresses of the weights: call ``reset_graph()`` after anything that re-allocates them
-        (``optim.FlatAdamW`` re-points ``p.data``; ``load_state_dict`` copies in place and is fine)."""
+        (``optim.FlatAdamW`` re-points ``p.data``; ``load_state_dict`` copies in place and is fine).  The graphs also hold the
+        addresses of the state tensors: reset a stream's state by writing INTO ``pcen`` / ``h`` / ``ola`` (``sd.h[rows].zero_()``), not
+        by rebinding the attributes."""
         if net.training:
             raise ValueError("StreamingDenoiser needs net.eval()")
         self.net, self.beta, self.t = net, beta, 0
